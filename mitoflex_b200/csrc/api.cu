@@ -1,0 +1,286 @@
+// api.cu -- the C ABI of libmfsdbg.so (include/mfsdbg.h): argument checking, error convention, no exceptions out.
+#include <cstring>
+#include <mutex>
+#include <new>
+#include "engine.cuh"
+#include "hostio.h"
+#include "mfsdbg.h"
+
+namespace mf {
+void dev_synth(Ctx &c, const mfsdbg_synth_spec &sp, ReadsView *out);
+void dev_pack_fastq(Ctx &c, const uint8_t *const *texts, const int64_t *n_bytes, int n_texts, int n_policy, ReadsView *out,
+                    int *max_len);
+}  // namespace mf
+
+struct mfsdbg_ctx {
+  mf::Ctx c;
+  explicit mfsdbg_ctx(int dev) : c(dev) {}
+};
+
+static thread_local std::string g_err;
+static std::mutex g_job_mutex;   // one job owns the GPUs at a time (SURVEY.md 8b threading)
+
+const char *mfsdbg_last_error(void) { return g_err.c_str(); }
+int mfsdbg_version(void) { return MFSDBG_VERSION; }
+int mfsdbg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+template <class F>
+static int guarded(F &&f) {
+  try {
+    g_err.clear();
+    f();
+    return MFSDBG_OK;
+  } catch (const mf::CudaError &e) {
+    g_err = e.what();
+    cudaGetLastError();
+    return MFSDBG_ECUDA;
+  } catch (const mf::IoError &e) {
+    g_err = e.what();
+    return MFSDBG_EIO;
+  } catch (const std::invalid_argument &e) {
+    g_err = e.what();
+    return MFSDBG_EINVAL;
+  } catch (const std::bad_alloc &) {
+    g_err = "host memory exhausted";
+    return MFSDBG_ENOMEM;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return MFSDBG_EINTERNAL;
+  } catch (...) {
+    g_err = "unknown failure";
+    return MFSDBG_EINTERNAL;
+  }
+}
+
+mfsdbg_ctx *mfsdbg_ctx_create(int32_t device) {
+  if (device < 0 || device >= mfsdbg_device_count()) {
+    g_err = "no usable CUDA device " + std::to_string(device) + " (libmfsdbg has no CPU fallback)";
+    return nullptr;
+  }
+  mfsdbg_ctx *ctx = nullptr;
+  int rc = guarded([&] { ctx = new mfsdbg_ctx(device); });
+  return rc == MFSDBG_OK ? ctx : nullptr;
+}
+void mfsdbg_ctx_destroy(mfsdbg_ctx *ctx) { delete ctx; }
+int mfsdbg_ctx_set_mem_limit(mfsdbg_ctx *ctx, uint64_t bytes) {
+  if (!ctx) return MFSDBG_EINVAL;
+  ctx->c.mem_limit = (size_t)bytes;
+  return MFSDBG_OK;
+}
+void *mfsdbg_ctx_stream(mfsdbg_ctx *ctx) { return ctx ? (void *)ctx->c.stream : nullptr; }
+int64_t mfsdbg_ctx_launches(mfsdbg_ctx *ctx) { return ctx ? ctx->c.launches : 0; }
+int mfsdbg_ctx_set_profiling(mfsdbg_ctx *ctx, int32_t on) {
+  if (!ctx) return MFSDBG_EINVAL;
+  ctx->c.profiling = on != 0;
+  return MFSDBG_OK;
+}
+const char *mfsdbg_ctx_last_profile(mfsdbg_ctx *ctx) { return ctx ? ctx->c.profile.c_str() : ""; }
+int32_t mfsdbg_words_per_key(int32_t k) { return mf::words_key(k); }
+int32_t mfsdbg_words_per_edge(int32_t k) { return mf::words_edge(k); }
+
+static mf::ReadsView view(const mfsdbg_dev_reads *r) {
+  if (!r || r->n_reads < 0 || r->n_bases < 0 || (r->n_bases > 0 && (!r->packed || !r->starts)))
+    throw std::invalid_argument("bad mfsdbg_dev_reads");
+  return mf::ReadsView{r->packed, r->starts, r->n_reads, r->n_bases};
+}
+static void fill(mfsdbg_dev_edges *o, const mf::EdgesView &e) {
+  o->edges = e.edges;
+  o->n_edges = e.n_edges;
+  o->k = e.k;
+  o->words_per_edge = e.words;
+  o->n_keys = e.n_keys;
+}
+static void fill(mfsdbg_dev_sdbg *o, const mf::SdbgView &g, mf::Ctx &c) {
+  o->rec = g.rec;
+  o->tip_labels = g.labels;
+  o->bucket_items = nullptr;
+  o->n_items = g.n_items;
+  o->n_tips = g.n_tips;
+  o->n_large = g.n_large;
+  o->k = g.k;
+  o->words_per_tip = g.words_tip;
+  (void)c;
+}
+
+int mfsdbg_dev_count(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int32_t k, int32_t min_count, mfsdbg_dev_edges *out,
+                     int64_t *counting_host) {
+  if (!ctx || !out) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::EdgesView e;
+    mf::dev_count(ctx->c, view(reads), k, min_count, &e, counting_host);
+    ctx->c.end_call();
+    fill(out, e);
+  });
+}
+int mfsdbg_dev_seq2sdbg(mfsdbg_ctx *ctx, const uint32_t *edges, int64_t n_edges, int32_t k, int32_t tip_mode,
+                        mfsdbg_dev_sdbg *out) {
+  if (!ctx || !out || n_edges < 0 || (n_edges > 0 && !edges)) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::SdbgView g;
+    mf::dev_seq2sdbg(ctx->c, edges, n_edges, mf::SeqsView{}, k, tip_mode, &g);
+    ctx->c.end_call();
+    fill(out, g, ctx->c);
+  });
+}
+int mfsdbg_dev_read2sdbg(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int32_t k, int32_t min_count, mfsdbg_dev_sdbg *out) {
+  if (!ctx || !out) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::EdgesView e;
+    mf::dev_count(ctx->c, view(reads), k, min_count, &e, nullptr);
+    mf::SdbgView g;
+    mf::dev_seq2sdbg(ctx->c, e.edges, e.n_edges, mf::SeqsView{}, k, 1, &g);
+    ctx->c.end_call();
+    fill(out, g, ctx->c);
+  });
+}
+int mfsdbg_dev_pack_fastq(mfsdbg_ctx *ctx, const uint8_t *text, int64_t n_bytes, int32_t n_policy, mfsdbg_dev_reads *out,
+                          int32_t *max_len) {
+  if (!ctx || !out || n_bytes < 0 || (n_bytes > 0 && !text)) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::ReadsView r;
+    int ml = 0;
+    mf::dev_pack_fastq(ctx->c, &text, &n_bytes, 1, n_policy, &r, &ml);
+    ctx->c.end_call();
+    out->packed = r.packed;
+    out->starts = r.starts;
+    out->n_reads = r.n_reads;
+    out->n_bases = r.n_bases;
+    if (max_len) *max_len = ml;
+  });
+}
+int mfsdbg_dev_count_hist(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int32_t k, int32_t l1_bits, uint64_t *hist_dev) {
+  if (!ctx || !hist_dev) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::dev_count_hist(ctx->c, view(reads), k, l1_bits, reinterpret_cast<unsigned long long *>(hist_dev));
+    ctx->c.end_call();
+  });
+}
+int mfsdbg_dev_count_scatter(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int32_t k, int32_t l1_bits, const uint64_t *hist_dev,
+                             uint32_t *keys_out, int64_t capacity) {
+  if (!ctx || !hist_dev || (!keys_out && capacity > 0)) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::dev_count_scatter(ctx->c, view(reads), k, l1_bits, reinterpret_cast<const unsigned long long *>(hist_dev), keys_out,
+                          capacity);
+    ctx->c.end_call();
+  });
+}
+int mfsdbg_dev_count_finish(mfsdbg_ctx *ctx, uint32_t *keys, uint32_t *scratch, int64_t n_keys, const int64_t *chunk_start,
+                            const int64_t *chunk_size, const int32_t *chunk_seg, int32_t n_chunks, int32_t n_segs, int32_t k,
+                            int32_t l1_bits, int32_t min_count, mfsdbg_dev_edges *out, int64_t *counting_host) {
+  if (!ctx || !out || n_keys < 0 || n_chunks < 0 || n_segs < 1) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::EdgesView e;
+    mf::dev_count_finish(ctx->c, keys, scratch, n_keys, chunk_start, chunk_size, chunk_seg, n_chunks, n_segs, k, l1_bits,
+                         min_count, &e, counting_host);
+    ctx->c.end_call();
+    fill(out, e);
+  });
+}
+int mfsdbg_dev_synth_reads(mfsdbg_ctx *ctx, const mfsdbg_synth_spec *spec, mfsdbg_dev_reads *out) {
+  if (!ctx || !spec || !out) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::ReadsView r;
+    mf::dev_synth(ctx->c, *spec, &r);
+    ctx->c.end_call();
+    out->packed = r.packed;
+    out->starts = r.starts;
+    out->n_reads = r.n_reads;
+    out->n_bases = r.n_bases;
+  });
+}
+
+int mfsdbg_dev_copy(mfsdbg_ctx *ctx, void *dst, const void *src, uint64_t bytes, int32_t kind) {
+  if (!ctx || kind < 0 || kind > 2 || (bytes && (!dst || !src))) return MFSDBG_EINVAL;
+  return guarded([&] {
+    MF_CUDA(cudaSetDevice(ctx->c.device));
+    const cudaMemcpyKind kk = kind == 0 ? cudaMemcpyDeviceToHost : kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (bytes) MF_CUDA(cudaMemcpyAsync(dst, src, bytes, kk, ctx->c.stream));
+    MF_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  });
+}
+int mfsdbg_ctx_edge_bucket_counts(mfsdbg_ctx *ctx, int64_t *out) {
+  if (!ctx || !out) return MFSDBG_EINVAL;
+  memcpy(out, ctx->c.edge_bucket_counts.data(), sizeof(int64_t) * mf::kNumBuckets);
+  return MFSDBG_OK;
+}
+int mfsdbg_ctx_sdbg_bucket_stats(mfsdbg_ctx *ctx, int64_t *out) {
+  if (!ctx || !out) return MFSDBG_EINVAL;
+  memcpy(out, ctx->c.sdbg_bucket_stats.data(), sizeof(int64_t) * mf::kNumBuckets * 3);
+  return MFSDBG_OK;
+}
+
+// ---- file-level entry points ------------------------------------------------------------------
+static int pick_device(const mfsdbg_opts *o) {
+  if (o && o->n_gpus > 0 && o->gpu_ids) return o->gpu_ids[0];
+  return 0;
+}
+static int need_device() {
+  if (mfsdbg_device_count() < 1) {
+    g_err = "no CUDA device visible: libmfsdbg has no CPU fallback";
+    return MFSDBG_ENODEV;
+  }
+  return MFSDBG_OK;
+}
+int mfsdbg_buildlib(const char *lib_file, const char *out_prefix, int32_t n_policy) {
+  if (!lib_file || !out_prefix) return MFSDBG_EINVAL;
+  if (int rc = need_device()) return rc;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    mf::Ctx c(0);
+    mf::file_buildlib(c, lib_file, out_prefix, n_policy);
+  });
+}
+int mfsdbg_count(const mfsdbg_opts *o) {
+  if (!o || !o->read_lib_file || !o->output_prefix) { g_err = "count needs --read_lib_file and --output_prefix"; return MFSDBG_EINVAL; }
+  if (o->need_mercy) { g_err = "--need_mercy is not supported (MitoFlex never passes it: configurations.py:67)"; return MFSDBG_EINVAL; }
+  if (int rc = need_device()) return rc;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    mf::Ctx c(pick_device(o));
+    mf::file_count(c, o->read_lib_file, o->k, o->min_count, o->output_prefix, std::max(1, o->num_cpu_threads));
+  });
+}
+int mfsdbg_seq2sdbg(const mfsdbg_opts *o) {
+  if (!o || !o->output_prefix) { g_err = "seq2sdbg needs --output_prefix"; return MFSDBG_EINVAL; }
+  if (o->need_mercy) { g_err = "--need_mercy is not supported (MitoFlex never passes it: configurations.py:67)"; return MFSDBG_EINVAL; }
+  if (int rc = need_device()) return rc;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    mf::Ctx c(pick_device(o));
+    mf::file_seq2sdbg(c, o->k, o->kmer_from, o->input_prefix, o->contig, o->bubble, o->addi_contig, o->local_contig,
+                      o->output_prefix, std::max(1, o->num_cpu_threads));
+  });
+}
+int mfsdbg_read2sdbg(const mfsdbg_opts *o) {
+  if (!o || !o->read_lib_file || !o->output_prefix) { g_err = "read2sdbg needs --read_lib_file and --output_prefix"; return MFSDBG_EINVAL; }
+  if (o->need_mercy) { g_err = "--need_mercy is not supported (MitoFlex never passes it: configurations.py:67)"; return MFSDBG_EINVAL; }
+  if (int rc = need_device()) return rc;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    mf::Ctx c(pick_device(o));
+    mf::file_read2sdbg(c, o->read_lib_file, o->k, o->min_count, o->output_prefix, std::max(1, o->num_cpu_threads));
+  });
+}

@@ -1,0 +1,885 @@
+// engine.cu -- device pipelines of libmfsdbg: count, seq2sdbg, read2sdbg (sm_100a).
+//
+// count (megahit_core count, KmerCounter):
+//   P0 k_level_hist<ReadsProducer>    prefix histogram of canonical (k+1)-mers straight from packed reads
+//   P1 k_level_scatter<ReadsProducer> keys computed again and scattered by their top l1 bits (no unsorted key pass)
+//   P2 k_level_hist<RecordsProducer>  per-partition histogram of the next l2 bits
+//   P3 k_level_scatter<RecordsProducer>
+//   P4 k_local<kCountEmit>            bucket in shared memory: sub-split, serial finish, run lengths, -m filter
+//   P5 k_gather_edges                 compact per-bucket edge runs into the globally sorted edge array
+// seq2sdbg (SeqToSdbg): k_items_from_edges / k_items_from_seqs, the same partition levels over item words,
+//   k_local<kSdbgCount> -> scans -> k_local<kSdbgEmit>.
+#include "engine.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "items.cuh"
+#include "local.cuh"
+#include "partition.cuh"
+
+namespace mf {
+
+// ------------------------------------------------------------------ memory
+void DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return;
+  release();
+  MF_CUDA(cudaMalloc(&p, bytes));
+  cap = bytes;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+Ctx::Ctx(int dev) : device(dev) {
+  MF_CUDA(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  MF_CUDA(cudaGetDeviceProperties(&prop, dev));
+  sm_count = prop.multiProcessorCount;
+  MF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  edge_bucket_counts.assign(kNumBuckets, 0);
+  sdbg_bucket_stats.assign((size_t)kNumBuckets * 3, 0);
+}
+Ctx::~Ctx() {
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  for (DevBuf *b : {&edges, &sdbg_rec, &sdbg_labels, &sdbg_buckets, &sbits, &pack_words, &pack_starts, &synth_words, &synth_starts})
+    b->release();
+  if (slab) cudaFree(slab);
+  for (auto &s : stages) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
+  if (stream) cudaStreamDestroy(stream);
+}
+size_t Ctx::budget() {
+  if (mem_limit) return mem_limit;
+  size_t fr = 0, tot = 0;
+  MF_CUDA(cudaMemGetInfo(&fr, &tot));
+  mem_limit = (size_t)((double)(fr + slab_bytes) * 0.85);
+  return mem_limit;
+}
+void Ctx::slab_reserve(size_t bytes) {
+  slab_off = 0;
+  if (bytes <= slab_bytes) return;
+  MF_CUDA(cudaStreamSynchronize(stream));
+  if (slab) MF_CUDA(cudaFree(slab));
+  slab = nullptr;
+  slab_bytes = 0;
+  bytes = (bytes + (size_t)(64 << 20)) & ~(size_t)((1 << 20) - 1);
+  cudaError_t e = cudaMalloc(&slab, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw CudaError("out of device memory reserving workspace of " + std::to_string(bytes >> 20) + " MiB");
+  }
+  slab_bytes = bytes;
+}
+void *Ctx::slab_alloc(size_t bytes) {
+  size_t off = (slab_off + 255) & ~(size_t)255;
+  if (off + bytes > slab_bytes) throw CudaError("workspace slab exhausted (internal sizing error)");
+  slab_off = off + bytes;
+  return slab + off;
+}
+void Ctx::begin_call() {
+  MF_CUDA(cudaSetDevice(device));
+  for (auto &s : stages) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
+  stages.clear();
+  open_stages.clear();
+  profile.clear();
+}
+void Ctx::end_call() {
+  MF_CUDA(cudaStreamSynchronize(stream));
+  if (profiling) {
+    char buf[128];
+    for (auto &s : stages) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, s.e0, s.e1);
+      snprintf(buf, sizeof buf, "%s=%.4f;", s.name.c_str(), ms);
+      profile += buf;
+    }
+  }
+}
+void Ctx::stage_begin(const char *name) {
+  if (!profiling) return;
+  StageRec r;
+  r.name = name;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, stream);
+  stages.push_back(r);
+  open_stages.push_back((int)stages.size() - 1);
+}
+void Ctx::stage_end() {
+  if (!profiling || open_stages.empty()) return;
+  cudaEventRecord(stages[open_stages.back()].e1, stream);
+  open_stages.pop_back();
+}
+
+#define MF_W_CASES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10)
+#define MF_DISPATCH_W(Wv, CALL)                                         \
+  switch (Wv) {                                                         \
+    MF_W_CASES(MF_DISPATCH_CASE_##CALL)                                 \
+    default: throw std::runtime_error("unsupported record width (k too large, max k = 150)"); \
+  }
+
+template <class K>
+static void set_smem(K kernel, size_t bytes) {
+  if (bytes > 227 * 1024) throw std::runtime_error("kernel shared memory request exceeds 227 KB");
+  MF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+// ------------------------------------------------------------------ small kernels
+__global__ void k_start_bits(const int64_t *starts, int64_t n_reads, uint32_t *sbits) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_reads) return;
+  int64_t g = starts[i];
+  atomicOr(sbits + (g >> 5), 1u << (g & 31));
+}
+__global__ void k_gather_edges(const uint32_t *__restrict__ arena, const int64_t *__restrict__ desc_off,
+                               const int64_t *__restrict__ desc_cnt, const int64_t *__restrict__ out_off, int nslots, int We,
+                               uint32_t *__restrict__ out) {
+  int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (slot >= nslots) return;
+  int64_t words = desc_cnt[slot] * We;
+  const uint32_t *src = arena + desc_off[slot] * We;
+  uint32_t *dst = out + out_off[slot] * We;
+  for (int64_t x = threadIdx.x & 31; x < words; x += 32) dst[x] = src[x];
+}
+__global__ void k_edge_buckets(const uint32_t *edges, int64_t n, int We, unsigned long long *counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(counts + (edges[i * We] >> 16), 1ull);
+}
+
+// ------------------------------------------------------------------ plan
+struct Plan {
+  int W, l1_bits, l2_bits, sb_bits, cap;
+};
+static int cap_for(int W) {
+  int cap = (60 * 1024 / 4) / W;
+  cap &= ~1;
+  return std::min(cap, 65534);
+}
+static int ceil_log2(double x) {
+  int b = 0;
+  while ((double)(1ull << b) < x && b < 62) ++b;
+  return b;
+}
+// part_limit: bits partition levels + in-bucket split may consume (count: 2(k+1); sdbg: 2(k-1))
+static Plan make_plan(int W, int part_limit, int64_t n_est, int forced_l1 = -1) {
+  Plan p;
+  p.W = W;
+  p.cap = cap_for(W);
+  const double target = p.cap * 0.4;
+  int bits = std::max(1, ceil_log2((double)std::max<int64_t>(n_est, 1) / target));
+  bits = std::min(bits, 2 * kMaxDigitBits);
+  if (forced_l1 >= 0) {
+    p.l1_bits = forced_l1;
+  } else {
+    p.l1_bits = bits <= kMaxDigitBits ? bits : (bits + 1) / 2;
+  }
+  p.l1_bits = std::max(1, std::min(p.l1_bits, std::min(kMaxDigitBits, part_limit)));
+  p.l2_bits = std::max(0, std::min({bits - p.l1_bits, kMaxDigitBits, part_limit - p.l1_bits}));
+  int sb = ceil_log2(std::max(1.0, target / 2.0));
+  p.sb_bits = std::max(0, std::min({sb, kMaxDigitBits, part_limit - p.l1_bits - p.l2_bits}));
+  return p;
+}
+
+// ------------------------------------------------------------------ partition level launcher
+template <int W>
+struct TileCfg {
+  static constexpr int NT = 512;
+  static constexpr int IPT_S = W <= 2 ? 8 : (W <= 4 ? 4 : 2);   // scatter: records held in registers
+  static constexpr int IPT_H = 16;                              // histogram: nothing held
+  static constexpr int TS = NT * IPT_S;
+  static constexpr int TH = NT * IPT_H;
+};
+
+template <int W>
+static void launch_reads_hist(Ctx &c, const ReadsView &r, const uint32_t *sbits, int k, LevelArgs a, unsigned long long *hist) {
+  using C = TileCfg<W>;
+  ReadsProducer<W> p{r.packed, sbits, r.n_bases, k, C::TH};
+  int64_t tiles = div_ceil64(r.n_bases, C::TH);
+  if (tiles == 0) return;
+  size_t smem = ((size_t)((C::NT / 32) << a.nbits) + 1) / 2 * 4 + (size_t)ReadsProducer<W>::smem_words(C::TH, k) * 4;
+  auto kern = k_level_hist<ReadsProducer<W>, W, C::NT, C::IPT_H>;
+  set_smem(kern, smem);
+  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(p, a, hist);
+  MF_LAUNCH_CHECK();
+  c.launches++;
+}
+template <int W>
+static void launch_reads_scatter(Ctx &c, const ReadsView &r, const uint32_t *sbits, int k, LevelArgs a, unsigned long long *cursor,
+                                 uint32_t *out) {
+  using C = TileCfg<W>;
+  ReadsProducer<W> p{r.packed, sbits, r.n_bases, k, C::TS};
+  int64_t tiles = div_ceil64(r.n_bases, C::TS);
+  if (tiles == 0) return;
+  size_t smem = scatter_smem_bytes<W>(C::NT, C::TS, a.nbits, ReadsProducer<W>::smem_words(C::TS, k));
+  auto kern = k_level_scatter<ReadsProducer<W>, W, C::NT, C::IPT_S>;
+  set_smem(kern, smem);
+  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(p, a, cursor, out);
+  MF_LAUNCH_CHECK();
+  c.launches++;
+}
+
+struct HostChunks {
+  std::vector<int64_t> start, size;
+  std::vector<int32_t> seg;
+  std::vector<int64_t> seg_out_start;   // [nseg]
+  int nseg = 0;
+};
+struct DevBuckets {
+  int64_t *start = nullptr, *size = nullptr;
+  int nslots = 0;
+};
+
+// Partition `in` (chunks) by nbits at bit_off into `out`; segments land at seg_out_start.  Returns the bucket table
+// (nseg << nbits slots, slot = seg * nbins + digit) allocated from `alloc`.
+template <int W, class Alloc>
+static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, const HostChunks &hc, int bit_off, int nbits,
+                                  Alloc &&alloc) {
+  using C = TileCfg<W>;
+  const int nchunk = (int)hc.start.size(), nseg = hc.nseg, nbins = 1 << nbits;
+  std::vector<int64_t> tb_h(nchunk + 1), tb_s(nchunk + 1);
+  tb_h[0] = tb_s[0] = 0;
+  for (int i = 0; i < nchunk; ++i) {
+    tb_h[i + 1] = tb_h[i] + div_ceil64(hc.size[i], C::TH);
+    tb_s[i + 1] = tb_s[i] + div_ceil64(hc.size[i], C::TS);
+  }
+  int64_t *d_start = (int64_t *)alloc(sizeof(int64_t) * nchunk), *d_size = (int64_t *)alloc(sizeof(int64_t) * nchunk);
+  int32_t *d_seg = (int32_t *)alloc(sizeof(int32_t) * nchunk);
+  int64_t *d_tbh = (int64_t *)alloc(sizeof(int64_t) * (nchunk + 1)), *d_tbs = (int64_t *)alloc(sizeof(int64_t) * (nchunk + 1));
+  int64_t *d_sos = (int64_t *)alloc(sizeof(int64_t) * nseg);
+  const size_t nsl = (size_t)nseg * nbins;
+  unsigned long long *d_hist = (unsigned long long *)alloc(sizeof(unsigned long long) * nsl);
+  unsigned long long *d_cur = (unsigned long long *)alloc(sizeof(unsigned long long) * nsl);
+  DevBuckets b;
+  b.start = (int64_t *)alloc(sizeof(int64_t) * nsl);
+  b.size = (int64_t *)alloc(sizeof(int64_t) * nsl);
+  b.nslots = (int)nsl;
+  MF_CUDA(cudaMemcpyAsync(d_start, hc.start.data(), sizeof(int64_t) * nchunk, cudaMemcpyHostToDevice, c.stream));
+  MF_CUDA(cudaMemcpyAsync(d_size, hc.size.data(), sizeof(int64_t) * nchunk, cudaMemcpyHostToDevice, c.stream));
+  MF_CUDA(cudaMemcpyAsync(d_seg, hc.seg.data(), sizeof(int32_t) * nchunk, cudaMemcpyHostToDevice, c.stream));
+  MF_CUDA(cudaMemcpyAsync(d_tbh, tb_h.data(), sizeof(int64_t) * (nchunk + 1), cudaMemcpyHostToDevice, c.stream));
+  MF_CUDA(cudaMemcpyAsync(d_tbs, tb_s.data(), sizeof(int64_t) * (nchunk + 1), cudaMemcpyHostToDevice, c.stream));
+  MF_CUDA(cudaMemcpyAsync(d_sos, hc.seg_out_start.data(), sizeof(int64_t) * nseg, cudaMemcpyHostToDevice, c.stream));
+  MF_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nsl, c.stream));
+  // the pageable host vectors above die with this frame: make sure the copies have been consumed
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  LevelArgs a{bit_off, nbits, 0u, (uint32_t)nbins};
+  if (tb_h[nchunk] > 0) {
+    RecordsProducer<W> ph{in, ChunkTable{d_start, d_size, d_seg, d_tbh, nchunk}, C::TH};
+    size_t smem = ((size_t)((C::NT / 32) << nbits) + 1) / 2 * 4 + 16;
+    auto kern = k_level_hist<RecordsProducer<W>, W, C::NT, C::IPT_H>;
+    set_smem(kern, smem);
+    Stage st(c, "level_hist");
+    kern<<<(unsigned)tb_h[nchunk], C::NT, smem, c.stream>>>(ph, a, d_hist);
+    MF_LAUNCH_CHECK();
+    c.launches++;
+  }
+  k_level_scan<<<nseg, kMaxBins, 0, c.stream>>>(d_hist, nbins, d_sos, d_cur, b.start, b.size);
+  MF_LAUNCH_CHECK();
+  c.launches++;
+  if (tb_s[nchunk] > 0) {
+    RecordsProducer<W> ps{in, ChunkTable{d_start, d_size, d_seg, d_tbs, nchunk}, C::TS};
+    size_t smem = scatter_smem_bytes<W>(C::NT, C::TS, nbits, 4);
+    auto kern = k_level_scatter<RecordsProducer<W>, W, C::NT, C::IPT_S>;
+    set_smem(kern, smem);
+    Stage st(c, "level_scatter");
+    kern<<<(unsigned)tb_s[nchunk], C::NT, smem, c.stream>>>(ps, a, d_cur, out);
+    MF_LAUNCH_CHECK();
+    c.launches++;
+  }
+  return b;
+}
+
+// ------------------------------------------------------------------ local finish launcher
+constexpr int kLocalNT = 256;
+template <int W, int MODE>
+static void launch_local(Ctx &c, const LocalArgs &a, int grid) {
+  if (grid <= 0) return;
+  size_t smem = local_smem_bytes<W>(kLocalNT, a.cap, a.sb_bits);
+  auto kern = k_local<W, kLocalNT, MODE>;
+  set_smem(kern, smem);
+  kern<<<grid, kLocalNT, smem, c.stream>>>(a);
+  MF_LAUNCH_CHECK();
+  c.launches++;
+}
+template <int W, int MODE>
+static void launch_serial(Ctx &c, const LocalArgs &a, int nwork) {
+  if (nwork <= 0) return;
+  k_serial<W, MODE><<<div_ceil(nwork, 32), 32, 0, c.stream>>>(a, nwork);
+  MF_LAUNCH_CHECK();
+  c.launches++;
+}
+
+struct Range {
+  int64_t start, size;
+};
+// Fully sort the given ranges of `cur` in place (all `sort_bits` leading bits matter); `other` is scratch with the same
+// layout.  Recursive MSD levels; only reached by buckets the shared-memory finish could not take.
+template <int W>
+static void sort_ranges(Ctx &c, uint32_t *cur, uint32_t *other, const std::vector<Range> &ranges, int bit_off, int sort_bits) {
+  if (ranges.empty() || bit_off >= sort_bits) return;
+  const int nbits = std::min(kMaxDigitBits, sort_bits - bit_off);
+  const int cap = cap_for(W);
+  std::vector<void *> tmp;
+  auto alloc = [&](size_t bytes) {
+    void *p = nullptr;
+    MF_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+    tmp.push_back(p);
+    return p;
+  };
+  HostChunks hc;
+  hc.nseg = (int)ranges.size();
+  for (int i = 0; i < hc.nseg; ++i) {
+    hc.start.push_back(ranges[i].start);
+    hc.size.push_back(ranges[i].size);
+    hc.seg.push_back(i);
+    hc.seg_out_start.push_back(ranges[i].start);
+  }
+  DevBuckets b = partition_level<W>(c, cur, other, hc, bit_off, nbits, alloc);
+  int32_t *d_bail = (int32_t *)alloc(sizeof(int32_t) * b.nslots);
+  int *d_flags = (int *)alloc(sizeof(int) * 4);
+  MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, c.stream));
+  LocalArgs a{};
+  a.in = other;
+  a.out = cur;
+  a.bkt_start = b.start;
+  a.bkt_size = b.size;
+  a.work = nullptr;
+  a.bit_off = bit_off + nbits;
+  a.sb_bits = std::max(0, std::min(kMaxDigitBits, sort_bits - a.bit_off));
+  a.cap = cap;
+  a.bail_list = d_bail;
+  a.bail_count = d_flags;
+  a.overflow_flag = d_flags + 1;
+  launch_local<W, kSortOnly>(c, a, b.nslots);
+  int nbail = 0;
+  MF_CUDA(cudaMemcpyAsync(&nbail, d_flags, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  if (nbail > 0) {
+    std::vector<int32_t> bl(nbail);
+    std::vector<int64_t> st(b.nslots), sz(b.nslots);
+    MF_CUDA(cudaMemcpy(bl.data(), d_bail, sizeof(int32_t) * nbail, cudaMemcpyDeviceToHost));
+    MF_CUDA(cudaMemcpy(st.data(), b.start, sizeof(int64_t) * b.nslots, cudaMemcpyDeviceToHost));
+    MF_CUDA(cudaMemcpy(sz.data(), b.size, sizeof(int64_t) * b.nslots, cudaMemcpyDeviceToHost));
+    std::vector<Range> sub;
+    for (int s : bl) sub.push_back(Range{st[s], sz[s]});
+    sort_ranges<W>(c, other, cur, sub, bit_off + nbits, sort_bits);
+    for (auto &r : sub)
+      MF_CUDA(cudaMemcpyAsync(cur + r.start * W, other + r.start * W, (size_t)r.size * W * 4, cudaMemcpyDeviceToDevice, c.stream));
+  }
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  for (void *p : tmp) cudaFree(p);
+}
+
+// read the bail list and turn it into host ranges
+static std::vector<Range> fetch_bails(Ctx &c, const DevBuckets &b, const int32_t *d_bail, int nbail, std::vector<int32_t> *slots) {
+  std::vector<Range> out;
+  if (nbail <= 0) return out;
+  slots->resize(nbail);
+  MF_CUDA(cudaMemcpy(slots->data(), d_bail, sizeof(int32_t) * nbail, cudaMemcpyDeviceToHost));
+  std::sort(slots->begin(), slots->end());
+  std::vector<int64_t> st(b.nslots), sz(b.nslots);
+  MF_CUDA(cudaMemcpy(st.data(), b.start, sizeof(int64_t) * b.nslots, cudaMemcpyDeviceToHost));
+  MF_CUDA(cudaMemcpy(sz.data(), b.size, sizeof(int64_t) * b.nslots, cudaMemcpyDeviceToHost));
+  for (int s : *slots) out.push_back(Range{st[s], sz[s]});
+  return out;
+}
+
+// ------------------------------------------------------------------ count: finish from l1-partitioned keys
+template <int W>
+static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n, const HostChunks &l1, int k, int l1_bits,
+                              int min_count, bool append, EdgesView *out, unsigned long long *d_counting) {
+  const int key_bits = 2 * (k + 1), We = words_edge(k);
+  Plan p = make_plan(W, key_bits, n, l1_bits);
+  auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
+  DevBuckets b;
+  int bit_off = l1_bits;
+  if (p.l2_bits > 0 || (int)l1.start.size() != l1.nseg) {
+    int nb = std::max(1, p.l2_bits);
+    b = partition_level<W>(c, cur, other, l1, l1_bits, nb, salloc);
+    std::swap(cur, other);
+    bit_off += nb;
+  } else {
+    b.nslots = l1.nseg;
+    b.start = c.alloc<int64_t>(b.nslots);
+    b.size = c.alloc<int64_t>(b.nslots);
+    MF_CUDA(cudaMemcpy(b.start, l1.start.data(), sizeof(int64_t) * b.nslots, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(b.size, l1.size.data(), sizeof(int64_t) * b.nslots, cudaMemcpyHostToDevice));
+  }
+  const int sb_bits = std::max(0, std::min(p.sb_bits, key_bits - bit_off));
+  int64_t *d_desc_off = c.alloc<int64_t>(b.nslots), *d_desc_cnt = c.alloc<int64_t>(b.nslots);
+  int64_t *d_out_off = c.alloc<int64_t>(b.nslots + 1);
+  int32_t *d_bail = c.alloc<int32_t>(b.nslots);
+  int *d_flags = c.alloc<int>(4);
+  unsigned long long *d_cursor = c.alloc<unsigned long long>(2);
+  // arena: everything left in the slab (edges are a small fraction of the keys unless -m 1)
+  size_t arena_cap;
+  {
+    const size_t want_max = (size_t)(min_count > 1 ? n / min_count + 1 : n);
+    const size_t guess = std::min(want_max, (size_t)std::max<int64_t>(n / 6 + 1, 1 << 16));
+    const size_t room = c.slab_bytes - ((c.slab_off + 255) & ~(size_t)255);
+    arena_cap = std::min(guess, room / ((size_t)We * 4));
+  }
+  uint32_t *d_arena = c.alloc<uint32_t>(arena_cap * We);
+  DevBuf big_arena;   // only if the slab share overflowed
+  std::vector<int32_t> bail_slots;
+  bool fallback_sorted = false;
+  for (int attempt = 0;; ++attempt) {
+    MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, c.stream));
+    MF_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long) * 2, c.stream));
+    MF_CUDA(cudaMemsetAsync(d_desc_cnt, 0, sizeof(int64_t) * b.nslots, c.stream));
+    LocalArgs a{};
+    a.in = cur;
+    a.bkt_start = b.start;
+    a.bkt_size = b.size;
+    a.bit_off = bit_off;
+    a.sb_bits = sb_bits;
+    a.cap = p.cap;
+    a.k = k;
+    a.min_count = min_count;
+    a.words_edge = We;
+    a.arena = d_arena;
+    a.arena_cursor = d_cursor;
+    a.arena_cap = arena_cap;
+    a.desc_off = d_desc_off;
+    a.desc_cnt = d_desc_cnt;
+    a.counting = attempt == 0 ? d_counting : nullptr;   // a retry must not count the histogram twice
+    a.bail_list = d_bail;
+    a.bail_count = d_flags;
+    a.overflow_flag = d_flags + 1;
+    {
+      Stage st(c, "local_count");
+      launch_local<W, kCountEmit>(c, a, b.nslots);
+    }
+    int flags[2];
+    MF_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, c.stream));
+    MF_CUDA(cudaStreamSynchronize(c.stream));
+    if (flags[0] > 0) {
+      Stage st(c, "fallback");
+      std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &bail_slots);
+      if (!fallback_sorted) sort_ranges<W>(c, cur, other, rs, bit_off, key_bits);
+      fallback_sorted = true;
+      MF_CUDA(cudaMemcpyAsync(d_bail, bail_slots.data(), sizeof(int32_t) * bail_slots.size(), cudaMemcpyHostToDevice, c.stream));
+      a.work = d_bail;
+      launch_serial<W, kCountEmit>(c, a, (int)bail_slots.size());
+      MF_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, c.stream));
+      MF_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    if (!flags[1]) break;
+    // arena overflow: the true demand is in the cursor; take it from a dedicated allocation and redo the finish
+    unsigned long long need = 0;
+    MF_CUDA(cudaMemcpy(&need, d_cursor, sizeof need, cudaMemcpyDeviceToHost));
+    if (attempt >= 2) throw std::runtime_error("edge arena overflow persisted");
+    big_arena.reserve((size_t)need * We * 4);
+    d_arena = big_arena.as<uint32_t>();
+    arena_cap = need;
+  }
+  // gather
+  Stage st(c, "gather");
+  k_scan_i64<<<1, 1024, 0, c.stream>>>(d_desc_cnt, b.nslots, 0, d_out_off);
+  MF_LAUNCH_CHECK();
+  c.launches++;
+  int64_t E = 0;
+  MF_CUDA(cudaMemcpyAsync(&E, d_out_off + b.nslots, sizeof E, cudaMemcpyDeviceToHost, c.stream));
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  const int64_t prev = append ? out->n_edges : 0;
+  if (append && prev > 0) {
+    DevBuf grown;
+    grown.reserve((size_t)(prev + E) * We * 4 + 256);
+    MF_CUDA(cudaMemcpyAsync(grown.p, c.edges.p, (size_t)prev * We * 4, cudaMemcpyDeviceToDevice, c.stream));
+    MF_CUDA(cudaStreamSynchronize(c.stream));
+    c.edges.release();
+    c.edges = grown;
+  } else {
+    c.edges.reserve((size_t)std::max<int64_t>(E, 1) * We * 4 + 256);
+  }
+  uint32_t *d_edges = c.edges.as<uint32_t>() + prev * We;
+  if (E > 0) {
+    k_gather_edges<<<div_ceil(b.nslots, 8), 256, 0, c.stream>>>(d_arena, d_desc_off, d_desc_cnt, d_out_off, b.nslots, We, d_edges);
+    MF_LAUNCH_CHECK();
+    c.launches++;
+  }
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  big_arena.release();
+  out->edges = c.edges.as<uint32_t>();
+  out->n_edges = prev + E;
+  out->k = k;
+  out->words = We;
+}
+
+static void edge_bucket_counts(Ctx &c, const EdgesView &e) {
+  unsigned long long *d = nullptr;
+  MF_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * kNumBuckets));
+  MF_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * kNumBuckets, c.stream));
+  if (e.n_edges > 0) {
+    k_edge_buckets<<<(unsigned)div_ceil64(e.n_edges, 256), 256, 0, c.stream>>>(e.edges, e.n_edges, e.words, d);
+    MF_LAUNCH_CHECK();
+    c.launches++;
+  }
+  MF_CUDA(cudaMemcpyAsync(c.edge_bucket_counts.data(), d, sizeof(int64_t) * kNumBuckets, cudaMemcpyDeviceToHost, c.stream));
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  cudaFree(d);
+}
+
+static const uint32_t *build_start_bits(Ctx &c, const ReadsView &r) {
+  size_t words = (size_t)((r.n_bases + 31) >> 5) + 64;
+  c.sbits.reserve(words * 4);
+  MF_CUDA(cudaMemsetAsync(c.sbits.p, 0, words * 4, c.stream));
+  if (r.n_reads > 0) {
+    k_start_bits<<<(unsigned)div_ceil64(r.n_reads, 256), 256, 0, c.stream>>>(r.starts, r.n_reads, c.sbits.as<uint32_t>());
+    MF_LAUNCH_CHECK();
+    c.launches++;
+  }
+  return c.sbits.as<uint32_t>();
+}
+
+template <int W>
+static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, EdgesView *out, int64_t *counting_host) {
+  const int key_bits = 2 * (k + 1), We = words_edge(k);
+  const uint32_t *sbits;
+  {
+    Stage st(c, "start_bits");
+    sbits = build_start_bits(c, r);
+  }
+  // the plan needs the key count: it is at most one key per base
+  Plan p = make_plan(W, key_bits, std::max<int64_t>(r.n_bases, 1));
+  const int nb1 = 1 << p.l1_bits;
+  unsigned long long *d_small = nullptr;   // hist | counting
+  MF_CUDA(cudaMalloc(&d_small, sizeof(unsigned long long) * (nb1 + kNumBuckets)));
+  unsigned long long *d_hist = d_small, *d_counting = d_small + nb1;
+  MF_CUDA(cudaMemsetAsync(d_small, 0, sizeof(unsigned long long) * (nb1 + kNumBuckets), c.stream));
+  {
+    Stage st(c, "reads_hist");
+    launch_reads_hist<W>(c, r, sbits, k, LevelArgs{0, p.l1_bits, 0u, (uint32_t)nb1}, d_hist);
+  }
+  std::vector<unsigned long long> hist(nb1);
+  MF_CUDA(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned long long) * nb1, cudaMemcpyDeviceToHost, c.stream));
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  int64_t n_keys = 0;
+  for (auto h : hist) n_keys += (int64_t)h;
+  out->n_keys = n_keys;
+  out->n_edges = 0;
+  out->k = k;
+  out->words = We;
+  // rounds over contiguous l1-bin ranges so that two key buffers + tables fit the budget
+  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1 << kMaxDigitBits) * 96;
+  const size_t budget = (size_t)((double)c.budget() * 0.9);   // a tenth is left for the resulting edges / sdbg
+  const double per_key = 2.0 * W * 4 + (min_count > 1 ? (double)We * 4 / std::min(min_count, 6) : (double)We * 4);
+  int64_t max_keys = budget > table_bytes ? (int64_t)((double)(budget - table_bytes) / per_key) : 0;
+  if (max_keys < 1024) throw std::runtime_error("device memory budget too small for count");
+  std::vector<std::pair<int, int>> rounds;
+  for (int lo = 0; lo < nb1;) {
+    int hi = lo;
+    int64_t acc = 0;
+    while (hi < nb1 && (acc + (int64_t)hist[hi] <= max_keys || hi == lo)) acc += (int64_t)hist[hi++];
+    if (acc > max_keys) throw std::runtime_error("a single prefix bin exceeds the device memory budget");
+    rounds.emplace_back(lo, hi);
+    lo = hi;
+  }
+  int64_t round_max = 0;
+  for (auto &rd : rounds) {
+    int64_t acc = 0;
+    for (int b = rd.first; b < rd.second; ++b) acc += (int64_t)hist[b];
+    round_max = std::max(round_max, acc);
+  }
+  c.slab_reserve((size_t)((double)round_max * per_key) + table_bytes + (1 << 20));
+  for (size_t ri = 0; ri < rounds.size(); ++ri) {
+    const int lo = rounds[ri].first, hi = rounds[ri].second;
+    c.slab_reset();
+    HostChunks l1;
+    l1.nseg = hi - lo;
+    std::vector<unsigned long long> cursor(nb1, 0);
+    int64_t acc = 0;
+    for (int b = lo; b < hi; ++b) {
+      cursor[b] = (unsigned long long)acc;
+      l1.start.push_back(acc);
+      l1.size.push_back((int64_t)hist[b]);
+      l1.seg.push_back(b - lo);
+      l1.seg_out_start.push_back(acc);
+      acc += (int64_t)hist[b];
+    }
+    if (acc == 0) continue;
+    uint32_t *bufA = c.alloc<uint32_t>((size_t)acc * W + 16), *bufB = c.alloc<uint32_t>((size_t)acc * W + 16);
+    unsigned long long *d_cursor = c.alloc<unsigned long long>(nb1);
+    MF_CUDA(cudaMemcpy(d_cursor, cursor.data(), sizeof(unsigned long long) * nb1, cudaMemcpyHostToDevice));
+    {
+      Stage st(c, "reads_scatter");
+      launch_reads_scatter<W>(c, r, sbits, k, LevelArgs{0, p.l1_bits, (uint32_t)lo, (uint32_t)hi}, d_cursor, bufA);
+    }
+    count_finish_impl<W>(c, bufA, bufB, acc, l1, k, p.l1_bits, min_count, ri > 0, out, d_counting);
+  }
+  if (out->n_edges == 0) {
+    c.edges.reserve(256);
+    out->edges = c.edges.as<uint32_t>();
+  }
+  if (counting_host)
+    MF_CUDA(cudaMemcpy(counting_host, d_counting, sizeof(int64_t) * kNumBuckets, cudaMemcpyDeviceToHost));
+  cudaFree(d_small);
+  Stage st(c, "edge_buckets");
+  edge_bucket_counts(c, *out);
+}
+
+#define MF_DISPATCH_CASE_COUNT(Wn) \
+  case Wn: dev_count_impl<Wn>(c, r, k, min_count, out, counting_host); break;
+void dev_count(Ctx &c, const ReadsView &r, int k, int min_count, EdgesView *out, int64_t *counting_host) {
+  if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
+  if (min_count < 1) throw std::invalid_argument("min_count must be >= 1");
+  MF_DISPATCH_W(words_key(k), COUNT)
+}
+
+// staged API for the multi-GPU driver
+template <int W>
+static void dev_count_hist_impl(Ctx &c, const ReadsView &r, int k, int l1_bits, unsigned long long *hist_dev) {
+  const uint32_t *sbits = build_start_bits(c, r);
+  const int nb1 = 1 << l1_bits;
+  MF_CUDA(cudaMemsetAsync(hist_dev, 0, sizeof(unsigned long long) * nb1, c.stream));
+  Stage st(c, "reads_hist");
+  launch_reads_hist<W>(c, r, sbits, k, LevelArgs{0, l1_bits, 0u, (uint32_t)nb1}, hist_dev);
+}
+#define MF_DISPATCH_CASE_CHIST(Wn) \
+  case Wn: dev_count_hist_impl<Wn>(c, r, k, l1_bits, hist_dev); break;
+void dev_count_hist(Ctx &c, const ReadsView &r, int k, int l1_bits, unsigned long long *hist_dev) {
+  if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
+  if (l1_bits < 1 || l1_bits > kMaxDigitBits) throw std::invalid_argument("l1_bits must be in [1, 10]");
+  MF_DISPATCH_W(words_key(k), CHIST)
+}
+__global__ void k_excl_scan_u64_small(const unsigned long long *in, int n, unsigned long long *out) {
+  // n <= 1024, one block
+  __shared__ unsigned long long s[1024];
+  int t = threadIdx.x;
+  s[t] = t < n ? in[t] : 0ull;
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < n; ++i) { unsigned long long v = s[i]; s[i] = run; run += v; }
+  }
+  __syncthreads();
+  if (t < n) out[t] = s[t];
+}
+template <int W>
+static void dev_count_scatter_impl(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev,
+                                   uint32_t *keys_out) {
+  const uint32_t *sbits = c.sbits.as<uint32_t>();
+  if (!sbits) sbits = build_start_bits(c, r);
+  const int nb1 = 1 << l1_bits;
+  c.slab_reserve(1 << 20);
+  unsigned long long *d_cursor = c.alloc<unsigned long long>(nb1);
+  k_excl_scan_u64_small<<<1, 1024, 0, c.stream>>>(hist_dev, nb1, d_cursor);
+  MF_LAUNCH_CHECK();
+  c.launches++;
+  Stage st(c, "reads_scatter");
+  launch_reads_scatter<W>(c, r, sbits, k, LevelArgs{0, l1_bits, 0u, (uint32_t)nb1}, d_cursor, keys_out);
+}
+#define MF_DISPATCH_CASE_CSCAT(Wn) \
+  case Wn: dev_count_scatter_impl<Wn>(c, r, k, l1_bits, hist_dev, keys_out); break;
+void dev_count_scatter(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev, uint32_t *keys_out,
+                       int64_t) {
+  MF_DISPATCH_W(words_key(k), CSCAT)
+}
+template <int W>
+static void dev_count_finish_w(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys, const HostChunks &hc, int k, int l1_bits,
+                               int min_count, EdgesView *out, int64_t *counting_host) {
+  const int We = words_edge(k);
+  unsigned long long *d_counting = nullptr;
+  MF_CUDA(cudaMalloc(&d_counting, sizeof(unsigned long long) * kNumBuckets));
+  MF_CUDA(cudaMemsetAsync(d_counting, 0, sizeof(unsigned long long) * kNumBuckets, c.stream));
+  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)hc.nseg << kMaxDigitBits) * 96;
+  const size_t arena = (size_t)(min_count > 1 ? n_keys / std::min(min_count, 6) + 1 : n_keys) * We * 4;
+  c.slab_reserve(table_bytes + arena + (1 << 20));
+  out->n_edges = 0;
+  out->n_keys = n_keys;
+  out->k = k;
+  out->words = We;
+  if (n_keys > 0) count_finish_impl<W>(c, keys, scratch, n_keys, hc, k, l1_bits, min_count, false, out, d_counting);
+  if (out->n_edges == 0) {
+    c.edges.reserve(256);
+    out->edges = c.edges.as<uint32_t>();
+  }
+  if (counting_host) MF_CUDA(cudaMemcpy(counting_host, d_counting, sizeof(int64_t) * kNumBuckets, cudaMemcpyDeviceToHost));
+  cudaFree(d_counting);
+  edge_bucket_counts(c, *out);
+}
+#define MF_DISPATCH_CASE_CFIN(Wn) \
+  case Wn: dev_count_finish_w<Wn>(c, keys, scratch, n_keys, hc, k, l1_bits, min_count, out, counting_host); break;
+void dev_count_finish(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys, const int64_t *chunk_start,
+                      const int64_t *chunk_size, const int32_t *chunk_seg, int n_chunks, int n_segs, int k, int l1_bits,
+                      int min_count, EdgesView *out, int64_t *counting_host) {
+  HostChunks hc;
+  hc.nseg = n_segs;
+  hc.start.assign(chunk_start, chunk_start + n_chunks);
+  hc.size.assign(chunk_size, chunk_size + n_chunks);
+  hc.seg.assign(chunk_seg, chunk_seg + n_chunks);
+  std::vector<int64_t> tot(n_segs, 0);
+  for (int i = 0; i < n_chunks; ++i) {
+    if (chunk_seg[i] < 0 || chunk_seg[i] >= n_segs) throw std::invalid_argument("chunk_seg out of range");
+    tot[chunk_seg[i]] += chunk_size[i];
+  }
+  int64_t acc = 0;
+  for (int s = 0; s < n_segs; ++s) { hc.seg_out_start.push_back(acc); acc += tot[s]; }
+  if (acc != n_keys) throw std::invalid_argument("chunk sizes do not add up to n_keys");
+  MF_DISPATCH_W(words_key(k), CFIN)
+}
+
+// ------------------------------------------------------------------ seq2sdbg
+template <int WI>
+static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, int tip_mode, SdbgView *out) {
+  const int WK = words_key(k), WE = words_edge(k), Wt = words_tip(k);
+  const int part_limit = 2 * (k - 1);
+  const int64_t n_items = 6 * n_edges + sq.n_items;
+  out->k = k;
+  out->words_tip = Wt;
+  out->n_items = out->n_tips = out->n_large = 0;
+  c.sdbg_buckets.reserve(sizeof(unsigned long long) * kNumBuckets * 3);
+  unsigned long long *d_bstats = c.sdbg_buckets.as<unsigned long long>();
+  MF_CUDA(cudaMemsetAsync(d_bstats, 0, sizeof(unsigned long long) * kNumBuckets * 3, c.stream));
+  out->bucket_items = nullptr;
+  if (n_items == 0) {
+    c.sdbg_rec.reserve(256);
+    c.sdbg_labels.reserve(256);
+    out->rec = c.sdbg_rec.as<uint32_t>();
+    out->labels = c.sdbg_labels.as<uint32_t>();
+    std::fill(c.sdbg_bucket_stats.begin(), c.sdbg_bucket_stats.end(), 0);
+    MF_CUDA(cudaStreamSynchronize(c.stream));
+    return;
+  }
+  Plan p = make_plan(WI, part_limit, n_items);
+  const int nb1 = 1 << p.l1_bits;
+  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1 << kMaxDigitBits) * 96;
+  c.slab_reserve((size_t)n_items * WI * 4 * 2 + table_bytes + (1 << 20));
+  uint32_t *bufA = c.alloc<uint32_t>((size_t)n_items * WI + 16), *bufB = c.alloc<uint32_t>((size_t)n_items * WI + 16);
+  {
+    Stage st(c, "items");
+    if (n_edges > 0) {
+      const unsigned grid = (unsigned)div_ceil64(n_edges, 128);
+      // (WK, WE, WI) is one of (w,w,w), (w-1,w-1,w), (w-1,w,w) with w = WI >= 2
+      if constexpr (WI >= 2) {
+        if (WK == WI) k_items_from_edges<WI, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, bufA);
+        else if (WE == WK) k_items_from_edges<WI - 1, WI - 1, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, bufA);
+        else k_items_from_edges<WI - 1, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, bufA);
+      }
+      MF_LAUNCH_CHECK();
+      c.launches++;
+    }
+    if (sq.n_items > 0) {
+      k_items_from_seqs<WI><<<(unsigned)div_ceil64(sq.n_items, 128), 128, 0, c.stream>>>(
+          sq.packed, sq.starts, sq.mult, sq.item_base, sq.nseq, sq.n_items, k, bufA + (size_t)6 * n_edges * WI);
+      MF_LAUNCH_CHECK();
+      c.launches++;
+    }
+  }
+  auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
+  // level 1 over the whole item array
+  HostChunks whole;
+  whole.nseg = 1;
+  whole.start = {0};
+  whole.size = {n_items};
+  whole.seg = {0};
+  whole.seg_out_start = {0};
+  DevBuckets b1 = partition_level<WI>(c, bufA, bufB, whole, 0, p.l1_bits, salloc);
+  uint32_t *cur = bufB, *other = bufA;
+  DevBuckets b = b1;
+  int bit_off = p.l1_bits;
+  if (p.l2_bits > 0) {
+    std::vector<int64_t> st(nb1), sz(nb1);
+    MF_CUDA(cudaMemcpy(st.data(), b1.start, sizeof(int64_t) * nb1, cudaMemcpyDeviceToHost));
+    MF_CUDA(cudaMemcpy(sz.data(), b1.size, sizeof(int64_t) * nb1, cudaMemcpyDeviceToHost));
+    HostChunks l1;
+    l1.nseg = nb1;
+    for (int i = 0; i < nb1; ++i) {
+      l1.start.push_back(st[i]);
+      l1.size.push_back(sz[i]);
+      l1.seg.push_back(i);
+      l1.seg_out_start.push_back(st[i]);
+    }
+    b = partition_level<WI>(c, cur, other, l1, p.l1_bits, p.l2_bits, salloc);
+    std::swap(cur, other);
+    bit_off += p.l2_bits;
+  }
+  const int sb_bits = std::max(0, std::min(p.sb_bits, part_limit - bit_off));
+  int64_t *d_items = c.alloc<int64_t>(b.nslots), *d_tips = c.alloc<int64_t>(b.nslots), *d_large = c.alloc<int64_t>(b.nslots);
+  int64_t *d_item_off = c.alloc<int64_t>(b.nslots + 1), *d_tip_off = c.alloc<int64_t>(b.nslots + 1),
+          *d_large_off = c.alloc<int64_t>(b.nslots + 1);
+  int32_t *d_bail = c.alloc<int32_t>(b.nslots);
+  int *d_flags = c.alloc<int>(4);
+  MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, c.stream));
+  MF_CUDA(cudaMemsetAsync(d_items, 0, sizeof(int64_t) * b.nslots, c.stream));
+  MF_CUDA(cudaMemsetAsync(d_tips, 0, sizeof(int64_t) * b.nslots, c.stream));
+  MF_CUDA(cudaMemsetAsync(d_large, 0, sizeof(int64_t) * b.nslots, c.stream));
+  LocalArgs a{};
+  a.in = cur;
+  a.bkt_start = b.start;
+  a.bkt_size = b.size;
+  a.bit_off = bit_off;
+  a.sb_bits = sb_bits;
+  a.cap = p.cap;
+  a.k = k;
+  a.tip_mode = tip_mode;
+  a.words_tip = Wt;
+  a.sd_items = d_items;
+  a.sd_tips = d_tips;
+  a.sd_large = d_large;
+  a.bucket_stats = d_bstats;
+  a.bail_list = d_bail;
+  a.bail_count = d_flags;
+  a.overflow_flag = d_flags + 1;
+  {
+    Stage st(c, "local_sdbg_count");
+    launch_local<WI, kSdbgCount>(c, a, b.nslots);
+  }
+  int nbail = 0;
+  MF_CUDA(cudaMemcpyAsync(&nbail, d_flags, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  std::vector<int32_t> bail_slots;
+  int32_t *d_bail_sorted = nullptr;
+  if (nbail > 0) {
+    Stage st(c, "fallback");
+    std::vector<Range> rs = fetch_bails(c, b, d_bail, nbail, &bail_slots);
+    sort_ranges<WI>(c, cur, other, rs, bit_off, 32 * WI);
+    d_bail_sorted = c.alloc<int32_t>(bail_slots.size());
+    MF_CUDA(cudaMemcpy(d_bail_sorted, bail_slots.data(), sizeof(int32_t) * bail_slots.size(), cudaMemcpyHostToDevice));
+    a.work = d_bail_sorted;
+    launch_serial<WI, kSdbgCount>(c, a, (int)bail_slots.size());
+    a.work = nullptr;
+  }
+  k_scan_i64<<<1, 1024, 0, c.stream>>>(d_items, b.nslots, 0, d_item_off);
+  k_scan_i64<<<1, 1024, 0, c.stream>>>(d_tips, b.nslots, 0, d_tip_off);
+  k_scan_i64<<<1, 1024, 0, c.stream>>>(d_large, b.nslots, 0, d_large_off);
+  MF_LAUNCH_CHECK();
+  c.launches += 3;
+  int64_t tot[3];
+  MF_CUDA(cudaMemcpyAsync(&tot[0], d_item_off + b.nslots, 8, cudaMemcpyDeviceToHost, c.stream));
+  MF_CUDA(cudaMemcpyAsync(&tot[1], d_tip_off + b.nslots, 8, cudaMemcpyDeviceToHost, c.stream));
+  MF_CUDA(cudaMemcpyAsync(&tot[2], d_large_off + b.nslots, 8, cudaMemcpyDeviceToHost, c.stream));
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  c.sdbg_rec.reserve((size_t)std::max<int64_t>(tot[0], 1) * 4 + 256);
+  c.sdbg_labels.reserve((size_t)std::max<int64_t>(tot[1], 1) * Wt * 4 + 256);
+  a.sd_item_off = d_item_off;
+  a.sd_tip_off = d_tip_off;
+  a.sd_rec = c.sdbg_rec.as<uint32_t>();
+  a.sd_labels = c.sdbg_labels.as<uint32_t>();
+  MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, c.stream));
+  {
+    Stage st(c, "local_sdbg_emit");
+    launch_local<WI, kSdbgEmit>(c, a, b.nslots);
+  }
+  if (nbail > 0) {
+    a.work = d_bail_sorted;
+    launch_serial<WI, kSdbgEmit>(c, a, (int)bail_slots.size());
+  }
+  MF_CUDA(cudaMemcpyAsync(c.sdbg_bucket_stats.data(), d_bstats, sizeof(int64_t) * kNumBuckets * 3, cudaMemcpyDeviceToHost, c.stream));
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  out->rec = c.sdbg_rec.as<uint32_t>();
+  out->labels = c.sdbg_labels.as<uint32_t>();
+  out->n_items = tot[0];
+  out->n_tips = tot[1];
+  out->n_large = tot[2];
+}
+#define MF_DISPATCH_CASE_SDBG(Wn) \
+  case Wn: sdbg_impl<Wn>(c, edges, n_edges, seqs, k, tip_mode, out); break;
+void dev_seq2sdbg(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &seqs, int k, int tip_mode, SdbgView *out) {
+  if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
+  MF_DISPATCH_W(words_item(k), SDBG)
+}
+
+}  // namespace mf

@@ -1,0 +1,98 @@
+// engine.cuh -- host-side orchestration of the device pipelines (one context per GPU).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+namespace mf {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes);
+  void release();
+  template <class T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct StageRec {
+  std::string name;
+  cudaEvent_t e0, e1;
+};
+
+struct Ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  char *slab = nullptr;
+  size_t slab_bytes = 0, slab_off = 0;
+  size_t mem_limit = 0;
+  int64_t launches = 0;
+  bool profiling = false;
+  std::vector<StageRec> stages;
+  std::vector<int> open_stages;
+  std::string profile;
+  // results that outlive a call
+  DevBuf edges, sdbg_rec, sdbg_labels, sdbg_buckets, sbits, pack_words, pack_starts, synth_words, synth_starts;
+  // tables read back by the file-level API
+  std::vector<int64_t> edge_bucket_counts;   // 65536
+  std::vector<int64_t> sdbg_bucket_stats;    // 65536 * 3 (items, tips, large)
+
+  explicit Ctx(int dev);
+  ~Ctx();
+  size_t budget();                 // bytes this context may hold (slab + results)
+  void slab_reserve(size_t bytes); // (re)allocate the slab; invalidates earlier slab pointers
+  void slab_reset() { slab_off = 0; }
+  void *slab_alloc(size_t bytes);
+  template <class T>
+  T *alloc(size_t n) { return reinterpret_cast<T *>(slab_alloc(n * sizeof(T))); }
+  void begin_call();
+  void end_call();
+  void stage_begin(const char *name);
+  void stage_end();
+};
+
+struct Stage {
+  Ctx &c;
+  Stage(Ctx &ctx, const char *name) : c(ctx) { c.stage_begin(name); }
+  ~Stage() { c.stage_end(); }
+};
+
+struct ReadsView {
+  const uint32_t *packed;
+  const int64_t *starts;
+  int64_t n_reads, n_bases;
+};
+struct EdgesView {
+  const uint32_t *edges = nullptr;
+  int64_t n_edges = 0, n_keys = 0;
+  int k = 0, words = 0;
+};
+struct SdbgView {
+  const uint32_t *rec = nullptr, *labels = nullptr;
+  const int64_t *bucket_items = nullptr;
+  int64_t n_items = 0, n_tips = 0, n_large = 0;
+  int k = 0, words_tip = 0;
+};
+struct SeqsView {          // general sequences (contigs), stored orientation, on device
+  const uint32_t *packed = nullptr;
+  const int64_t *starts = nullptr;   // device, nseq+1
+  const uint16_t *mult = nullptr;    // device
+  const int64_t *item_base = nullptr;  // device, nseq+1
+  int nseq = 0;
+  int64_t n_items = 0;
+};
+
+// pipelines
+void dev_count(Ctx &c, const ReadsView &r, int k, int min_count, EdgesView *out, int64_t *counting_host);
+void dev_seq2sdbg(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &seqs, int k, int tip_mode, SdbgView *out);
+void dev_count_hist(Ctx &c, const ReadsView &r, int k, int l1_bits, unsigned long long *hist_dev);
+void dev_count_scatter(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev, uint32_t *keys_out,
+                       int64_t capacity);
+void dev_count_finish(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys, const int64_t *chunk_start,
+                      const int64_t *chunk_size, const int32_t *chunk_seg, int n_chunks, int n_segs, int k, int l1_bits,
+                      int min_count, EdgesView *out, int64_t *counting_host);
+
+}  // namespace mf

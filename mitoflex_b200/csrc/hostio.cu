@@ -1,0 +1,396 @@
+// hostio.cu -- files in, files out, the device pipelines in between.  The on-disk layouts restate what
+// megahit v1.2.9 reads and writes (EdgeWriter/EdgeIoMetadata, SdbgWriter/SdbgMeta, BinaryWriter, lib_info,
+// ContigReader); the reference only fixes the file NAMES (assemble/assemble_wrapper.py:93-97,166-200,228-250).
+#include "hostio.h"
+#include <zlib.h>
+#include <algorithm>
+#include <cerrno>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include "mfsdbg.h"
+
+namespace mf {
+
+namespace {
+
+std::string errno_msg(const std::string &what, const std::string &path) {
+  return what + " " + path + ": " + strerror(errno);
+}
+// whole file (plain, gzip or FIFO) into memory
+std::vector<uint8_t> slurp(const std::string &path) {
+  gzFile f = gzopen(path.c_str(), "rb");
+  if (!f) throw IoError(errno_msg("cannot open", path));
+  gzbuffer(f, 1 << 20);
+  std::vector<uint8_t> buf;
+  size_t cap = 1 << 22, len = 0;
+  buf.resize(cap);
+  for (;;) {
+    if (len == cap) { cap *= 2; buf.resize(cap); }
+    int want = (int)std::min<size_t>(cap - len, 1u << 30);
+    int got = gzread(f, buf.data() + len, want);
+    if (got < 0) { gzclose(f); throw IoError("read error on " + path); }
+    if (got == 0) break;
+    len += got;
+  }
+  gzclose(f);
+  buf.resize(len);
+  return buf;
+}
+struct File {
+  FILE *fp = nullptr;
+  std::string path;
+  File(const std::string &p, const char *mode) : path(p) {
+    fp = fopen(p.c_str(), mode);
+    if (!fp) throw IoError(errno_msg(mode[0] == 'r' ? "cannot open" : "cannot create", p));
+  }
+  ~File() { if (fp) fclose(fp); }
+  void write(const void *d, size_t n) {
+    if (n && fwrite(d, 1, n, fp) != n) throw IoError(errno_msg("write failed on", path));
+  }
+  void close() {
+    if (fp && fclose(fp) != 0) { fp = nullptr; throw IoError(errno_msg("close failed on", path)); }
+    fp = nullptr;
+  }
+};
+struct DevMem {   // scoped cudaMalloc
+  void *p = nullptr;
+  explicit DevMem(size_t bytes) { MF_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16))); }
+  ~DevMem() { if (p) cudaFree(p); }
+  template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+int bucket_file(int bucket, int n_files) { return (int)((int64_t)bucket * n_files / kNumBuckets); }
+
+}  // namespace
+
+// ---------------------------------------------------------------- buildlib
+void file_buildlib(Ctx &c, const char *lib_file, const char *out_prefix, int n_policy) {
+  std::ifstream lib(lib_file);
+  if (!lib) throw IoError(errno_msg("cannot open", lib_file));
+  File bin(std::string(out_prefix) + ".bin", "wb");
+  std::ostringstream info;
+  int64_t total_reads = 0, total_bases = 0;
+  std::string meta, spec;
+  while (std::getline(lib, meta)) {
+    if (!std::getline(lib, spec)) break;
+    std::istringstream ss(spec);
+    std::string type, f1, f2;
+    ss >> type >> f1 >> f2;
+    std::vector<std::vector<uint8_t>> texts;
+    bool paired = false;
+    if (type == "pe" && !f2.empty()) {
+      // open both before reading either: MitoFlex may hand over two FIFOs fed by `gzip -dc` children
+      texts.push_back(slurp(f1));
+      texts.push_back(slurp(f2));
+      paired = true;
+    } else if (type == "se" && !f1.empty()) {
+      texts.push_back(slurp(f1));
+    } else if (type == "interleaved" && !f1.empty()) {
+      texts.push_back(slurp(f1));
+      paired = true;
+    } else {
+      throw IoError("bad library line in " + std::string(lib_file) + ": " + spec);
+    }
+    std::vector<DevMem *> dev;
+    const uint8_t *ptrs[2] = {nullptr, nullptr};
+    int64_t sizes[2] = {0, 0};
+    try {
+      for (size_t i = 0; i < texts.size(); ++i) {
+        dev.push_back(new DevMem(texts[i].size() + 64));
+        MF_CUDA(cudaMemcpy(dev.back()->p, texts[i].data(), texts[i].size(), cudaMemcpyHostToDevice));
+        ptrs[i] = dev.back()->as<uint8_t>();
+        sizes[i] = (int64_t)texts[i].size();
+        std::vector<uint8_t>().swap(texts[i]);
+      }
+      ReadsView r;
+      int max_len = 0;
+      dev_pack_fastq(c, ptrs, sizes, (int)dev.size(), n_policy, &r, &max_len);
+      for (auto *d : dev) delete d;
+      dev.clear();
+      std::vector<uint32_t> stream;
+      reads_to_bin_stream(c, r, &stream);
+      bin.write(stream.data(), stream.size() * 4);
+      info << meta << '\n' << (paired ? "pe " : "se ") << total_reads << ' ' << total_reads + r.n_reads - 1 << ' ' << max_len << '\n';
+      total_reads += r.n_reads;
+      total_bases += r.n_bases;
+    } catch (...) {
+      for (auto *d : dev) delete d;
+      throw;
+    }
+  }
+  bin.close();
+  File fi(std::string(out_prefix) + ".lib_info", "w");   // meta file last
+  std::string head = std::to_string(total_bases) + " " + std::to_string(total_reads) + "\n" + info.str();
+  fi.write(head.data(), head.size());
+  fi.close();
+}
+
+static void load_read_lib(Ctx &c, const char *read_lib_file, ReadsView *r) {
+  std::vector<uint8_t> raw = slurp(std::string(read_lib_file) + ".bin");
+  if (raw.size() % 4) throw IoError("read library .bin is not a whole number of words");
+  bin_stream_to_reads(c, reinterpret_cast<const uint32_t *>(raw.data()), (int64_t)(raw.size() / 4), r);
+}
+
+// ---------------------------------------------------------------- edges files
+static void write_edges(Ctx &c, const EdgesView &e, const std::string &prefix, int n_files) {
+  std::vector<uint32_t> host((size_t)e.n_edges * e.words);
+  if (e.n_edges) MF_CUDA(cudaMemcpy(host.data(), e.edges, host.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<std::unique_ptr<File>> files;
+  for (int f = 0; f < n_files; ++f) files.emplace_back(new File(prefix + ".edges." + std::to_string(f), "wb"));
+  std::ostringstream info;
+  info << "kmer_size " << e.k << "\nwords_per_edge " << e.words << "\nnum_files " << n_files << "\nnum_buckets " << kNumBuckets
+       << "\nnum_edges " << e.n_edges << "\nis_sorted 1\n";
+  std::vector<int64_t> foff(n_files, 0);
+  int64_t pos = 0;
+  for (int b = 0; b < kNumBuckets; ++b) {
+    const int64_t cnt = c.edge_bucket_counts[b];
+    if (!cnt) { info << b << " -1 0 0\n"; continue; }
+    const int f = bucket_file(b, n_files);
+    files[f]->write(host.data() + pos * e.words, (size_t)cnt * e.words * 4);
+    info << b << ' ' << f << ' ' << foff[f] << ' ' << cnt << '\n';
+    foff[f] += cnt;
+    pos += cnt;
+  }
+  if (pos != e.n_edges) throw std::runtime_error("bucket counts do not add up to the edge count");
+  for (auto &f : files) f->close();
+  File fi(prefix + ".edges.info", "w");   // meta file last: a failed run leaves nothing parseable
+  const std::string s = info.str();
+  fi.write(s.data(), s.size());
+  fi.close();
+}
+struct HostEdges {
+  int k = 0, words = 0;
+  bool sorted = false;
+  int64_t n = 0;
+  std::vector<uint32_t> data;
+};
+static void expect_field(std::istream &is, const char *name, long long *v) {
+  std::string tok;
+  if (!(is >> tok >> *v) || tok != name) throw IoError(std::string("malformed edges/sdbg info: expected ") + name);
+}
+static HostEdges read_edges(const std::string &prefix) {
+  std::ifstream is(prefix + ".edges.info");
+  if (!is) throw IoError(errno_msg("cannot open", prefix + ".edges.info"));
+  long long k, words, nfiles, nbuckets, nedges, sorted;
+  expect_field(is, "kmer_size", &k);
+  expect_field(is, "words_per_edge", &words);
+  expect_field(is, "num_files", &nfiles);
+  expect_field(is, "num_buckets", &nbuckets);
+  expect_field(is, "num_edges", &nedges);
+  expect_field(is, "is_sorted", &sorted);
+  HostEdges e;
+  e.k = (int)k; e.words = (int)words; e.sorted = sorted != 0; e.n = nedges;
+  e.data.resize((size_t)nedges * words);
+  std::vector<std::vector<uint8_t>> fdata(nfiles);
+  for (int f = 0; f < nfiles; ++f) fdata[f] = slurp(prefix + ".edges." + std::to_string(f));
+  int64_t pos = 0;
+  const size_t rec = (size_t)words * 4;
+  if (e.sorted) {
+    for (int b = 0; b < nbuckets; ++b) {
+      long long bid, fid, off, cnt;
+      if (!(is >> bid >> fid >> off >> cnt) || bid != b) throw IoError("Invalid format: bucket id not matched!");
+      if (fid < 0 || cnt == 0) continue;
+      if (fid >= nfiles || (size_t)(off + cnt) * rec > fdata[fid].size() || pos + cnt > nedges) throw IoError("edge file shorter than its meta says");
+      memcpy(e.data.data() + pos * words, fdata[fid].data() + (size_t)off * rec, (size_t)cnt * rec);
+      pos += cnt;
+    }
+  } else {
+    for (int f = 0; f < nfiles; ++f) {
+      const int64_t cnt = (int64_t)(fdata[f].size() / rec);
+      if (pos + cnt > nedges) throw IoError("more edges on disk than the meta says");
+      memcpy(e.data.data() + pos * words, fdata[f].data(), (size_t)cnt * rec);
+      pos += cnt;
+    }
+  }
+  if (pos != nedges) throw IoError("edge count mismatch between meta and files");
+  return e;
+}
+
+void file_count(Ctx &c, const char *read_lib_file, int k, int min_count, const char *out_prefix, int n_files) {
+  ReadsView r;
+  load_read_lib(c, read_lib_file, &r);
+  EdgesView e;
+  std::vector<int64_t> counting(kNumBuckets, 0);
+  c.begin_call();
+  dev_count(c, r, k, min_count, &e, counting.data());
+  c.end_call();
+  write_edges(c, e, out_prefix, n_files);
+  // KmerCounter::Lv0Postprocess: cumulative distinct-edge histogram
+  File fc(std::string(out_prefix) + ".counting", "w");
+  std::ostringstream ss;
+  long long acc = 0;
+  for (int i = 1; i <= kMaxMul; ++i) { acc += counting[i]; ss << i << ' ' << acc << '\n'; }
+  const std::string s = ss.str();
+  fc.write(s.data(), s.size());
+  fc.close();
+}
+
+// ---------------------------------------------------------------- contigs
+namespace {
+struct HostSeqs {
+  std::vector<uint32_t> packed;    // 2-bit, back to back, stored (reversed) orientation
+  std::vector<int64_t> starts{0};
+  std::vector<uint16_t> mult;
+  std::vector<int64_t> item_base{0};
+  void add(const std::vector<uint8_t> &codes, int m, int k) {
+    const int64_t s = starts.back();
+    const int64_t L = (int64_t)codes.size();
+    packed.resize((size_t)((s + L + 15) >> 4) + 1, 0u);
+    for (int64_t i = 0; i < L; ++i) {
+      const int64_t g = s + i;
+      packed[g >> 4] |= (uint32_t)codes[i] << (30 - 2 * (g & 15));
+    }
+    starts.push_back(s + L);
+    mult.push_back((uint16_t)m);
+    item_base.push_back(item_base.back() + (L >= k + 1 ? 2 * (L - k + 2) : 0));
+  }
+};
+inline uint8_t code_of(char ch) {
+  switch (ch) {
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': case 'N': case 'n': return 2;
+    case 'T': case 't': return 3;
+    default: return 0;
+  }
+}
+// ContigReader: ">id flag=F multi=M len=L", sequence on the following line(s); contig_reverse = true;
+// loop contigs (flag & 2) get their first k_to-k_from bases appended; multiplicity = min(65535, int(M + 0.5)).
+void add_contigs(HostSeqs *hs, const std::string &path, int k, bool extend_loop, int k_from, int k_to) {
+  std::vector<uint8_t> raw = slurp(path);
+  const int min_len = k + 1;
+  size_t p = 0, n = raw.size();
+  std::vector<uint8_t> codes;
+  while (p < n) {
+    while (p < n && raw[p] != '>' && raw[p] != '@') { while (p < n && raw[p] != '\n') ++p; if (p < n) ++p; }
+    if (p >= n) break;
+    const bool fq = raw[p] == '@';
+    size_t h = p + 1;
+    while (p < n && raw[p] != '\n') ++p;
+    std::string header((const char *)raw.data() + h, p - h);
+    if (p < n) ++p;
+    codes.clear();
+    while (p < n && raw[p] != '>' && raw[p] != '+' && raw[p] != '@') {
+      while (p < n && raw[p] != '\n') { if (raw[p] != '\r') codes.push_back(code_of((char)raw[p])); ++p; }
+      if (p < n) ++p;
+    }
+    if (fq && p < n && raw[p] == '+') {   // skip quality
+      while (p < n && raw[p] != '\n') ++p;
+      if (p < n) ++p;
+      size_t q = 0;
+      while (p < n && q < codes.size()) { while (p < n && raw[p] != '\n') { if (raw[p] != '\r') ++q; ++p; } if (p < n) ++p; }
+    }
+    unsigned flag = 0;
+    float multi = 1.0f;
+    size_t sp = header.find_first_of(" \t");
+    if (sp != std::string::npos) {
+      std::string comment = header.substr(header.find_first_not_of(" \t", sp) == std::string::npos ? header.size() : header.find_first_not_of(" \t", sp));
+      sscanf(comment.c_str(), "flag=%u multi=%f", &flag, &multi);
+    }
+    size_t ext = (extend_loop && (flag & 2u)) ? (size_t)std::max(0, k_to - k_from) : 0;
+    ext = std::min(ext, codes.size());
+    if ((int64_t)(codes.size() + ext) < min_len) continue;
+    for (size_t i = 0; i < ext; ++i) codes.push_back(codes[i]);
+    std::reverse(codes.begin(), codes.end());
+    int m = (int)(multi + 0.5f);
+    hs->add(codes, std::min(m, kMaxMul), k);
+  }
+}
+}  // namespace
+
+// ---------------------------------------------------------------- sdbg files
+// SdbgWriter::Write: uint16 (w | last<<4 | tip<<5 | min(mult,255)<<8) [+ uint16 mult if > 254] [+ tip label words]
+static void write_sdbg(Ctx &c, const SdbgView &g, const std::string &prefix, int n_files) {
+  std::vector<uint32_t> rec((size_t)g.n_items), labels((size_t)g.n_tips * g.words_tip);
+  if (g.n_items) MF_CUDA(cudaMemcpy(rec.data(), g.rec, rec.size() * 4, cudaMemcpyDeviceToHost));
+  if (g.n_tips) MF_CUDA(cudaMemcpy(labels.data(), g.labels, labels.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<std::unique_ptr<File>> files;
+  for (int f = 0; f < n_files; ++f) files.emplace_back(new File(prefix + ".sdbg." + std::to_string(f), "wb"));
+  std::ostringstream info;
+  info << "k " << g.k << "\nwords_per_tip_label " << g.words_tip << "\nnum_buckets " << kNumBuckets << "\nnum_files " << n_files << '\n';
+  std::vector<int64_t> foff(n_files, 0);
+  std::vector<uint8_t> buf;
+  int64_t pos = 0, tpos = 0, large = 0;
+  for (int b = 0; b < kNumBuckets; ++b) {
+    const int64_t items = c.sdbg_bucket_stats[(size_t)b * 3], tips = c.sdbg_bucket_stats[(size_t)b * 3 + 1],
+                  lg = c.sdbg_bucket_stats[(size_t)b * 3 + 2];
+    if (!items) { info << b << " -1 0 0 0 0\n"; continue; }
+    const int f = bucket_file(b, n_files);
+    buf.clear();
+    for (int64_t i = pos; i < pos + items; ++i) {
+      const uint32_t r = rec[(size_t)i];
+      const uint32_t m = r >> 8;
+      const uint16_t small = (uint16_t)((r & 0x3f) | (std::min<uint32_t>(m, 255) << 8));
+      buf.insert(buf.end(), (const uint8_t *)&small, (const uint8_t *)&small + 2);
+      if (m > 254) { const uint16_t mm = (uint16_t)m; buf.insert(buf.end(), (const uint8_t *)&mm, (const uint8_t *)&mm + 2); ++large; }
+      if (r & 0x20) {
+        const uint8_t *lp = (const uint8_t *)(labels.data() + (size_t)tpos * g.words_tip);
+        buf.insert(buf.end(), lp, lp + 4 * g.words_tip);
+        ++tpos;
+      }
+    }
+    files[f]->write(buf.data(), buf.size());
+    info << b << ' ' << f << ' ' << foff[f] << ' ' << items << ' ' << tips << ' ' << lg << '\n';
+    foff[f] += (int64_t)buf.size();
+    pos += items;
+  }
+  if (pos != g.n_items || tpos != g.n_tips) throw std::runtime_error("sdbg bucket statistics do not add up");
+  info << "item_count " << g.n_items << "\ntip_count " << g.n_tips << "\nlarge_mul_count " << large << '\n';
+  for (auto &f : files) f->close();
+  File fi(prefix + ".sdbg_info", "w");
+  const std::string s = info.str();
+  fi.write(s.data(), s.size());
+  fi.close();
+}
+
+void file_seq2sdbg(Ctx &c, int k, int k_from, const char *input_prefix, const char *contig, const char *bubble,
+                   const char *addi_contig, const char *local_contig, const char *out_prefix, int n_files) {
+  HostEdges he;
+  if (input_prefix && *input_prefix) {
+    he = read_edges(input_prefix);
+    if (he.k != k) throw IoError("edges were built for k=" + std::to_string(he.k) + ", not " + std::to_string(k));
+  }
+  HostSeqs hs;
+  if (contig && *contig) add_contigs(&hs, contig, k, true, k_from, k);
+  if (bubble && *bubble) add_contigs(&hs, bubble, k, true, k_from, k);
+  if (addi_contig && *addi_contig) add_contigs(&hs, addi_contig, k, false, 0, 0);
+  if (local_contig && *local_contig) add_contigs(&hs, local_contig, k, false, 0, 0);
+  const int nseq = (int)hs.mult.size();
+  DevMem d_edges(he.data.size() * 4 + 64), d_packed(hs.packed.size() * 4 + 256), d_starts(sizeof(int64_t) * (nseq + 1)),
+      d_mult(sizeof(uint16_t) * (nseq + 1)), d_ibase(sizeof(int64_t) * (nseq + 1));
+  if (he.n) MF_CUDA(cudaMemcpy(d_edges.p, he.data.data(), he.data.size() * 4, cudaMemcpyHostToDevice));
+  SeqsView sv;
+  if (nseq) {
+    MF_CUDA(cudaMemset(d_packed.p, 0, hs.packed.size() * 4 + 256));
+    MF_CUDA(cudaMemcpy(d_packed.p, hs.packed.data(), hs.packed.size() * 4, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(d_starts.p, hs.starts.data(), sizeof(int64_t) * (nseq + 1), cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(d_mult.p, hs.mult.data(), sizeof(uint16_t) * nseq, cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemcpy(d_ibase.p, hs.item_base.data(), sizeof(int64_t) * (nseq + 1), cudaMemcpyHostToDevice));
+    sv.packed = d_packed.as<uint32_t>();
+    sv.starts = d_starts.as<int64_t>();
+    sv.mult = d_mult.as<uint16_t>();
+    sv.item_base = d_ibase.as<int64_t>();
+    sv.nseq = nseq;
+    sv.n_items = hs.item_base.back();
+  }
+  SdbgView g;
+  c.begin_call();
+  dev_seq2sdbg(c, d_edges.as<uint32_t>(), he.n, sv, k, 0, &g);
+  c.end_call();
+  write_sdbg(c, g, out_prefix, n_files);
+}
+
+void file_read2sdbg(Ctx &c, const char *read_lib_file, int k, int min_count, const char *out_prefix, int n_files) {
+  ReadsView r;
+  load_read_lib(c, read_lib_file, &r);
+  EdgesView e;
+  SdbgView g;
+  c.begin_call();
+  dev_count(c, r, k, min_count, &e, nullptr);
+  dev_seq2sdbg(c, e.edges, e.n_edges, SeqsView{}, k, 1, &g);
+  c.end_call();
+  write_sdbg(c, g, out_prefix, n_files);
+}
+
+}  // namespace mf

@@ -1,0 +1,148 @@
+// items.cuh -- sdbg item generation (SeqToSdbg::Lv0CalcBucketSize / Lv2ExtractSubString).
+// Every stored sequence of length L >= k+1 yields, on both strands, items at offsets 0..L-k+1:
+//   "$xxxx, xxxxx, ..., xxxx$"  = k bases (k-1 for the last), the preceding base b (or $), the multiplicity
+// (only for real edges).  Item word layout: bases left aligned, last word low 20 bits =
+// flag(k bases present)<<19 | b<<16 | (65535 - multiplicity), so a plain ascending sort over all words puts
+// larger multiplicities first.
+#pragma once
+#include "common.cuh"
+
+namespace mf {
+
+// shift a WS-word left-aligned base string left by `chars` bases, keep `nchars` bases, emit WD words
+template <int WS, int WD>
+__device__ __forceinline__ void window_item(const uint32_t (&t)[WS], int chars, int nchars, uint32_t flag, uint32_t prev,
+                                            uint32_t cnt, uint32_t (&out)[WD]) {
+  const int sh = 2 * chars;   // 0, 2 or 4
+#pragma unroll
+  for (int i = 0; i < WD; ++i) {
+    uint32_t hi = i < WS ? t[i] : 0u, lo = (i + 1) < WS ? t[i + 1] : 0u;
+    out[i] = __funnelshift_l(lo, hi, sh);
+  }
+  const int nb = 2 * nchars, wm = nb >> 5, rem = nb & 31;
+#pragma unroll
+  for (int i = 0; i < WD; ++i) {
+    if (i > wm) out[i] = 0;
+    else if (i == wm) out[i] &= rem ? (0xffffffffu << (32 - rem)) : 0u;
+  }
+  out[WD - 1] |= (flag << 19) | (prev << 16) | (uint32_t)(kMaxMul - (int)cnt);
+}
+
+// reverse complement of `nchars` left-aligned bases held in WS words
+template <int WS>
+__device__ __forceinline__ void revcomp_words(const uint32_t (&t)[WS], int nchars, uint32_t (&out)[WS]) {
+  const int nb = 2 * nchars, wm = nb >> 5, rem = nb & 31;
+  const int pad = 32 * WS - nb, pw = pad >> 5, pb = pad & 31;
+  uint32_t rr[WS];
+#pragma unroll
+  for (int i = 0; i < WS; ++i) {
+    const int s = WS - 1 - i;
+    uint32_t c = ~t[s];
+    if (s > wm) c = 0;                                         // word entirely inside the pad
+    else if (s == wm) c &= rem ? (0xffffffffu << (32 - rem)) : 0u;
+    uint32_t x = __brev(c);
+    rr[i] = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+  }
+  // the reversed string sits right aligned: shift left by `pad` bits across words
+#pragma unroll
+  for (int i = 0; i < WS; ++i) {
+    uint32_t hi = 0, lo = 0;
+#pragma unroll
+    for (int q = 0; q < WS; ++q) {
+      if (q == i + pw) hi = rr[q];
+      if (q == i + pw + 1) lo = rr[q];
+    }
+    out[i] = __funnelshift_l(lo, hi, pb);
+  }
+}
+
+// One thread per edge record ((k+1)-mer + multiplicity in the low 16 bits of the last word): 6 items.
+// WK = words of the (k+1)-mer, WE = words of the edge record, WI = words of an item.
+template <int WK, int WE, int WI>
+__global__ void k_items_from_edges(const uint32_t *__restrict__ edges, int64_t n_edges, int k, uint32_t *__restrict__ items) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  uint32_t fw[WK], rc[WK];
+  const uint32_t *src = edges + e * WE;
+#pragma unroll
+  for (int i = 0; i < WK; ++i) fw[i] = src[i];
+  const uint32_t mult = src[WE - 1] & 0xffffu;
+  const int pad = 32 * WK - 2 * (k + 1);
+  fw[WK - 1] &= 0xffffffffu << pad;        // drop the multiplicity if it shares the last key word
+  revcomp_words<WK>(fw, k + 1, rc);
+  uint32_t *dst = items + e * 6 * WI;
+#pragma unroll
+  for (int strand = 0; strand < 2; ++strand) {
+    const uint32_t(&t)[WK] = strand ? rc : fw;
+    const uint32_t c0 = t[0] >> 30, c1 = (t[0] >> 28) & 3;
+    uint32_t it[WI];
+    window_item<WK, WI>(t, 0, k, 1, kSentinel, 0, it);
+#pragma unroll
+    for (int i = 0; i < WI; ++i) dst[i] = it[i];
+    window_item<WK, WI>(t, 1, k, 1, c0, mult, it);
+#pragma unroll
+    for (int i = 0; i < WI; ++i) dst[WI + i] = it[i];
+    window_item<WK, WI>(t, 2, k - 1, 0, c1, 0, it);
+#pragma unroll
+    for (int i = 0; i < WI; ++i) dst[2 * WI + i] = it[i];
+    dst += 3 * WI;
+  }
+}
+
+// General sequences (contigs etc.), stored orientation, 2-bit packed back to back.
+// One thread per item; item -> sequence by binary search over item_base (sequences are long, few).
+template <int WI>
+__global__ void k_items_from_seqs(const uint32_t *__restrict__ packed, const int64_t *__restrict__ seq_start,
+                                  const uint16_t *__restrict__ seq_mult, const int64_t *__restrict__ item_base, int nseq,
+                                  int64_t n_items, int k, uint32_t *__restrict__ items) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n_items) return;
+  int lo = 0, hi = nseq;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (item_base[mid] <= x) lo = mid; else hi = mid;
+  }
+  const int64_t s0 = seq_start[lo];
+  const int L = (int)(seq_start[lo + 1] - s0);
+  const int per = L - k + 2;
+  int64_t r = x - item_base[lo];
+  const int strand = r >= per;
+  const int of = (int)(strand ? r - per : r);
+  const int nchars = (of + k > L) ? k - 1 : k;
+  const uint32_t cnt = (of > 0 && of + k <= L) ? seq_mult[lo] : 0u;
+  auto base_at = [&](int64_t g) -> uint32_t { return (packed[g >> 4] >> (30 - 2 * (int)(g & 15))) & 3u; };
+  // forward window start (in the stored string) covering the item's bases
+  const int f = strand ? (L - of - nchars) : of;
+  uint32_t raw[WI + 1];
+  {
+    const int64_t g = s0 + f;
+    const int64_t wi = g >> 4;
+    const int sh = (int)(g & 15) * 2;
+#pragma unroll
+    for (int i = 0; i < WI; ++i) raw[i] = __funnelshift_l(packed[wi + i + 1], packed[wi + i], sh);
+  }
+  const int nb = 2 * nchars, wm = nb >> 5, rem = nb & 31;
+  uint32_t w[WI];
+#pragma unroll
+  for (int i = 0; i < WI; ++i) {
+    w[i] = raw[i];
+    if (i > wm) w[i] = 0;
+    else if (i == wm) w[i] &= rem ? (0xffffffffu << (32 - rem)) : 0u;
+  }
+  uint32_t prev;
+  if (strand) {
+    uint32_t t[WI];
+    revcomp_words<WI>(w, nchars, t);
+#pragma unroll
+    for (int i = 0; i < WI; ++i) w[i] = t[i];
+    prev = of == 0 ? (uint32_t)kSentinel : 3u - base_at(s0 + L - of);
+  } else {
+    prev = of == 0 ? (uint32_t)kSentinel : base_at(s0 + of - 1);
+  }
+  w[WI - 1] |= ((uint32_t)(nchars == k) << 19) | (prev << 16) | (uint32_t)(kMaxMul - (int)cnt);
+  uint32_t *dst = items + x * WI;
+#pragma unroll
+  for (int i = 0; i < WI; ++i) dst[i] = w[i];
+}
+
+}  // namespace mf

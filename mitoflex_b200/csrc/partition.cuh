@@ -1,0 +1,382 @@
+// partition.cuh -- one MSD radix-partition level over W-word records.
+//
+// The same three kernels serve every level of the "bucketed" sort:
+//   k_level_hist    : digit histogram per output segment          (read only)
+//   k_level_scan    : histogram -> absolute cursors + bucket table (tiny)
+//   k_level_scatter : rank in shared memory, stage, coalesced copy-out
+// A Producer feeds a tile of records: ReadsProducer computes canonical (k+1)-mer keys straight from
+// 2-bit packed reads (so unsorted keys are never written to HBM), RecordsProducer re-reads records that
+// an earlier level wrote.  Ranking is warp-private (match.any + one leader update), never a per-key
+// shared-memory atomic.  Keys only, so the partition need not be stable.
+#pragma once
+#include "common.cuh"
+
+namespace mf {
+
+// ---- chunk table: input chunks -> output segments (several chunks may feed one segment, which is how
+// data received from several GPUs for the same prefix range is merged without an extra pass) ----------
+struct ChunkTable {
+  const int64_t *start;      // [nchunk] first record of the chunk in the input buffer
+  const int64_t *size;       // [nchunk]
+  const int32_t *seg;        // [nchunk] output segment id
+  const int64_t *tile_base;  // [nchunk+1] exclusive prefix of ceil(size / T)
+  int nchunk;
+};
+
+struct LevelArgs {
+  int bit_off;          // bits already consumed above this digit
+  int nbits;            // digit width, 1..kMaxDigitBits
+  uint32_t dlo, dhi;    // keep only digits in [dlo, dhi) (out-of-core rounds / multi-GPU ownership)
+};
+
+// ============================================================ producers
+template <int W>
+struct RecordsProducer {
+  const uint32_t *in;
+  ChunkTable ct;
+  int T;
+  static constexpr bool kNeedsSmem = false;
+  __host__ __device__ static int smem_words(int, int) { return 4; }
+
+  struct Tile {
+    int64_t base;
+    int n;
+    int seg;
+  };
+  __device__ __forceinline__ Tile setup(int64_t tile, uint32_t *sm) const {
+    if (threadIdx.x == 0) {
+      int lo = 0, hi = ct.nchunk;  // last chunk with tile_base <= tile
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (ct.tile_base[mid] <= tile) lo = mid; else hi = mid;
+      }
+      int64_t off = (tile - ct.tile_base[lo]) * (int64_t)T;
+      int64_t rem = ct.size[lo] - off;
+      int64_t base = ct.start[lo] + off;
+      sm[0] = (uint32_t)base;
+      sm[1] = (uint32_t)(base >> 32);
+      sm[2] = (uint32_t)(rem < T ? rem : T);
+      sm[3] = (uint32_t)ct.seg[lo];
+    }
+    __syncthreads();
+    Tile t;
+    t.base = (int64_t)(((uint64_t)sm[1] << 32) | sm[0]);
+    t.n = (int)sm[2];
+    t.seg = (int)sm[3];
+    return t;
+  }
+  __device__ __forceinline__ bool get(const Tile &t, const uint32_t *, int j, uint32_t (&r)[W]) const {
+    if (j >= t.n) return false;
+    const uint32_t *p = in + (t.base + j) * (int64_t)W;
+    if constexpr (W == 2) {
+      uint2 v = *reinterpret_cast<const uint2 *>(p);
+      r[0] = v.x; r[1] = v.y;
+    } else if constexpr (W == 4) {
+      uint4 v = *reinterpret_cast<const uint4 *>(p);
+      r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i) r[i] = p[i];
+    }
+    return true;
+  }
+};
+
+// Canonical (k+1)-mer keys of the REVERSED read, computed per base position from true-orientation packed
+// reads: stored edge = reverse(e), its reverse complement = complement(e); key = min of the two
+// (megahit KmerCounter reads the library with is_reverse=true; strand tie -> the edge itself).
+template <int W>
+struct ReadsProducer {
+  const uint32_t *packed;   // 16 bases / word, first base in the top bits, reads back to back
+  const uint32_t *sbits;    // bit g (LSB-first within word) set iff a read starts at base g
+  int64_t n_bases;
+  int k;
+  int T;
+  static constexpr bool kNeedsSmem = true;
+  __host__ __device__ static int n_seq_words(int T) { return T / 16 + W + 2; }
+  __host__ __device__ static int n_bit_words(int T, int k) { return T / 32 + (k + 31) / 32 + 2; }
+  __host__ __device__ static int smem_words(int T, int k) { return n_seq_words(T) + n_bit_words(T, k); }
+
+  struct Tile {
+    int64_t base;  // first base position of the tile
+    int n;
+    int seg;
+  };
+  __device__ __forceinline__ Tile setup(int64_t tile, uint32_t *sm) const {
+    Tile t;
+    t.base = tile * (int64_t)T;
+    int64_t rem = n_bases - t.base;
+    t.n = (int)(rem < T ? rem : T);
+    t.seg = 0;
+    const int64_t total_words = (n_bases + 15) >> 4;
+    const int64_t w0 = t.base >> 4;  // T is a multiple of 32 so tiles are word aligned
+    const int nsw = n_seq_words(T);
+    for (int i = threadIdx.x; i < nsw; i += blockDim.x) sm[i] = (w0 + i < total_words) ? packed[w0 + i] : 0u;
+    const int64_t total_bw = (n_bases + 31) >> 5;
+    const int64_t b0 = t.base >> 5;
+    const int nbw = n_bit_words(T, k);
+    uint32_t *sb = sm + nsw;
+    for (int i = threadIdx.x; i < nbw; i += blockDim.x) sb[i] = (b0 + i < total_bw) ? sbits[b0 + i] : 0u;
+    __syncthreads();
+    return t;
+  }
+  __device__ __forceinline__ bool get(const Tile &t, const uint32_t *sm, int j, uint32_t (&key)[W]) const {
+    const int K1 = k + 1;
+    bool valid = j < t.n && (t.base + j + K1 <= n_bases);
+    // no read may start inside (j, j+k]
+    const uint32_t *sb = sm + n_seq_words(T);
+    {
+      int bit = j + 1, left = k;
+      while (left > 0) {
+        int wi = bit >> 5, sh = bit & 31;
+        uint32_t v = __funnelshift_r(sb[wi], sb[wi + 1], sh);
+        if (left < 32) v &= (1u << left) - 1u;
+        valid = valid && (v == 0);
+        bit += 32;
+        left -= 32;
+      }
+    }
+    // raw = 2*K1 bits at base j, left aligned
+    const int wi = j >> 4, sh = (j & 15) * 2;
+    uint32_t raw[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) raw[i] = __funnelshift_l(sm[wi + i + 1], sm[wi + i], sh);
+    const int pad = 32 * W - 2 * K1;  // 0..30
+    raw[W - 1] &= 0xffffffffu << pad;
+    // complement(e): same direction, bases 3-c
+    uint32_t cmpl[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) cmpl[i] = ~raw[i];
+    cmpl[W - 1] &= 0xffffffffu << pad;
+    // reverse(e): reverse base order (bit reverse, then swap the two bits of every base back)
+    uint32_t rr[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      uint32_t x = __brev(raw[W - 1 - i]);
+      rr[i] = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+    }
+    uint32_t rev[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) rev[i] = __funnelshift_l(i + 1 < W ? rr[i + 1] : 0u, rr[i], pad);
+    // min(rev, cmpl)
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      if (c == 0 && rev[i] != cmpl[i]) c = rev[i] < cmpl[i] ? -1 : 1;
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) key[i] = c <= 0 ? rev[i] : cmpl[i];
+    return valid;
+  }
+};
+
+// ============================================================ histogram
+// grid.x = number of tiles; dynamic smem = whist (u16 [NT/32][nbins]) + producer words
+template <class P, int W, int NT, int IPT>
+__global__ void __launch_bounds__(NT) k_level_hist(P prod, LevelArgs a, unsigned long long *__restrict__ hist) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int nbins = 1 << a.nbits;
+  constexpr int NWARP = NT / 32;
+  uint16_t *whist = reinterpret_cast<uint16_t *>(smem);                 // [NWARP][nbins]
+  uint32_t *psm = smem + (NWARP * nbins + 1) / 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < (NWARP * nbins + 1) / 2; i += NT) smem[i] = 0;
+  typename P::Tile t = prod.setup(blockIdx.x, psm);   // contains a __syncthreads
+  uint16_t *wh = whist + warp * nbins;
+#pragma unroll 4
+  for (int i = 0; i < IPT; ++i) {
+    uint32_t r[W];
+    int j = i * NT + tid;
+    bool valid = prod.get(t, psm, j, r);
+    uint32_t d = rec_digit<W>(r, a.bit_off, a.nbits);
+    valid = valid && d >= a.dlo && d < a.dhi;
+    unsigned m = match_digit(d, valid);
+    if (valid && lane == (unsigned)(__ffs(m) - 1)) wh[d] = (uint16_t)(wh[d] + __popc(m));
+    __syncwarp();
+  }
+  __syncthreads();
+  unsigned long long *h = hist + (size_t)t.seg * nbins;
+  for (int b = tid; b < nbins; b += NT) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) acc += whist[w * nbins + b];
+    if (acc) atomicAdd(h + b, (unsigned long long)acc);
+  }
+}
+
+// ============================================================ scan: hist -> cursors + bucket table
+// seg_total[s] = sum_d hist[s][d]
+__global__ void k_seg_totals(const unsigned long long *hist, int nbins, int nseg, int64_t *seg_total) {
+  int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= nseg) return;
+  unsigned long long acc = 0;
+  for (int b = threadIdx.x & 31; b < nbins; b += 32) acc += hist[(size_t)s * nbins + b];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) seg_total[s] = (int64_t)acc;
+}
+// single-block exclusive scan of int64 v[0..n) -> out[0..n], out[n] = total (+base)
+__global__ void k_scan_i64(const int64_t *v, int64_t n, int64_t base, int64_t *out) {
+  __shared__ int64_t s_part[1024];
+  __shared__ int64_t s_run;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_run = base;
+  __syncthreads();
+  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
+  const int64_t b = tid * per, e = b + per < n ? b + per : n;
+  int64_t sum = 0;
+  for (int64_t i = b; i < e; ++i) sum += v[i];
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    int64_t run = s_run;
+    for (int i = 0; i < (int)blockDim.x; ++i) { int64_t x = s_part[i]; s_part[i] = run; run += x; }
+    out[n] = run;
+  }
+  __syncthreads();
+  int64_t run = s_part[tid];
+  for (int64_t i = b; i < e; ++i) { int64_t x = v[i]; out[i] = run; run += x; }
+}
+// per segment: cursor[s][d] = seg_out_start[s] + exclusive prefix of hist[s][.]; bucket table likewise.
+__global__ void k_level_scan(const unsigned long long *hist, int nbins, const int64_t *seg_out_start,
+                             unsigned long long *cursor, int64_t *bkt_start, int64_t *bkt_size) {
+  __shared__ unsigned long long s_w[32];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // blockDim.x == kMaxBins threads; bins beyond nbins contribute 0
+  unsigned long long v = tid < nbins ? hist[(size_t)s * nbins + tid] : 0ull, inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long x = lane < (int)(blockDim.x >> 5) ? s_w[lane] : 0ull, xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) xi += t;
+    }
+    s_w[lane] = xi - x;
+  }
+  __syncthreads();
+  if (tid < nbins) {
+    unsigned long long st = (unsigned long long)seg_out_start[s] + s_w[warp] + inc - v;
+    size_t idx = (size_t)s * nbins + tid;
+    cursor[idx] = st;
+    bkt_start[idx] = (int64_t)st;
+    bkt_size[idx] = (int64_t)v;
+  }
+}
+
+// ============================================================ scatter
+// dynamic smem layout (uint32 units):
+//   whist   u16 [NWARP][nbins]
+//   s_tot   u32 [nbins]      bin totals, then exclusive starts
+//   s_gd    i64 [nbins]      global record index of the bin's first staged record minus its staged index
+//   scratch u32 [34]
+//   stage   u32 [T*W]
+//   producer words
+template <int W>
+__host__ __device__ inline size_t scatter_smem_bytes(int NT, int T, int nbits, int prod_words) {
+  size_t nb = (size_t)1 << nbits;
+  size_t words = ((NT / 32) * nb + 1) / 2 + nb + 2 * nb + 34 + 2 + (size_t)T * W + prod_words;
+  return words * 4;
+}
+
+template <class P, int W, int NT, int IPT>
+__global__ void __launch_bounds__(NT) k_level_scatter(P prod, LevelArgs a, unsigned long long *__restrict__ cursor,
+                                                      uint32_t *__restrict__ out) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int NWARP = NT / 32;
+  constexpr int T = NT * IPT;
+  const int nbins = 1 << a.nbits;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint16_t *whist = reinterpret_cast<uint16_t *>(smem);
+  uint32_t *s_tot = smem + (NWARP * nbins + 1) / 2;
+  uint32_t *s_gd32 = s_tot + nbins;
+  if ((reinterpret_cast<uintptr_t>(s_gd32) & 7) != 0) s_gd32 += 1;   // 8-byte align
+  long long *s_gd = reinterpret_cast<long long *>(s_gd32);
+  uint32_t *scratch = s_gd32 + 2 * nbins;
+  uint32_t *stage = scratch + 34;
+  if ((reinterpret_cast<uintptr_t>(stage) & 7) != 0) stage += 1;
+  uint32_t *psm = stage + (size_t)T * W;
+
+  for (int i = tid; i < (NWARP * nbins + 1) / 2; i += NT) smem[i] = 0;
+  typename P::Tile t = prod.setup(blockIdx.x, psm);   // contains a __syncthreads
+
+  uint32_t rec[IPT][W];
+  uint32_t rk[IPT];   // digit << 16 | rank within (warp, digit); 0xffffffff = dropped
+  uint16_t *wh = whist + warp * nbins;
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    int j = i * NT + tid;
+    bool valid = prod.get(t, psm, j, rec[i]);
+    uint32_t d = rec_digit<W>(rec[i], a.bit_off, a.nbits);
+    valid = valid && d >= a.dlo && d < a.dhi;
+    unsigned m = match_digit(d, valid);
+    unsigned leader = (unsigned)(__ffs(m) - 1);
+    uint32_t old = 0;
+    if (valid && lane == leader) {
+      old = wh[d];
+      wh[d] = (uint16_t)(old + __popc(m));
+    }
+    old = __shfl_sync(0xffffffffu, old, valid ? leader : 0);
+    rk[i] = valid ? ((d << 16) | (old + __popc(m & lanemask_lt()))) : 0xffffffffu;
+    __syncwarp();
+  }
+  __syncthreads();
+  // per-bin: exclusive prefix over warps, total per bin
+  for (int b = tid; b < nbins; b += NT) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) {
+      uint32_t c = whist[w * nbins + b];
+      whist[w * nbins + b] = (uint16_t)acc;
+      acc += c;
+    }
+    s_tot[b] = acc;
+    s_gd[b] = (long long)acc;   // stash the count for the reservation below
+  }
+  __syncthreads();
+  const uint32_t total = block_excl_scan<NT>(s_tot, nbins, scratch);
+  for (int b = tid; b < nbins; b += NT) {
+    long long c = s_gd[b];
+    if (c) {
+      unsigned long long g = atomicAdd(cursor + (size_t)t.seg * nbins + b, (unsigned long long)c);
+      s_gd[b] = (long long)g - (long long)s_tot[b];
+    }
+  }
+  // stage records in bin order
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) {
+    if (rk[i] != 0xffffffffu) {
+      uint32_t d = rk[i] >> 16;
+      uint32_t pos = s_tot[d] + wh[d] + (rk[i] & 0xffffu);
+#pragma unroll
+      for (int c = 0; c < W; ++c) stage[(size_t)pos * W + c] = rec[i][c];
+    }
+  }
+  __syncthreads();
+  // coalesced copy-out: consecutive staged records of a bin go to consecutive global records
+  if constexpr (W == 2) {
+    const uint2 *st2 = reinterpret_cast<const uint2 *>(stage);
+    uint2 *out2 = reinterpret_cast<uint2 *>(out);
+    for (uint32_t j = tid; j < total; j += NT) {
+      uint2 v = st2[j];
+      uint32_t r2[2] = {v.x, v.y};
+      uint32_t d = rec_digit<2>(r2, a.bit_off, a.nbits);
+      out2[s_gd[d] + (long long)j] = v;
+    }
+  } else {
+    const uint32_t total_words = total * W;
+    for (uint32_t x = tid; x < total_words; x += NT) {
+      uint32_t j = x / W, c = x - j * W;
+      uint32_t d = rec_digit_mem<W>(stage + (size_t)j * W, a.bit_off, a.nbits);
+      out[(s_gd[d] + (long long)j) * W + c] = stage[x];
+    }
+  }
+}
+
+}  // namespace mf

@@ -1,0 +1,144 @@
+"""GPU parity: libmfsdbg (through its C ABI) against the CPU oracle, bit-exact (integer / byte work).
+Every test here needs a B200; run with `pytest -m gpu`."""
+import os
+
+import numpy as np
+import pytest
+
+from gpu_common import assert_edges_equal, assert_sdbg_equal, make_reads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from mitoflex_b200 import lib
+    c = lib.Context(0)
+    yield c
+    c.close()
+
+
+def _orc_reads(oracle, bases, starts):
+    return oracle.Reads(bases, starts)
+
+
+# k values cover every key width class: 1 word (k<=15), 2 (<=31), 3, 4, 5 (k=79), 7 (k=99), 8 (k=119), 9 (k=141)
+COUNT_CASES = [(9, 1), (9, 2), (15, 2), (16, 1), (21, 1), (21, 2), (21, 3), (31, 2), (32, 2), (47, 1), (59, 2), (63, 2),
+               (79, 2), (99, 2), (119, 2), (141, 2)]
+
+
+@pytest.mark.parametrize("k,m", COUNT_CASES)
+def test_count_parity(ctx, oracle, k, m):
+    bases, starts = make_reads(100 + k * 7 + m, 3000, k, genome_len=6000, max_len=max(150, k + 40))
+    e_gpu = ctx.count(ctx.upload_reads(bases, starts), k, m, want_counting=True)
+    e_orc = oracle.count(_orc_reads(oracle, bases, starts), k, m, threads=4)
+    assert_edges_equal(e_gpu, e_orc)
+    assert np.array_equal(e_gpu.counting, e_orc.counting)
+
+
+@pytest.mark.parametrize("k,m", [(21, 2), (31, 2), (59, 2)])
+def test_count_parity_medium(ctx, oracle, k, m):
+    """enough keys for two partition levels (>> one bucket)."""
+    bases, starts = make_reads(7 + k, 120000, k, genome_len=400000, max_len=150, err=0.005)
+    e_gpu = ctx.count(ctx.upload_reads(bases, starts), k, m)
+    e_orc = oracle.count(_orc_reads(oracle, bases, starts), k, m, threads=8)
+    assert_edges_equal(e_gpu, e_orc)
+
+
+def test_count_edge_cases(ctx, oracle):
+    # empty library, only short reads, a single read
+    for seqs in ([], [np.zeros(5, np.uint8)], [np.arange(40, dtype=np.uint8) & 3]):
+        starts = np.zeros(len(seqs) + 1, np.int64)
+        starts[1:] = np.cumsum([len(s) for s in seqs])
+        bases = np.concatenate(seqs).astype(np.uint8) if seqs else np.zeros(0, np.uint8)
+        e_gpu = ctx.count(ctx.upload_reads(bases, starts), 21, 1)
+        e_orc = oracle.count(_orc_reads(oracle, bases, starts), 21, 1)
+        assert_edges_equal(e_gpu, e_orc)
+
+
+def test_count_skewed_buckets(ctx, oracle):
+    """one read repeated 70000 times (multiplicity cap 65535, buckets far larger than shared memory -> fallback path),
+    poly-A reads, and a low-complexity family sharing long prefixes."""
+    k = 21
+    bases, starts = make_reads(5, 2000, k, dup_boost=70000)
+    rng = np.random.default_rng(9)
+    extra = [np.zeros(150, np.uint8) for _ in range(300)]
+    stem = rng.integers(0, 4, 60, dtype=np.uint8)
+    for _ in range(20000):
+        tail = rng.integers(0, 4, 30, dtype=np.uint8)
+        extra.append(np.concatenate([stem, tail]))
+    seqs = [bases[starts[i]:starts[i + 1]] for i in range(len(starts) - 1)] + extra
+    starts2 = np.zeros(len(seqs) + 1, np.int64)
+    starts2[1:] = np.cumsum([len(s) for s in seqs])
+    bases2 = np.concatenate(seqs).astype(np.uint8)
+    for m in (1, 2):
+        e_gpu = ctx.count(ctx.upload_reads(bases2, starts2), k, m, want_counting=True)
+        e_orc = oracle.count(_orc_reads(oracle, bases2, starts2), k, m, threads=8)
+        assert_edges_equal(e_gpu, e_orc)
+        assert np.array_equal(e_gpu.counting, e_orc.counting)
+
+
+@pytest.mark.parametrize("k,m", [(9, 1), (13, 2), (15, 2), (16, 2), (21, 2), (24, 1), (31, 2), (32, 2), (47, 2), (63, 2), (79, 2),
+                                 (141, 2)])
+def test_seq2sdbg_parity(ctx, oracle, k, m):
+    bases, starts = make_reads(300 + k, 2500, k, genome_len=5000, max_len=max(150, k + 40))
+    e_gpu = ctx.count(ctx.upload_reads(bases, starts), k, m)
+    g_gpu = ctx.seq2sdbg(e_gpu, k)
+    e_orc = oracle.count(_orc_reads(oracle, bases, starts), k, m, threads=4)
+    s = oracle.Seqs()
+    s.add_edges(e_orc)
+    g_orc = oracle.seq2sdbg(s, k, threads=4)
+    assert_sdbg_equal(g_gpu, g_orc)
+
+
+@pytest.mark.parametrize("k,m", [(9, 2), (15, 2), (21, 1), (21, 2), (31, 2), (47, 2), (141, 2)])
+def test_read2sdbg_parity(ctx, oracle, k, m):
+    bases, starts = make_reads(500 + k, 2500, k, genome_len=5000, max_len=max(150, k + 40))
+    g_gpu = ctx.read2sdbg(ctx.upload_reads(bases, starts), k, m)
+    g_orc = oracle.read2sdbg(_orc_reads(oracle, bases, starts), k, m, threads=4)
+    assert_sdbg_equal(g_gpu, g_orc)
+
+
+def test_sdbg_medium(ctx, oracle):
+    k, m = 21, 2
+    bases, starts = make_reads(77, 100000, k, genome_len=300000, max_len=150, err=0.005)
+    g_gpu = ctx.read2sdbg(ctx.upload_reads(bases, starts), k, m)
+    g_orc = oracle.read2sdbg(_orc_reads(oracle, bases, starts), k, m, threads=8)
+    assert_sdbg_equal(g_gpu, g_orc)
+
+
+def test_high_multiplicity_sdbg(ctx, oracle):
+    """multiplicities around the 254/255 inline limit and the 65535 cap."""
+    k = 21
+    rng = np.random.default_rng(3)
+    base_reads = [rng.integers(0, 4, 60, dtype=np.uint8) for _ in range(4)]
+    seqs = []
+    for r, copies in zip(base_reads, (254, 255, 256, 66000)):
+        seqs += [r] * copies
+    starts = np.zeros(len(seqs) + 1, np.int64)
+    starts[1:] = np.cumsum([len(s) for s in seqs])
+    bases = np.concatenate(seqs).astype(np.uint8)
+    g_gpu = ctx.read2sdbg(ctx.upload_reads(bases, starts), k, 2)
+    g_orc = oracle.read2sdbg(_orc_reads(oracle, bases, starts), k, 2, threads=4)
+    assert_sdbg_equal(g_gpu, g_orc)
+    assert g_orc.n_large > 0
+
+
+def test_synth_generator_and_properties(ctx, oracle):
+    """the in-HBM generator feeds both sides: download its reads, run the oracle on them."""
+    reads = ctx.synth(n_pairs=20000, nuclear_len=200000, mito_len=16500, mito_fraction=0.05, error_rate=0.005, seed=1001)
+    bases, starts = ctx.download_reads(reads)
+    lens = np.diff(starts)
+    assert reads.n_reads == 40000 and lens.max() == 150 and lens.min() >= 0 and (lens < 150).any()
+    e_gpu = ctx.count(reads, 21, 2, want_counting=True)
+    e_orc = oracle.count(oracle.Reads(bases, starts), 21, 2, threads=8)
+    assert_edges_equal(e_gpu, e_orc)
+    # size-independent property: the multiplicity histogram accounts for every (k+1)-mer occurrence below the cap
+    n_keys = int(np.maximum(lens - 21, 0).sum())
+    assert e_gpu.s.n_keys == n_keys
+    c = e_gpu.counting
+    assert (c[:65535] * np.arange(65535)).sum() + c[65535] * 65535 <= n_keys
+    assert (c[:65535] * np.arange(65535)).sum() == n_keys - 0 or c[65535] > 0
+    g_gpu = ctx.read2sdbg(reads, 21, 2)
+    g_orc = oracle.read2sdbg(oracle.Reads(bases, starts), 21, 2, threads=8)
+    assert_sdbg_equal(g_gpu, g_orc)
