@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sDBG-construction path (BASELINE.json metric).
+
+A "step" is one `read2sdbg -k 21 -m 2` (k-mer count + succinct de Bruijn graph build, fused in HBM) over one
+batch of synthetic PE150 reads generated in HBM (SURVEY.md 8d generator: 16.5 kb mitogenome at 5 % of the pairs
+over a 50 Mb nuclear background, 0.5 % substitution errors).  At N=1 the batch is BASELINE.json configs[1]'s read
+set (16 666 667 pairs = 5.0 Gbp).  With N>1 (torchrun, one rank per GPU) every rank holds its own 5 Gbp shard,
+keys are routed to their owner GPU by prefix bucket with an NCCL all-to-all, and value = all bases / max-over-ranks
+time (weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl reference]
+
+`--impl reference` times the CPU restatement of megahit_core (oracle/, all host threads) on a bounded sample of the
+same workload: megahit v1.2.9 itself is not vendored in the reference tree and no binary exists in this image.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bases/s k-mer count+sDBG build (k=21)"
+K, MIN_COUNT, READ_LEN = 21, 2, 150
+FULL_PAIRS = 16_666_667
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=FULL_PAIRS, help="read pairs per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(pairs):
+    return (f"read2sdbg k={K} -m {MIN_COUNT} on synthetic {pairs}xPE{READ_LEN} ({2 * pairs * READ_LEN / 1e9:.2f} Gbp/GPU): "
+            "16.5 kb mitogenome at 5% of pairs + 50 Mb nuclear background, 0.5% errors (BASELINE configs[1] read set)")
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.rows = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ roofline bookkeeping
+def stage_bytes(n_bases, n_keys, n_edges, n_items_gen, k):
+    """ALGORITHMIC bytes per stage launch (DESIGN.md 'kernels'): what the stage must read + write once."""
+    W = 4 * ((2 * (k + 1) + 31) // 32)
+    We = 4 * ((2 * (k + 1) + 16 + 31) // 32)
+    Wi = 4 * ((2 * k + 20 + 31) // 32)
+    return {
+        "reads_hist": n_bases / 4,
+        "reads_scatter": n_bases / 4 + n_keys * W,
+        "count_l2_hist": n_keys * W,
+        "count_l2_scatter": 2 * n_keys * W,
+        "local_count": n_keys * W + n_edges * We,
+        "items": n_edges * We + n_items_gen * Wi,
+        "sdbg_l1_hist": n_items_gen * Wi,
+        "sdbg_l1_scatter": 2 * n_items_gen * Wi,
+        "sdbg_l2_hist": n_items_gen * Wi,
+        "sdbg_l2_scatter": 2 * n_items_gen * Wi,
+        "local_sdbg_count": n_items_gen * Wi,
+        "local_sdbg_emit": n_items_gen * Wi,
+    }
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except (ValueError, KeyError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ CPU arm
+def cpu_run(bases, starts, threads):
+    from oracle import oracle
+    t0 = time.perf_counter()
+    g = oracle.read2sdbg(oracle.Reads(bases, starts), K, MIN_COUNT, threads=threads)
+    dt = time.perf_counter() - t0
+    return dt, g.n
+
+
+def cpu_sample(ctx, reads, n_sample_reads):
+    """first n reads of the device-resident workload, on the host as 1 byte/base."""
+    from mitoflex_b200 import lib
+    n = min(n_sample_reads, reads.n_reads)
+    starts = ctx.d2h(reads.s.starts, (n + 1) * 8, np.int64)
+    nb = int(starts[-1])
+    words = ctx.d2h(reads.s.packed, ((nb + 15) // 16) * 4, np.uint32)
+    return lib.unpack_reads(words, nb), starts
+
+
+def cpu_baseline(ctx, reads, target_seconds):
+    threads = os.cpu_count() or 1
+    pilot_reads = 200_000
+    b, s = cpu_sample(ctx, reads, pilot_reads)
+    dt, _ = cpu_run(b, s, threads)
+    rate = len(b) / dt
+    n = int(min(reads.n_reads, max(pilot_reads, rate * target_seconds / READ_LEN)))
+    n = min(n, 8_000_000)
+    if n > pilot_reads * 1.5:
+        b, s = cpu_sample(ctx, reads, n)
+        dt, _ = cpu_run(b, s, threads)
+    return {"value": len(b) / dt, "unit": "bases/s", "cores": threads, "kind": "port",
+            "sample": f"first {len(s) - 1} reads ({len(b) / 1e6:.1f} Mbp) of the same synthetic read set, oracle read2sdbg "
+                      f"(CPU restatement of megahit_core, OpenMP) in {dt:.2f} s; megahit itself is not vendored"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement on host cores, bounded sample per step (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mitoflex_b200 import lib
+    threads = os.cpu_count() or 1
+    ctx = lib.Context(0)
+    pairs = min(args.pairs, 1_000_000)
+    reads = ctx.synth(n_pairs=pairs, seed=1002)
+    pilot_b, pilot_s = cpu_sample(ctx, reads, 200_000)
+    dt, _ = cpu_run(pilot_b, pilot_s, threads)
+    n = int(min(reads.n_reads, max(200_000, (len(pilot_b) / dt) * 6.0 / READ_LEN)))
+    b, s = cpu_sample(ctx, reads, n)
+    ctx.close()
+    for _ in range(args.warmup):
+        cpu_run(b, s, threads)
+    times = [cpu_run(b, s, threads)[0] for _ in range(args.steps)]
+    tot = sum(times)
+    v = len(b) * args.steps / tot
+    sample = f"first {len(s) - 1} reads ({len(b) / 1e6:.1f} Mbp) of the synthetic read set per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(args.pairs), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "bases/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------ GPU arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    from mitoflex_b200 import lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = lib.Context(local_rank)
+    stream = torch.cuda.Stream(dev)            # a dedicated stream shared with the library, so that torch's
+    torch.cuda.set_stream(stream)              # CUDA events bracket exactly the kernels the library launches
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_profiling(True)
+    reads = ctx.synth(n_pairs=args.pairs, seed=1002 + 7919 * rank)
+    n_bases = reads.n_bases
+
+    if world > 1:
+        from mitoflex_b200 import dist as mdist
+        runner = mdist.DistRead2Sdbg(ctx, K, MIN_COUNT)
+        step = lambda: runner.run(reads)   # noqa: E731
+    else:
+        step = lambda: ctx.read2sdbg(reads, K, MIN_COUNT)   # noqa: E731
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
+    launches0 = ctx.launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    prof = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    stage_sum = {}
+    res = None
+    for _ in range(args.steps):
+        res = step()
+        for name, ms in ctx.last_profile().items():
+            stage_sum[name] = stage_sum.get(name, 0.0) + ms
+    ev1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    # device time of the K steps: CUDA events on the stream the library launches on (set_stream above)
+    t_ms = ev0.elapsed_time(ev1)
+    wall_ms = t_wall * 1e3
+    if world > 1:
+        t = torch.tensor([t_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t.item())
+        nb = torch.tensor([n_bases], device=dev, dtype=torch.int64)
+        dist.all_reduce(nb)
+        total_bases = int(nb.item())
+    else:
+        total_bases = n_bases
+    value = total_bases * args.steps / (t_ms / 1e3)
+
+    # ---- e2e: host buffers in, host buffers out, through the C ABI (rank-local, N=1 semantics per rank)
+    e2e = None
+    if not args.no_e2e and world == 1:
+        nw = (n_bases + 15) // 16
+        hw = torch.empty(nw + 16, dtype=torch.int32, pin_memory=True)
+        hs = torch.empty(reads.n_reads + 1, dtype=torch.int64, pin_memory=True)
+        # copy the device reads into pinned host buffers once, outside the timed region
+        from ctypes import c_void_p
+        L = lib.load()
+        lib._check(L.mfsdbg_dev_copy(ctx._h, c_void_p(hw.data_ptr()), reads.s.packed, nw * 4, 0))
+        lib._check(L.mfsdbg_dev_copy(ctx._h, c_void_p(hs.data_ptr()), reads.s.starts, (reads.n_reads + 1) * 8, 0))
+        for _ in range(2):
+            out = ctx.host_read2sdbg(hw.data_ptr(), hs.data_ptr(), reads.n_reads, n_bases, K, MIN_COUNT)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = ctx.host_read2sdbg(hw.data_ptr(), hs.data_ptr(), reads.n_reads, n_bases, K, MIN_COUNT)
+        te = time.perf_counter() - t0
+        assert out.n_items == res.n
+        e2e = {"value": n_bases * args.steps / te, "unit": "bases/s", "h2d_bytes_per_step": int(out.h2d_bytes),
+               "d2h_bytes_per_step": int(out.d2h_bytes), "ms_per_step": 1e3 * te / args.steps,
+               "api": "mfsdbg_host_read2sdbg (pinned host packed reads in, sdbg arrays out)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant stage, from the live CUDA-event stage timings of the timed steps
+    n_keys = getattr(res, "n_keys", None)
+    info = getattr(res, "info", {})
+    e_cnt = ctx.count(reads, K, MIN_COUNT) if world == 1 else None
+    n_keys = e_cnt.s.n_keys if e_cnt is not None else info.get("n_keys", 0)
+    n_edges = e_cnt.n if e_cnt is not None else info.get("n_edges", 0)
+    sb = stage_bytes(n_bases, n_keys, n_edges, 6 * n_edges, K)
+    per_step = {k2: v / args.steps for k2, v in stage_sum.items()}
+    dom = max((k2 for k2 in per_step if k2 in sb), key=lambda k2: per_step[k2], default=None)
+    peak, peak_src = measured_peak()
+    roofline = None
+    if dom:
+        ach = sb[dom] / (per_step[dom] / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "ms_per_launch": per_step[dom],
+                    "algorithmic_bytes_per_launch": sb[dom],
+                    "stages_ms": {k2: round(v, 3) for k2, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            try:
+                roofline["traffic"] = json.load(open(tr)).get(dom)
+            except ValueError:
+                pass
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_baseline(ctx, reads, args.cpu_seconds)
+    out = {
+        "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.pairs), "bases_per_gpu": n_bases, "keys_per_gpu": n_keys, "solid_edges": n_edges,
+                   "sdbg_items": res.n if res is not None else None, "l2_flush": "inputs and key buffers (>= 1 GB) exceed the 126 MB L2",
+                   "parallelism": "reads sharded by GPU, keys routed by 10-bit prefix (NCCL all-to-all)" if world > 1 else "1 GPU"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,9 @@ void mfsdbg_ctx_destroy(mfsdbg_ctx *ctx);
 int mfsdbg_ctx_set_mem_limit(mfsdbg_ctx *ctx, uint64_t bytes);
 /* the stream every kernel of this context is launched on (a cudaStream_t) */
 void *mfsdbg_ctx_stream(mfsdbg_ctx *ctx);
+/* run on a caller-owned stream instead (e.g. the host framework's current stream, so that the caller's CUDA
+ * events bracket the library's kernels); NULL restores the context's own stream */
+int mfsdbg_ctx_set_stream(mfsdbg_ctx *ctx, void *cuda_stream);
 /* kernels launched by this context since creation (for bench.py's gpu_launches) */
 int64_t mfsdbg_ctx_launches(mfsdbg_ctx *ctx);
 /* per-stage device milliseconds of the last call, as "name=ms;name=ms;..." (profiling must be enabled) */
@@ -152,6 +155,20 @@ int mfsdbg_dev_count_finish(mfsdbg_ctx *ctx, uint32_t *keys, uint32_t *scratch, 
                             mfsdbg_dev_edges *out, int64_t *counting_host);
 int32_t mfsdbg_words_per_key(int32_t k);
 int32_t mfsdbg_words_per_edge(int32_t k);
+
+/* ---- host-buffer entry point: what a caller holding the packed library in host memory uses ------------ */
+/* The sdbg in (pinned, library-owned) host memory; valid until the next mfsdbg_host_* call on the context. */
+typedef struct mfsdbg_host_sdbg {
+  const uint32_t *rec;         /* host, n_items: w | last<<4 | tip<<5 | multiplicity<<8 */
+  const uint32_t *tip_labels;  /* host, n_tips * words_per_tip */
+  int64_t n_items, n_tips, n_large;
+  int32_t k, words_per_tip;
+  int64_t h2d_bytes, d2h_bytes; /* bytes this call moved over PCIe */
+} mfsdbg_host_sdbg;
+/* read2sdbg with HOST inputs and outputs: copies packed reads (same layout as mfsdbg_dev_reads, host pointers;
+ * pinned memory makes the copies asynchronous-fast) to HBM, builds the graph, copies the sdbg back. */
+int mfsdbg_host_read2sdbg(mfsdbg_ctx *ctx, const uint32_t *packed_host, const int64_t *starts_host, int64_t n_reads,
+                          int64_t n_bases, int32_t k, int32_t min_count, mfsdbg_host_sdbg *out);
 
 /* plain copies on the context's stream, synchronous for the caller; kind: 0 = device->host, 1 = host->device,
  * 2 = device->device.  Lets ctypes hosts move results without a CUDA binding of their own. */

@@ -74,6 +74,12 @@ int mfsdbg_ctx_set_mem_limit(mfsdbg_ctx *ctx, uint64_t bytes) {
   ctx->c.mem_limit = (size_t)bytes;
   return MFSDBG_OK;
 }
+int mfsdbg_ctx_set_stream(mfsdbg_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return MFSDBG_EINVAL;
+  cudaStreamSynchronize(ctx->c.stream);
+  ctx->c.stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->c.own_stream;
+  return MFSDBG_OK;
+}
 void *mfsdbg_ctx_stream(mfsdbg_ctx *ctx) { return ctx ? (void *)ctx->c.stream : nullptr; }
 int64_t mfsdbg_ctx_launches(mfsdbg_ctx *ctx) { return ctx ? ctx->c.launches : 0; }
 int mfsdbg_ctx_set_profiling(mfsdbg_ctx *ctx, int32_t on) {
@@ -209,6 +215,48 @@ int mfsdbg_dev_synth_reads(mfsdbg_ctx *ctx, const mfsdbg_synth_spec *spec, mfsdb
     out->starts = r.starts;
     out->n_reads = r.n_reads;
     out->n_bases = r.n_bases;
+  });
+}
+
+int mfsdbg_host_read2sdbg(mfsdbg_ctx *ctx, const uint32_t *packed_host, const int64_t *starts_host, int64_t n_reads,
+                          int64_t n_bases, int32_t k, int32_t min_count, mfsdbg_host_sdbg *out) {
+  if (!ctx || !out || n_reads < 0 || n_bases < 0 || (n_bases > 0 && (!packed_host || !starts_host))) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    mf::Ctx &c = ctx->c;
+    c.begin_call();
+    const size_t wbytes = (size_t)((n_bases + 15) >> 4) * 4, sbytes = sizeof(int64_t) * (size_t)(n_reads + 1);
+    c.in_words.reserve(wbytes + 64);
+    c.in_starts.reserve(sbytes);
+    {
+      mf::Stage st(c, "h2d");
+      MF_CUDA(cudaMemsetAsync((char *)c.in_words.p + wbytes, 0, 64, c.stream));
+      if (wbytes) MF_CUDA(cudaMemcpyAsync(c.in_words.p, packed_host, wbytes, cudaMemcpyHostToDevice, c.stream));
+      MF_CUDA(cudaMemcpyAsync(c.in_starts.p, starts_host, sbytes, cudaMemcpyHostToDevice, c.stream));
+    }
+    mf::ReadsView r{c.in_words.as<uint32_t>(), c.in_starts.as<int64_t>(), n_reads, n_bases};
+    mf::EdgesView e;
+    mf::dev_count(c, r, k, min_count, &e, nullptr);
+    mf::SdbgView g;
+    mf::dev_seq2sdbg(c, e.edges, e.n_edges, mf::SeqsView{}, k, 1, &g);
+    const size_t rb = (size_t)g.n_items * 4, lb = (size_t)g.n_tips * g.words_tip * 4;
+    c.out_rec.reserve(rb + 64);
+    c.out_labels.reserve(lb + 64);
+    {
+      mf::Stage st(c, "d2h");
+      if (rb) MF_CUDA(cudaMemcpyAsync(c.out_rec.p, g.rec, rb, cudaMemcpyDeviceToHost, c.stream));
+      if (lb) MF_CUDA(cudaMemcpyAsync(c.out_labels.p, g.labels, lb, cudaMemcpyDeviceToHost, c.stream));
+    }
+    c.end_call();
+    out->rec = c.out_rec.as<uint32_t>();
+    out->tip_labels = c.out_labels.as<uint32_t>();
+    out->n_items = g.n_items;
+    out->n_tips = g.n_tips;
+    out->n_large = g.n_large;
+    out->k = g.k;
+    out->words_per_tip = g.words_tip;
+    out->h2d_bytes = (int64_t)(wbytes + sbytes);
+    out->d2h_bytes = (int64_t)(rb + lb);
   });
 }
 

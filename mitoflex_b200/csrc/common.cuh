@@ -11,7 +11,7 @@ namespace mf {
 constexpr int kNumBuckets = 65536;   // megahit bucket = first 8 bases (definitions.h kBucketPrefixLength)
 constexpr int kMaxMul = 65535;       // mul_t = uint16
 constexpr int kSentinel = 4;         // '$'
-constexpr int kMaxDigitBits = 10;    // widest MSD digit a partition level uses
+constexpr int kMaxDigitBits = 11;    // widest MSD digit a partition level uses
 constexpr int kMaxBins = 1 << kMaxDigitBits;
 
 struct CudaError : std::runtime_error {

@@ -12,6 +12,7 @@
 #include "engine.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "items.cuh"
 #include "local.cuh"
@@ -32,23 +33,40 @@ void DevBuf::release() {
   cap = 0;
 }
 
+void HostBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return;
+  release();
+  MF_CUDA(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+  cap = bytes;
+}
+void HostBuf::release() {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+}
+
 Ctx::Ctx(int dev) : device(dev) {
   MF_CUDA(cudaSetDevice(dev));
   cudaDeviceProp prop;
   MF_CUDA(cudaGetDeviceProperties(&prop, dev));
   sm_count = prop.multiProcessorCount;
-  MF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  MF_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+  stream = own_stream;
   edge_bucket_counts.assign(kNumBuckets, 0);
   sdbg_bucket_stats.assign((size_t)kNumBuckets * 3, 0);
 }
 Ctx::~Ctx() {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
-  for (DevBuf *b : {&edges, &sdbg_rec, &sdbg_labels, &sdbg_buckets, &sbits, &pack_words, &pack_starts, &synth_words, &synth_starts})
+  for (DevBuf *b : {&edges, &sdbg_rec, &sdbg_labels, &sdbg_buckets, &sbits, &pack_words, &pack_starts, &synth_words, &synth_starts,
+                    &in_words, &in_starts})
     b->release();
+  for (DevBuf &b : ov) b.release();
+  out_rec.release();
+  out_labels.release();
   if (slab) cudaFree(slab);
   for (auto &s : stages) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
-  if (stream) cudaStreamDestroy(stream);
+  if (own_stream) cudaStreamDestroy(own_stream);
 }
 size_t Ctx::budget() {
   if (mem_limit) return mem_limit;
@@ -77,6 +95,14 @@ void *Ctx::slab_alloc(size_t bytes) {
   if (off + bytes > slab_bytes) throw CudaError("workspace slab exhausted (internal sizing error)");
   slab_off = off + bytes;
   return slab + off;
+}
+void Ctx::d2h(void *dst, const void *src, size_t bytes) {
+  if (bytes) MF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+  MF_CUDA(cudaStreamSynchronize(stream));
+}
+void Ctx::h2d(void *dst, const void *src, size_t bytes) {
+  if (bytes) MF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+  MF_CUDA(cudaStreamSynchronize(stream));
 }
 void Ctx::begin_call() {
   MF_CUDA(cudaSetDevice(device));
@@ -150,35 +176,36 @@ __global__ void k_edge_buckets(const uint32_t *edges, int64_t n, int We, unsigne
 
 // ------------------------------------------------------------------ plan
 struct Plan {
-  int W, l1_bits, l2_bits, sb_bits, cap;
+  int W, l1_bits, l2_bits, cap;
 };
-static int cap_for(int W) {
-  int cap = (60 * 1024 / 4) / W;
-  cap &= ~1;
-  return std::min(cap, 65534);
-}
 static int ceil_log2(double x) {
   int b = 0;
   while ((double)(1ull << b) < x && b < 62) ++b;
   return b;
 }
-// part_limit: bits partition levels + in-bucket split may consume (count: 2(k+1); sdbg: 2(k-1))
-static Plan make_plan(int W, int part_limit, int64_t n_est, int forced_l1 = -1) {
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+// part_limit: bits the partition levels may consume (count: 2(k+1); sdbg: 2(k-1), so that a (k-1)-prefix group never
+// straddles a bucket).  density: how much denser than average the densest prefix range is (canonical keys = min of the two
+// strands pile up at small prefixes with density 2(1-u); sdbg items come from both strands and are flat).
+static Plan make_plan(int W, int part_limit, int64_t n_est, double density, int forced_l1 = -1) {
   Plan p;
   p.W = W;
-  p.cap = cap_for(W);
-  const double target = p.cap * 0.4;
+  p.cap = local_cap(W, false);
+  const double target = p.cap * 0.65 / density;
   int bits = std::max(1, ceil_log2((double)std::max<int64_t>(n_est, 1) / target));
   bits = std::min(bits, 2 * kMaxDigitBits);
+  bits = env_int("MFSDBG_PART_BITS", bits);
+  if (forced_l1 < 0) forced_l1 = env_int("MFSDBG_L1_BITS", -1);
   if (forced_l1 >= 0) {
     p.l1_bits = forced_l1;
   } else {
-    p.l1_bits = bits <= kMaxDigitBits ? bits : (bits + 1) / 2;
+    p.l1_bits = bits <= 10 ? bits : bits / 2;   // the reads-fed level gets the narrower digit
   }
   p.l1_bits = std::max(1, std::min(p.l1_bits, std::min(kMaxDigitBits, part_limit)));
   p.l2_bits = std::max(0, std::min({bits - p.l1_bits, kMaxDigitBits, part_limit - p.l1_bits}));
-  int sb = ceil_log2(std::max(1.0, target / 2.0));
-  p.sb_bits = std::max(0, std::min({sb, kMaxDigitBits, part_limit - p.l1_bits - p.l2_bits}));
   return p;
 }
 
@@ -235,7 +262,8 @@ struct DevBuckets {
 // (nseg << nbits slots, slot = seg * nbins + digit) allocated from `alloc`.
 template <int W, class Alloc>
 static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, const HostChunks &hc, int bit_off, int nbits,
-                                  Alloc &&alloc) {
+                                  Alloc &&alloc, const char *tag) {
+  const std::string tag_h = std::string(tag) + "_hist", tag_s = std::string(tag) + "_scatter";
   using C = TileCfg<W>;
   const int nchunk = (int)hc.start.size(), nseg = hc.nseg, nbins = 1 << nbits;
   std::vector<int64_t> tb_h(nchunk + 1), tb_s(nchunk + 1);
@@ -270,12 +298,12 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
     size_t smem = ((size_t)((C::NT / 32) << nbits) + 1) / 2 * 4 + 16;
     auto kern = k_level_hist<RecordsProducer<W>, W, C::NT, C::IPT_H>;
     set_smem(kern, smem);
-    Stage st(c, "level_hist");
+    Stage st(c, tag_h.c_str());
     kern<<<(unsigned)tb_h[nchunk], C::NT, smem, c.stream>>>(ph, a, d_hist);
     MF_LAUNCH_CHECK();
     c.launches++;
   }
-  k_level_scan<<<nseg, kMaxBins, 0, c.stream>>>(d_hist, nbins, d_sos, d_cur, b.start, b.size);
+  k_level_scan<<<nseg, 1024, 0, c.stream>>>(d_hist, nbins, d_sos, d_cur, b.start, b.size);
   MF_LAUNCH_CHECK();
   c.launches++;
   if (tb_s[nchunk] > 0) {
@@ -283,7 +311,7 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
     size_t smem = scatter_smem_bytes<W>(C::NT, C::TS, nbits, 4);
     auto kern = k_level_scatter<RecordsProducer<W>, W, C::NT, C::IPT_S>;
     set_smem(kern, smem);
-    Stage st(c, "level_scatter");
+    Stage st(c, tag_s.c_str());
     kern<<<(unsigned)tb_s[nchunk], C::NT, smem, c.stream>>>(ps, a, d_cur, out);
     MF_LAUNCH_CHECK();
     c.launches++;
@@ -292,11 +320,11 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
 }
 
 // ------------------------------------------------------------------ local finish launcher
-constexpr int kLocalNT = 256;
 template <int W, int MODE>
 static void launch_local(Ctx &c, const LocalArgs &a, int grid) {
   if (grid <= 0) return;
-  size_t smem = local_smem_bytes<W>(kLocalNT, a.cap, a.sb_bits);
+  constexpr bool weighted = MODE == kCountMerge;
+  size_t smem = local_smem_bytes(weighted ? W + 1 : W, a.cap, weighted);
   auto kern = k_local<W, kLocalNT, MODE>;
   set_smem(kern, smem);
   kern<<<grid, kLocalNT, smem, c.stream>>>(a);
@@ -315,12 +343,11 @@ struct Range {
   int64_t start, size;
 };
 // Fully sort the given ranges of `cur` in place (all `sort_bits` leading bits matter); `other` is scratch with the same
-// layout.  Recursive MSD levels; only reached by buckets the shared-memory finish could not take.
+// layout.  Recursive MSD levels; only reached by buckets with more DISTINCT keys than shared memory holds.
 template <int W>
 static void sort_ranges(Ctx &c, uint32_t *cur, uint32_t *other, const std::vector<Range> &ranges, int bit_off, int sort_bits) {
   if (ranges.empty() || bit_off >= sort_bits) return;
   const int nbits = std::min(kMaxDigitBits, sort_bits - bit_off);
-  const int cap = cap_for(W);
   std::vector<void *> tmp;
   auto alloc = [&](size_t bytes) {
     void *p = nullptr;
@@ -336,7 +363,7 @@ static void sort_ranges(Ctx &c, uint32_t *cur, uint32_t *other, const std::vecto
     hc.seg.push_back(i);
     hc.seg_out_start.push_back(ranges[i].start);
   }
-  DevBuckets b = partition_level<W>(c, cur, other, hc, bit_off, nbits, alloc);
+  DevBuckets b = partition_level<W>(c, cur, other, hc, bit_off, nbits, alloc, "fallback");
   int32_t *d_bail = (int32_t *)alloc(sizeof(int32_t) * b.nslots);
   int *d_flags = (int *)alloc(sizeof(int) * 4);
   MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, c.stream));
@@ -347,21 +374,20 @@ static void sort_ranges(Ctx &c, uint32_t *cur, uint32_t *other, const std::vecto
   a.bkt_size = b.size;
   a.work = nullptr;
   a.bit_off = bit_off + nbits;
-  a.sb_bits = std::max(0, std::min(kMaxDigitBits, sort_bits - a.bit_off));
-  a.cap = cap;
+  a.sort_bits = sort_bits;
+  a.cap = local_cap(W, false);
   a.bail_list = d_bail;
   a.bail_count = d_flags;
   a.overflow_flag = d_flags + 1;
   launch_local<W, kSortOnly>(c, a, b.nslots);
   int nbail = 0;
-  MF_CUDA(cudaMemcpyAsync(&nbail, d_flags, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  MF_CUDA(cudaStreamSynchronize(c.stream));
+  c.d2h(&nbail, d_flags, sizeof(int));
   if (nbail > 0) {
     std::vector<int32_t> bl(nbail);
     std::vector<int64_t> st(b.nslots), sz(b.nslots);
-    MF_CUDA(cudaMemcpy(bl.data(), d_bail, sizeof(int32_t) * nbail, cudaMemcpyDeviceToHost));
-    MF_CUDA(cudaMemcpy(st.data(), b.start, sizeof(int64_t) * b.nslots, cudaMemcpyDeviceToHost));
-    MF_CUDA(cudaMemcpy(sz.data(), b.size, sizeof(int64_t) * b.nslots, cudaMemcpyDeviceToHost));
+    c.d2h(bl.data(), d_bail, sizeof(int32_t) * nbail);
+    c.d2h(st.data(), b.start, sizeof(int64_t) * b.nslots);
+    c.d2h(sz.data(), b.size, sizeof(int64_t) * b.nslots);
     std::vector<Range> sub;
     for (int s : bl) sub.push_back(Range{st[s], sz[s]});
     sort_ranges<W>(c, other, cur, sub, bit_off + nbits, sort_bits);
@@ -372,17 +398,28 @@ static void sort_ranges(Ctx &c, uint32_t *cur, uint32_t *other, const std::vecto
   for (void *p : tmp) cudaFree(p);
 }
 
-// read the bail list and turn it into host ranges
+// (start, size) of the listed slots, gathered on the device so that the whole table never crosses PCIe
+__global__ void k_gather_slots(const int32_t *slots, int n, const int64_t *bkt_start, const int64_t *bkt_size, int64_t *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { out[2 * i] = bkt_start[slots[i]]; out[2 * i + 1] = bkt_size[slots[i]]; }
+}
 static std::vector<Range> fetch_bails(Ctx &c, const DevBuckets &b, const int32_t *d_bail, int nbail, std::vector<int32_t> *slots) {
   std::vector<Range> out;
   if (nbail <= 0) return out;
   slots->resize(nbail);
-  MF_CUDA(cudaMemcpy(slots->data(), d_bail, sizeof(int32_t) * nbail, cudaMemcpyDeviceToHost));
+  c.d2h(slots->data(), d_bail, sizeof(int32_t) * nbail);
   std::sort(slots->begin(), slots->end());
-  std::vector<int64_t> st(b.nslots), sz(b.nslots);
-  MF_CUDA(cudaMemcpy(st.data(), b.start, sizeof(int64_t) * b.nslots, cudaMemcpyDeviceToHost));
-  MF_CUDA(cudaMemcpy(sz.data(), b.size, sizeof(int64_t) * b.nslots, cudaMemcpyDeviceToHost));
-  for (int s : *slots) out.push_back(Range{st[s], sz[s]});
+  c.ov[8].reserve(sizeof(int32_t) * nbail);
+  c.ov[9].reserve(sizeof(int64_t) * 2 * nbail);
+  int32_t *d_s = c.ov[8].as<int32_t>();
+  int64_t *d_o = c.ov[9].as<int64_t>();
+  c.h2d(d_s, slots->data(), sizeof(int32_t) * nbail);
+  k_gather_slots<<<div_ceil(nbail, 256), 256, 0, c.stream>>>(d_s, nbail, b.start, b.size, d_o);
+  MF_LAUNCH_CHECK();
+  c.launches++;
+  std::vector<int64_t> ss(2 * (size_t)nbail);
+  c.d2h(ss.data(), d_o, sizeof(int64_t) * 2 * nbail);
+  for (int i = 0; i < nbail; ++i) out.push_back(Range{ss[2 * i], ss[2 * i + 1]});
   return out;
 }
 
@@ -391,29 +428,28 @@ template <int W>
 static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n, const HostChunks &l1, int k, int l1_bits,
                               int min_count, bool append, EdgesView *out, unsigned long long *d_counting) {
   const int key_bits = 2 * (k + 1), We = words_edge(k);
-  Plan p = make_plan(W, key_bits, n, l1_bits);
+  Plan p = make_plan(W, key_bits, n, 2.0, l1_bits);
   auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
   DevBuckets b;
   int bit_off = l1_bits;
   if (p.l2_bits > 0 || (int)l1.start.size() != l1.nseg) {
     int nb = std::max(1, p.l2_bits);
-    b = partition_level<W>(c, cur, other, l1, l1_bits, nb, salloc);
+    b = partition_level<W>(c, cur, other, l1, l1_bits, nb, salloc, "count_l2");
     std::swap(cur, other);
     bit_off += nb;
   } else {
     b.nslots = l1.nseg;
     b.start = c.alloc<int64_t>(b.nslots);
     b.size = c.alloc<int64_t>(b.nslots);
-    MF_CUDA(cudaMemcpy(b.start, l1.start.data(), sizeof(int64_t) * b.nslots, cudaMemcpyHostToDevice));
-    MF_CUDA(cudaMemcpy(b.size, l1.size.data(), sizeof(int64_t) * b.nslots, cudaMemcpyHostToDevice));
+    c.h2d(b.start, l1.start.data(), sizeof(int64_t) * b.nslots);
+    c.h2d(b.size, l1.size.data(), sizeof(int64_t) * b.nslots);
   }
-  const int sb_bits = std::max(0, std::min(p.sb_bits, key_bits - bit_off));
   int64_t *d_desc_off = c.alloc<int64_t>(b.nslots), *d_desc_cnt = c.alloc<int64_t>(b.nslots);
   int64_t *d_out_off = c.alloc<int64_t>(b.nslots + 1);
   int32_t *d_bail = c.alloc<int32_t>(b.nslots);
   int *d_flags = c.alloc<int>(4);
   unsigned long long *d_cursor = c.alloc<unsigned long long>(2);
-  // arena: everything left in the slab (edges are a small fraction of the keys unless -m 1)
+  // arena: what is left of the slab (edges are a small fraction of the keys unless -m 1)
   size_t arena_cap;
   {
     const size_t want_max = (size_t)(min_count > 1 ? n / min_count + 1 : n);
@@ -423,7 +459,6 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
   }
   uint32_t *d_arena = c.alloc<uint32_t>(arena_cap * We);
   DevBuf big_arena;   // only if the slab share overflowed
-  std::vector<int32_t> bail_slots;
   bool fallback_sorted = false;
   for (int attempt = 0;; ++attempt) {
     MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, c.stream));
@@ -434,7 +469,7 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
     a.bkt_start = b.start;
     a.bkt_size = b.size;
     a.bit_off = bit_off;
-    a.sb_bits = sb_bits;
+    a.sort_bits = key_bits;
     a.cap = p.cap;
     a.k = k;
     a.min_count = min_count;
@@ -452,24 +487,103 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
       Stage st(c, "local_count");
       launch_local<W, kCountEmit>(c, a, b.nslots);
     }
-    int flags[2];
-    MF_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, c.stream));
-    MF_CUDA(cudaStreamSynchronize(c.stream));
+    int flags[3];
+    c.d2h(flags, d_flags, sizeof(int) * 3);
     if (flags[0] > 0) {
-      Stage st(c, "fallback");
-      std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &bail_slots);
-      if (!fallback_sorted) sort_ranges<W>(c, cur, other, rs, bit_off, key_bits);
-      fallback_sorted = true;
-      MF_CUDA(cudaMemcpyAsync(d_bail, bail_slots.data(), sizeof(int32_t) * bail_slots.size(), cudaMemcpyHostToDevice, c.stream));
-      a.work = d_bail;
-      launch_serial<W, kCountEmit>(c, a, (int)bail_slots.size());
-      MF_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, c.stream));
-      MF_CUDA(cudaStreamSynchronize(c.stream));
+      // Buckets larger than shared memory.  With deep coverage (a mitogenome at 10^4 x) they are a few keys repeated
+      // thousands of times: combine chunk by chunk into (key, count) pairs, then merge the pairs of each bucket.
+      Stage st(c, "oversized");
+      std::vector<int32_t> slots;
+      std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &slots);
+      std::vector<WorkItem> chunks, merges;
+      for (size_t i = 0; i < rs.size(); ++i) {
+        WorkItem m{(int64_t)chunks.size(), 0, slots[i]};
+        for (int64_t off = 0; off < rs[i].size; off += p.cap) {
+          chunks.push_back(WorkItem{rs[i].start + off, (int32_t)std::min<int64_t>(p.cap, rs[i].size - off), slots[i]});
+          m.n++;
+        }
+        merges.push_back(m);
+      }
+      int64_t total = 0;
+      for (auto &r : rs) total += r.size;
+      DevBuf &d_chunks = c.ov[0], &d_merges = c.ov[1], &d_poff = c.ov[2], &d_pcnt = c.ov[3], &d_pairs = c.ov[4], &d_bail2 = c.ov[5],
+             &d_pcur = c.ov[6];
+      d_chunks.reserve(sizeof(WorkItem) * chunks.size());
+      d_merges.reserve(sizeof(WorkItem) * merges.size());
+      d_poff.reserve(sizeof(int64_t) * chunks.size());
+      d_pcnt.reserve(sizeof(int32_t) * chunks.size());
+      d_bail2.reserve(sizeof(int32_t) * merges.size());
+      d_pcur.reserve(64);
+      c.h2d(d_chunks.p, chunks.data(), sizeof(WorkItem) * chunks.size());
+      c.h2d(d_merges.p, merges.data(), sizeof(WorkItem) * merges.size());
+      size_t pair_cap = (size_t)std::min<int64_t>(total, total / 8 + (1 << 20));
+      std::vector<int32_t> hard;   // buckets whose DISTINCT keys do not fit either
+      for (int ptry = 0;; ++ptry) {
+        d_pairs.reserve(pair_cap * (W + 1) * 4);
+        MF_CUDA(cudaMemsetAsync(d_pcur.p, 0, 64, c.stream));
+        MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, c.stream));
+        LocalArgs pa = a;
+        pa.work = d_chunks.as<WorkItem>();
+        pa.counting = nullptr;
+        pa.pair_arena = d_pairs.as<uint32_t>();
+        pa.pair_cursor = d_pcur.as<unsigned long long>();
+        pa.pair_cap = pair_cap;
+        pa.piece_off = d_poff.as<int64_t>();
+        pa.piece_cnt = d_pcnt.as<int32_t>();
+        {
+          Stage st2(c, "oversized_pairs");
+          launch_local<W, kCountPairs>(c, pa, (int)chunks.size());
+        }
+        int pf[3];
+        c.d2h(pf, d_flags, sizeof(int) * 3);
+        if (pf[2]) {   // pair arena too small: every key distinct is the bound
+          if (ptry) throw std::runtime_error("pair arena overflow persisted");
+          pair_cap = (size_t)total;
+          continue;
+        }
+        LocalArgs ma = pa;
+        ma.work = d_merges.as<WorkItem>();
+        ma.cap = local_cap(W + 1, true);
+        ma.counting = a.counting;
+        ma.bail_list = d_bail2.as<int32_t>();
+        {
+          Stage st2(c, "oversized_merge");
+          launch_local<W, kCountMerge>(c, ma, (int)merges.size());
+        }
+        c.d2h(pf, d_flags, sizeof(int) * 3);
+        flags[1] |= pf[1];
+        if (pf[0] > 0) {
+          hard.resize(pf[0]);
+          c.d2h(hard.data(), d_bail2.p, sizeof(int32_t) * pf[0]);
+        }
+        break;
+      }
+      if (!hard.empty()) {
+        std::sort(hard.begin(), hard.end());
+        std::vector<Range> hr;
+        std::vector<WorkItem> hw;
+        for (size_t i = 0; i < rs.size(); ++i)
+          if (std::binary_search(hard.begin(), hard.end(), slots[i])) {
+            hr.push_back(rs[i]);
+            hw.push_back(WorkItem{rs[i].start, 0, slots[i]});
+          }
+        if (!fallback_sorted) sort_ranges<W>(c, cur, other, hr, bit_off, key_bits);
+        fallback_sorted = true;
+        DevBuf &d_hw = c.ov[7];
+        d_hw.reserve(sizeof(WorkItem) * hw.size());
+        c.h2d(d_hw.p, hw.data(), sizeof(WorkItem) * hw.size());
+        LocalArgs sa = a;
+        sa.work = d_hw.as<WorkItem>();
+        launch_serial<W, kCountEmit>(c, sa, (int)hw.size());
+        int sf[3];
+        c.d2h(sf, d_flags, sizeof(int) * 3);
+        flags[1] |= sf[1];
+      }
     }
     if (!flags[1]) break;
     // arena overflow: the true demand is in the cursor; take it from a dedicated allocation and redo the finish
     unsigned long long need = 0;
-    MF_CUDA(cudaMemcpy(&need, d_cursor, sizeof need, cudaMemcpyDeviceToHost));
+    c.d2h(&need, d_cursor, sizeof need);
     if (attempt >= 2) throw std::runtime_error("edge arena overflow persisted");
     big_arena.reserve((size_t)need * We * 4);
     d_arena = big_arena.as<uint32_t>();
@@ -543,7 +657,7 @@ static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, Edg
     sbits = build_start_bits(c, r);
   }
   // the plan needs the key count: it is at most one key per base
-  Plan p = make_plan(W, key_bits, std::max<int64_t>(r.n_bases, 1));
+  Plan p = make_plan(W, key_bits, std::max<int64_t>(r.n_bases - r.n_reads * (int64_t)k, 1), 2.0);   // one key per base minus k per read
   const int nb1 = 1 << p.l1_bits;
   unsigned long long *d_small = nullptr;   // hist | counting
   MF_CUDA(cudaMalloc(&d_small, sizeof(unsigned long long) * (nb1 + kNumBuckets)));
@@ -602,19 +716,19 @@ static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, Edg
     if (acc == 0) continue;
     uint32_t *bufA = c.alloc<uint32_t>((size_t)acc * W + 16), *bufB = c.alloc<uint32_t>((size_t)acc * W + 16);
     unsigned long long *d_cursor = c.alloc<unsigned long long>(nb1);
-    MF_CUDA(cudaMemcpy(d_cursor, cursor.data(), sizeof(unsigned long long) * nb1, cudaMemcpyHostToDevice));
+    c.h2d(d_cursor, cursor.data(), sizeof(unsigned long long) * nb1);
     {
       Stage st(c, "reads_scatter");
       launch_reads_scatter<W>(c, r, sbits, k, LevelArgs{0, p.l1_bits, (uint32_t)lo, (uint32_t)hi}, d_cursor, bufA);
     }
-    count_finish_impl<W>(c, bufA, bufB, acc, l1, k, p.l1_bits, min_count, ri > 0, out, d_counting);
+    count_finish_impl<W>(c, bufA, bufB, acc, l1, k, p.l1_bits, min_count, ri > 0, out, counting_host ? d_counting : nullptr);
   }
   if (out->n_edges == 0) {
     c.edges.reserve(256);
     out->edges = c.edges.as<uint32_t>();
   }
   if (counting_host)
-    MF_CUDA(cudaMemcpy(counting_host, d_counting, sizeof(int64_t) * kNumBuckets, cudaMemcpyDeviceToHost));
+    c.d2h(counting_host, d_counting, sizeof(int64_t) * kNumBuckets);
   cudaFree(d_small);
   Stage st(c, "edge_buckets");
   edge_bucket_counts(c, *out);
@@ -641,21 +755,20 @@ static void dev_count_hist_impl(Ctx &c, const ReadsView &r, int k, int l1_bits, 
   case Wn: dev_count_hist_impl<Wn>(c, r, k, l1_bits, hist_dev); break;
 void dev_count_hist(Ctx &c, const ReadsView &r, int k, int l1_bits, unsigned long long *hist_dev) {
   if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
-  if (l1_bits < 1 || l1_bits > kMaxDigitBits) throw std::invalid_argument("l1_bits must be in [1, 10]");
+  if (l1_bits < 1 || l1_bits > kMaxDigitBits) throw std::invalid_argument("l1_bits must be in [1, 11]");
   MF_DISPATCH_W(words_key(k), CHIST)
 }
 __global__ void k_excl_scan_u64_small(const unsigned long long *in, int n, unsigned long long *out) {
-  // n <= 1024, one block
-  __shared__ unsigned long long s[1024];
-  int t = threadIdx.x;
-  s[t] = t < n ? in[t] : 0ull;
+  // n <= kMaxBins, one block
+  __shared__ unsigned long long s[kMaxBins];
+  for (int t = threadIdx.x; t < n; t += blockDim.x) s[t] = in[t];
   __syncthreads();
-  if (t == 0) {
+  if (threadIdx.x == 0) {
     unsigned long long run = 0;
     for (int i = 0; i < n; ++i) { unsigned long long v = s[i]; s[i] = run; run += v; }
   }
   __syncthreads();
-  if (t < n) out[t] = s[t];
+  for (int t = threadIdx.x; t < n; t += blockDim.x) out[t] = s[t];
 }
 template <int W>
 static void dev_count_scatter_impl(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev,
@@ -691,12 +804,12 @@ static void dev_count_finish_w(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_
   out->n_keys = n_keys;
   out->k = k;
   out->words = We;
-  if (n_keys > 0) count_finish_impl<W>(c, keys, scratch, n_keys, hc, k, l1_bits, min_count, false, out, d_counting);
+  if (n_keys > 0) count_finish_impl<W>(c, keys, scratch, n_keys, hc, k, l1_bits, min_count, false, out, counting_host ? d_counting : nullptr);
   if (out->n_edges == 0) {
     c.edges.reserve(256);
     out->edges = c.edges.as<uint32_t>();
   }
-  if (counting_host) MF_CUDA(cudaMemcpy(counting_host, d_counting, sizeof(int64_t) * kNumBuckets, cudaMemcpyDeviceToHost));
+  if (counting_host) c.d2h(counting_host, d_counting, sizeof(int64_t) * kNumBuckets);
   cudaFree(d_counting);
   edge_bucket_counts(c, *out);
 }
@@ -743,7 +856,7 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
     MF_CUDA(cudaStreamSynchronize(c.stream));
     return;
   }
-  Plan p = make_plan(WI, part_limit, n_items);
+  Plan p = make_plan(WI, part_limit, n_items, 1.0);
   const int nb1 = 1 << p.l1_bits;
   const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1 << kMaxDigitBits) * 96;
   c.slab_reserve((size_t)n_items * WI * 4 * 2 + table_bytes + (1 << 20));
@@ -776,14 +889,14 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
   whole.size = {n_items};
   whole.seg = {0};
   whole.seg_out_start = {0};
-  DevBuckets b1 = partition_level<WI>(c, bufA, bufB, whole, 0, p.l1_bits, salloc);
+  DevBuckets b1 = partition_level<WI>(c, bufA, bufB, whole, 0, p.l1_bits, salloc, "sdbg_l1");
   uint32_t *cur = bufB, *other = bufA;
   DevBuckets b = b1;
   int bit_off = p.l1_bits;
   if (p.l2_bits > 0) {
     std::vector<int64_t> st(nb1), sz(nb1);
-    MF_CUDA(cudaMemcpy(st.data(), b1.start, sizeof(int64_t) * nb1, cudaMemcpyDeviceToHost));
-    MF_CUDA(cudaMemcpy(sz.data(), b1.size, sizeof(int64_t) * nb1, cudaMemcpyDeviceToHost));
+    c.d2h(st.data(), b1.start, sizeof(int64_t) * nb1);
+    c.d2h(sz.data(), b1.size, sizeof(int64_t) * nb1);
     HostChunks l1;
     l1.nseg = nb1;
     for (int i = 0; i < nb1; ++i) {
@@ -792,11 +905,10 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
       l1.seg.push_back(i);
       l1.seg_out_start.push_back(st[i]);
     }
-    b = partition_level<WI>(c, cur, other, l1, p.l1_bits, p.l2_bits, salloc);
+    b = partition_level<WI>(c, cur, other, l1, p.l1_bits, p.l2_bits, salloc, "sdbg_l2");
     std::swap(cur, other);
     bit_off += p.l2_bits;
   }
-  const int sb_bits = std::max(0, std::min(p.sb_bits, part_limit - bit_off));
   int64_t *d_items = c.alloc<int64_t>(b.nslots), *d_tips = c.alloc<int64_t>(b.nslots), *d_large = c.alloc<int64_t>(b.nslots);
   int64_t *d_item_off = c.alloc<int64_t>(b.nslots + 1), *d_tip_off = c.alloc<int64_t>(b.nslots + 1),
           *d_large_off = c.alloc<int64_t>(b.nslots + 1);
@@ -811,7 +923,7 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
   a.bkt_start = b.start;
   a.bkt_size = b.size;
   a.bit_off = bit_off;
-  a.sb_bits = sb_bits;
+  a.sort_bits = 32 * WI;
   a.cap = p.cap;
   a.k = k;
   a.tip_mode = tip_mode;
@@ -831,13 +943,15 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
   MF_CUDA(cudaMemcpyAsync(&nbail, d_flags, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   MF_CUDA(cudaStreamSynchronize(c.stream));
   std::vector<int32_t> bail_slots;
-  int32_t *d_bail_sorted = nullptr;
+  WorkItem *d_bail_sorted = nullptr;
   if (nbail > 0) {
     Stage st(c, "fallback");
     std::vector<Range> rs = fetch_bails(c, b, d_bail, nbail, &bail_slots);
     sort_ranges<WI>(c, cur, other, rs, bit_off, 32 * WI);
-    d_bail_sorted = c.alloc<int32_t>(bail_slots.size());
-    MF_CUDA(cudaMemcpy(d_bail_sorted, bail_slots.data(), sizeof(int32_t) * bail_slots.size(), cudaMemcpyHostToDevice));
+    std::vector<WorkItem> hw;
+    for (size_t i = 0; i < rs.size(); ++i) hw.push_back(WorkItem{rs[i].start, 0, bail_slots[i]});
+    d_bail_sorted = c.alloc<WorkItem>(hw.size());
+    c.h2d(d_bail_sorted, hw.data(), sizeof(WorkItem) * hw.size());
     a.work = d_bail_sorted;
     launch_serial<WI, kSdbgCount>(c, a, (int)bail_slots.size());
     a.work = nullptr;

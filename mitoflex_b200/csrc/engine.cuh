@@ -17,6 +17,15 @@ struct DevBuf {
   T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+struct HostBuf {   // pinned host memory
+  void *p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes);
+  void release();
+  template <class T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
 struct StageRec {
   std::string name;
   cudaEvent_t e0, e1;
@@ -26,6 +35,7 @@ struct Ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   char *slab = nullptr;
   size_t slab_bytes = 0, slab_off = 0;
   size_t mem_limit = 0;
@@ -35,7 +45,9 @@ struct Ctx {
   std::vector<int> open_stages;
   std::string profile;
   // results that outlive a call
-  DevBuf edges, sdbg_rec, sdbg_labels, sdbg_buckets, sbits, pack_words, pack_starts, synth_words, synth_starts;
+  DevBuf edges, sdbg_rec, sdbg_labels, sdbg_buckets, sbits, pack_words, pack_starts, synth_words, synth_starts, in_words, in_starts;
+  HostBuf out_rec, out_labels;
+  DevBuf ov[10];   // scratch of the oversized-bucket path, kept across calls (cudaMalloc/cudaFree are slow and synchronise)
   // tables read back by the file-level API
   std::vector<int64_t> edge_bucket_counts;   // 65536
   std::vector<int64_t> sdbg_bucket_stats;    // 65536 * 3 (items, tips, large)
@@ -48,6 +60,9 @@ struct Ctx {
   void *slab_alloc(size_t bytes);
   template <class T>
   T *alloc(size_t n) { return reinterpret_cast<T *>(slab_alloc(n * sizeof(T))); }
+  // synchronous copies ordered on this context's stream (never the legacy default stream)
+  void d2h(void *dst, const void *src, size_t bytes);
+  void h2d(void *dst, const void *src, size_t bytes);
   void begin_call();
   void end_call();
   void stage_begin(const char *name);

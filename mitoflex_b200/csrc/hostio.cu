@@ -99,7 +99,7 @@ void file_buildlib(Ctx &c, const char *lib_file, const char *out_prefix, int n_p
     try {
       for (size_t i = 0; i < texts.size(); ++i) {
         dev.push_back(new DevMem(texts[i].size() + 64));
-        MF_CUDA(cudaMemcpy(dev.back()->p, texts[i].data(), texts[i].size(), cudaMemcpyHostToDevice));
+        c.h2d(dev.back()->p, texts[i].data(), texts[i].size());
         ptrs[i] = dev.back()->as<uint8_t>();
         sizes[i] = (int64_t)texts[i].size();
         std::vector<uint8_t>().swap(texts[i]);
@@ -136,7 +136,7 @@ static void load_read_lib(Ctx &c, const char *read_lib_file, ReadsView *r) {
 // ---------------------------------------------------------------- edges files
 static void write_edges(Ctx &c, const EdgesView &e, const std::string &prefix, int n_files) {
   std::vector<uint32_t> host((size_t)e.n_edges * e.words);
-  if (e.n_edges) MF_CUDA(cudaMemcpy(host.data(), e.edges, host.size() * 4, cudaMemcpyDeviceToHost));
+  if (e.n_edges) c.d2h(host.data(), e.edges, host.size() * 4);
   std::vector<std::unique_ptr<File>> files;
   for (int f = 0; f < n_files; ++f) files.emplace_back(new File(prefix + ".edges." + std::to_string(f), "wb"));
   std::ostringstream info;
@@ -303,8 +303,8 @@ void add_contigs(HostSeqs *hs, const std::string &path, int k, bool extend_loop,
 // SdbgWriter::Write: uint16 (w | last<<4 | tip<<5 | min(mult,255)<<8) [+ uint16 mult if > 254] [+ tip label words]
 static void write_sdbg(Ctx &c, const SdbgView &g, const std::string &prefix, int n_files) {
   std::vector<uint32_t> rec((size_t)g.n_items), labels((size_t)g.n_tips * g.words_tip);
-  if (g.n_items) MF_CUDA(cudaMemcpy(rec.data(), g.rec, rec.size() * 4, cudaMemcpyDeviceToHost));
-  if (g.n_tips) MF_CUDA(cudaMemcpy(labels.data(), g.labels, labels.size() * 4, cudaMemcpyDeviceToHost));
+  if (g.n_items) c.d2h(rec.data(), g.rec, rec.size() * 4);
+  if (g.n_tips) c.d2h(labels.data(), g.labels, labels.size() * 4);
   std::vector<std::unique_ptr<File>> files;
   for (int f = 0; f < n_files; ++f) files.emplace_back(new File(prefix + ".sdbg." + std::to_string(f), "wb"));
   std::ostringstream info;
@@ -359,14 +359,14 @@ void file_seq2sdbg(Ctx &c, int k, int k_from, const char *input_prefix, const ch
   const int nseq = (int)hs.mult.size();
   DevMem d_edges(he.data.size() * 4 + 64), d_packed(hs.packed.size() * 4 + 256), d_starts(sizeof(int64_t) * (nseq + 1)),
       d_mult(sizeof(uint16_t) * (nseq + 1)), d_ibase(sizeof(int64_t) * (nseq + 1));
-  if (he.n) MF_CUDA(cudaMemcpy(d_edges.p, he.data.data(), he.data.size() * 4, cudaMemcpyHostToDevice));
+  if (he.n) c.h2d(d_edges.p, he.data.data(), he.data.size() * 4);
   SeqsView sv;
   if (nseq) {
-    MF_CUDA(cudaMemset(d_packed.p, 0, hs.packed.size() * 4 + 256));
-    MF_CUDA(cudaMemcpy(d_packed.p, hs.packed.data(), hs.packed.size() * 4, cudaMemcpyHostToDevice));
-    MF_CUDA(cudaMemcpy(d_starts.p, hs.starts.data(), sizeof(int64_t) * (nseq + 1), cudaMemcpyHostToDevice));
-    MF_CUDA(cudaMemcpy(d_mult.p, hs.mult.data(), sizeof(uint16_t) * nseq, cudaMemcpyHostToDevice));
-    MF_CUDA(cudaMemcpy(d_ibase.p, hs.item_base.data(), sizeof(int64_t) * (nseq + 1), cudaMemcpyHostToDevice));
+    MF_CUDA(cudaMemsetAsync(d_packed.p, 0, hs.packed.size() * 4 + 256, c.stream));
+    c.h2d(d_packed.p, hs.packed.data(), hs.packed.size() * 4);
+    c.h2d(d_starts.p, hs.starts.data(), sizeof(int64_t) * (nseq + 1));
+    c.h2d(d_mult.p, hs.mult.data(), sizeof(uint16_t) * nseq);
+    c.h2d(d_ibase.p, hs.item_base.data(), sizeof(int64_t) * (nseq + 1));
     sv.packed = d_packed.as<uint32_t>();
     sv.starts = d_starts.as<int64_t>();
     sv.mult = d_mult.as<uint16_t>();

@@ -185,9 +185,9 @@ static void index_lines(Ctx &c, const uint8_t *text, int64_t n, DevBuf *line_buf
   c.launches++;
   device_excl_scan_i64(c, d_cnt, nb, d_cnt + nb);
   int64_t total = 0;
-  MF_CUDA(cudaMemcpy(&total, d_cnt + 2 * nb, 8, cudaMemcpyDeviceToHost));
+  c.d2h(&total, d_cnt + 2 * nb, 8);
   uint8_t last = '\n';
-  if (n > 0) MF_CUDA(cudaMemcpy(&last, text + n - 1, 1, cudaMemcpyDeviceToHost));
+  if (n > 0) c.d2h(&last, text + n - 1, 1);
   *n_lines = total + (n > 0 && last != '\n');
   line_buf->reserve(sizeof(int64_t) * (total + 3));
   k_newline_fill<<<(unsigned)nb, kNlThreads, 0, c.stream>>>(text, n, d_cnt + nb, line_buf->as<int64_t>());
@@ -208,7 +208,7 @@ void dev_pack_fastq(Ctx &c, const uint8_t *const *texts, const int64_t *n_bytes,
   ts.n_texts = n_texts;
   DevBuf lines[2];
   uint8_t first = 0;
-  if (n_bytes[0] > 0) MF_CUDA(cudaMemcpy(&first, texts[0], 1, cudaMemcpyDeviceToHost));
+  if (n_bytes[0] > 0) c.d2h(&first, texts[0], 1);
   ts.lines_per_rec = first == '>' ? 2 : 4;
   int64_t n_rec[2] = {0, 0};
   for (int f = 0; f < n_texts; ++f) {
@@ -241,8 +241,8 @@ void dev_pack_fastq(Ctx &c, const uint8_t *const *texts, const int64_t *n_bytes,
   device_excl_scan_i64(c, d_cnt, n_rec_total, d_base);
   int64_t n_reads = 0;
   int flags[2];
-  MF_CUDA(cudaMemcpy(&n_reads, d_base + n_rec_total, 8, cudaMemcpyDeviceToHost));
-  MF_CUDA(cudaMemcpy(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost));
+  c.d2h(&n_reads, d_base + n_rec_total, 8);
+  c.d2h(flags, d_flags, sizeof flags);
   if (flags[0]) {
     cudaFree(d_cnt); cudaFree(d_base); cudaFree(d_flags);
     for (auto &l : lines) l.release();
@@ -261,8 +261,8 @@ void dev_pack_fastq(Ctx &c, const uint8_t *const *texts, const int64_t *n_bytes,
   int64_t *d_starts = c.pack_starts.as<int64_t>();
   device_excl_scan_i64(c, d_len, n_reads, d_starts);
   int64_t n_bases = 0;
-  MF_CUDA(cudaMemcpy(&n_bases, d_starts + n_reads, 8, cudaMemcpyDeviceToHost));
-  MF_CUDA(cudaMemcpy(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost));
+  c.d2h(&n_bases, d_starts + n_reads, 8);
+  c.d2h(flags, d_flags, sizeof flags);
   const int64_t n_words = ((n_bases + 15) >> 4) + 16;
   c.pack_words.reserve((size_t)n_words * 4);
   k_pack_words<<<(unsigned)div_ceil64(n_words, 256), 256, 0, c.stream>>>(ts, n_reads, d_starts, d_off, n_bases,
@@ -334,7 +334,7 @@ void reads_to_bin_stream(Ctx &c, const ReadsView &r, std::vector<uint32_t> *stre
   c.launches++;
   device_excl_scan_i64(c, d_sz, r.n_reads, d_off);
   int64_t total = 0;
-  MF_CUDA(cudaMemcpy(&total, d_off + r.n_reads, 8, cudaMemcpyDeviceToHost));
+  c.d2h(&total, d_off + r.n_reads, 8);
   uint32_t *d_stream = nullptr;
   MF_CUDA(cudaMalloc(&d_stream, (size_t)total * 4));
   k_bin_stream<<<(unsigned)div_ceil64(r.n_reads, 256), 256, 0, c.stream>>>(r.packed, r.starts, r.n_reads, d_off, d_stream);

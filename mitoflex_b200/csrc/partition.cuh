@@ -240,10 +240,18 @@ __global__ void k_scan_i64(const int64_t *v, int64_t n, int64_t base, int64_t *o
 // per segment: cursor[s][d] = seg_out_start[s] + exclusive prefix of hist[s][.]; bucket table likewise.
 __global__ void k_level_scan(const unsigned long long *hist, int nbins, const int64_t *seg_out_start,
                              unsigned long long *cursor, int64_t *bkt_start, int64_t *bkt_size) {
+  // one block of 1024 threads per segment; each thread owns kMaxBins/1024 consecutive bins
+  constexpr int PER = kMaxBins / 1024;
   __shared__ unsigned long long s_w[32];
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // blockDim.x == kMaxBins threads; bins beyond nbins contribute 0
-  unsigned long long v = tid < nbins ? hist[(size_t)s * nbins + tid] : 0ull, inc = v;
+  unsigned long long v[PER], sum = 0;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int b = tid * PER + q;
+    v[q] = b < nbins ? hist[(size_t)s * nbins + b] : 0ull;
+    sum += v[q];
+  }
+  unsigned long long inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -252,7 +260,7 @@ __global__ void k_level_scan(const unsigned long long *hist, int nbins, const in
   if (lane == 31) s_w[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    unsigned long long x = lane < (int)(blockDim.x >> 5) ? s_w[lane] : 0ull, xi = x;
+    unsigned long long x = s_w[lane], xi = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       unsigned long long t = __shfl_up_sync(0xffffffffu, xi, o);
@@ -261,12 +269,17 @@ __global__ void k_level_scan(const unsigned long long *hist, int nbins, const in
     s_w[lane] = xi - x;
   }
   __syncthreads();
-  if (tid < nbins) {
-    unsigned long long st = (unsigned long long)seg_out_start[s] + s_w[warp] + inc - v;
-    size_t idx = (size_t)s * nbins + tid;
-    cursor[idx] = st;
-    bkt_start[idx] = (int64_t)st;
-    bkt_size[idx] = (int64_t)v;
+  unsigned long long run = (unsigned long long)seg_out_start[s] + s_w[warp] + inc - sum;
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int b = tid * PER + q;
+    if (b < nbins) {
+      const size_t idx = (size_t)s * nbins + b;
+      cursor[idx] = run;
+      bkt_start[idx] = (int64_t)run;
+      bkt_size[idx] = (int64_t)v[q];
+      run += v[q];
+    }
   }
 }
 

@@ -43,6 +43,12 @@ class DevSdbg(C.Structure):
                 ("n_tips", C.c_int64), ("n_large", C.c_int64), ("k", C.c_int32), ("words_per_tip", C.c_int32)]
 
 
+class HostSdbg(C.Structure):
+    _fields_ = [("rec", C.c_void_p), ("tip_labels", C.c_void_p), ("n_items", C.c_int64), ("n_tips", C.c_int64),
+                ("n_large", C.c_int64), ("k", C.c_int32), ("words_per_tip", C.c_int32), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64)]
+
+
 class SynthSpec(C.Structure):
     _fields_ = [("n_pairs", C.c_int64), ("read_len", C.c_int32), ("mito_len", C.c_int64), ("nuclear_len", C.c_int64),
                 ("mito_fraction", C.c_double), ("error_rate", C.c_double), ("n_rate", C.c_double),
@@ -62,6 +68,7 @@ SYMBOLS = {
     "mfsdbg_ctx_destroy": (None, [C.c_void_p]),
     "mfsdbg_ctx_set_mem_limit": (C.c_int, [C.c_void_p, C.c_uint64]),
     "mfsdbg_ctx_stream": (C.c_void_p, [C.c_void_p]),
+    "mfsdbg_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mfsdbg_ctx_launches": (C.c_int64, [C.c_void_p]),
     "mfsdbg_ctx_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "mfsdbg_ctx_last_profile": (C.c_char_p, [C.c_void_p]),
@@ -75,6 +82,8 @@ SYMBOLS = {
                                           C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DevEdges), C.c_void_p]),
     "mfsdbg_words_per_key": (C.c_int32, [C.c_int32]),
     "mfsdbg_words_per_edge": (C.c_int32, [C.c_int32]),
+    "mfsdbg_host_read2sdbg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                        C.POINTER(HostSdbg)]),
     "mfsdbg_dev_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32]),
     "mfsdbg_ctx_edge_bucket_counts": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mfsdbg_ctx_sdbg_bucket_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -200,6 +209,9 @@ class Context:
     def set_mem_limit(self, nbytes):
         _check(load().mfsdbg_ctx_set_mem_limit(self._h, int(nbytes)))
 
+    def set_stream(self, cuda_stream):
+        _check(load().mfsdbg_ctx_set_stream(self._h, cuda_stream))
+
     def set_profiling(self, on=True):
         _check(load().mfsdbg_ctx_set_profiling(self._h, int(on)))
 
@@ -279,6 +291,13 @@ class Context:
         out = DevSdbg()
         _check(load().mfsdbg_dev_read2sdbg(self._h, C.byref(reads.s), k, min_count, C.byref(out)))
         return Sdbg(self, out)
+
+    def host_read2sdbg(self, packed_host_ptr, starts_host_ptr, n_reads, n_bases, k, min_count):
+        """read2sdbg with host inputs/outputs (H2D + D2H inside the call). Returns the HostSdbg struct."""
+        out = HostSdbg()
+        _check(load().mfsdbg_host_read2sdbg(self._h, packed_host_ptr, starts_host_ptr, n_reads, n_bases, k, min_count,
+                                            C.byref(out)))
+        return out
 
     # -- staged count (multi-GPU driver)
     def count_hist(self, reads, k, l1_bits, hist_ptr):

@@ -451,24 +451,50 @@ orc_edges *orc_count(const uint8_t *bases, const int64_t *starts, int64_t n_read
   if (threads < 1) threads = 1;
   int Wk = div_ceil(2 * (k + 1), 32), We = div_ceil(2 * (k + 1) + 16, 32);
   uint32_t *keys; int64_t n = gen_count_keys(bases, starts, n_reads, k, Wk, threads, &keys);
-  sort_records(keys, n, Wk, threads, NULL);
+  int64_t *bstart = xmalloc(sizeof(int64_t) * (ORC_NUM_BUCKETS + 1));
+  sort_records(keys, n, Wk, threads, bstart);
   orc_edges *e = xmalloc(sizeof *e);
   memset(e, 0, sizeof *e);
   e->k = k; e->words = We; e->sorted = 1;
-  int64_t cap = 1024; e->data = xmalloc(cap * We * 4);
-  /* KmerCounter::Lv2Postprocess: runs of equal keys -> count, histogram, solid filter */
-  for (int64_t i = 0, j; i < n; i = j) {
-    j = i + 1;
-    while (j < n && cmp_words(keys + i * Wk, keys + j * Wk, Wk) == 0) ++j;
-    int64_t c = j - i;
-    e->counting[c > ORC_MAX_MUL ? ORC_MAX_MUL : c]++;
-    if (c >= min_count) {
-      if (e->n == cap) { cap *= 2; e->data = xrealloc(e->data, cap * We * 4); }
-      pack_edge(e->data + e->n * We, keys + i * Wk, k, Wk, We, c);
-      e->bucket_counts[keys[i * Wk] >> 16]++;
-      e->n++;
+  /* KmerCounter::Lv2Postprocess: runs of equal keys -> count, histogram, solid filter.  Runs never straddle a
+   * bucket, so buckets are processed independently (first pass counts, second pass writes). */
+  int64_t *hist = xmalloc(sizeof(int64_t) * (size_t)threads * (ORC_MAX_MUL + 1));
+  memset(hist, 0, sizeof(int64_t) * (size_t)threads * (ORC_MAX_MUL + 1));
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+  for (int b = 0; b < ORC_NUM_BUCKETS; ++b) {
+#ifdef _OPENMP
+    int64_t *h = hist + (size_t)omp_get_thread_num() * (ORC_MAX_MUL + 1);
+#else
+    int64_t *h = hist;
+#endif
+    int64_t solid = 0;
+    for (int64_t i = bstart[b], j; i < bstart[b + 1]; i = j) {
+      j = i + 1;
+      while (j < bstart[b + 1] && cmp_words(keys + i * Wk, keys + j * Wk, Wk) == 0) ++j;
+      int64_t c = j - i;
+      h[c > ORC_MAX_MUL ? ORC_MAX_MUL : c]++;
+      solid += c >= min_count;
+    }
+    e->bucket_counts[b] = solid;
+  }
+  for (int t = 0; t < threads; ++t)
+    for (int c = 0; c <= ORC_MAX_MUL; ++c) e->counting[c] += hist[(size_t)t * (ORC_MAX_MUL + 1) + c];
+  free(hist);
+  int64_t *eoff = xmalloc(sizeof(int64_t) * (ORC_NUM_BUCKETS + 1));
+  eoff[0] = 0;
+  for (int b = 0; b < ORC_NUM_BUCKETS; ++b) eoff[b + 1] = eoff[b] + e->bucket_counts[b];
+  e->n = eoff[ORC_NUM_BUCKETS];
+  e->data = xmalloc((size_t)e->n * We * 4);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+  for (int b = 0; b < ORC_NUM_BUCKETS; ++b) {
+    int64_t o = eoff[b];
+    for (int64_t i = bstart[b], j; i < bstart[b + 1]; i = j) {
+      j = i + 1;
+      while (j < bstart[b + 1] && cmp_words(keys + i * Wk, keys + j * Wk, Wk) == 0) ++j;
+      if (j - i >= min_count) pack_edge(e->data + (o++) * We, keys + i * Wk, k, Wk, We, j - i);
     }
   }
+  free(eoff); free(bstart);
   free(keys);
   return e;
 }
@@ -721,14 +747,14 @@ static inline int it_diff_km1(const item_fmt *f, const uint32_t *x, const uint32
   for (int i = full - 1; i >= 0; --i) if (x[i] != y[i]) return 1;
   return 0;
 }
-/* SeqToSdbg::Lv2Postprocess / Read2SdbgS2::Lv2Postprocess over a fully sorted item array. */
-static orc_sdbg *sdbg_postprocess(const uint32_t *items, int64_t n, const item_fmt *f) {
-  orc_sdbg *g = sdbg_new(f->k, n / 2 + 16);
-  int W = f->W, Wd = g->words_per_tip;
-  uint32_t tip_label[64];
-  for (int64_t s = 0, e; s < n; s = e) {
+/* SeqToSdbg::Lv2Postprocess / Read2SdbgS2::Lv2Postprocess over the sorted items [from, to) (whole (k-1)-prefix groups).
+ * g == NULL: only tally into cnt[3] (items, tips, large); else write at item offset *io / tip offset *to_. */
+static void sdbg_walk_range(const uint32_t *items, int64_t from, int64_t to, const item_fmt *f, orc_sdbg *g, int64_t *cnt,
+                            int64_t *io, int64_t *to_) {
+  int W = f->W, Wd = div_ceil(2 * f->k, 32);
+  for (int64_t s = from, e; s < to; s = e) {
     e = s + 1;
-    while (e < n && !it_diff_km1(f, items + s * W, items + e * W)) ++e;
+    while (e < to && !it_diff_km1(f, items + s * W, items + e * W)) ++e;
     int has_solid_a = 0, has_solid_b = 0, outputed_b = 0;
     int64_t last_a[4] = {-1, -1, -1, -1};
     for (int64_t i = s; i < e; ++i) {
@@ -756,10 +782,42 @@ static orc_sdbg *sdbg_postprocess(const uint32_t *items, int64_t n, const item_f
       int w = (b == ORC_SENTINEL) ? 0 : ((outputed_b & (1 << b)) ? b + 5 : b + 1);
       outputed_b |= 1 << b;
       int last = (a == ORC_SENTINEL) ? 0 : (last_a[a] == j - 1 ? 1 : 0);
-      if (is_dollar) for (int t = 0; t < Wd; ++t) tip_label[t] = cur[t];
-      sdbg_push(g, (int)(cur[0] >> 16), w, last, is_dollar, mul, tip_label);
+      if (!g) {
+        cnt[0]++; cnt[1] += is_dollar; cnt[2] += mul > 254;
+      } else {
+        int64_t o = (*io)++;
+        g->w[o] = (uint8_t)w; g->last[o] = (uint8_t)last; g->tip[o] = (uint8_t)is_dollar; g->mul[o] = (uint16_t)mul;
+        if (is_dollar) memcpy(g->tip_labels + ((*to_)++) * Wd, cur, 4 * Wd);   /* raw first words of the item */
+      }
     }
   }
+}
+static orc_sdbg *sdbg_postprocess(const uint32_t *items, int64_t n, const item_fmt *f, const int64_t *bstart, int threads) {
+  orc_sdbg *g = sdbg_new(f->k, 16);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+  for (int b = 0; b < ORC_NUM_BUCKETS; ++b) {
+    int64_t cnt[3] = {0, 0, 0};
+    if (bstart[b + 1] > bstart[b]) sdbg_walk_range(items, bstart[b], bstart[b + 1], f, NULL, cnt, NULL, NULL);
+    g->bucket_items[b] = cnt[0]; g->bucket_tips[b] = cnt[1]; g->bucket_large[b] = cnt[2];
+  }
+  int64_t *io = xmalloc(sizeof(int64_t) * (ORC_NUM_BUCKETS + 1)), *to = xmalloc(sizeof(int64_t) * (ORC_NUM_BUCKETS + 1));
+  io[0] = to[0] = 0;
+  for (int b = 0; b < ORC_NUM_BUCKETS; ++b) {
+    io[b + 1] = io[b] + g->bucket_items[b]; to[b + 1] = to[b] + g->bucket_tips[b];
+    g->n_large += g->bucket_large[b];
+  }
+  g->n = io[ORC_NUM_BUCKETS]; g->n_tips = to[ORC_NUM_BUCKETS];
+  free(g->w); free(g->last); free(g->tip); free(g->mul); free(g->tip_labels);
+  g->cap = g->n + 1; g->cap_tips = g->n_tips + 1;
+  g->w = xmalloc(g->cap); g->last = xmalloc(g->cap); g->tip = xmalloc(g->cap); g->mul = xmalloc(2 * g->cap);
+  g->tip_labels = xmalloc(4 * g->cap_tips * g->words_per_tip);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+  for (int b = 0; b < ORC_NUM_BUCKETS; ++b) {
+    int64_t i0 = io[b], t0 = to[b];
+    if (bstart[b + 1] > bstart[b]) sdbg_walk_range(items, bstart[b], bstart[b + 1], f, g, NULL, &i0, &t0);
+  }
+  free(io); free(to);
+  (void)n;
   return g;
 }
 orc_sdbg *orc_seq2sdbg(const orc_seqs *s, int k, int threads) {
@@ -805,8 +863,10 @@ orc_sdbg *orc_seq2sdbg(const orc_seqs *s, int k, int threads) {
     free(rc);
   }
   free(off);
-  sort_records(items, n, W, threads, NULL);
-  orc_sdbg *g = sdbg_postprocess(items, n, &f);
+  int64_t *bstart = xmalloc(sizeof(int64_t) * (ORC_NUM_BUCKETS + 1));
+  sort_records(items, n, W, threads, bstart);
+  orc_sdbg *g = sdbg_postprocess(items, n, &f, bstart, threads);
+  free(bstart);
   free(items);
   return g;
 }
@@ -840,55 +900,89 @@ orc_sdbg *orc_read2sdbg(const uint8_t *bases, const int64_t *starts, int64_t n_r
   if (min_count > 1) { solid = orc_count(bases, starts, n_reads, k, min_count, threads); if (!solid) return NULL; }
   item_fmt f = {k, div_ceil(2 * k + 4, 32), 1};
   int W = f.W;
-  int64_t n = 0, cap = 1 << 16;
-  uint32_t *items = xmalloc((size_t)cap * W * 4);
-  int64_t scap = 1024; uint8_t *s = xmalloc(scap), *rcs = xmalloc(scap), *sol = xmalloc(scap);
-  uint32_t a[64], b[64];
+  /* pass 0: per-position solid flags (stage 1's bitmap); pass 1: item counts per read; pass 2: fill */
+  int64_t tot_pos = 0;
+  int64_t *pos_off = xmalloc(sizeof(int64_t) * (n_reads + 1));
   for (int64_t r = 0; r < n_reads; ++r) {
     int64_t L = starts[r + 1] - starts[r];
-    if (L < k + 1) continue;
-    if (L > scap) { scap = L * 2; s = xrealloc(s, scap); rcs = xrealloc(rcs, scap); sol = xrealloc(sol, scap); }
-    const uint8_t *c = bases + starts[r];
-    for (int64_t j = 0; j < L; ++j) s[j] = c[L - 1 - j];
-    for (int64_t j = 0; j < L; ++j) rcs[j] = 3 - s[L - 1 - j];
-    int64_t npos = L - k;
-    for (int64_t i = 0; i < npos; ++i) {
-      if (!solid) { sol[i] = 1; continue; }
-      pack_chars(s + i, k + 1, a, Wk);
-      pack_chars(rcs + (L - 1 - i - k), k + 1, b, Wk);
-      sol[i] = (uint8_t)edge_is_solid(solid, cmp_words(b, a, Wk) < 0 ? b : a, Wk);
+    pos_off[r] = tot_pos;
+    tot_pos += L >= k + 1 ? L - k : 0;
+  }
+  pos_off[n_reads] = tot_pos;
+  uint8_t *sol = xmalloc(tot_pos + 1);
+  int64_t *item_off = xmalloc(sizeof(int64_t) * (n_reads + 1));
+  uint32_t *items = NULL;
+  int64_t n = 0;
+  for (int pass = 0; pass < 3; ++pass) {
+    if (pass == 2) {
+      int64_t acc = 0;
+      for (int64_t r = 0; r < n_reads; ++r) { int64_t c = item_off[r]; item_off[r] = acc; acc += c; }
+      n = acc;
+      items = xmalloc((size_t)n * W * 4 + 16);
     }
-    for (int64_t i = 0; i < npos; ++i) {
-      if (!sol[i]) continue;
-      const uint8_t *e = s + i, *rc = rcs + (L - 1 - i - k);
-      int pal = memcmp(e, rc, k + 1) == 0;
-      int first = (i == 0) || !sol[i - 1], lastp = (i == npos - 1) || !sol[i + 1];
-      if (n + 8 > cap) { cap *= 2; items = xrealloc(items, (size_t)cap * W * 4); }
-#define PUSH_ITEM(ptr, nch, prevc)                                              \
-  do {                                                                          \
-    uint32_t *o_ = items + n * W;                                               \
-    pack_chars((ptr), (nch), o_, W);                                            \
-    o_[W - 1] |= (uint32_t)((nch) == k) << 3;                                   \
-    o_[W - 1] |= (uint32_t)(prevc);                                             \
-    ++n;                                                                        \
+#pragma omp parallel num_threads(threads)
+    {
+      int64_t scap = 1024; uint8_t *s = xmalloc(scap), *rcs = xmalloc(scap);
+      uint32_t a[64], b[64];
+#pragma omp for schedule(dynamic, 2048)
+      for (int64_t r = 0; r < n_reads; ++r) {
+        int64_t L = starts[r + 1] - starts[r];
+        if (L < k + 1) { if (pass == 1) item_off[r] = 0; continue; }
+        if (L > scap) { scap = L * 2; s = xrealloc(s, scap); rcs = xrealloc(rcs, scap); }
+        const uint8_t *c = bases + starts[r];
+        for (int64_t j = 0; j < L; ++j) s[j] = c[L - 1 - j];
+        for (int64_t j = 0; j < L; ++j) rcs[j] = 3 - s[L - 1 - j];
+        int64_t npos = L - k;
+        uint8_t *so = sol + pos_off[r];
+        if (pass == 0) {
+          for (int64_t i = 0; i < npos; ++i) {
+            if (!solid) { so[i] = 1; continue; }
+            pack_chars(s + i, k + 1, a, Wk);
+            pack_chars(rcs + (L - 1 - i - k), k + 1, b, Wk);
+            so[i] = (uint8_t)edge_is_solid(solid, cmp_words(b, a, Wk) < 0 ? b : a, Wk);
+          }
+          continue;
+        }
+        int64_t cnt = 0;
+        uint32_t *o = pass == 2 ? items + item_off[r] * W : NULL;
+#define PUSH_ITEM(ptr, nch, prevc)                                            \
+  do {                                                                        \
+    if (o) {                                                                  \
+      pack_chars((ptr), (nch), o, W);                                         \
+      o[W - 1] |= (uint32_t)((nch) == k) << 3;                                \
+      o[W - 1] |= (uint32_t)(prevc);                                          \
+      o += W;                                                                 \
+    }                                                                         \
+    ++cnt;                                                                    \
   } while (0)
-      PUSH_ITEM(e + 1, k, e[0]);
-      if (!pal) PUSH_ITEM(rc + 1, k, rc[0]);
-      if (first) {
-        PUSH_ITEM(e, k, ORC_SENTINEL);
-        if (!pal) PUSH_ITEM(rc + 2, k - 1, rc[1]);
-      }
-      if (lastp) {
-        PUSH_ITEM(e + 2, k - 1, e[1]);
-        if (!pal) PUSH_ITEM(rc, k, ORC_SENTINEL);
-      }
+        for (int64_t i = 0; i < npos; ++i) {
+          if (!so[i]) continue;
+          const uint8_t *e = s + i, *rc = rcs + (L - 1 - i - k);
+          int pal = memcmp(e, rc, k + 1) == 0;
+          int first = (i == 0) || !so[i - 1], lastp = (i == npos - 1) || !so[i + 1];
+          PUSH_ITEM(e + 1, k, e[0]);
+          if (!pal) PUSH_ITEM(rc + 1, k, rc[0]);
+          if (first) {
+            PUSH_ITEM(e, k, ORC_SENTINEL);
+            if (!pal) PUSH_ITEM(rc + 2, k - 1, rc[1]);
+          }
+          if (lastp) {
+            PUSH_ITEM(e + 2, k - 1, e[1]);
+            if (!pal) PUSH_ITEM(rc, k, ORC_SENTINEL);
+          }
+        }
 #undef PUSH_ITEM
+        if (pass == 1) item_off[r] = cnt;
+      }
+      free(s); free(rcs);
     }
   }
-  free(s); free(rcs); free(sol);
+  free(sol); free(pos_off); free(item_off);
   if (solid) orc_edges_free(solid);
-  sort_records(items, n, W, threads, NULL);
-  orc_sdbg *g = sdbg_postprocess(items, n, &f);
+  int64_t *bstart = xmalloc(sizeof(int64_t) * (ORC_NUM_BUCKETS + 1));
+  sort_records(items, n, W, threads, bstart);
+  orc_sdbg *g = sdbg_postprocess(items, n, &f, bstart, threads);
+  free(bstart);
   free(items);
   return g;
 }
