@@ -8,7 +8,7 @@
 //   P4 k_local<kCountEmit>            bucket in shared memory: sub-split, serial finish, run lengths, -m filter
 //   P5 k_gather_edges                 compact per-bucket edge runs into the globally sorted edge array
 // seq2sdbg (SeqToSdbg): k_items_from_edges / k_items_from_seqs, the same partition levels over item words,
-//   k_local<kSdbgCount> -> scans -> k_local<kSdbgEmit>.
+//   k_local<kSdbgEmit> (sort, BOSS emission into arenas) -> k_gather_edges.
 #include "engine.cuh"
 #include <algorithm>
 #include <cmath>
@@ -190,10 +190,10 @@ static int env_int(const char *name, int dflt) {
 // part_limit: bits the partition levels may consume (count: 2(k+1); sdbg: 2(k-1), so that a (k-1)-prefix group never
 // straddles a bucket).  density: how much denser than average the densest prefix range is (canonical keys = min of the two
 // strands pile up at small prefixes with density 2(1-u); sdbg items come from both strands and are flat).
-static Plan make_plan(int W, int part_limit, int64_t n_est, double density, int forced_l1 = -1) {
+static Plan make_plan(int W, int part_limit, int64_t n_est, double density, bool hash_family, int forced_l1 = -1) {
   Plan p;
   p.W = W;
-  p.cap = local_cap(W, false);
+  p.cap = local_cap(W, hash_family, false);
   const double target = p.cap * 0.65 / density;
   int bits = std::max(1, ceil_log2((double)std::max<int64_t>(n_est, 1) / target));
   bits = std::min(bits, 2 * kMaxDigitBits);
@@ -225,7 +225,7 @@ static void launch_reads_hist(Ctx &c, const ReadsView &r, const uint32_t *sbits,
   ReadsProducer<W> p{r.packed, sbits, r.n_bases, k, C::TH};
   int64_t tiles = div_ceil64(r.n_bases, C::TH);
   if (tiles == 0) return;
-  size_t smem = ((size_t)((C::NT / 32) << a.nbits) + 1) / 2 * 4 + (size_t)ReadsProducer<W>::smem_words(C::TH, k) * 4;
+  size_t smem = ((size_t)1 << a.nbits) * 4 + (size_t)ReadsProducer<W>::smem_words(C::TH, k) * 4;
   auto kern = k_level_hist<ReadsProducer<W>, W, C::NT, C::IPT_H>;
   set_smem(kern, smem);
   kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(p, a, hist);
@@ -295,7 +295,7 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   LevelArgs a{bit_off, nbits, 0u, (uint32_t)nbins};
   if (tb_h[nchunk] > 0) {
     RecordsProducer<W> ph{in, ChunkTable{d_start, d_size, d_seg, d_tbh, nchunk}, C::TH};
-    size_t smem = ((size_t)((C::NT / 32) << nbits) + 1) / 2 * 4 + 16;
+    size_t smem = ((size_t)1 << nbits) * 4 + 16;
     auto kern = k_level_hist<RecordsProducer<W>, W, C::NT, C::IPT_H>;
     set_smem(kern, smem);
     Stage st(c, tag_h.c_str());
@@ -323,11 +323,18 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
 template <int W, int MODE>
 static void launch_local(Ctx &c, const LocalArgs &a, int grid) {
   if (grid <= 0) return;
-  constexpr bool weighted = MODE == kCountMerge;
-  size_t smem = local_smem_bytes(weighted ? W + 1 : W, a.cap, weighted);
-  auto kern = k_local<W, kLocalNT, MODE>;
-  set_smem(kern, smem);
-  kern<<<grid, kLocalNT, smem, c.stream>>>(a);
+  if constexpr (MODE == kSortOnly || MODE == kSdbgEmit) {
+    size_t smem = local_smem_bytes(W, a.cap, false, false);
+    auto kern = k_local<W, kLocalNT, MODE>;
+    set_smem(kern, smem);
+    kern<<<grid, kLocalNT, smem, c.stream>>>(a);
+  } else {
+    constexpr bool weighted = MODE == kCountMerge;
+    size_t smem = local_smem_bytes(weighted ? W + 1 : W, a.cap, true, weighted);
+    auto kern = k_count<W, kLocalNT, MODE>;
+    set_smem(kern, smem);
+    kern<<<grid, kLocalNT, smem, c.stream>>>(a);
+  }
   MF_LAUNCH_CHECK();
   c.launches++;
 }
@@ -375,7 +382,7 @@ static void sort_ranges(Ctx &c, uint32_t *cur, uint32_t *other, const std::vecto
   a.work = nullptr;
   a.bit_off = bit_off + nbits;
   a.sort_bits = sort_bits;
-  a.cap = local_cap(W, false);
+  a.cap = local_cap(W, false, false);
   a.bail_list = d_bail;
   a.bail_count = d_flags;
   a.overflow_flag = d_flags + 1;
@@ -428,7 +435,7 @@ template <int W>
 static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n, const HostChunks &l1, int k, int l1_bits,
                               int min_count, bool append, EdgesView *out, unsigned long long *d_counting) {
   const int key_bits = 2 * (k + 1), We = words_edge(k);
-  Plan p = make_plan(W, key_bits, n, 2.0, l1_bits);
+  Plan p = make_plan(W, key_bits, n, 2.0, true, l1_bits);
   auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
   DevBuckets b;
   int bit_off = l1_bits;
@@ -543,7 +550,7 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
         }
         LocalArgs ma = pa;
         ma.work = d_merges.as<WorkItem>();
-        ma.cap = local_cap(W + 1, true);
+        ma.cap = local_cap(W + 1, true, true);
         ma.counting = a.counting;
         ma.bail_list = d_bail2.as<int32_t>();
         {
@@ -657,7 +664,7 @@ static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, Edg
     sbits = build_start_bits(c, r);
   }
   // the plan needs the key count: it is at most one key per base
-  Plan p = make_plan(W, key_bits, std::max<int64_t>(r.n_bases - r.n_reads * (int64_t)k, 1), 2.0);   // one key per base minus k per read
+  Plan p = make_plan(W, key_bits, std::max<int64_t>(r.n_bases - r.n_reads * (int64_t)k, 1), 2.0, true);   // one key per base minus k per read
   const int nb1 = 1 << p.l1_bits;
   unsigned long long *d_small = nullptr;   // hist | counting
   MF_CUDA(cudaMalloc(&d_small, sizeof(unsigned long long) * (nb1 + kNumBuckets)));
@@ -856,7 +863,7 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
     MF_CUDA(cudaStreamSynchronize(c.stream));
     return;
   }
-  Plan p = make_plan(WI, part_limit, n_items, 1.0);
+  Plan p = make_plan(WI, part_limit, n_items, 1.0, false);
   const int nb1 = 1 << p.l1_bits;
   const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1 << kMaxDigitBits) * 96;
   c.slab_reserve((size_t)n_items * WI * 4 * 2 + table_bytes + (1 << 20));
@@ -910,52 +917,77 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
     bit_off += p.l2_bits;
   }
   int64_t *d_items = c.alloc<int64_t>(b.nslots), *d_tips = c.alloc<int64_t>(b.nslots), *d_large = c.alloc<int64_t>(b.nslots);
+  int64_t *d_item_src = c.alloc<int64_t>(b.nslots), *d_tip_src = c.alloc<int64_t>(b.nslots);
   int64_t *d_item_off = c.alloc<int64_t>(b.nslots + 1), *d_tip_off = c.alloc<int64_t>(b.nslots + 1),
           *d_large_off = c.alloc<int64_t>(b.nslots + 1);
   int32_t *d_bail = c.alloc<int32_t>(b.nslots);
   int *d_flags = c.alloc<int>(4);
-  MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, c.stream));
-  MF_CUDA(cudaMemsetAsync(d_items, 0, sizeof(int64_t) * b.nslots, c.stream));
-  MF_CUDA(cudaMemsetAsync(d_tips, 0, sizeof(int64_t) * b.nslots, c.stream));
-  MF_CUDA(cudaMemsetAsync(d_large, 0, sizeof(int64_t) * b.nslots, c.stream));
-  LocalArgs a{};
-  a.in = cur;
-  a.bkt_start = b.start;
-  a.bkt_size = b.size;
-  a.bit_off = bit_off;
-  a.sort_bits = 32 * WI;
-  a.cap = p.cap;
-  a.k = k;
-  a.tip_mode = tip_mode;
-  a.words_tip = Wt;
-  a.sd_items = d_items;
-  a.sd_tips = d_tips;
-  a.sd_large = d_large;
-  a.bucket_stats = d_bstats;
-  a.bail_list = d_bail;
-  a.bail_count = d_flags;
-  a.overflow_flag = d_flags + 1;
-  {
-    Stage st(c, "local_sdbg_count");
-    launch_local<WI, kSdbgCount>(c, a, b.nslots);
-  }
-  int nbail = 0;
-  MF_CUDA(cudaMemcpyAsync(&nbail, d_flags, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  MF_CUDA(cudaStreamSynchronize(c.stream));
+  unsigned long long *d_cursor = c.alloc<unsigned long long>(2);
+  // arenas: emitted items <= generated items; tip labels are a small share (retry with the exact demand otherwise)
+  size_t item_cap = (size_t)n_items, tip_cap = (size_t)n_items / 8 + (1 << 16);
+  c.ov[0].reserve(item_cap * 4 + 256);
+  DevBuf &tip_arena = c.ov[1];
   std::vector<int32_t> bail_slots;
   WorkItem *d_bail_sorted = nullptr;
-  if (nbail > 0) {
-    Stage st(c, "fallback");
-    std::vector<Range> rs = fetch_bails(c, b, d_bail, nbail, &bail_slots);
-    sort_ranges<WI>(c, cur, other, rs, bit_off, 32 * WI);
-    std::vector<WorkItem> hw;
-    for (size_t i = 0; i < rs.size(); ++i) hw.push_back(WorkItem{rs[i].start, 0, bail_slots[i]});
-    d_bail_sorted = c.alloc<WorkItem>(hw.size());
-    c.h2d(d_bail_sorted, hw.data(), sizeof(WorkItem) * hw.size());
-    a.work = d_bail_sorted;
-    launch_serial<WI, kSdbgCount>(c, a, (int)bail_slots.size());
-    a.work = nullptr;
+  bool sorted_fallback = false;
+  for (int attempt = 0;; ++attempt) {
+    tip_arena.reserve(tip_cap * Wt * 4 + 256);
+    MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, c.stream));
+    MF_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long) * 2, c.stream));
+    MF_CUDA(cudaMemsetAsync(d_items, 0, sizeof(int64_t) * b.nslots, c.stream));
+    MF_CUDA(cudaMemsetAsync(d_tips, 0, sizeof(int64_t) * b.nslots, c.stream));
+    MF_CUDA(cudaMemsetAsync(d_large, 0, sizeof(int64_t) * b.nslots, c.stream));
+    MF_CUDA(cudaMemsetAsync(d_bstats, 0, sizeof(unsigned long long) * kNumBuckets * 3, c.stream));
+    LocalArgs a{};
+    a.in = cur;
+    a.bkt_start = b.start;
+    a.bkt_size = b.size;
+    a.bit_off = bit_off;
+    a.sort_bits = 32 * WI;
+    a.cap = p.cap;
+    a.k = k;
+    a.tip_mode = tip_mode;
+    a.words_tip = Wt;
+    a.sd_items = d_items;
+    a.sd_tips = d_tips;
+    a.sd_large = d_large;
+    a.sd_item_off = d_item_src;
+    a.sd_tip_off = d_tip_src;
+    a.sd_rec = c.ov[0].as<uint32_t>();
+    a.sd_labels = tip_arena.as<uint32_t>();
+    a.sd_cursor = d_cursor;
+    a.sd_item_cap = item_cap;
+    a.sd_tip_cap = tip_cap;
+    a.bucket_stats = d_bstats;
+    a.bail_list = d_bail;
+    a.bail_count = d_flags;
+    a.overflow_flag = d_flags + 1;
+    {
+      Stage st(c, "local_sdbg");
+      launch_local<WI, kSdbgEmit>(c, a, b.nslots);
+    }
+    int flags[2];
+    c.d2h(flags, d_flags, sizeof(int) * 2);
+    if (flags[0] > 0) {
+      Stage st(c, "fallback");
+      std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &bail_slots);
+      if (!sorted_fallback) sort_ranges<WI>(c, cur, other, rs, bit_off, 32 * WI);
+      sorted_fallback = true;
+      std::vector<WorkItem> hw;
+      for (size_t i = 0; i < rs.size(); ++i) hw.push_back(WorkItem{rs[i].start, 0, bail_slots[i]});
+      if (!d_bail_sorted) d_bail_sorted = c.alloc<WorkItem>(hw.size());
+      c.h2d(d_bail_sorted, hw.data(), sizeof(WorkItem) * hw.size());
+      a.work = d_bail_sorted;
+      launch_serial<WI, kSdbgEmit>(c, a, (int)hw.size());
+      c.d2h(flags, d_flags, sizeof(int) * 2);
+    }
+    if (!flags[1]) break;
+    unsigned long long need[2];
+    c.d2h(need, d_cursor, sizeof need);
+    if (attempt >= 2) throw std::runtime_error("sdbg arena overflow persisted");
+    tip_cap = std::max<size_t>(tip_cap, (size_t)need[1]);
   }
+  Stage st(c, "sdbg_gather");
   k_scan_i64<<<1, 1024, 0, c.stream>>>(d_items, b.nslots, 0, d_item_off);
   k_scan_i64<<<1, 1024, 0, c.stream>>>(d_tips, b.nslots, 0, d_tip_off);
   k_scan_i64<<<1, 1024, 0, c.stream>>>(d_large, b.nslots, 0, d_large_off);
@@ -968,18 +1000,13 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
   MF_CUDA(cudaStreamSynchronize(c.stream));
   c.sdbg_rec.reserve((size_t)std::max<int64_t>(tot[0], 1) * 4 + 256);
   c.sdbg_labels.reserve((size_t)std::max<int64_t>(tot[1], 1) * Wt * 4 + 256);
-  a.sd_item_off = d_item_off;
-  a.sd_tip_off = d_tip_off;
-  a.sd_rec = c.sdbg_rec.as<uint32_t>();
-  a.sd_labels = c.sdbg_labels.as<uint32_t>();
-  MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, c.stream));
-  {
-    Stage st(c, "local_sdbg_emit");
-    launch_local<WI, kSdbgEmit>(c, a, b.nslots);
-  }
-  if (nbail > 0) {
-    a.work = d_bail_sorted;
-    launch_serial<WI, kSdbgEmit>(c, a, (int)bail_slots.size());
+  if (tot[0] > 0) {
+    k_gather_edges<<<div_ceil(b.nslots, 8), 256, 0, c.stream>>>(c.ov[0].as<uint32_t>(), d_item_src, d_items, d_item_off, b.nslots, 1,
+                                                              c.sdbg_rec.as<uint32_t>());
+    k_gather_edges<<<div_ceil(b.nslots, 8), 256, 0, c.stream>>>(tip_arena.as<uint32_t>(), d_tip_src, d_tips, d_tip_off, b.nslots, Wt,
+                                                              c.sdbg_labels.as<uint32_t>());
+    MF_LAUNCH_CHECK();
+    c.launches += 2;
   }
   MF_CUDA(cudaMemcpyAsync(c.sdbg_bucket_stats.data(), d_bstats, sizeof(int64_t) * kNumBuckets * 3, cudaMemcpyDeviceToHost, c.stream));
   MF_CUDA(cudaStreamSynchronize(c.stream));

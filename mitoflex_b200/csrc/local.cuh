@@ -8,14 +8,14 @@
 //                 at 10^4 x, make buckets that no shared memory holds; their chunks are combined first)
 //   kCountMerge : the pairs of all chunks of one bucket -> summed multiplicities -> filter -> edge records
 //   kSortOnly   : write the bucket back fully sorted (recursive fallback for buckets with too many DISTINCT keys)
-//   kSdbgCount / kSdbgEmit : BOSS emission per (k-1)-prefix group (SeqToSdbg::Lv2Postprocess), one thread per group run
+//   kSdbgEmit   : BOSS emission per (k-1)-prefix group (SeqToSdbg::Lv2Postprocess), threads own runs of groups
 // k_serial runs the same walkers single-threaded over an already sorted global range (last-resort path).
 #pragma once
 #include "common.cuh"
 
 namespace mf {
 
-enum LocalMode { kCountEmit = 0, kSortOnly = 1, kSdbgCount = 2, kSdbgEmit = 3, kCountPairs = 4, kCountMerge = 5 };
+enum LocalMode { kCountEmit = 0, kSortOnly = 1, kSdbgEmit = 3, kCountPairs = 4, kCountMerge = 5 };
 
 struct WorkItem {
   int64_t start;   // first record (kCountMerge: first piece index)
@@ -59,27 +59,41 @@ struct LocalArgs {
   int64_t *sd_tips;                      // [nslots]
   int64_t *sd_large;                     // [nslots]
   unsigned long long *bucket_stats;      // [65536][3] items / tips / large per megahit bucket (count phase)
-  const int64_t *sd_item_off;            // [nslots] (emit phase) global item offset
-  const int64_t *sd_tip_off;             // [nslots]
-  uint32_t *sd_rec;                      // emitted: w | last<<4 | tip<<5 | mult<<8
-  uint32_t *sd_labels;                   // words_tip per tip
+  int64_t *sd_item_off;                  // [nslots] arena offset of the bucket's items
+  int64_t *sd_tip_off;                   // [nslots] arena offset of the bucket's tip labels
+  uint32_t *sd_rec;                      // item arena: w | last<<4 | tip<<5 | mult<<8
+  uint32_t *sd_labels;                   // tip-label arena, words_tip per tip
+  unsigned long long *sd_cursor;         // [2] item / tip arena cursors
+  unsigned long long sd_item_cap, sd_tip_cap;
 };
 
 constexpr int kLocalDigitBits = 10;
 constexpr int kLocalBins = 1 << kLocalDigitBits;
 constexpr int kLocalNT = 256;
+constexpr int kHashSlots = 8192;     // open-addressing table of the count consumers (> any cap, so it never fills)
+constexpr int kSolidMax = 2048;      // distinct solid keys a bucket may hold on the fast path
+constexpr uint32_t kEmptySlot = 0xffffffffu;
 
-// shared memory: rec[cap*WR] | idxA,idxB,rk u16[cap] | aux u32[weighted ? cap+2 : 2NT+2] | whist u16[NWARP][1024] | bins u32[1025] | scratch
-inline size_t local_smem_bytes(int WR, int cap, bool weighted) {
-  size_t aux = weighted ? (size_t)cap + 2 : 2 * kLocalNT + 2;
-  size_t words = (size_t)cap * WR + 3 * ((size_t)cap / 2) + aux + (size_t)(kLocalNT / 32) * kLocalBins / 2 + kLocalBins + 1 + 48;
+__host__ __device__ inline bool mode_is_hash(int mode) { return mode == 0 /*kCountEmit*/ || mode == 4 /*kCountPairs*/ || mode == 5 /*kCountMerge*/; }
+
+// shared memory (uint32 words)
+//  LSD family : rec[cap*WR] | idxA,idxB,rk u16[cap] | aux u32[2NT+2] | whist u16[NWARP][1024] | bins u32[1025] | scratch[48]
+//  hash family: rec[cap*WR] | table u32[8192] (| tcnt u32[8192] if weighted) | sidx,permA,permB,rk u16[2048] | scnt u32[2048]
+//               | small u32[64] | strip u32[NT+1] | scratch[48]          (whist/bins of the solid-key sort alias the table)
+inline size_t local_fixed_words(bool hash, bool weighted) {
+  if (hash) return (size_t)kHashSlots * (weighted ? 2 : 1) + 4 * (kSolidMax / 2) + kSolidMax + 64 + (kLocalNT + 1) + 48;
+  return (size_t)(2 * kLocalNT + 2) + (size_t)(kLocalNT / 32) * kLocalBins / 2 + kLocalBins + 1 + 48;
+}
+inline size_t local_smem_bytes(int WR, int cap, bool hash, bool weighted) {
+  size_t words = (size_t)cap * WR + local_fixed_words(hash, weighted) + (hash ? 0 : 3 * ((size_t)cap / 2));
   return words * 4;
 }
 // records per CTA such that two CTAs fit an SM (110 KB each)
-inline int local_cap(int WR, bool weighted) {
-  const int fixed = (kLocalNT / 32) * kLocalBins * 2 + (kLocalBins + 1) * 4 + 48 * 4 + (weighted ? 8 : (2 * kLocalNT + 2) * 4);
-  int cap = (110 * 1024 - fixed) / (WR * 4 + 6 + (weighted ? 4 : 0));
+inline int local_cap(int WR, bool hash, bool weighted) {
+  const int budget = 110 * 1024 - (int)local_fixed_words(hash, weighted) * 4;
+  int cap = budget / (WR * 4 + (hash ? 0 : 6));
   cap &= ~1;
+  if (hash && cap > kHashSlots - 256) cap = kHashSlots - 256;   // the table must keep free slots
   return cap > 65534 ? 65534 : cap;
 }
 
@@ -199,9 +213,21 @@ __device__ __forceinline__ void write_edge(uint32_t *dst, const uint32_t *key, i
 
 // One stable LSD pass over the index array.  Returns false (and leaves idx_in as the current order) when every record
 // has the same digit.  Warps own contiguous blocks of positions, so warp order == position order == stability.
+// peer mask of lanes holding the same digit, by ballots (the ADU pipe takes ~3.6 cycles per ballot, ~63 per match.any)
+__device__ __forceinline__ unsigned peers_by_ballot(uint32_t d, bool valid, int nbits) {
+  unsigned m = __ballot_sync(0xffffffffu, valid);
+  for (int b = 0; b < nbits; ++b) {
+    const bool bit = (d >> b) & 1;
+    const unsigned v = __ballot_sync(0xffffffffu, bit);
+    m &= bit ? v : ~v;
+  }
+  return valid ? m : 0u;
+}
+// `via` (nullable) maps sorted entities to records: record = via[entity]
 template <int WR, int W, int NT>
 __device__ __forceinline__ bool lsd_pass(const uint32_t *rec, const uint16_t *idx_in, uint16_t *idx_out, uint16_t *rk, int n,
-                                         int bit_lo, int nbits, uint16_t *whist, uint32_t *bins, uint32_t *scratch) {
+                                         int bit_lo, int nbits, uint16_t *whist, uint32_t *bins, uint32_t *scratch,
+                                         const uint16_t *via = nullptr) {
   constexpr int NWARP = NT / 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = 1 << nbits;
@@ -216,10 +242,11 @@ __device__ __forceinline__ bool lsd_pass(const uint32_t *rec, const uint16_t *id
     const bool valid = p < n;
     uint32_t d = 0;
     if (valid) {
-      const int r = idx_in ? idx_in[p] : p;
+      int r = idx_in ? idx_in[p] : p;
+      if (via) r = via[r];
       d = rec_digit_mem<W>(rec + (size_t)r * WR, bit_lo, nbits);
     }
-    const unsigned m = match_digit(d, valid);
+    const unsigned m = peers_by_ballot(d, valid, nbits);
     const unsigned leader = (unsigned)(__ffs(m) - 1);
     uint32_t old = 0;
     if (valid && lane == leader) {
@@ -250,9 +277,10 @@ __device__ __forceinline__ bool lsd_pass(const uint32_t *rec, const uint16_t *id
   for (int it = 0; it < per_warp; it += 32) {
     const int p = p0 + it + lane;
     if (p < n) {
-      const int r = idx_in ? idx_in[p] : p;
+      const int e = idx_in ? idx_in[p] : p;
+      const int r = via ? via[e] : e;
       const uint32_t d = rec_digit_mem<W>(rec + (size_t)r * WR, bit_lo, nbits);
-      idx_out[bins[d] + wh[d] + rk[p]] = (uint16_t)r;
+      idx_out[bins[d] + wh[d] + rk[p]] = (uint16_t)e;
     }
   }
   __syncthreads();
@@ -263,7 +291,7 @@ __device__ __forceinline__ bool lsd_pass(const uint32_t *rec, const uint16_t *id
 // flag(p) is evaluated twice.  Threads own contiguous strips, so the list is ordered.
 template <int NT, class F>
 __device__ __forceinline__ uint32_t compact_positions(int n, F flag, uint16_t *list, uint32_t *strip_cnt /*[NT+1]*/,
-                                                      uint32_t *scratch) {
+                                                      uint32_t *scratch, uint32_t max_out = 0xffffffffu) {
   const int tid = threadIdx.x;
   const int per = (n + NT - 1) / NT;
   const int b = min(n, tid * per), e = min(n, b + per);
@@ -273,19 +301,22 @@ __device__ __forceinline__ uint32_t compact_positions(int n, F flag, uint16_t *l
   if (tid == 0) strip_cnt[NT] = 0;
   __syncthreads();
   const uint32_t total = block_excl_scan<NT>(strip_cnt, NT + 1, scratch);
-  uint32_t o = strip_cnt[tid];
-  for (int p = b; p < e; ++p)
-    if (flag(p)) list[o++] = (uint16_t)p;
+  if (total <= max_out) {
+    uint32_t o = strip_cnt[tid];
+    for (int p = b; p < e; ++p)
+      if (flag(p)) list[o++] = (uint16_t)p;
+  }
   __syncthreads();
   return total;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// LSD family: kSortOnly (fallback) and kSdbgEmit.  The whole bucket is sorted (all sort_bits), then consumed.
 template <int W, int NT, int MODE>
 __global__ void __launch_bounds__(NT) k_local(LocalArgs a) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr int NWARP = NT / 32;
-  constexpr bool WEIGHTED = MODE == kCountMerge;
-  constexpr int WR = WEIGHTED ? W + 1 : W;
+  constexpr int WR = W;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cap = a.cap;
 
@@ -293,13 +324,12 @@ __global__ void __launch_bounds__(NT) k_local(LocalArgs a) {
   uint16_t *idxA = reinterpret_cast<uint16_t *>(rec + (size_t)cap * WR);      // [cap]
   uint16_t *idxB = idxA + cap;                                                // [cap]
   uint16_t *rk = idxB + cap;                                                  // [cap]
-  uint32_t *aux = reinterpret_cast<uint32_t *>(rk + cap);                     // [WEIGHTED ? cap+2 : 2NT+2]
-  uint16_t *whist = reinterpret_cast<uint16_t *>(aux + (WEIGHTED ? cap + 2 : 2 * NT + 2));   // [NWARP][1024]
+  uint32_t *aux = reinterpret_cast<uint32_t *>(rk + cap);                     // [2NT+2]
+  uint16_t *whist = reinterpret_cast<uint16_t *>(aux + 2 * NT + 2);           // [NWARP][1024]
   uint32_t *bins = reinterpret_cast<uint32_t *>(whist + NWARP * kLocalBins);  // [1025]
   uint32_t *scratch = bins + kLocalBins + 1;                                  // [34]
   int *s_flag = reinterpret_cast<int *>(scratch + 34);                        // [8]
 
-  // ---- work item
   int slot;
   int64_t start, n64;
   if (a.work) {
@@ -313,41 +343,15 @@ __global__ void __launch_bounds__(NT) k_local(LocalArgs a) {
     n64 = a.bkt_size[slot];
   }
   if (n64 == 0) return;
-  int n;
-  // ---- 1. load
-  if constexpr (MODE == kCountMerge) {
-    // `start` / `n64` index pieces: gather every chunk's pairs
-    const int first = (int)start, np = (int)n64;
-    int total = 0;
-    for (int q = 0; q < np; ++q) total += a.piece_cnt[first + q];
-    if (total > cap) {
-      if (tid == 0) {
-        int p = atomicAdd(a.bail_count, 1);
-        a.bail_list[p] = slot;
-      }
-      return;
+  if (n64 > cap) {                       // does not fit: the fallback path takes it
+    if (tid == 0) {
+      int p = atomicAdd(a.bail_count, 1);
+      a.bail_list[p] = slot;
     }
-    int o = 0;
-    for (int q = 0; q < np; ++q) {
-      const int c = a.piece_cnt[first + q];
-      const uint32_t *src = a.pair_arena + a.piece_off[first + q] * (int64_t)WR;
-      for (int i = tid; i < c * WR; i += NT) rec[(size_t)o * WR + i] = src[i];
-      o += c;
-    }
-    n = total;
-    if (n == 0) {
-      if (tid == 0) { a.desc_off[slot] = 0; a.desc_cnt[slot] = 0; }
-      return;
-    }
-  } else {
-    if (n64 > cap) {                       // does not fit: the chunked / fallback path takes it
-      if (tid == 0) {
-        int p = atomicAdd(a.bail_count, 1);
-        a.bail_list[p] = slot;
-      }
-      return;
-    }
-    n = (int)n64;
+    return;
+  }
+  const int n = (int)n64;
+  {
     const uint32_t *src = a.in + start * (int64_t)W;
     const int nw = n * W;
     if constexpr (W % 2 == 0) {
@@ -361,7 +365,7 @@ __global__ void __launch_bounds__(NT) k_local(LocalArgs a) {
   if (tid < 8) s_flag[tid] = 0;
   __syncthreads();
 
-  // ---- 2. LSD sort of the index array over bits [bit_off, sort_bits), least significant digit first
+  // LSD sort of the index array over bits [bit_off, sort_bits), least significant digit first
   const uint16_t *cur = nullptr;   // nullptr == identity order
   {
     uint16_t *nxt = idxA;
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(NT) k_local(LocalArgs a) {
       __syncthreads();
     }
   }
-  uint16_t *list = (cur == idxA) ? idxB : idxA;   // the free index array: head / group positions
+  uint16_t *list = (cur == idxA) ? idxB : idxA;   // the free index array: group positions
   const SmemAcc<WR> acc{rec, cur};
   uint32_t *strip = bins;   // [NT+1] fits in bins[1025]
 
@@ -394,91 +398,8 @@ __global__ void __launch_bounds__(NT) k_local(LocalArgs a) {
     return;
   }
 
-  if constexpr (MODE == kCountEmit || MODE == kCountPairs || MODE == kCountMerge) {
-    // ---- 3. runs of equal keys
-    auto is_head = [&](int p) { return p == 0 || cmp_rec<W>(acc(p), acc(p - 1)) != 0; };
-    const uint32_t nh = compact_positions<NT>(n, is_head, list, strip, scratch);
-    if constexpr (WEIGHTED) {
-      // aux[p] = sum of the counts of sorted positions < p (pairs carry their chunk's count in word W)
-      const int per = (n + NT - 1) / NT;
-      const int b = min(n, tid * per), e = min(n, b + per);
-      uint32_t s = 0;
-      for (int p = b; p < e; ++p) s += acc(p)[W];
-      strip[tid] = s;
-      if (tid == 0) strip[NT] = 0;
-      __syncthreads();
-      const uint32_t tot = block_excl_scan<NT>(strip, NT + 1, scratch);
-      uint32_t run = strip[tid];
-      for (int p = b; p < e; ++p) { aux[p] = run; run += acc(p)[W]; }
-      if (tid == 0) aux[n] = tot;
-      __syncthreads();
-    }
-    auto run_count = [&](uint32_t j) -> uint32_t {
-      const int p0 = list[j], p1 = (j + 1 < nh) ? (int)list[j + 1] : n;
-      if constexpr (WEIGHTED) return aux[p1] - aux[p0];
-      else return (uint32_t)(p1 - p0);
-    };
-    if constexpr (MODE == kCountPairs) {
-      // every distinct key of this chunk with its count -> pair arena
-      if (tid == 0) {
-        unsigned long long base = atomicAdd(a.pair_cursor, (unsigned long long)nh);
-        int ok = base + nh <= a.pair_cap;
-        if (!ok) atomicExch(a.overflow_flag + 1, 1);
-        a.piece_off[blockIdx.x] = (int64_t)base;
-        a.piece_cnt[blockIdx.x] = ok ? (int32_t)nh : 0;
-        s_flag[1] = ok;
-        s_flag[2] = (int)(uint32_t)base;
-        s_flag[3] = (int)(uint32_t)(base >> 32);
-      }
-      __syncthreads();
-      if (!s_flag[1]) return;
-      const unsigned long long base = ((unsigned long long)(uint32_t)s_flag[3] << 32) | (uint32_t)s_flag[2];
-      for (uint32_t j = tid; j < nh; j += NT) {
-        const uint32_t *key = acc(list[j]);
-        uint32_t *dst = a.pair_arena + (base + j) * (unsigned long long)(W + 1);
-#pragma unroll
-        for (int t = 0; t < W; ++t) dst[t] = key[t];
-        dst[W] = run_count(j);
-      }
-      return;
-    } else {
-      // ---- 4. solid filter + emission; rk is free after the sort and takes the solid-run list
-      uint16_t *solid = rk;
-      auto is_solid = [&](int j) { return run_count((uint32_t)j) >= (uint32_t)a.min_count; };
-      const uint32_t ns = compact_positions<NT>((int)nh, is_solid, solid, strip, scratch);
-      if (tid == 0) {
-        unsigned long long base = atomicAdd(a.arena_cursor, (unsigned long long)ns);
-        int ok = base + ns <= a.arena_cap;
-        if (!ok) atomicExch(a.overflow_flag, 1);
-        a.desc_off[slot] = (int64_t)base;
-        a.desc_cnt[slot] = ok ? (int64_t)ns : 0;
-        s_flag[1] = ok;
-        s_flag[2] = (int)(uint32_t)base;
-        s_flag[3] = (int)(uint32_t)(base >> 32);
-      }
-      __syncthreads();
-      if (a.counting) {
-        // distinct-edge multiplicity histogram (<prefix>.counting): warp-aggregate equal counts before the atomic
-        for (uint32_t j = tid; j < ((nh + 31) & ~31u); j += NT) {
-          const bool v = j < nh;
-          const uint32_t c = v ? min(run_count(j), (uint32_t)kMaxMul) : 0u;
-          const unsigned m = match_digit(c, v);
-          if (v && lane == (unsigned)(__ffs(m) - 1)) atomicAdd(a.counting + c, (unsigned long long)__popc(m));
-        }
-      }
-      if (!s_flag[1]) return;
-      const unsigned long long base = ((unsigned long long)(uint32_t)s_flag[3] << 32) | (uint32_t)s_flag[2];
-      const int We = a.words_edge;
-      for (uint32_t q = tid; q < ns; q += NT) {
-        const uint32_t j = solid[q];
-        write_edge<W>(a.arena + (base + q) * (unsigned long long)We, acc(list[j]), We, run_count(j));
-      }
-      return;
-    }
-  }
-
-  if constexpr (MODE == kSdbgCount || MODE == kSdbgEmit) {
-    // ---- groups of equal (k-1)-prefix; threads own contiguous runs of groups (groups are a handful of items)
+  if constexpr (MODE == kSdbgEmit) {
+    // groups of equal (k-1)-prefix; threads own contiguous runs of groups (a group is a handful of items)
     auto is_ghead = [&](int p) { return p == 0 || item_diff_km1<W>(acc(p), acc(p - 1), a.k); };
     const uint32_t ng = compact_positions<NT>(n, is_ghead, list, strip, scratch);
     uint32_t my_items = 0, my_tips = 0, my_large = 0;
@@ -486,8 +407,7 @@ __global__ void __launch_bounds__(NT) k_local(LocalArgs a) {
     const int gb = min((int)ng, tid * gper), ge = min((int)ng, gb + gper);
     for (int g = gb; g < ge; ++g) {
       const int p0 = list[g], p1 = (g + 1 < (int)ng) ? (int)list[g + 1] : n;
-      SdbgTally t = sdbg_walk<W, false>(acc, p0, p1, a.k, a.words_tip, a.tip_mode, nullptr, nullptr,
-                                        MODE == kSdbgCount ? a.bucket_stats : nullptr);
+      SdbgTally t = sdbg_walk<W, false>(acc, p0, p1, a.k, a.words_tip, a.tip_mode, nullptr, nullptr, a.bucket_stats);
       my_items += t.items;
       my_tips += t.tips;
       my_large += t.large;
@@ -499,28 +419,265 @@ __global__ void __launch_bounds__(NT) k_local(LocalArgs a) {
     __syncthreads();
     const uint32_t tot_items = block_excl_scan<NT>(s_items, NT + 1, scratch);
     const uint32_t tot_tips = block_excl_scan<NT>(s_tips, NT + 1, scratch);
-    if constexpr (MODE == kSdbgCount) {
 #pragma unroll
-      for (int o = 16; o; o >>= 1) my_large += __shfl_xor_sync(0xffffffffu, my_large, o);
-      if (lane == 0) scratch[warp] = my_large;
-      __syncthreads();
-      if (tid == 0) {
-        uint32_t L = 0;
-        for (int w = 0; w < NWARP; ++w) L += scratch[w];
-        a.sd_items[slot] = (int64_t)tot_items;
-        a.sd_tips[slot] = (int64_t)tot_tips;
-        a.sd_large[slot] = (int64_t)L;
-      }
+    for (int o = 16; o; o >>= 1) my_large += __shfl_xor_sync(0xffffffffu, my_large, o);
+    if (lane == 0) scratch[warp] = my_large;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t L = 0;
+      for (int w = 0; w < NWARP; ++w) L += scratch[w];
+      const unsigned long long ib = atomicAdd(a.sd_cursor, (unsigned long long)tot_items);
+      const unsigned long long tb = atomicAdd(a.sd_cursor + 1, (unsigned long long)tot_tips);
+      const int ok = ib + tot_items <= a.sd_item_cap && tb + tot_tips <= a.sd_tip_cap;
+      if (!ok) atomicExch(a.overflow_flag, 1);
+      a.sd_item_off[slot] = (int64_t)ib;
+      a.sd_tip_off[slot] = (int64_t)tb;
+      a.sd_items[slot] = ok ? (int64_t)tot_items : 0;
+      a.sd_tips[slot] = ok ? (int64_t)tot_tips : 0;
+      a.sd_large[slot] = ok ? (int64_t)L : 0;
+      s_flag[1] = ok;
+      s_flag[2] = (int)(uint32_t)ib; s_flag[3] = (int)(uint32_t)(ib >> 32);
+      s_flag[4] = (int)(uint32_t)tb; s_flag[5] = (int)(uint32_t)(tb >> 32);
+    }
+    __syncthreads();
+    if (!s_flag[1]) return;
+    const int64_t item_base = (int64_t)(((unsigned long long)(uint32_t)s_flag[3] << 32) | (uint32_t)s_flag[2]) + s_items[tid];
+    const int64_t tip_base = (int64_t)(((unsigned long long)(uint32_t)s_flag[5] << 32) | (uint32_t)s_flag[4]) + s_tips[tid];
+    uint32_t oi = 0, ot = 0;
+    for (int g = gb; g < ge; ++g) {
+      const int p0 = list[g], p1 = (g + 1 < (int)ng) ? (int)list[g + 1] : n;
+      SdbgTally t = sdbg_walk<W, true>(acc, p0, p1, a.k, a.words_tip, a.tip_mode, a.sd_rec + item_base + oi,
+                                       a.sd_labels + (tip_base + ot) * (int64_t)a.words_tip);
+      oi += t.items;
+      ot += t.tips;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// hash family: count consumers.  Equal keys are grouped by an open-addressing table in shared memory (one CAS to claim or
+// find the slot, one atomicAdd for the count); only the distinct SOLID keys -- a few per cent of the bucket at
+// assembly depths -- are then sorted (ballot-ranked stable LSD over the unconsumed key bits) and emitted.
+template <int W>
+__device__ __forceinline__ uint32_t hash_key(const uint32_t *k) {
+  uint32_t h = 0x9e3779b9u;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    h ^= k[i];
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+  }
+  h *= 0xc2b2ae35u;
+  return h ^ (h >> 16);
+}
+
+template <int W, int NT, int MODE>
+__global__ void __launch_bounds__(NT) k_count(LocalArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int NWARP = NT / 32;
+  constexpr bool WEIGHTED = MODE == kCountMerge;
+  constexpr int WR = WEIGHTED ? W + 1 : W;
+  const int tid = threadIdx.x;
+  const int cap = a.cap;
+
+  uint32_t *rec = smem;                                                  // [cap*WR]
+  uint32_t *table = rec + (size_t)cap * WR;                              // [8192] owner<<16 | count   (weighted: owner)
+  uint32_t *tcnt = table + kHashSlots;                                   // [8192] weighted only
+  uint16_t *sidx = reinterpret_cast<uint16_t *>(WEIGHTED ? tcnt + kHashSlots : tcnt);   // [2048] solid key -> record
+  uint16_t *permA = sidx + kSolidMax, *permB = permA + kSolidMax, *rk = permB + kSolidMax;
+  uint32_t *scnt = reinterpret_cast<uint32_t *>(rk + kSolidMax);         // [2048] solid key -> multiplicity
+  uint32_t *s_small = scnt + kSolidMax;                                  // [64]
+  uint32_t *strip = s_small + 64;                                        // [NT+1]
+  uint32_t *scratch = strip + NT + 1;                                    // [34]
+  int *s_flag = reinterpret_cast<int *>(scratch + 34);                   // [8]
+  // the solid-key sort reuses the table once it has been drained
+  uint16_t *whist = reinterpret_cast<uint16_t *>(table);                 // [NWARP][1024] = 16 KB
+  uint32_t *bins = table + NWARP * kLocalBins / 2;                       // [1025]
+
+  int slot;
+  int64_t start, n64;
+  if (a.work) {
+    const WorkItem wi = a.work[blockIdx.x];
+    slot = wi.slot;
+    start = wi.start;
+    n64 = wi.n;
+  } else {
+    slot = (int)blockIdx.x;
+    start = a.bkt_start[slot];
+    n64 = a.bkt_size[slot];
+  }
+  if (n64 == 0) return;
+  int n;
+  auto bail = [&]() {
+    if (tid == 0) {
+      int p = atomicAdd(a.bail_count, 1);
+      a.bail_list[p] = slot;
+    }
+  };
+  // ---- 1. load
+  if constexpr (MODE == kCountMerge) {
+    const int first = (int)start, np = (int)n64;   // pieces: every chunk's (key, count) pairs
+    int total = 0;
+    for (int q = 0; q < np; ++q) total += a.piece_cnt[first + q];
+    if (total > cap) { bail(); return; }
+    int o = 0;
+    for (int q = 0; q < np; ++q) {
+      const int c = a.piece_cnt[first + q];
+      const uint32_t *src = a.pair_arena + a.piece_off[first + q] * (int64_t)WR;
+      for (int i = tid; i < c * WR; i += NT) rec[(size_t)o * WR + i] = src[i];
+      o += c;
+    }
+    n = total;
+    if (n == 0) {
+      if (tid == 0) { a.desc_off[slot] = 0; a.desc_cnt[slot] = 0; }
+      return;
+    }
+  } else {
+    if (n64 > cap) { bail(); return; }
+    n = (int)n64;
+    const uint32_t *src = a.in + start * (int64_t)W;
+    const int nw = n * W;
+    if constexpr (W % 2 == 0) {
+      const uint2 *s2 = reinterpret_cast<const uint2 *>(src);
+      uint2 *d2 = reinterpret_cast<uint2 *>(rec);
+      for (int i = tid; i < nw / 2; i += NT) d2[i] = s2[i];
     } else {
-      const int64_t item_base = a.sd_item_off[slot] + s_items[tid], tip_base = a.sd_tip_off[slot] + s_tips[tid];
-      uint32_t oi = 0, ot = 0;
-      for (int g = gb; g < ge; ++g) {
-        const int p0 = list[g], p1 = (g + 1 < (int)ng) ? (int)list[g + 1] : n;
-        SdbgTally t = sdbg_walk<W, true>(acc, p0, p1, a.k, a.words_tip, a.tip_mode, a.sd_rec + item_base + oi,
-                                         a.sd_labels + (tip_base + ot) * (int64_t)a.words_tip);
-        oi += t.items;
-        ot += t.tips;
+      for (int i = tid; i < nw; i += NT) rec[i] = src[i];
+    }
+  }
+  // table size follows the bucket: a power of two >= 2n keeps probes short, and every block-wide sweep is over `ts` slots
+  int ts = 256;
+  while (ts < 2 * n && ts < kHashSlots) ts <<= 1;
+  const uint32_t tmask = (uint32_t)ts - 1;
+  for (int i = tid; i < ts; i += NT) {
+    table[i] = kEmptySlot;
+    if constexpr (WEIGHTED) tcnt[i] = 0u;
+  }
+  if (tid < 64) s_small[tid] = 0;
+  if (tid < 8) s_flag[tid] = 0;
+  __syncthreads();
+
+  // ---- 2. group equal keys
+  for (int i = tid; i < n; i += NT) {
+    const uint32_t *key = rec + (size_t)i * WR;
+    uint32_t h = hash_key<W>(key) & tmask;
+    for (;;) {
+      uint32_t cur = *reinterpret_cast<volatile uint32_t *>(table + h);
+      if (cur == kEmptySlot) {
+        const uint32_t mine = WEIGHTED ? (uint32_t)i : (((uint32_t)i << 16) | 1u);
+        cur = atomicCAS(table + h, kEmptySlot, mine);
+        if (cur == kEmptySlot) {
+          if constexpr (WEIGHTED) atomicAdd(tcnt + h, key[W]);
+          break;
+        }
       }
+      const uint32_t owner = WEIGHTED ? cur : (cur >> 16);
+      if (cmp_rec<W>(rec + (size_t)owner * WR, key) == 0) {
+        if constexpr (WEIGHTED) atomicAdd(tcnt + h, key[W]);
+        else atomicAdd(table + h, 1u);
+        break;
+      }
+      h = (h + 1) & tmask;
+    }
+  }
+  __syncthreads();
+  auto slot_count = [&](int h) -> uint32_t { return WEIGHTED ? tcnt[h] : (table[h] & 0xffffu); };
+  auto slot_owner = [&](int h) -> uint32_t { return WEIGHTED ? table[h] : (table[h] >> 16); };
+
+  if constexpr (MODE == kCountPairs) {
+    // every distinct key of this chunk with its count -> pair arena (unsorted: the merge groups them again)
+    const int PER = ts / NT;   // ts >= 256 == NT
+    uint32_t c = 0;
+    for (int h = tid * PER; h < (tid + 1) * PER; ++h) c += table[h] != kEmptySlot;
+    strip[tid] = c;
+    if (tid == 0) strip[NT] = 0;
+    __syncthreads();
+    const uint32_t nd = block_excl_scan<NT>(strip, NT + 1, scratch);
+    if (tid == 0) {
+      unsigned long long base = atomicAdd(a.pair_cursor, (unsigned long long)nd);
+      int ok = base + nd <= a.pair_cap;
+      if (!ok) atomicExch(a.overflow_flag + 1, 1);
+      a.piece_off[blockIdx.x] = (int64_t)base;
+      a.piece_cnt[blockIdx.x] = ok ? (int32_t)nd : 0;
+      s_flag[1] = ok;
+      s_flag[2] = (int)(uint32_t)base;
+      s_flag[3] = (int)(uint32_t)(base >> 32);
+    }
+    __syncthreads();
+    if (!s_flag[1]) return;
+    const unsigned long long base = ((unsigned long long)(uint32_t)s_flag[3] << 32) | (uint32_t)s_flag[2];
+    uint32_t o = strip[tid];
+    for (int h = tid * PER; h < (tid + 1) * PER; ++h) {
+      if (table[h] == kEmptySlot) continue;
+      const uint32_t *key = rec + (size_t)slot_owner(h) * WR;
+      uint32_t *dst = a.pair_arena + (base + o) * (unsigned long long)(W + 1);
+#pragma unroll
+      for (int t = 0; t < W; ++t) dst[t] = key[t];
+      dst[W] = slot_count(h);
+      ++o;
+    }
+    return;
+  } else {
+    // ---- 3. solid keys: compact (bail before any side effect if they exceed the fast path)
+    auto is_solid = [&](int h) { return table[h] != kEmptySlot && slot_count(h) >= (uint32_t)a.min_count; };
+    const uint32_t ns = compact_positions<NT>(ts, is_solid, permB /* slot list */, strip, scratch, kSolidMax);
+    if (ns > (uint32_t)kSolidMax) { bail(); return; }
+    // distinct-edge multiplicity histogram (<prefix>.counting), hot small counts stay in shared memory
+    if (a.counting) {
+      for (int h = tid; h < ts; h += NT) {
+        if (table[h] == kEmptySlot) continue;
+        const uint32_t c = min(slot_count(h), (uint32_t)kMaxMul);
+        if (c < 64) atomicAdd(s_small + c, 1u);
+        else atomicAdd(a.counting + c, 1ull);
+      }
+      __syncthreads();
+      if (tid < 64 && s_small[tid]) atomicAdd(a.counting + tid, (unsigned long long)s_small[tid]);
+    }
+    for (uint32_t q = tid; q < ns; q += NT) {
+      const int h = permB[q];
+      sidx[q] = (uint16_t)slot_owner(h);
+      scnt[q] = slot_count(h);
+    }
+    if (tid == 0) {
+      unsigned long long base = atomicAdd(a.arena_cursor, (unsigned long long)ns);
+      int ok = base + ns <= a.arena_cap;
+      if (!ok) atomicExch(a.overflow_flag, 1);
+      a.desc_off[slot] = (int64_t)base;
+      a.desc_cnt[slot] = ok ? (int64_t)ns : 0;
+      s_flag[1] = ok;
+      s_flag[2] = (int)(uint32_t)base;
+      s_flag[3] = (int)(uint32_t)(base >> 32);
+    }
+    __syncthreads();   // the table is dead from here on (whist / bins alias it)
+    if (!s_flag[1] || ns == 0) return;
+    // ---- 4. order the solid keys.  A handful (the usual case): rank by all-pairs comparison; many: stable LSD passes.
+    const uint16_t *cur = nullptr;
+    if (ns > 1 && ns <= 128) {
+      for (uint32_t q = tid; q < ns; q += NT) {   // keys are distinct: rank = number of smaller keys
+        const uint32_t *kq = rec + (size_t)sidx[q] * WR;
+        uint32_t r = 0;
+        for (uint32_t o = 0; o < ns; ++o) r += cmp_rec<W>(rec + (size_t)sidx[o] * WR, kq) < 0;
+        permA[r] = (uint16_t)q;
+      }
+      __syncthreads();
+      cur = permA;
+    } else if (ns > 128) {
+      uint16_t *nxt = permA;
+      int hi = a.sort_bits;
+      while (hi > a.bit_off) {
+        const int nb = min(kLocalDigitBits, hi - a.bit_off);
+        if (lsd_pass<WR, W, NT>(rec, cur, nxt, rk, (int)ns, hi - nb, nb, whist, bins, scratch, sidx)) {
+          cur = nxt;
+          nxt = (nxt == permA) ? permB : permA;
+        }
+        hi -= nb;
+      }
+    }
+    const unsigned long long base = ((unsigned long long)(uint32_t)s_flag[3] << 32) | (uint32_t)s_flag[2];
+    const int We = a.words_edge;
+    for (uint32_t q = tid; q < ns; q += NT) {
+      const uint32_t e = cur ? cur[q] : q;
+      write_edge<W>(a.arena + (base + q) * (unsigned long long)We, rec + (size_t)sidx[e] * WR, We, scnt[e]);
     }
   }
 }
@@ -557,14 +714,19 @@ __global__ void k_serial(LocalArgs a, int nwork) {
         ++o;
       }
     }
-  } else if constexpr (MODE == kSdbgCount) {
-    SdbgTally t = sdbg_walk<W, false>(acc, (int64_t)0, n, a.k, a.words_tip, a.tip_mode, nullptr, nullptr, a.bucket_stats);
-    a.sd_items[slot] = (int64_t)t.items;
-    a.sd_tips[slot] = (int64_t)t.tips;
-    a.sd_large[slot] = (int64_t)t.large;
   } else if constexpr (MODE == kSdbgEmit) {
-    sdbg_walk<W, true>(acc, (int64_t)0, n, a.k, a.words_tip, a.tip_mode, a.sd_rec + a.sd_item_off[slot],
-                       a.sd_labels + a.sd_tip_off[slot] * (int64_t)a.words_tip);
+    SdbgTally t = sdbg_walk<W, false>(acc, (int64_t)0, n, a.k, a.words_tip, a.tip_mode, nullptr, nullptr, a.bucket_stats);
+    const unsigned long long ib = atomicAdd(a.sd_cursor, (unsigned long long)t.items);
+    const unsigned long long tb = atomicAdd(a.sd_cursor + 1, (unsigned long long)t.tips);
+    const bool ok = ib + t.items <= a.sd_item_cap && tb + t.tips <= a.sd_tip_cap;
+    if (!ok) atomicExch(a.overflow_flag, 1);
+    a.sd_item_off[slot] = (int64_t)ib;
+    a.sd_tip_off[slot] = (int64_t)tb;
+    a.sd_items[slot] = ok ? (int64_t)t.items : 0;
+    a.sd_tips[slot] = ok ? (int64_t)t.tips : 0;
+    a.sd_large[slot] = ok ? (int64_t)t.large : 0;
+    if (ok)
+      sdbg_walk<W, true>(acc, (int64_t)0, n, a.k, a.words_tip, a.tip_mode, a.sd_rec + ib, a.sd_labels + tb * (unsigned long long)a.words_tip);
   }
 }
 

@@ -6,8 +6,8 @@
 //   k_level_scatter : rank in shared memory, stage, coalesced copy-out
 // A Producer feeds a tile of records: ReadsProducer computes canonical (k+1)-mer keys straight from
 // 2-bit packed reads (so unsorted keys are never written to HBM), RecordsProducer re-reads records that
-// an earlier level wrote.  Ranking is warp-private (match.any + one leader update), never a per-key
-// shared-memory atomic.  Keys only, so the partition need not be stable.
+// an earlier level wrote.  Ranking is one shared-memory atomicAdd per record on a CTA-wide counter array (keys only, so
+// the partition need not be stable; on B200 that is ~20x cheaper than match.any, see tools/ubench.cu).
 #pragma once
 #include "common.cuh"
 
@@ -171,36 +171,31 @@ struct ReadsProducer {
 };
 
 // ============================================================ histogram
-// grid.x = number of tiles; dynamic smem = whist (u16 [NT/32][nbins]) + producer words
+// grid.x = number of tiles; dynamic smem = CTA histogram (u32 [nbins]) + producer words.
+// Shared-memory atomics are the ranking primitive: measured on B200 (tools/ubench.cu) a warp-wide shared atomicAdd on
+// scattered counters costs ~3 SM-cycles, match.any ~63 and a 10-ballot loop ~36 (both saturate the ADU pipe).
 template <class P, int W, int NT, int IPT>
 __global__ void __launch_bounds__(NT) k_level_hist(P prod, LevelArgs a, unsigned long long *__restrict__ hist) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int nbins = 1 << a.nbits;
-  constexpr int NWARP = NT / 32;
-  uint16_t *whist = reinterpret_cast<uint16_t *>(smem);                 // [NWARP][nbins]
-  uint32_t *psm = smem + (NWARP * nbins + 1) / 2;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < (NWARP * nbins + 1) / 2; i += NT) smem[i] = 0;
+  uint32_t *s_hist = smem;                 // [nbins]
+  uint32_t *psm = smem + nbins;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < nbins; i += NT) s_hist[i] = 0;
   typename P::Tile t = prod.setup(blockIdx.x, psm);   // contains a __syncthreads
-  uint16_t *wh = whist + warp * nbins;
 #pragma unroll 4
   for (int i = 0; i < IPT; ++i) {
     uint32_t r[W];
     int j = i * NT + tid;
     bool valid = prod.get(t, psm, j, r);
     uint32_t d = rec_digit<W>(r, a.bit_off, a.nbits);
-    valid = valid && d >= a.dlo && d < a.dhi;
-    unsigned m = match_digit(d, valid);
-    if (valid && lane == (unsigned)(__ffs(m) - 1)) wh[d] = (uint16_t)(wh[d] + __popc(m));
-    __syncwarp();
+    if (valid && d >= a.dlo && d < a.dhi) atomicAdd(s_hist + d, 1u);
   }
   __syncthreads();
   unsigned long long *h = hist + (size_t)t.seg * nbins;
   for (int b = tid; b < nbins; b += NT) {
-    uint32_t acc = 0;
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) acc += whist[w * nbins + b];
-    if (acc) atomicAdd(h + b, (unsigned long long)acc);
+    uint32_t c = s_hist[b];
+    if (c) atomicAdd(h + b, (unsigned long long)c);
   }
 }
 
@@ -285,8 +280,7 @@ __global__ void k_level_scan(const unsigned long long *hist, int nbins, const in
 
 // ============================================================ scatter
 // dynamic smem layout (uint32 units):
-//   whist   u16 [NWARP][nbins]
-//   s_tot   u32 [nbins]      bin totals, then exclusive starts
+//   s_cnt   u32 [nbins]      per-bin counters (rank = atomicAdd), then exclusive starts
 //   s_gd    i64 [nbins]      global record index of the bin's first staged record minus its staged index
 //   scratch u32 [34]
 //   stage   u32 [T*W]
@@ -294,7 +288,7 @@ __global__ void k_level_scan(const unsigned long long *hist, int nbins, const in
 template <int W>
 __host__ __device__ inline size_t scatter_smem_bytes(int NT, int T, int nbits, int prod_words) {
   size_t nb = (size_t)1 << nbits;
-  size_t words = ((NT / 32) * nb + 1) / 2 + nb + 2 * nb + 34 + 2 + (size_t)T * W + prod_words;
+  size_t words = nb + 2 * nb + 34 + 4 + (size_t)T * W + prod_words;
   return words * 4;
 }
 
@@ -302,13 +296,11 @@ template <class P, int W, int NT, int IPT>
 __global__ void __launch_bounds__(NT) k_level_scatter(P prod, LevelArgs a, unsigned long long *__restrict__ cursor,
                                                       uint32_t *__restrict__ out) {
   extern __shared__ __align__(16) uint32_t smem[];
-  constexpr int NWARP = NT / 32;
   constexpr int T = NT * IPT;
   const int nbins = 1 << a.nbits;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint16_t *whist = reinterpret_cast<uint16_t *>(smem);
-  uint32_t *s_tot = smem + (NWARP * nbins + 1) / 2;
-  uint32_t *s_gd32 = s_tot + nbins;
+  const int tid = threadIdx.x;
+  uint32_t *s_cnt = smem;
+  uint32_t *s_gd32 = s_cnt + nbins;
   if ((reinterpret_cast<uintptr_t>(s_gd32) & 7) != 0) s_gd32 += 1;   // 8-byte align
   long long *s_gd = reinterpret_cast<long long *>(s_gd32);
   uint32_t *scratch = s_gd32 + 2 * nbins;
@@ -316,57 +308,35 @@ __global__ void __launch_bounds__(NT) k_level_scatter(P prod, LevelArgs a, unsig
   if ((reinterpret_cast<uintptr_t>(stage) & 7) != 0) stage += 1;
   uint32_t *psm = stage + (size_t)T * W;
 
-  for (int i = tid; i < (NWARP * nbins + 1) / 2; i += NT) smem[i] = 0;
+  for (int i = tid; i < nbins; i += NT) s_cnt[i] = 0;
   typename P::Tile t = prod.setup(blockIdx.x, psm);   // contains a __syncthreads
 
   uint32_t rec[IPT][W];
-  uint32_t rk[IPT];   // digit << 16 | rank within (warp, digit); 0xffffffff = dropped
-  uint16_t *wh = whist + warp * nbins;
+  uint32_t rk[IPT];   // digit << 16 | rank within the bin; 0xffffffff = dropped
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
     int j = i * NT + tid;
     bool valid = prod.get(t, psm, j, rec[i]);
     uint32_t d = rec_digit<W>(rec[i], a.bit_off, a.nbits);
     valid = valid && d >= a.dlo && d < a.dhi;
-    unsigned m = match_digit(d, valid);
-    unsigned leader = (unsigned)(__ffs(m) - 1);
-    uint32_t old = 0;
-    if (valid && lane == leader) {
-      old = wh[d];
-      wh[d] = (uint16_t)(old + __popc(m));
-    }
-    old = __shfl_sync(0xffffffffu, old, valid ? leader : 0);
-    rk[i] = valid ? ((d << 16) | (old + __popc(m & lanemask_lt()))) : 0xffffffffu;
-    __syncwarp();
+    rk[i] = valid ? ((d << 16) | atomicAdd(s_cnt + d, 1u)) : 0xffffffffu;
   }
   __syncthreads();
-  // per-bin: exclusive prefix over warps, total per bin
-  for (int b = tid; b < nbins; b += NT) {
-    uint32_t acc = 0;
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) {
-      uint32_t c = whist[w * nbins + b];
-      whist[w * nbins + b] = (uint16_t)acc;
-      acc += c;
-    }
-    s_tot[b] = acc;
-    s_gd[b] = (long long)acc;   // stash the count for the reservation below
-  }
+  for (int b = tid; b < nbins; b += NT) s_gd[b] = (long long)s_cnt[b];   // stash the counts for the reservation below
   __syncthreads();
-  const uint32_t total = block_excl_scan<NT>(s_tot, nbins, scratch);
+  const uint32_t total = block_excl_scan<NT>(s_cnt, nbins, scratch);
   for (int b = tid; b < nbins; b += NT) {
     long long c = s_gd[b];
     if (c) {
       unsigned long long g = atomicAdd(cursor + (size_t)t.seg * nbins + b, (unsigned long long)c);
-      s_gd[b] = (long long)g - (long long)s_tot[b];
+      s_gd[b] = (long long)g - (long long)s_cnt[b];
     }
   }
   // stage records in bin order
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
     if (rk[i] != 0xffffffffu) {
-      uint32_t d = rk[i] >> 16;
-      uint32_t pos = s_tot[d] + wh[d] + (rk[i] & 0xffffu);
+      uint32_t pos = s_cnt[rk[i] >> 16] + (rk[i] & 0xffffu);
 #pragma unroll
       for (int c = 0; c < W; ++c) stage[(size_t)pos * W + c] = rec[i][c];
     }
