@@ -59,6 +59,7 @@ __device__ __forceinline__ int cmp_rec(const uint32_t *a, const uint32_t *b) {
 // nbits (1..kMaxDigitBits) starting bit_off bits below the MSB of word 0 of a W-word record held in registers.
 template <int W>
 __device__ __forceinline__ uint32_t rec_digit(const uint32_t (&r)[W], int bit_off, int nbits) {
+  if (bit_off + nbits <= 32) return (r[0] << bit_off) >> (32 - nbits);   // the partition levels live in word 0
   int wi = bit_off >> 5, sh = bit_off & 31;
   uint32_t hi = 0, lo = 0;
 #pragma unroll
@@ -71,6 +72,7 @@ __device__ __forceinline__ uint32_t rec_digit(const uint32_t (&r)[W], int bit_of
 // same, record in memory
 template <int W>
 __device__ __forceinline__ uint32_t rec_digit_mem(const uint32_t *r, int bit_off, int nbits) {
+  if (bit_off + nbits <= 32) return (r[0] << bit_off) >> (32 - nbits);
   int wi = bit_off >> 5, sh = bit_off & 31;
   uint32_t hi = r[wi], lo = (wi + 1 < W) ? r[wi + 1] : 0u;
   return __funnelshift_l(lo, hi, sh) >> (32 - nbits);

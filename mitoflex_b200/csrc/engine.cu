@@ -338,6 +338,18 @@ static void launch_local(Ctx &c, const LocalArgs &a, int grid) {
   MF_LAUNCH_CHECK();
   c.launches++;
 }
+template <int W>
+static void launch_count_fast(Ctx &c, const LocalArgs &a, int grid) {
+  if (grid <= 0) return;
+  if constexpr (W <= 2) {
+    size_t smem = fast_smem_bytes();
+    auto kern = k_count_fast<W, kLocalNT>;
+    set_smem(kern, smem);
+    kern<<<grid, kLocalNT, smem, c.stream>>>(a);
+    MF_LAUNCH_CHECK();
+    c.launches++;
+  }
+}
 template <int W, int MODE>
 static void launch_serial(Ctx &c, const LocalArgs &a, int nwork) {
   if (nwork <= 0) return;
@@ -490,12 +502,37 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
     a.bail_list = d_bail;
     a.bail_count = d_flags;
     a.overflow_flag = d_flags + 1;
-    {
+    int flags[3];
+    if constexpr (W <= 2) {
+      // keys of <= 64 bits: stream every bucket through the key-resident hash table (any bucket size)
+      {
+        Stage st(c, "local_count");
+        launch_count_fast<W>(c, a, b.nslots);
+      }
+      c.d2h(flags, d_flags, sizeof(int) * 3);
+      if (flags[0] > 0) {
+        // buckets with too many distinct keys for the table: general path on exactly those slots
+        Stage st(c, "local_count_general");
+        std::vector<int32_t> slots(flags[0]);
+        c.d2h(slots.data(), d_bail, sizeof(int32_t) * flags[0]);
+        std::sort(slots.begin(), slots.end());
+        std::vector<WorkItem> wi;
+        for (int sl : slots) wi.push_back(WorkItem{0, 0, sl});
+        std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &slots);
+        for (size_t i = 0; i < rs.size(); ++i) { wi[i].start = rs[i].start; wi[i].n = (int32_t)std::min<int64_t>(rs[i].size, INT32_MAX); }
+        c.ov[7].reserve(sizeof(WorkItem) * wi.size());
+        c.h2d(c.ov[7].p, wi.data(), sizeof(WorkItem) * wi.size());
+        MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), c.stream));
+        LocalArgs ga = a;
+        ga.work = c.ov[7].as<WorkItem>();
+        launch_local<W, kCountEmit>(c, ga, (int)wi.size());
+        c.d2h(flags, d_flags, sizeof(int) * 3);
+      }
+    } else {
       Stage st(c, "local_count");
       launch_local<W, kCountEmit>(c, a, b.nslots);
+      c.d2h(flags, d_flags, sizeof(int) * 3);
     }
-    int flags[3];
-    c.d2h(flags, d_flags, sizeof(int) * 3);
     if (flags[0] > 0) {
       // Buckets larger than shared memory.  With deep coverage (a mitogenome at 10^4 x) they are a few keys repeated
       // thousands of times: combine chunk by chunk into (key, count) pairs, then merge the pairs of each bucket.

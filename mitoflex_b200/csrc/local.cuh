@@ -223,8 +223,17 @@ __device__ __forceinline__ unsigned peers_by_ballot(uint32_t d, bool valid, int 
   }
   return valid ? m : 0u;
 }
+template <int W, bool SWAP64>
+__device__ __forceinline__ uint32_t lsd_digit(const uint32_t *r, int bit_lo, int nbits) {
+  if constexpr (SWAP64) {   // a u64 key stored natively: word 1 is the high half
+    const unsigned long long key = ((unsigned long long)r[1] << 32) | r[0];
+    return (uint32_t)((key << bit_lo) >> (64 - nbits));
+  } else {
+    return rec_digit_mem<W>(r, bit_lo, nbits);
+  }
+}
 // `via` (nullable) maps sorted entities to records: record = via[entity]
-template <int WR, int W, int NT>
+template <int WR, int W, int NT, bool SWAP64 = false>
 __device__ __forceinline__ bool lsd_pass(const uint32_t *rec, const uint16_t *idx_in, uint16_t *idx_out, uint16_t *rk, int n,
                                          int bit_lo, int nbits, uint16_t *whist, uint32_t *bins, uint32_t *scratch,
                                          const uint16_t *via = nullptr) {
@@ -244,7 +253,7 @@ __device__ __forceinline__ bool lsd_pass(const uint32_t *rec, const uint16_t *id
     if (valid) {
       int r = idx_in ? idx_in[p] : p;
       if (via) r = via[r];
-      d = rec_digit_mem<W>(rec + (size_t)r * WR, bit_lo, nbits);
+      d = lsd_digit<W, SWAP64>(rec + (size_t)r * WR, bit_lo, nbits);
     }
     const unsigned m = peers_by_ballot(d, valid, nbits);
     const unsigned leader = (unsigned)(__ffs(m) - 1);
@@ -279,7 +288,7 @@ __device__ __forceinline__ bool lsd_pass(const uint32_t *rec, const uint16_t *id
     if (p < n) {
       const int e = idx_in ? idx_in[p] : p;
       const int r = via ? via[e] : e;
-      const uint32_t d = rec_digit_mem<W>(rec + (size_t)r * WR, bit_lo, nbits);
+      const uint32_t d = lsd_digit<W, SWAP64>(rec + (size_t)r * WR, bit_lo, nbits);
       idx_out[bins[d] + wh[d] + rk[p]] = (uint16_t)e;
     }
   }
@@ -679,6 +688,155 @@ __global__ void __launch_bounds__(NT) k_count(LocalArgs a) {
       const uint32_t e = cur ? cur[q] : q;
       write_edge<W>(a.arena + (base + q) * (unsigned long long)We, rec + (size_t)sidx[e] * WR, We, scnt[e]);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast count path for keys of at most 64 bits (k <= 31): the bucket is STREAMED from global memory into a shared hash
+// table that stores the keys themselves (64-bit CAS) and 32-bit counts, so a bucket of any size fits as long as its
+// DISTINCT keys do -- a mitochondrial (k+1)-mer seen 10^4 times is one slot.  A thread whose atomicAdd carries a count
+// across --min-count appends the slot to the solid list; only those keys are ordered and emitted.
+constexpr int kFastSlots = 4096;
+constexpr int kFastProbeLimit = 96;
+constexpr unsigned long long kEmptyKey = 0xffffffffffffffffull;   // never a canonical key
+
+inline size_t fast_smem_bytes() {
+  // tkeys u64[4096] | tcnt u32[4096] | sidx,permA,permB,rk u16[2048] | scnt u32[2048] | bins u32[1025] | small u32[64] | scratch
+  return (size_t)kFastSlots * 12 + 4 * kSolidMax * 2 + kSolidMax * 4 + (kLocalBins + 1) * 4 + 64 * 4 + 64 * 4;
+}
+
+template <int W, int NT>
+__global__ void __launch_bounds__(NT) k_count_fast(LocalArgs a) {
+  static_assert(W <= 2, "keys must fit 64 bits");
+  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int NWARP = NT / 32;
+  const int tid = threadIdx.x;
+  unsigned long long *tkeys = reinterpret_cast<unsigned long long *>(smem);            // [4096]
+  uint32_t *tcnt = smem + 2 * kFastSlots;                                              // [4096]
+  uint16_t *sidx = reinterpret_cast<uint16_t *>(tcnt + kFastSlots);                    // [2048] solid -> slot
+  uint16_t *permA = sidx + kSolidMax, *permB = permA + kSolidMax, *rk = permB + kSolidMax;
+  uint32_t *scnt = reinterpret_cast<uint32_t *>(rk + kSolidMax);                       // [2048]
+  uint32_t *bins = scnt + kSolidMax;                                                   // [1025]
+  uint32_t *s_small = bins + kLocalBins + 1;                                           // [64]
+  uint32_t *scratch = s_small + 64;                                                    // [34]
+  int *s_flag = reinterpret_cast<int *>(scratch + 34);                                 // [8]: 0 bail, 1 ok, 2..3 base, 4 ns
+  uint16_t *whist = reinterpret_cast<uint16_t *>(tcnt);                                // LSD scratch aliases the counts
+
+  const int slot = a.work ? a.work[blockIdx.x].slot : (int)blockIdx.x;
+  const int64_t start = a.bkt_start[slot];
+  const int64_t n = a.bkt_size[slot];
+  if (n == 0) return;
+  for (int i = tid; i < kFastSlots; i += NT) {
+    tkeys[i] = kEmptyKey;
+    tcnt[i] = 0u;
+  }
+  if (tid < 64) s_small[tid] = 0;
+  if (tid < 8) s_flag[tid] = 0;
+  __syncthreads();
+
+  // ---- 1. stream the bucket through the table
+  const uint32_t m = (uint32_t)a.min_count;
+  auto insert = [&](unsigned long long key) {
+    uint32_t h = (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> (64 - 12));
+    for (int probe = 0; probe < kFastProbeLimit; ++probe) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tkeys + h);
+      if (cur == kEmptyKey) cur = atomicCAS(tkeys + h, kEmptyKey, key);
+      if (cur == kEmptyKey || cur == key) {
+        const uint32_t old = atomicAdd(tcnt + h, 1u);
+        if (old + 1 == m) {
+          const int q = atomicAdd(s_flag + 4, 1);
+          if (q < kSolidMax) sidx[q] = (uint16_t)h;
+        }
+        return;
+      }
+      h = (h + 1) & (kFastSlots - 1);
+    }
+    s_flag[0] = 1;   // table too crowded: this bucket takes the general path
+  };
+  if constexpr (W == 2) {
+    const uint2 *src = reinterpret_cast<const uint2 *>(a.in) + start;
+    int64_t i = tid;
+    for (; i + 3 * NT < n; i += 4 * NT) {
+      const uint2 v0 = src[i], v1 = src[i + NT], v2 = src[i + 2 * NT], v3 = src[i + 3 * NT];
+      insert(((unsigned long long)v0.x << 32) | v0.y);
+      insert(((unsigned long long)v1.x << 32) | v1.y);
+      insert(((unsigned long long)v2.x << 32) | v2.y);
+      insert(((unsigned long long)v3.x << 32) | v3.y);
+    }
+    for (; i < n; i += NT) {
+      const uint2 v = src[i];
+      insert(((unsigned long long)v.x << 32) | v.y);
+    }
+  } else {
+    const uint32_t *src = a.in + start;
+    for (int64_t i = tid; i < n; i += NT) insert((unsigned long long)src[i] << 32);
+  }
+  __syncthreads();
+  const int ns_raw = s_flag[4];
+  if (s_flag[0] || ns_raw > kSolidMax) {
+    if (tid == 0) {
+      int p = atomicAdd(a.bail_count, 1);
+      a.bail_list[p] = slot;
+    }
+    return;
+  }
+  const uint32_t ns = (uint32_t)ns_raw;
+  // ---- 2. distinct-edge multiplicity histogram (<prefix>.counting)
+  if (a.counting) {
+    for (int h = tid; h < kFastSlots; h += NT) {
+      if (tkeys[h] == kEmptyKey) continue;
+      const uint32_t c = min(tcnt[h], (uint32_t)kMaxMul);
+      if (c < 64) atomicAdd(s_small + c, 1u);
+      else atomicAdd(a.counting + c, 1ull);
+    }
+    __syncthreads();
+    if (tid < 64 && s_small[tid]) atomicAdd(a.counting + tid, (unsigned long long)s_small[tid]);
+  }
+  for (uint32_t q = tid; q < ns; q += NT) scnt[q] = tcnt[sidx[q]];
+  if (tid == 0) {
+    unsigned long long base = atomicAdd(a.arena_cursor, (unsigned long long)ns);
+    int ok = base + ns <= a.arena_cap;
+    if (!ok) atomicExch(a.overflow_flag, 1);
+    a.desc_off[slot] = (int64_t)base;
+    a.desc_cnt[slot] = ok ? (int64_t)ns : 0;
+    s_flag[1] = ok;
+    s_flag[2] = (int)(uint32_t)base;
+    s_flag[3] = (int)(uint32_t)(base >> 32);
+  }
+  __syncthreads();   // tcnt is dead from here on (the LSD scratch aliases it)
+  if (!s_flag[1] || ns == 0) return;
+  // ---- 3. order the solid keys (distinct): all-pairs rank for a handful, stable LSD passes otherwise
+  const uint16_t *cur = nullptr;
+  if (ns > 1 && ns <= 160) {
+    for (uint32_t q = tid; q < ns; q += NT) {
+      const unsigned long long kq = tkeys[sidx[q]];
+      uint32_t r = 0;
+      for (uint32_t o = 0; o < ns; ++o) r += tkeys[sidx[o]] < kq;
+      permA[r] = (uint16_t)q;
+    }
+    __syncthreads();
+    cur = permA;
+  } else if (ns > 160) {
+    // keys live in the table as (hi, lo) words == little-endian u64: present them big-endian to the digit reader
+    const uint32_t *rec = reinterpret_cast<const uint32_t *>(tkeys);
+    uint16_t *nxt = permA;
+    int hi = a.sort_bits;
+    while (hi > a.bit_off) {
+      const int nb = min(kLocalDigitBits, hi - a.bit_off);
+      if (lsd_pass<2, 2, NT, true>(rec, cur, nxt, rk, (int)ns, hi - nb, nb, whist, bins, scratch, sidx)) {
+        cur = nxt;
+        nxt = (nxt == permA) ? permB : permA;
+      }
+      hi -= nb;
+    }
+  }
+  const unsigned long long base = ((unsigned long long)(uint32_t)s_flag[3] << 32) | (uint32_t)s_flag[2];
+  const int We = a.words_edge;
+  for (uint32_t q = tid; q < ns; q += NT) {
+    const uint32_t e = cur ? cur[q] : q;
+    const unsigned long long key = tkeys[sidx[e]];
+    const uint32_t kw[2] = {(uint32_t)(key >> 32), (uint32_t)key};
+    write_edge<W>(a.arena + (base + q) * (unsigned long long)We, kw, We, scnt[e]);
   }
 }
 

@@ -122,6 +122,29 @@ struct ReadsProducer {
   }
   __device__ __forceinline__ bool get(const Tile &t, const uint32_t *sm, int j, uint32_t (&key)[W]) const {
     const int K1 = k + 1;
+    if constexpr (W <= 2) {
+      // the whole (k+1)-mer fits 64 bits (k <= 31): one 64-bit window, one validity funnel shift
+      const uint32_t *sb = sm + n_seq_words(T);
+      const int bit = j + 1;
+      uint32_t v = __funnelshift_r(sb[bit >> 5], sb[(bit >> 5) + 1], bit & 31);
+      v &= (1u << k) - 1u;                                   // k <= 31
+      const bool valid = j < t.n && (t.base + j + K1 <= n_bases) && v == 0;
+      const int wi = j >> 4, sh = (j & 15) * 2;
+      const uint32_t w0 = sm[wi], w1 = sm[wi + 1], w2 = sm[wi + 2];
+      const unsigned long long raw0 =
+          ((unsigned long long)__funnelshift_l(w1, w0, sh) << 32) | __funnelshift_l(w2, w1, sh);
+      const int bits = 2 * K1;
+      const unsigned long long mask = ~0ull << (64 - bits);
+      const unsigned long long raw = raw0 & mask;
+      const unsigned long long cmpl = ~raw0 & mask;
+      unsigned long long rv = __brevll(raw);                 // reversed bit string, right aligned
+      rv = ((rv & 0x5555555555555555ull) << 1) | ((rv >> 1) & 0x5555555555555555ull);
+      rv <<= (64 - bits);
+      const unsigned long long kk = rv < cmpl ? rv : cmpl;
+      key[0] = (uint32_t)(kk >> 32);
+      if constexpr (W == 2) key[1] = (uint32_t)kk;
+      return valid;
+    }
     bool valid = j < t.n && (t.base + j + K1 <= n_bases);
     // no read may start inside (j, j+k]
     const uint32_t *sb = sm + n_seq_words(T);
@@ -313,12 +336,13 @@ __global__ void __launch_bounds__(NT) k_level_scatter(P prod, LevelArgs a, unsig
 
   uint32_t rec[IPT][W];
   uint32_t rk[IPT];   // digit << 16 | rank within the bin; 0xffffffff = dropped
+  bool ok[IPT];
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) ok[i] = prod.get(t, psm, i * NT + tid, rec[i]);   // all loads in flight before any atomic
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
-    int j = i * NT + tid;
-    bool valid = prod.get(t, psm, j, rec[i]);
-    uint32_t d = rec_digit<W>(rec[i], a.bit_off, a.nbits);
-    valid = valid && d >= a.dlo && d < a.dhi;
+    const uint32_t d = rec_digit<W>(rec[i], a.bit_off, a.nbits);
+    const bool valid = ok[i] && d >= a.dlo && d < a.dhi;
     rk[i] = valid ? ((d << 16) | atomicAdd(s_cnt + d, 1u)) : 0xffffffffu;
   }
   __syncthreads();
