@@ -169,9 +169,19 @@ __global__ void k_gather_edges(const uint32_t *__restrict__ arena, const int64_t
   uint32_t *dst = out + out_off[slot] * We;
   for (int64_t x = threadIdx.x & 31; x < words; x += 32) dst[x] = src[x];
 }
+// edges are sorted: bucket b holds [lower_bound(b << 16), lower_bound((b + 1) << 16)) of the first key word
 __global__ void k_edge_buckets(const uint32_t *edges, int64_t n, int We, unsigned long long *counts) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(counts + (edges[i * We] >> 16), 1ull);
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= kNumBuckets) return;
+  auto lower = [&](uint32_t bucket) -> int64_t {   // first edge whose bucket >= `bucket`
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if ((edges[mid * We] >> 16) < bucket) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  counts[b] = (unsigned long long)((b + 1 < kNumBuckets ? lower((uint32_t)b + 1) : n) - lower((uint32_t)b));
 }
 
 // ------------------------------------------------------------------ plan
@@ -671,7 +681,7 @@ static void edge_bucket_counts(Ctx &c, const EdgesView &e) {
   MF_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * kNumBuckets));
   MF_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * kNumBuckets, c.stream));
   if (e.n_edges > 0) {
-    k_edge_buckets<<<(unsigned)div_ceil64(e.n_edges, 256), 256, 0, c.stream>>>(e.edges, e.n_edges, e.words, d);
+    k_edge_buckets<<<kNumBuckets / 256, 256, 0, c.stream>>>(e.edges, e.n_edges, e.words, d);
     MF_LAUNCH_CHECK();
     c.launches++;
   }
@@ -980,7 +990,7 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
     a.bkt_start = b.start;
     a.bkt_size = b.size;
     a.bit_off = bit_off;
-    a.sort_bits = 32 * WI;
+    a.sort_bits = 32 * WI - 16;   // the walker takes the largest multiplicity of equal (k-mer, b) items itself
     a.cap = p.cap;
     a.k = k;
     a.tip_mode = tip_mode;
@@ -1008,7 +1018,7 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
     if (flags[0] > 0) {
       Stage st(c, "fallback");
       std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &bail_slots);
-      if (!sorted_fallback) sort_ranges<WI>(c, cur, other, rs, bit_off, 32 * WI);
+      if (!sorted_fallback) sort_ranges<WI>(c, cur, other, rs, bit_off, 32 * WI - 16);
       sorted_fallback = true;
       std::vector<WorkItem> hw;
       for (size_t i = 0; i < rs.size(); ++i) hw.push_back(WorkItem{rs[i].start, 0, bail_slots[i]});

@@ -160,9 +160,11 @@ __device__ __forceinline__ SdbgTally sdbg_walk(const Acc &acc, I b, I e, int k, 
       const uint32_t *it = acc(i);
       const int ca = item_a<W>(it, k), cb = item_b<W>(it);
       j = i + 1;
+      uint32_t inv_mul = it[W - 1] & 0xffffu;   // 65535 - multiplicity: the smallest wins (megahit sorts it first)
       while (j < ge) {
         const uint32_t *nx = acc(j);
         if (item_a<W>(nx, k) != ca || item_b<W>(nx) != cb) break;
+        inv_mul = min(inv_mul, nx[W - 1] & 0xffffu);
         ++j;
       }
       int is_dollar = 0;
@@ -177,7 +179,7 @@ __device__ __forceinline__ SdbgTally sdbg_walk(const Acc &acc, I b, I e, int k, 
       outputed_b |= 1 << cb;
       const I la = ca == 0 ? last_a0 : ca == 1 ? last_a1 : ca == 2 ? last_a2 : last_a3;
       const int last = (ca == kSentinel) ? 0 : (la == j - 1 ? 1 : 0);
-      const int mul = kMaxMul - (int)(it[W - 1] & 0xffffu);
+      const int mul = kMaxMul - (int)inv_mul;
       if (WRITING) {
         rec_out[t.items] = (uint32_t)w | ((uint32_t)last << 4) | ((uint32_t)is_dollar << 5) | ((uint32_t)mul << 8);
         if (is_dollar) {
@@ -726,7 +728,11 @@ __global__ void __launch_bounds__(NT) k_count_fast(LocalArgs a) {
   const int64_t start = a.bkt_start[slot];
   const int64_t n = a.bkt_size[slot];
   if (n == 0) return;
-  for (int i = tid; i < kFastSlots; i += NT) {
+  // table size follows the bucket (distinct keys are a fraction of it): fewer slots to clear and to sweep
+  int ts_log = 9;
+  while ((1 << ts_log) < n && ts_log < 12) ++ts_log;
+  const int ts = 1 << ts_log;
+  for (int i = tid; i < ts; i += NT) {
     tkeys[i] = kEmptyKey;
     tcnt[i] = 0u;
   }
@@ -737,7 +743,7 @@ __global__ void __launch_bounds__(NT) k_count_fast(LocalArgs a) {
   // ---- 1. stream the bucket through the table
   const uint32_t m = (uint32_t)a.min_count;
   auto insert = [&](unsigned long long key) {
-    uint32_t h = (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> (64 - 12));
+    uint32_t h = (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> (64 - ts_log));
     for (int probe = 0; probe < kFastProbeLimit; ++probe) {
       unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tkeys + h);
       if (cur == kEmptyKey) cur = atomicCAS(tkeys + h, kEmptyKey, key);
@@ -749,7 +755,7 @@ __global__ void __launch_bounds__(NT) k_count_fast(LocalArgs a) {
         }
         return;
       }
-      h = (h + 1) & (kFastSlots - 1);
+      h = (h + 1) & (ts - 1);
     }
     s_flag[0] = 1;   // table too crowded: this bucket takes the general path
   };
@@ -783,7 +789,7 @@ __global__ void __launch_bounds__(NT) k_count_fast(LocalArgs a) {
   const uint32_t ns = (uint32_t)ns_raw;
   // ---- 2. distinct-edge multiplicity histogram (<prefix>.counting)
   if (a.counting) {
-    for (int h = tid; h < kFastSlots; h += NT) {
+    for (int h = tid; h < ts; h += NT) {
       if (tkeys[h] == kEmptyKey) continue;
       const uint32_t c = min(tcnt[h], (uint32_t)kMaxMul);
       if (c < 64) atomicAdd(s_small + c, 1u);
