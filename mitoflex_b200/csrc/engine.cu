@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include "items.cuh"
 #include "local.cuh"
 #include "partition.cuh"
@@ -104,7 +105,11 @@ void Ctx::h2d(void *dst, const void *src, size_t bytes) {
   if (bytes) MF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
   MF_CUDA(cudaStreamSynchronize(stream));
 }
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 void Ctx::begin_call() {
+  call_t0 = now_ms();
   MF_CUDA(cudaSetDevice(device));
   for (auto &s : stages) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
   stages.clear();
@@ -113,6 +118,7 @@ void Ctx::begin_call() {
 }
 void Ctx::end_call() {
   MF_CUDA(cudaStreamSynchronize(stream));
+  if (profiling && getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] call took %.3f ms on the host clock\n", now_ms() - call_t0);
   if (profiling) {
     char buf[128];
     for (auto &s : stages) {
@@ -120,6 +126,7 @@ void Ctx::end_call() {
       cudaEventElapsedTime(&ms, s.e0, s.e1);
       snprintf(buf, sizeof buf, "%s=%.4f;", s.name.c_str(), ms);
       profile += buf;
+      if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] %-20s host+%9.3f ms  device %9.3f ms\n", s.name.c_str(), s.host_ms, ms);
     }
   }
 }
@@ -127,6 +134,7 @@ void Ctx::stage_begin(const char *name) {
   if (!profiling) return;
   StageRec r;
   r.name = name;
+  r.host_ms = now_ms() - call_t0;
   cudaEventCreate(&r.e0);
   cudaEventCreate(&r.e1);
   cudaEventRecord(r.e0, stream);
@@ -204,10 +212,12 @@ static Plan make_plan(int W, int part_limit, int64_t n_est, double density, bool
   Plan p;
   p.W = W;
   p.cap = local_cap(W, hash_family, false);
-  const double target = p.cap * 0.65 / density;
+  // buckets of <= 64-bit keys are streamed through a key-resident table (any size, ~10-40 % of it distinct): ~5000 keys
+  // on average keeps the densest ones (2x) well inside its 4096 slots; everything else must fit shared memory whole
+  const double target = (hash_family && W <= 2) ? 5000.0 : p.cap * 0.65 / density;
   int bits = std::max(1, ceil_log2((double)std::max<int64_t>(n_est, 1) / target));
   bits = std::min(bits, 2 * kMaxDigitBits);
-  bits = env_int("MFSDBG_PART_BITS", bits);
+  bits = env_int(hash_family ? "MFSDBG_COUNT_BITS" : "MFSDBG_SDBG_BITS", bits);
   if (forced_l1 < 0) forced_l1 = env_int("MFSDBG_L1_BITS", -1);
   if (forced_l1 >= 0) {
     p.l1_bits = forced_l1;
@@ -303,8 +313,18 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   // the pageable host vectors above die with this frame: make sure the copies have been consumed
   MF_CUDA(cudaStreamSynchronize(c.stream));
   LevelArgs a{bit_off, nbits, 0u, (uint32_t)nbins};
+  TileDesc *d_tiles_h = (TileDesc *)alloc(sizeof(TileDesc) * std::max<int64_t>(tb_h[nchunk], 1));
+  TileDesc *d_tiles_s = (TileDesc *)alloc(sizeof(TileDesc) * std::max<int64_t>(tb_s[nchunk], 1));
   if (tb_h[nchunk] > 0) {
-    RecordsProducer<W> ph{in, ChunkTable{d_start, d_size, d_seg, d_tbh, nchunk}, C::TH};
+    k_build_tiles<<<(unsigned)div_ceil64(tb_h[nchunk], 256), 256, 0, c.stream>>>(ChunkTable{d_start, d_size, d_seg, d_tbh, nchunk}, C::TH,
+                                                                              tb_h[nchunk], d_tiles_h);
+    k_build_tiles<<<(unsigned)div_ceil64(tb_s[nchunk], 256), 256, 0, c.stream>>>(ChunkTable{d_start, d_size, d_seg, d_tbs, nchunk}, C::TS,
+                                                                              tb_s[nchunk], d_tiles_s);
+    MF_LAUNCH_CHECK();
+    c.launches += 2;
+  }
+  if (tb_h[nchunk] > 0) {
+    RecordsProducer<W> ph{in, d_tiles_h, C::TH};
     size_t smem = ((size_t)1 << nbits) * 4 + 16;
     auto kern = k_level_hist<RecordsProducer<W>, W, C::NT, C::IPT_H>;
     set_smem(kern, smem);
@@ -317,7 +337,7 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   MF_LAUNCH_CHECK();
   c.launches++;
   if (tb_s[nchunk] > 0) {
-    RecordsProducer<W> ps{in, ChunkTable{d_start, d_size, d_seg, d_tbs, nchunk}, C::TS};
+    RecordsProducer<W> ps{in, d_tiles_s, C::TS};
     size_t smem = scatter_smem_bytes<W>(C::NT, C::TS, nbits, 4);
     auto kern = k_level_scatter<RecordsProducer<W>, W, C::NT, C::IPT_S>;
     set_smem(kern, smem);
@@ -353,9 +373,9 @@ static void launch_count_fast(Ctx &c, const LocalArgs &a, int grid) {
   if (grid <= 0) return;
   if constexpr (W <= 2) {
     size_t smem = fast_smem_bytes();
-    auto kern = k_count_fast<W, kLocalNT>;
+    auto kern = k_count_fast<W, kFastNT>;
     set_smem(kern, smem);
-    kern<<<grid, kLocalNT, smem, c.stream>>>(a);
+    kern<<<grid, kFastNT, smem, c.stream>>>(a);
     MF_LAUNCH_CHECK();
     c.launches++;
   }

@@ -29,6 +29,7 @@ struct HostBuf {   // pinned host memory
 struct StageRec {
   std::string name;
   cudaEvent_t e0, e1;
+  double host_ms = 0;   // host clock at stage_begin, relative to begin_call (MFSDBG_TRACE)
 };
 
 struct Ctx {
@@ -44,6 +45,7 @@ struct Ctx {
   std::vector<StageRec> stages;
   std::vector<int> open_stages;
   std::string profile;
+  double call_t0 = 0;
   // results that outlive a call
   DevBuf edges, sdbg_rec, sdbg_labels, sdbg_buckets, sbits, pack_words, pack_starts, synth_words, synth_starts, in_words, in_starts;
   HostBuf out_rec, out_labels;

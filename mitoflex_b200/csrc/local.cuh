@@ -700,11 +700,15 @@ __global__ void __launch_bounds__(NT) k_count(LocalArgs a) {
 // across --min-count appends the slot to the solid list; only those keys are ordered and emitted.
 constexpr int kFastSlots = 4096;
 constexpr int kFastProbeLimit = 96;
+constexpr int kFastNT = 512;
+constexpr int kFastSolidMax = 1024;   // distinct solid keys of one bucket on the fast path
 constexpr unsigned long long kEmptyKey = 0xffffffffffffffffull;   // never a canonical key
 
 inline size_t fast_smem_bytes() {
-  // tkeys u64[4096] | tcnt u32[4096] | sidx,permA,permB,rk u16[2048] | scnt u32[2048] | bins u32[1025] | small u32[64] | scratch
-  return (size_t)kFastSlots * 12 + 4 * kSolidMax * 2 + kSolidMax * 4 + (kLocalBins + 1) * 4 + 64 * 4 + 64 * 4;
+  // tkeys u64[4096] | tcnt u32[4096] | sidx,permA,permB,rk u16[1024] | scnt u32[1024] | bins u32[1025] | small u32[64] | scratch
+  // | whist u16[NWARP][1024]
+  return (size_t)kFastSlots * 12 + 4 * kFastSolidMax * 2 + kFastSolidMax * 4 + (kLocalBins + 1) * 4 + 64 * 4 + 64 * 4 +
+         (size_t)(kFastNT / 32) * kLocalBins * 2;
 }
 
 template <int W, int NT>
@@ -716,13 +720,13 @@ __global__ void __launch_bounds__(NT) k_count_fast(LocalArgs a) {
   unsigned long long *tkeys = reinterpret_cast<unsigned long long *>(smem);            // [4096]
   uint32_t *tcnt = smem + 2 * kFastSlots;                                              // [4096]
   uint16_t *sidx = reinterpret_cast<uint16_t *>(tcnt + kFastSlots);                    // [2048] solid -> slot
-  uint16_t *permA = sidx + kSolidMax, *permB = permA + kSolidMax, *rk = permB + kSolidMax;
-  uint32_t *scnt = reinterpret_cast<uint32_t *>(rk + kSolidMax);                       // [2048]
-  uint32_t *bins = scnt + kSolidMax;                                                   // [1025]
+  uint16_t *permA = sidx + kFastSolidMax, *permB = permA + kFastSolidMax, *rk = permB + kFastSolidMax;
+  uint32_t *scnt = reinterpret_cast<uint32_t *>(rk + kFastSolidMax);                       // [2048]
+  uint32_t *bins = scnt + kFastSolidMax;                                                   // [1025]
   uint32_t *s_small = bins + kLocalBins + 1;                                           // [64]
   uint32_t *scratch = s_small + 64;                                                    // [34]
   int *s_flag = reinterpret_cast<int *>(scratch + 34);                                 // [8]: 0 bail, 1 ok, 2..3 base, 4 ns
-  uint16_t *whist = reinterpret_cast<uint16_t *>(tcnt);                                // LSD scratch aliases the counts
+  uint16_t *whist = reinterpret_cast<uint16_t *>(s_small + 128);                       // [NWARP][1024] (many-solid-keys sort)
 
   const int slot = a.work ? a.work[blockIdx.x].slot : (int)blockIdx.x;
   const int64_t start = a.bkt_start[slot];
@@ -751,7 +755,7 @@ __global__ void __launch_bounds__(NT) k_count_fast(LocalArgs a) {
         const uint32_t old = atomicAdd(tcnt + h, 1u);
         if (old + 1 == m) {
           const int q = atomicAdd(s_flag + 4, 1);
-          if (q < kSolidMax) sidx[q] = (uint16_t)h;
+          if (q < kFastSolidMax) sidx[q] = (uint16_t)h;
         }
         return;
       }
@@ -779,7 +783,7 @@ __global__ void __launch_bounds__(NT) k_count_fast(LocalArgs a) {
   }
   __syncthreads();
   const int ns_raw = s_flag[4];
-  if (s_flag[0] || ns_raw > kSolidMax) {
+  if (s_flag[0] || ns_raw > kFastSolidMax) {
     if (tid == 0) {
       int p = atomicAdd(a.bail_count, 1);
       a.bail_list[p] = slot;
@@ -814,12 +818,15 @@ __global__ void __launch_bounds__(NT) k_count_fast(LocalArgs a) {
   // ---- 3. order the solid keys (distinct): all-pairs rank for a handful, stable LSD passes otherwise
   const uint16_t *cur = nullptr;
   if (ns > 1 && ns <= 160) {
-    for (uint32_t q = tid; q < ns; q += NT) {
-      const unsigned long long kq = tkeys[sidx[q]];
-      uint32_t r = 0;
-      for (uint32_t o = 0; o < ns; ++o) r += tkeys[sidx[o]] < kq;
-      permA[r] = (uint16_t)q;
+    uint32_t *rank = bins;   // [ns] <= 1025
+    for (uint32_t q = tid; q < ns; q += NT) rank[q] = 0;
+    __syncthreads();
+    for (uint32_t x = tid; x < ns * ns; x += NT) {   // every pair once, spread over the whole CTA
+      const uint32_t q = x / ns, o = x - q * ns;
+      if (tkeys[sidx[o]] < tkeys[sidx[q]]) atomicAdd(rank + q, 1u);
     }
+    __syncthreads();
+    for (uint32_t q = tid; q < ns; q += NT) permA[rank[q]] = (uint16_t)q;
     __syncthreads();
     cur = permA;
   } else if (ns > 160) {

@@ -29,11 +29,35 @@ struct LevelArgs {
   uint32_t dlo, dhi;    // keep only digits in [dlo, dhi) (out-of-core rounds / multi-GPU ownership)
 };
 
+// one tile of a level launch: where its records are and which segment they belong to (built by k_build_tiles so that
+// no CTA has to walk the chunk table with a chain of dependent loads)
+struct TileDesc {
+  int64_t base;
+  int32_t n;
+  int32_t seg;
+};
+__global__ void k_build_tiles(ChunkTable ct, int T, int64_t ntiles, TileDesc *out) {
+  const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= ntiles) return;
+  int lo = 0, hi = ct.nchunk;  // last chunk with tile_base <= tile
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (ct.tile_base[mid] <= tile) lo = mid; else hi = mid;
+  }
+  const int64_t off = (tile - ct.tile_base[lo]) * (int64_t)T;
+  const int64_t rem = ct.size[lo] - off;
+  TileDesc d;
+  d.base = ct.start[lo] + off;
+  d.n = (int32_t)(rem < T ? rem : T);
+  d.seg = ct.seg[lo];
+  out[tile] = d;
+}
+
 // ============================================================ producers
 template <int W>
 struct RecordsProducer {
   const uint32_t *in;
-  ChunkTable ct;
+  const TileDesc *tiles;
   int T;
   static constexpr bool kNeedsSmem = false;
   __host__ __device__ static int smem_words(int, int) { return 4; }
@@ -43,26 +67,13 @@ struct RecordsProducer {
     int n;
     int seg;
   };
-  __device__ __forceinline__ Tile setup(int64_t tile, uint32_t *sm) const {
-    if (threadIdx.x == 0) {
-      int lo = 0, hi = ct.nchunk;  // last chunk with tile_base <= tile
-      while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (ct.tile_base[mid] <= tile) lo = mid; else hi = mid;
-      }
-      int64_t off = (tile - ct.tile_base[lo]) * (int64_t)T;
-      int64_t rem = ct.size[lo] - off;
-      int64_t base = ct.start[lo] + off;
-      sm[0] = (uint32_t)base;
-      sm[1] = (uint32_t)(base >> 32);
-      sm[2] = (uint32_t)(rem < T ? rem : T);
-      sm[3] = (uint32_t)ct.seg[lo];
-    }
-    __syncthreads();
+  __device__ __forceinline__ Tile setup(int64_t tile, uint32_t *) const {
+    const TileDesc d = tiles[tile];   // same address for the whole CTA: one broadcast load
     Tile t;
-    t.base = (int64_t)(((uint64_t)sm[1] << 32) | sm[0]);
-    t.n = (int)sm[2];
-    t.seg = (int)sm[3];
+    t.base = d.base;
+    t.n = d.n;
+    t.seg = d.seg;
+    __syncthreads();                  // the callers zero shared counters before setup()
     return t;
   }
   __device__ __forceinline__ bool get(const Tile &t, const uint32_t *, int j, uint32_t (&r)[W]) const {
