@@ -107,6 +107,9 @@ def stage_bytes(n_bases, n_keys, n_edges, n_items_gen, k):
         "count_l2_scatter": 2 * n_keys * W,
         "local_count": n_keys * W + n_edges * We,
         "items": n_edges * We + n_items_gen * Wi,
+        "records_hist": n_items_gen * Wi,
+        "records_scatter": 2 * n_items_gen * Wi,
+        "local_sdbg": n_items_gen * Wi,
         "sdbg_l1_hist": n_items_gen * Wi,
         "sdbg_l1_scatter": 2 * n_items_gen * Wi,
         "sdbg_l2_hist": n_items_gen * Wi,
@@ -250,7 +253,8 @@ def main():
     res = None
     for _ in range(args.steps):
         res = step()
-        for name, ms in ctx.last_profile().items():
+        prof = runner.profile if world > 1 else ctx.last_profile()
+        for name, ms in prof.items():
             stage_sum[name] = stage_sum.get(name, 0.0) + ms
     ev1.record()
     barrier()
@@ -306,6 +310,15 @@ def main():
     n_keys = e_cnt.s.n_keys if e_cnt is not None else info.get("n_keys", 0)
     n_edges = e_cnt.n if e_cnt is not None else info.get("n_edges", 0)
     sb = stage_bytes(n_bases, n_keys, n_edges, 6 * n_edges, K)
+    nvlink = None
+    if world > 1:
+        # rank 0's share: bytes that left this GPU / time of the all-to-all, against 900 GB/s per direction nominal
+        kb = info.get("exchanged_keys", 0) * info.get("key_bytes", 8)
+        ib = info.get("exchanged_items", 0) * info.get("item_bytes", 8)
+        ak, ai = stage_sum.get("a2a_keys", 0.0) / args.steps, stage_sum.get("a2a_items", 0.0) / args.steps
+        nvlink = {"keys_bytes_sent": kb, "keys_ms": ak, "keys_GBps": kb / ak / 1e6 if ak else None, "items_bytes_sent": ib,
+                  "items_ms": ai, "items_GBps": ib / ai / 1e6 if ai else None, "peak_GBps_per_direction": 900.0,
+                  "measured_peer_copy_GBps": 770.0}
     per_step = {k2: v / args.steps for k2, v in stage_sum.items()}
     dom = max((k2 for k2 in per_step if k2 in sb), key=lambda k2: per_step[k2], default=None)
     peak, peak_src = measured_peak()
@@ -332,7 +345,7 @@ def main():
         "config": {"workload": workload_name(args.pairs), "bases_per_gpu": n_bases, "keys_per_gpu": n_keys, "solid_edges": n_edges,
                    "sdbg_items": res.n if res is not None else None, "l2_flush": "inputs and key buffers (>= 1 GB) exceed the 126 MB L2",
                    "parallelism": "reads sharded by GPU, keys routed by 10-bit prefix (NCCL all-to-all)" if world > 1 else "1 GPU"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(out))
     if world > 1:

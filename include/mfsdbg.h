@@ -153,6 +153,19 @@ int mfsdbg_dev_count_finish(mfsdbg_ctx *ctx, uint32_t *keys, uint32_t *scratch, 
                             const int64_t *chunk_start, const int64_t *chunk_size, const int32_t *chunk_seg,
                             int32_t n_chunks, int32_t n_segs, int32_t k, int32_t l1_bits, int32_t min_count,
                             mfsdbg_dev_edges *out, int64_t *counting_host);
+/* staged seq2sdbg, same shape: items of this GPU's edges -> (the driver exchanges them by prefix) -> finish.
+ * items_out holds 6 * n_edges records of mfsdbg_words_per_item(k) words. */
+int mfsdbg_dev_sdbg_items(mfsdbg_ctx *ctx, const uint32_t *edges, int64_t n_edges, int32_t k, uint32_t *items_out);
+/* histogram / partition of fixed-width records by their top l1_bits (bin b lands at the exclusive prefix of hist) */
+int mfsdbg_dev_records_hist(mfsdbg_ctx *ctx, const uint32_t *records, int64_t n, int32_t words, int32_t l1_bits,
+                            uint64_t *hist_dev);
+int mfsdbg_dev_records_scatter(mfsdbg_ctx *ctx, const uint32_t *records, int64_t n, int32_t words, int32_t l1_bits,
+                               const uint64_t *hist_dev, uint32_t *out);
+int mfsdbg_dev_sdbg_finish(mfsdbg_ctx *ctx, uint32_t *items, uint32_t *scratch, int64_t n_items,
+                           const int64_t *chunk_start, const int64_t *chunk_size, const int32_t *chunk_seg,
+                           int32_t n_chunks, int32_t n_segs, int32_t k, int32_t l1_bits, int32_t tip_mode,
+                           mfsdbg_dev_sdbg *out);
+int32_t mfsdbg_words_per_item(int32_t k);
 int32_t mfsdbg_words_per_key(int32_t k);
 int32_t mfsdbg_words_per_edge(int32_t k);
 

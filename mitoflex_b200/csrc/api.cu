@@ -203,6 +203,49 @@ int mfsdbg_dev_count_finish(mfsdbg_ctx *ctx, uint32_t *keys, uint32_t *scratch, 
     fill(out, e);
   });
 }
+int mfsdbg_dev_sdbg_items(mfsdbg_ctx *ctx, const uint32_t *edges, int64_t n_edges, int32_t k, uint32_t *items_out) {
+  if (!ctx || n_edges < 0 || (n_edges > 0 && (!edges || !items_out))) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::dev_sdbg_items(ctx->c, edges, n_edges, k, items_out);
+    ctx->c.end_call();
+  });
+}
+int mfsdbg_dev_records_hist(mfsdbg_ctx *ctx, const uint32_t *records, int64_t n, int32_t words, int32_t l1_bits, uint64_t *hist_dev) {
+  if (!ctx || !hist_dev || n < 0 || (n > 0 && !records)) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::dev_records_hist(ctx->c, records, n, words, l1_bits, reinterpret_cast<unsigned long long *>(hist_dev));
+    ctx->c.end_call();
+  });
+}
+int mfsdbg_dev_records_scatter(mfsdbg_ctx *ctx, const uint32_t *records, int64_t n, int32_t words, int32_t l1_bits,
+                               const uint64_t *hist_dev, uint32_t *out) {
+  if (!ctx || !hist_dev || n < 0 || (n > 0 && (!records || !out))) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::dev_records_scatter(ctx->c, records, n, words, l1_bits, reinterpret_cast<const unsigned long long *>(hist_dev), out);
+    ctx->c.end_call();
+  });
+}
+int mfsdbg_dev_sdbg_finish(mfsdbg_ctx *ctx, uint32_t *items, uint32_t *scratch, int64_t n_items, const int64_t *chunk_start,
+                           const int64_t *chunk_size, const int32_t *chunk_seg, int32_t n_chunks, int32_t n_segs, int32_t k,
+                           int32_t l1_bits, int32_t tip_mode, mfsdbg_dev_sdbg *out) {
+  if (!ctx || !out || n_items < 0 || n_chunks < 0 || n_segs < 1) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::SdbgView g;
+    mf::dev_sdbg_finish(ctx->c, items, scratch, n_items, chunk_start, chunk_size, chunk_seg, n_chunks, n_segs, k, l1_bits, tip_mode,
+                        &g);
+    ctx->c.end_call();
+    fill(out, g, ctx->c);
+  });
+}
+int32_t mfsdbg_words_per_item(int32_t k) { return mf::words_item(k); }
 int mfsdbg_dev_synth_reads(mfsdbg_ctx *ctx, const mfsdbg_synth_spec *spec, mfsdbg_dev_reads *out) {
   if (!ctx || !spec || !out) return MFSDBG_EINVAL;
   std::lock_guard<std::mutex> lk(g_job_mutex);

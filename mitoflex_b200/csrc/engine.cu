@@ -208,7 +208,8 @@ static int env_int(const char *name, int dflt) {
 // part_limit: bits the partition levels may consume (count: 2(k+1); sdbg: 2(k-1), so that a (k-1)-prefix group never
 // straddles a bucket).  density: how much denser than average the densest prefix range is (canonical keys = min of the two
 // strands pile up at small prefixes with density 2(1-u); sdbg items come from both strands and are flat).
-static Plan make_plan(int W, int part_limit, int64_t n_est, double density, bool hash_family, int forced_l1 = -1) {
+static Plan make_plan(int W, int part_limit, int64_t n_est, double density, bool hash_family, int forced_l1 = -1,
+                      int nseg = 0) {
   Plan p;
   p.W = W;
   p.cap = local_cap(W, hash_family, false);
@@ -226,6 +227,11 @@ static Plan make_plan(int W, int part_limit, int64_t n_est, double density, bool
   }
   p.l1_bits = std::max(1, std::min(p.l1_bits, std::min(kMaxDigitBits, part_limit)));
   p.l2_bits = std::max(0, std::min({bits - p.l1_bits, kMaxDigitBits, part_limit - p.l1_bits}));
+  if (nseg > 0) {
+    // the caller holds only `nseg` of the 2^l1 prefix bins (multi-GPU ownership): size the second level for those
+    const int need = ceil_log2((double)std::max<int64_t>(n_est, 1) / ((double)nseg * target));
+    p.l2_bits = std::max(0, std::min({need, kMaxDigitBits, part_limit - p.l1_bits}));
+  }
   return p;
 }
 
@@ -477,7 +483,7 @@ template <int W>
 static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n, const HostChunks &l1, int k, int l1_bits,
                               int min_count, bool append, EdgesView *out, unsigned long long *d_counting) {
   const int key_bits = 2 * (k + 1), We = words_edge(k);
-  Plan p = make_plan(W, key_bits, n, 2.0, true, l1_bits);
+  Plan p = make_plan(W, key_bits, n, 2.0, true, l1_bits, l1.nseg);
   auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
   DevBuckets b;
   int bit_off = l1_bits;
@@ -871,7 +877,7 @@ static void dev_count_finish_w(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_
   unsigned long long *d_counting = nullptr;
   MF_CUDA(cudaMalloc(&d_counting, sizeof(unsigned long long) * kNumBuckets));
   MF_CUDA(cudaMemsetAsync(d_counting, 0, sizeof(unsigned long long) * kNumBuckets, c.stream));
-  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)hc.nseg << kMaxDigitBits) * 96;
+  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)hc.nseg << kMaxDigitBits) * 96 + (size_t)(n_keys / 128);
   const size_t arena = (size_t)(min_count > 1 ? n_keys / std::min(min_count, 6) + 1 : n_keys) * We * 4;
   c.slab_reserve(table_bytes + arena + (1 << 20));
   out->n_edges = 0;
@@ -910,78 +916,67 @@ void dev_count_finish(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys,
 
 // ------------------------------------------------------------------ seq2sdbg
 template <int WI>
-static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, int tip_mode, SdbgView *out) {
-  const int WK = words_key(k), WE = words_edge(k), Wt = words_tip(k);
+static void sdbg_make_items(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, uint32_t *items) {
+  const int WK = words_key(k), WE = words_edge(k);
+  Stage st(c, "items");
+  if (n_edges > 0) {
+    const unsigned grid = (unsigned)div_ceil64(n_edges, 128);
+    // (WK, WE, WI) is one of (w,w,w), (w-1,w-1,w), (w-1,w,w) with w = WI >= 2
+    if constexpr (WI >= 2) {
+      if (WK == WI) k_items_from_edges<WI, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
+      else if (WE == WK) k_items_from_edges<WI - 1, WI - 1, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
+      else k_items_from_edges<WI - 1, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
+    }
+    MF_LAUNCH_CHECK();
+    c.launches++;
+  }
+  if (sq.n_items > 0) {
+    k_items_from_seqs<WI><<<(unsigned)div_ceil64(sq.n_items, 128), 128, 0, c.stream>>>(
+        sq.packed, sq.starts, sq.mult, sq.item_base, sq.nseq, sq.n_items, k, items + (size_t)6 * n_edges * WI);
+    MF_LAUNCH_CHECK();
+    c.launches++;
+  }
+}
+static void sdbg_empty(Ctx &c, int k, SdbgView *out) {
+  out->k = k;
+  out->words_tip = words_tip(k);
+  out->n_items = out->n_tips = out->n_large = 0;
+  out->bucket_items = nullptr;
+  c.sdbg_rec.reserve(256);
+  c.sdbg_labels.reserve(256);
+  out->rec = c.sdbg_rec.as<uint32_t>();
+  out->labels = c.sdbg_labels.as<uint32_t>();
+  std::fill(c.sdbg_bucket_stats.begin(), c.sdbg_bucket_stats.end(), 0);
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+// items in `cur` are partitioned by their top l1_bits into the chunks of `l1` (several chunks may feed one segment);
+// `other` is scratch of the same size; tables and arenas come from the slab.
+template <int WI>
+static void sdbg_finish(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n_items, const HostChunks &l1, int l1_bits, int k,
+                        int tip_mode, SdbgView *out) {
+  const int Wt = words_tip(k);
   const int part_limit = 2 * (k - 1);
-  const int64_t n_items = 6 * n_edges + sq.n_items;
   out->k = k;
   out->words_tip = Wt;
-  out->n_items = out->n_tips = out->n_large = 0;
+  out->bucket_items = nullptr;
   c.sdbg_buckets.reserve(sizeof(unsigned long long) * kNumBuckets * 3);
   unsigned long long *d_bstats = c.sdbg_buckets.as<unsigned long long>();
-  MF_CUDA(cudaMemsetAsync(d_bstats, 0, sizeof(unsigned long long) * kNumBuckets * 3, c.stream));
-  out->bucket_items = nullptr;
-  if (n_items == 0) {
-    c.sdbg_rec.reserve(256);
-    c.sdbg_labels.reserve(256);
-    out->rec = c.sdbg_rec.as<uint32_t>();
-    out->labels = c.sdbg_labels.as<uint32_t>();
-    std::fill(c.sdbg_bucket_stats.begin(), c.sdbg_bucket_stats.end(), 0);
-    MF_CUDA(cudaStreamSynchronize(c.stream));
-    return;
-  }
-  Plan p = make_plan(WI, part_limit, n_items, 1.0, false);
-  const int nb1 = 1 << p.l1_bits;
-  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1 << kMaxDigitBits) * 96;
-  c.slab_reserve((size_t)n_items * WI * 4 * 2 + table_bytes + (1 << 20));
-  uint32_t *bufA = c.alloc<uint32_t>((size_t)n_items * WI + 16), *bufB = c.alloc<uint32_t>((size_t)n_items * WI + 16);
-  {
-    Stage st(c, "items");
-    if (n_edges > 0) {
-      const unsigned grid = (unsigned)div_ceil64(n_edges, 128);
-      // (WK, WE, WI) is one of (w,w,w), (w-1,w-1,w), (w-1,w,w) with w = WI >= 2
-      if constexpr (WI >= 2) {
-        if (WK == WI) k_items_from_edges<WI, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, bufA);
-        else if (WE == WK) k_items_from_edges<WI - 1, WI - 1, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, bufA);
-        else k_items_from_edges<WI - 1, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, bufA);
-      }
-      MF_LAUNCH_CHECK();
-      c.launches++;
-    }
-    if (sq.n_items > 0) {
-      k_items_from_seqs<WI><<<(unsigned)div_ceil64(sq.n_items, 128), 128, 0, c.stream>>>(
-          sq.packed, sq.starts, sq.mult, sq.item_base, sq.nseq, sq.n_items, k, bufA + (size_t)6 * n_edges * WI);
-      MF_LAUNCH_CHECK();
-      c.launches++;
-    }
-  }
+  Plan p = make_plan(WI, part_limit, n_items, 1.0, false, l1_bits, l1.nseg);
   auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
-  // level 1 over the whole item array
-  HostChunks whole;
-  whole.nseg = 1;
-  whole.start = {0};
-  whole.size = {n_items};
-  whole.seg = {0};
-  whole.seg_out_start = {0};
-  DevBuckets b1 = partition_level<WI>(c, bufA, bufB, whole, 0, p.l1_bits, salloc, "sdbg_l1");
-  uint32_t *cur = bufB, *other = bufA;
-  DevBuckets b = b1;
-  int bit_off = p.l1_bits;
-  if (p.l2_bits > 0) {
-    std::vector<int64_t> st(nb1), sz(nb1);
-    c.d2h(st.data(), b1.start, sizeof(int64_t) * nb1);
-    c.d2h(sz.data(), b1.size, sizeof(int64_t) * nb1);
-    HostChunks l1;
-    l1.nseg = nb1;
-    for (int i = 0; i < nb1; ++i) {
-      l1.start.push_back(st[i]);
-      l1.size.push_back(sz[i]);
-      l1.seg.push_back(i);
-      l1.seg_out_start.push_back(st[i]);
-    }
-    b = partition_level<WI>(c, cur, other, l1, p.l1_bits, p.l2_bits, salloc, "sdbg_l2");
+  DevBuckets b;
+  int bit_off = l1_bits;
+  if (p.l2_bits > 0 || (int)l1.start.size() != l1.nseg) {
+    const int nb = std::max(1, p.l2_bits);
+    b = partition_level<WI>(c, cur, other, l1, l1_bits, nb, salloc, "sdbg_l2");
     std::swap(cur, other);
-    bit_off += p.l2_bits;
+    bit_off += nb;
+  } else {
+    b.nslots = l1.nseg;
+    b.start = c.alloc<int64_t>(b.nslots);
+    b.size = c.alloc<int64_t>(b.nslots);
+    c.h2d(b.start, l1.start.data(), sizeof(int64_t) * b.nslots);
+    c.h2d(b.size, l1.size.data(), sizeof(int64_t) * b.nslots);
   }
   int64_t *d_items = c.alloc<int64_t>(b.nslots), *d_tips = c.alloc<int64_t>(b.nslots), *d_large = c.alloc<int64_t>(b.nslots);
   int64_t *d_item_src = c.alloc<int64_t>(b.nslots), *d_tip_src = c.alloc<int64_t>(b.nslots);
@@ -1083,11 +1078,144 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
   out->n_tips = tot[1];
   out->n_large = tot[2];
 }
+
+template <int WI>
+static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, int tip_mode, SdbgView *out) {
+  const int64_t n_items = 6 * n_edges + sq.n_items;
+  if (n_items == 0) return sdbg_empty(c, k, out);
+  Plan p = make_plan(WI, 2 * (k - 1), n_items, 1.0, false);
+  const int nb1 = 1 << p.l1_bits;
+  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1 << kMaxDigitBits) * 96 + (size_t)(n_items / 128);
+  c.slab_reserve((size_t)n_items * WI * 4 * 2 + table_bytes + (1 << 20));
+  uint32_t *bufA = c.alloc<uint32_t>((size_t)n_items * WI + 16), *bufB = c.alloc<uint32_t>((size_t)n_items * WI + 16);
+  sdbg_make_items<WI>(c, edges, n_edges, sq, k, bufA);
+  auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
+  HostChunks whole;   // level 1 over the whole item array
+  whole.nseg = 1;
+  whole.start = {0};
+  whole.size = {n_items};
+  whole.seg = {0};
+  whole.seg_out_start = {0};
+  DevBuckets b1 = partition_level<WI>(c, bufA, bufB, whole, 0, p.l1_bits, salloc, "sdbg_l1");
+  std::vector<int64_t> st(nb1), sz(nb1);
+  c.d2h(st.data(), b1.start, sizeof(int64_t) * nb1);
+  c.d2h(sz.data(), b1.size, sizeof(int64_t) * nb1);
+  HostChunks l1;
+  l1.nseg = nb1;
+  for (int i = 0; i < nb1; ++i) {
+    l1.start.push_back(st[i]);
+    l1.size.push_back(sz[i]);
+    l1.seg.push_back(i);
+    l1.seg_out_start.push_back(st[i]);
+  }
+  sdbg_finish<WI>(c, bufB, bufA, n_items, l1, p.l1_bits, k, tip_mode, out);
+}
 #define MF_DISPATCH_CASE_SDBG(Wn) \
   case Wn: sdbg_impl<Wn>(c, edges, n_edges, seqs, k, tip_mode, out); break;
 void dev_seq2sdbg(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &seqs, int k, int tip_mode, SdbgView *out) {
   if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
   MF_DISPATCH_W(words_item(k), SDBG)
+}
+
+// ---- staged sdbg for the multi-GPU driver: items -> (caller exchanges them by prefix) -> finish
+#define MF_DISPATCH_CASE_SITEMS(Wn) \
+  case Wn: sdbg_make_items<Wn>(c, edges, n_edges, SeqsView{}, k, items_out); break;
+void dev_sdbg_items(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, uint32_t *items_out) {
+  if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
+  MF_DISPATCH_W(words_item(k), SITEMS)
+}
+// generic: histogram / partition of W-word records by their top l1_bits (one segment)
+template <int W>
+static void records_hist_impl(Ctx &c, const uint32_t *rec, int64_t n, int l1_bits, unsigned long long *hist_dev) {
+  using C = TileCfg<W>;
+  const int nb = 1 << l1_bits;
+  MF_CUDA(cudaMemsetAsync(hist_dev, 0, sizeof(unsigned long long) * nb, c.stream));
+  const int64_t tiles = div_ceil64(n, C::TH);
+  if (tiles == 0) return;
+  c.ov[2].reserve(sizeof(TileDesc) * tiles + 64);
+  c.ov[3].reserve(64);
+  int64_t h[4] = {0, n, 0, tiles};   // start, size, tile_base[0], tile_base[1]
+  int32_t seg0 = 0;
+  c.h2d(c.ov[3].p, h, sizeof h);
+  c.h2d((char *)c.ov[3].p + 40, &seg0, 4);
+  const int64_t *dp = c.ov[3].as<int64_t>();
+  ChunkTable ct{dp, dp + 1, reinterpret_cast<const int32_t *>((const char *)c.ov[3].p + 40), dp + 2, 1};
+  k_build_tiles<<<(unsigned)div_ceil64(tiles, 256), 256, 0, c.stream>>>(ct, C::TH, tiles, c.ov[2].as<TileDesc>());
+  RecordsProducer<W> ph{rec, c.ov[2].as<TileDesc>(), C::TH};
+  size_t smem = ((size_t)1 << l1_bits) * 4 + 16;
+  auto kern = k_level_hist<RecordsProducer<W>, W, C::NT, C::IPT_H>;
+  set_smem(kern, smem);
+  Stage st(c, "records_hist");
+  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ph, LevelArgs{0, l1_bits, 0u, (uint32_t)nb}, hist_dev);
+  MF_LAUNCH_CHECK();
+  c.launches += 2;
+}
+template <int W>
+static void records_scatter_impl(Ctx &c, const uint32_t *rec, int64_t n, int l1_bits, const unsigned long long *hist_dev, uint32_t *out) {
+  using C = TileCfg<W>;
+  const int nb = 1 << l1_bits;
+  const int64_t tiles = div_ceil64(n, C::TS);
+  if (tiles == 0) return;
+  c.ov[2].reserve(sizeof(TileDesc) * tiles + 64);
+  c.ov[3].reserve(64);
+  c.ov[4].reserve(sizeof(unsigned long long) * kMaxBins);
+  int64_t h[4] = {0, n, 0, tiles};
+  int32_t seg0 = 0;
+  c.h2d(c.ov[3].p, h, sizeof h);
+  c.h2d((char *)c.ov[3].p + 40, &seg0, 4);
+  const int64_t *dp = c.ov[3].as<int64_t>();
+  ChunkTable ct{dp, dp + 1, reinterpret_cast<const int32_t *>((const char *)c.ov[3].p + 40), dp + 2, 1};
+  k_build_tiles<<<(unsigned)div_ceil64(tiles, 256), 256, 0, c.stream>>>(ct, C::TS, tiles, c.ov[2].as<TileDesc>());
+  k_excl_scan_u64_small<<<1, 1024, 0, c.stream>>>(hist_dev, nb, c.ov[4].as<unsigned long long>());
+  RecordsProducer<W> ps{rec, c.ov[2].as<TileDesc>(), C::TS};
+  size_t smem = scatter_smem_bytes<W>(C::NT, C::TS, l1_bits, 4);
+  auto kern = k_level_scatter<RecordsProducer<W>, W, C::NT, C::IPT_S>;
+  set_smem(kern, smem);
+  Stage st(c, "records_scatter");
+  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ps, LevelArgs{0, l1_bits, 0u, (uint32_t)nb}, c.ov[4].as<unsigned long long>(), out);
+  MF_LAUNCH_CHECK();
+  c.launches += 3;
+}
+#define MF_DISPATCH_CASE_RHIST(Wn) \
+  case Wn: records_hist_impl<Wn>(c, rec, n, l1_bits, hist_dev); break;
+void dev_records_hist(Ctx &c, const uint32_t *rec, int64_t n, int words, int l1_bits, unsigned long long *hist_dev) {
+  if (l1_bits < 1 || l1_bits > kMaxDigitBits) throw std::invalid_argument("l1_bits must be in [1, 11]");
+  MF_DISPATCH_W(words, RHIST)
+}
+#define MF_DISPATCH_CASE_RSCAT(Wn) \
+  case Wn: records_scatter_impl<Wn>(c, rec, n, l1_bits, hist_dev, out); break;
+void dev_records_scatter(Ctx &c, const uint32_t *rec, int64_t n, int words, int l1_bits, const unsigned long long *hist_dev,
+                         uint32_t *out) {
+  if (l1_bits < 1 || l1_bits > kMaxDigitBits) throw std::invalid_argument("l1_bits must be in [1, 11]");
+  MF_DISPATCH_W(words, RSCAT)
+}
+template <int WI>
+static void dev_sdbg_finish_w(Ctx &c, uint32_t *items, uint32_t *scratch, int64_t n_items, const HostChunks &hc, int k, int l1_bits,
+                              int tip_mode, SdbgView *out) {
+  if (n_items == 0) return sdbg_empty(c, k, out);
+  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)hc.nseg << kMaxDigitBits) * 96 + (size_t)(n_items / 128);
+  c.slab_reserve(table_bytes + (1 << 20));
+  sdbg_finish<WI>(c, items, scratch, n_items, hc, l1_bits, k, tip_mode, out);
+}
+#define MF_DISPATCH_CASE_SFIN(Wn) \
+  case Wn: dev_sdbg_finish_w<Wn>(c, items, scratch, n_items, hc, k, l1_bits, tip_mode, out); break;
+void dev_sdbg_finish(Ctx &c, uint32_t *items, uint32_t *scratch, int64_t n_items, const int64_t *chunk_start,
+                     const int64_t *chunk_size, const int32_t *chunk_seg, int n_chunks, int n_segs, int k, int l1_bits, int tip_mode,
+                     SdbgView *out) {
+  HostChunks hc;
+  hc.nseg = n_segs;
+  hc.start.assign(chunk_start, chunk_start + n_chunks);
+  hc.size.assign(chunk_size, chunk_size + n_chunks);
+  hc.seg.assign(chunk_seg, chunk_seg + n_chunks);
+  std::vector<int64_t> tot(n_segs, 0);
+  for (int i = 0; i < n_chunks; ++i) {
+    if (chunk_seg[i] < 0 || chunk_seg[i] >= n_segs) throw std::invalid_argument("chunk_seg out of range");
+    tot[chunk_seg[i]] += chunk_size[i];
+  }
+  int64_t acc = 0;
+  for (int s2 = 0; s2 < n_segs; ++s2) { hc.seg_out_start.push_back(acc); acc += tot[s2]; }
+  if (acc != n_items) throw std::invalid_argument("chunk sizes do not add up to n_items");
+  MF_DISPATCH_W(words_item(k), SFIN)
 }
 
 }  // namespace mf

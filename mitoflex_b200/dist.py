@@ -1,0 +1,164 @@
+"""Multi-GPU driver of the sDBG path: one process per GPU (torch.distributed), reads sharded by GPU, records routed to the
+GPU that owns their prefix bin with ONE all-to-all per stage (NCCL over NVLink), then every GPU finishes a disjoint,
+contiguous key range on its own.  Concatenating the ranks' outputs in rank order gives the globally sorted streams, which
+is exactly how megahit's per-bucket meta files stitch several `.edges.N` / `.sdbg.N` files together.
+
+    count  : prefix histogram (per GPU) -> all_gather -> owners -> local partition -> all_to_all -> count_finish
+    sdbg   : items of the local edges -> prefix histogram -> all_gather -> owners -> partition -> all_to_all -> sdbg_finish
+
+The planning functions below are pure numpy (tested with gloo on CPU); only DistRead2Sdbg touches the GPU.
+"""
+import numpy as np
+
+L1_BITS = 10
+
+
+def assign_owners(global_hist, world):
+    """Contiguous bin ranges [lo_r, hi_r) per rank, balanced on the global histogram. Returns int64 array [world + 1]."""
+    h = np.asarray(global_hist, dtype=np.int64)
+    nb = len(h)
+    csum = np.concatenate([[0], np.cumsum(h)])
+    total = int(csum[-1])
+    bounds = np.zeros(world + 1, dtype=np.int64)
+    bounds[world] = nb
+    for r in range(1, world):
+        target = total * r // world
+        # first bin boundary whose cumulative count reaches the target
+        b = int(np.searchsorted(csum, target, side="left"))
+        bounds[r] = min(max(b, bounds[r - 1]), nb)
+    return bounds
+
+
+def exchange_plan(all_hists, rank):
+    """all_hists: [world, nbins] per-source-rank bin counts. Returns dict with the owner bounds, this rank's send / recv
+    splits (records) and the chunk table (start, size, seg) describing the receive buffer: source-major, bins ascending."""
+    H = np.asarray(all_hists, dtype=np.int64)
+    world, nb = H.shape
+    bounds = assign_owners(H.sum(axis=0), world)
+    send = np.array([H[rank, bounds[r]:bounds[r + 1]].sum() for r in range(world)], dtype=np.int64)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    recv = np.array([H[s, lo:hi].sum() for s in range(world)], dtype=np.int64)
+    starts, sizes, segs = [], [], []
+    off = 0
+    for s in range(world):
+        sz = H[s, lo:hi]
+        st = off + np.concatenate([[0], np.cumsum(sz)[:-1]]) if hi > lo else np.zeros(0, np.int64)
+        nz = sz > 0
+        starts.append(st[nz])
+        sizes.append(sz[nz])
+        segs.append(np.arange(hi - lo, dtype=np.int32)[nz])
+        off += int(sz.sum())
+    return dict(bounds=bounds, lo=lo, hi=hi, n_segs=max(hi - lo, 1), send=send, recv=recv,
+                chunk_start=np.concatenate(starts).astype(np.int64) if starts else np.zeros(0, np.int64),
+                chunk_size=np.concatenate(sizes).astype(np.int64) if sizes else np.zeros(0, np.int64),
+                chunk_seg=np.concatenate(segs).astype(np.int32) if segs else np.zeros(0, np.int32),
+                n_recv=int(recv.sum()))
+
+
+def all_to_all_records(send_rows, send_splits, recv_splits, group=None):
+    """send_rows: [n, W] tensor partitioned by destination rank (splits in rows). Returns the received [m, W] tensor."""
+    import torch
+    import torch.distributed as dist
+    out = torch.empty((int(sum(recv_splits)), send_rows.shape[1]), dtype=send_rows.dtype, device=send_rows.device)
+    dist.all_to_all_single(out, send_rows, output_split_sizes=[int(x) for x in recv_splits],
+                           input_split_sizes=[int(x) for x in send_splits], group=group)
+    return out
+
+
+class DistResult:
+    def __init__(self, sdbg, info):
+        self.sdbg, self.info = sdbg, info
+
+    @property
+    def n(self):
+        return self.sdbg.n
+
+
+class DistRead2Sdbg:
+    """read2sdbg over all ranks of the default process group; each rank ends with its prefix range of the graph."""
+
+    def __init__(self, ctx, k, min_count):
+        import torch
+        self.ctx, self.k, self.m = ctx, k, min_count
+        self.dev = torch.device("cuda", ctx.device)
+        from . import lib
+        self.Wk = lib.load().mfsdbg_words_per_key(k)
+        self.We = lib.load().mfsdbg_words_per_edge(k)
+        self.Wi = lib.load().mfsdbg_words_per_item(k)
+        self.profile = {}
+
+    def _acc(self):
+        for name, ms in self.ctx.last_profile().items():
+            self.profile[name] = self.profile.get(name, 0.0) + ms
+
+    def _timed_a2a(self, name, rows, send, recv):
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = all_to_all_records(rows, send, recv)
+        e1.record()
+        e1.synchronize()
+        self.profile[name] = self.profile.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
+    def _gather_hists(self, hist):
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size()
+        allh = torch.empty((world, hist.numel()), dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(allh, hist)
+        return allh.cpu().numpy()
+
+    def run(self, reads):
+        import torch
+        import torch.distributed as dist
+        ctx, k, nb = self.ctx, self.k, 1 << L1_BITS
+        rank = dist.get_rank()
+        stream = torch.cuda.current_stream(self.dev)
+        # ---- count: histogram, owners, local partition, exchange, finish
+        hist = torch.zeros(nb, dtype=torch.int64, device=self.dev)
+        stream.synchronize()
+        self.profile = {}
+        ctx.count_hist(reads, k, L1_BITS, hist.data_ptr())
+        self._acc()
+        plan = exchange_plan(self._gather_hists(hist), rank)
+        n_local = int(plan["send"].sum())
+        n_buf = max(n_local, plan["n_recv"], 1)
+        send = torch.empty((n_buf, self.Wk), dtype=torch.int32, device=self.dev)
+        stream.synchronize()
+        ctx.count_scatter(reads, k, L1_BITS, hist.data_ptr(), send.data_ptr(), n_buf)
+        self._acc()
+        recv = self._timed_a2a("a2a_keys", send[:n_local], plan["send"], plan["recv"])
+        stream.synchronize()
+        edges = ctx.count_finish(recv.data_ptr(), send.data_ptr(), plan["n_recv"], plan["chunk_start"], plan["chunk_size"],
+                                 plan["chunk_seg"], plan["n_segs"], k, L1_BITS, self.m)
+        self._acc()
+        info = dict(n_keys=plan["n_recv"], n_edges=edges.n, exchanged_keys=n_local - int(plan["send"][rank]),
+                    key_bytes=4 * self.Wk)
+        del recv, send
+        # ---- sdbg: items of the local edges, exchange by item prefix, finish
+        n_items = 6 * edges.n
+        items = torch.empty((max(n_items, 1), self.Wi), dtype=torch.int32, device=self.dev)
+        stream.synchronize()
+        ctx.sdbg_items(edges.s.edges, edges.n, k, items.data_ptr())
+        self._acc()
+        ihist = torch.zeros(nb, dtype=torch.int64, device=self.dev)
+        stream.synchronize()
+        ctx.records_hist(items.data_ptr(), n_items, self.Wi, L1_BITS, ihist.data_ptr())
+        self._acc()
+        iplan = exchange_plan(self._gather_hists(ihist), rank)
+        ibuf = max(n_items, iplan["n_recv"], 1)
+        isend = torch.empty((ibuf, self.Wi), dtype=torch.int32, device=self.dev)
+        stream.synchronize()
+        ctx.records_scatter(items.data_ptr(), n_items, self.Wi, L1_BITS, ihist.data_ptr(), isend.data_ptr())
+        self._acc()
+        del items
+        irecv = self._timed_a2a("a2a_items", isend[:n_items], iplan["send"], iplan["recv"])
+        stream.synchronize()
+        g = ctx.sdbg_finish(irecv.data_ptr(), isend.data_ptr(), iplan["n_recv"], iplan["chunk_start"], iplan["chunk_size"],
+                            iplan["chunk_seg"], iplan["n_segs"], k, L1_BITS, 1)
+        self._acc()
+        info.update(n_items=iplan["n_recv"], exchanged_items=n_items - int(iplan["send"][rank]), sdbg_items=g.n,
+                    item_bytes=4 * self.Wi)
+        del irecv, isend
+        return DistResult(g, info)

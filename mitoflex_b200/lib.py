@@ -80,6 +80,12 @@ SYMBOLS = {
     "mfsdbg_dev_count_scatter": (C.c_int, [C.c_void_p, C.POINTER(DevReads), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
     "mfsdbg_dev_count_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DevEdges), C.c_void_p]),
+    "mfsdbg_dev_sdbg_items": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "mfsdbg_dev_records_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "mfsdbg_dev_records_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mfsdbg_dev_sdbg_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DevSdbg)]),
+    "mfsdbg_words_per_item": (C.c_int32, [C.c_int32]),
     "mfsdbg_words_per_key": (C.c_int32, [C.c_int32]),
     "mfsdbg_words_per_edge": (C.c_int32, [C.c_int32]),
     "mfsdbg_host_read2sdbg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
@@ -317,6 +323,25 @@ class Context:
                                               cg.ctypes.data, len(cs), n_segs, k, l1_bits, min_count, C.byref(out),
                                               counting.ctypes.data if want_counting else None))
         return Edges(self, out, counting)
+
+
+    def sdbg_items(self, edges_ptr, n_edges, k, items_ptr):
+        _check(load().mfsdbg_dev_sdbg_items(self._h, edges_ptr, n_edges, k, items_ptr))
+
+    def records_hist(self, rec_ptr, n, words, l1_bits, hist_ptr):
+        _check(load().mfsdbg_dev_records_hist(self._h, rec_ptr, n, words, l1_bits, hist_ptr))
+
+    def records_scatter(self, rec_ptr, n, words, l1_bits, hist_ptr, out_ptr):
+        _check(load().mfsdbg_dev_records_scatter(self._h, rec_ptr, n, words, l1_bits, hist_ptr, out_ptr))
+
+    def sdbg_finish(self, items_ptr, scratch_ptr, n_items, chunk_start, chunk_size, chunk_seg, n_segs, k, l1_bits, tip_mode):
+        cs = np.ascontiguousarray(chunk_start, dtype=np.int64)
+        cz = np.ascontiguousarray(chunk_size, dtype=np.int64)
+        cg = np.ascontiguousarray(chunk_seg, dtype=np.int32)
+        out = DevSdbg()
+        _check(load().mfsdbg_dev_sdbg_finish(self._h, items_ptr, scratch_ptr, n_items, cs.ctypes.data, cz.ctypes.data,
+                                             cg.ctypes.data, len(cs), n_segs, k, l1_bits, tip_mode, C.byref(out)))
+        return Sdbg(self, out)
 
 
 class Edges:

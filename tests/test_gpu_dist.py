@@ -1,0 +1,63 @@
+"""Multi-GPU parity (needs >= 2 GPUs): reads sharded over 2 ranks, keys and items routed by prefix with NCCL all-to-all;
+the ranks' sdbg pieces concatenated in rank order must equal the oracle's graph of the whole read set, bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir, k, m, seed):
+    import sys
+    import torch
+    import torch.distributed as dist
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    sys.path.insert(0, os.path.dirname(here))
+    from gpu_common import make_reads
+    from mitoflex_b200 import dist as mdist
+    from mitoflex_b200 import lib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        bases, starts = make_reads(seed, 60000, k, genome_len=150000, max_len=150, err=0.005)
+        n = len(starts) - 1
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        sb = bases[starts[lo]:starts[hi]]
+        ss = starts[lo:hi + 1] - starts[lo]
+        ctx = lib.Context(rank)
+        res = mdist.DistRead2Sdbg(ctx, k, m).run(ctx.upload_reads(sb, ss))
+        g = res.sdbg.to_numpy()
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), w=g["w"], last=g["last"], tip=g["tip"], mul=g["mul"],
+                 tip_labels=g["tip_labels"])
+        dist.barrier()
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k,m", [(21, 2), (31, 1)])
+def test_two_gpu_read2sdbg_matches_oracle(oracle, tmp_path, k, m):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from gpu_common import make_reads
+    seed, world = 4242 + k, 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), k, m, seed), nprocs=world, join=True)
+    bases, starts = make_reads(seed, 60000, k, genome_len=150000, max_len=150, err=0.005)
+    g = oracle.read2sdbg(oracle.Reads(bases, starts), k, m, threads=8)
+    parts = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    for f in ("w", "last", "tip", "mul"):
+        assert np.array_equal(np.concatenate([p[f] for p in parts]), getattr(g, f)), f
+    assert np.array_equal(np.concatenate([p["tip_labels"] for p in parts]), g.tip_labels)
