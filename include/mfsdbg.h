@@ -166,6 +166,21 @@ int mfsdbg_dev_sdbg_finish(mfsdbg_ctx *ctx, uint32_t *items, uint32_t *scratch, 
                            int32_t n_chunks, int32_t n_segs, int32_t k, int32_t l1_bits, int32_t tip_mode,
                            mfsdbg_dev_sdbg *out);
 int32_t mfsdbg_words_per_item(int32_t k);
+
+/* ---- fused partition + exchange over NVLink peer memory ---------------------------------------------------
+ * The owner GPU allocates its receive buffer with mfsdbg_dev_alloc, exports it (CUDA IPC, 64-byte handle), the
+ * other ranks open it; the *_scatter_peer kernels then write every record of prefix bin b at byte address
+ * bin_base_dev[b] + (running count of bin b) * record size -- directly into the owner's HBM, no staging copy and no
+ * separate all-to-all.  bin_base_dev is a device array of 1 << l1_bits addresses. */
+int mfsdbg_dev_alloc(mfsdbg_ctx *ctx, uint64_t bytes, void **out);
+int mfsdbg_dev_free(mfsdbg_ctx *ctx, void *ptr);
+int mfsdbg_ipc_export(mfsdbg_ctx *ctx, void *ptr, uint8_t *handle64);
+int mfsdbg_ipc_open(mfsdbg_ctx *ctx, const uint8_t *handle64, void **out);
+int mfsdbg_ipc_close(mfsdbg_ctx *ctx, void *ptr);
+int mfsdbg_dev_count_scatter_peer(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int32_t k, int32_t l1_bits,
+                                  const uint64_t *bin_base_dev);
+int mfsdbg_dev_records_scatter_peer(mfsdbg_ctx *ctx, const uint32_t *records, int64_t n, int32_t words, int32_t l1_bits,
+                                    const uint64_t *bin_base_dev);
 int32_t mfsdbg_words_per_key(int32_t k);
 int32_t mfsdbg_words_per_edge(int32_t k);
 

@@ -184,8 +184,9 @@ int mfsdbg_dev_count_scatter(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int
   std::lock_guard<std::mutex> lk(g_job_mutex);
   return guarded([&] {
     ctx->c.begin_call();
+    (void)capacity;
     mf::dev_count_scatter(ctx->c, view(reads), k, l1_bits, reinterpret_cast<const unsigned long long *>(hist_dev), keys_out,
-                          capacity);
+                          nullptr);
     ctx->c.end_call();
   });
 }
@@ -227,7 +228,7 @@ int mfsdbg_dev_records_scatter(mfsdbg_ctx *ctx, const uint32_t *records, int64_t
   std::lock_guard<std::mutex> lk(g_job_mutex);
   return guarded([&] {
     ctx->c.begin_call();
-    mf::dev_records_scatter(ctx->c, records, n, words, l1_bits, reinterpret_cast<const unsigned long long *>(hist_dev), out);
+    mf::dev_records_scatter(ctx->c, records, n, words, l1_bits, reinterpret_cast<const unsigned long long *>(hist_dev), out, nullptr);
     ctx->c.end_call();
   });
 }
@@ -246,6 +247,72 @@ int mfsdbg_dev_sdbg_finish(mfsdbg_ctx *ctx, uint32_t *items, uint32_t *scratch, 
   });
 }
 int32_t mfsdbg_words_per_item(int32_t k) { return mf::words_item(k); }
+
+// ---- fused partition + exchange over peer memory (NVLink): buffers the library allocates are exportable through CUDA IPC
+int mfsdbg_dev_alloc(mfsdbg_ctx *ctx, uint64_t bytes, void **out) {
+  if (!ctx || !out) return MFSDBG_EINVAL;
+  return guarded([&] {
+    MF_CUDA(cudaSetDevice(ctx->c.device));
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 256);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      throw mf::CudaError("out of device memory allocating " + std::to_string(bytes >> 20) + " MiB");
+    }
+  });
+}
+int mfsdbg_dev_free(mfsdbg_ctx *ctx, void *ptr) {
+  if (!ctx) return MFSDBG_EINVAL;
+  return guarded([&] {
+    MF_CUDA(cudaSetDevice(ctx->c.device));
+    MF_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    if (ptr) MF_CUDA(cudaFree(ptr));
+  });
+}
+int mfsdbg_ipc_export(mfsdbg_ctx *ctx, void *ptr, uint8_t *handle64) {
+  if (!ctx || !ptr || !handle64) return MFSDBG_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  return guarded([&] {
+    MF_CUDA(cudaSetDevice(ctx->c.device));
+    cudaIpcMemHandle_t h;
+    MF_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle64, &h, 64);
+  });
+}
+int mfsdbg_ipc_open(mfsdbg_ctx *ctx, const uint8_t *handle64, void **out) {
+  if (!ctx || !handle64 || !out) return MFSDBG_EINVAL;
+  return guarded([&] {
+    MF_CUDA(cudaSetDevice(ctx->c.device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    MF_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  });
+}
+int mfsdbg_ipc_close(mfsdbg_ctx *ctx, void *ptr) {
+  if (!ctx) return MFSDBG_EINVAL;
+  return guarded([&] {
+    MF_CUDA(cudaSetDevice(ctx->c.device));
+    if (ptr) MF_CUDA(cudaIpcCloseMemHandle(ptr));
+  });
+}
+int mfsdbg_dev_count_scatter_peer(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int32_t k, int32_t l1_bits, const uint64_t *bin_base_dev) {
+  if (!ctx || !bin_base_dev) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::dev_count_scatter(ctx->c, view(reads), k, l1_bits, nullptr, nullptr, reinterpret_cast<const unsigned long long *>(bin_base_dev));
+    ctx->c.end_call();
+  });
+}
+int mfsdbg_dev_records_scatter_peer(mfsdbg_ctx *ctx, const uint32_t *records, int64_t n, int32_t words, int32_t l1_bits,
+                                    const uint64_t *bin_base_dev) {
+  if (!ctx || !bin_base_dev || n < 0 || (n > 0 && !records)) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::dev_records_scatter(ctx->c, records, n, words, l1_bits, nullptr, nullptr, reinterpret_cast<const unsigned long long *>(bin_base_dev));
+    ctx->c.end_call();
+  });
+}
 int mfsdbg_dev_synth_reads(mfsdbg_ctx *ctx, const mfsdbg_synth_spec *spec, mfsdbg_dev_reads *out) {
   if (!ctx || !spec || !out) return MFSDBG_EINVAL;
   std::lock_guard<std::mutex> lk(g_job_mutex);

@@ -195,6 +195,7 @@ __global__ void k_edge_buckets(const uint32_t *edges, int64_t n, int We, unsigne
 // ------------------------------------------------------------------ plan
 struct Plan {
   int W, l1_bits, l2_bits, cap;
+  int rest_bits;   // bits still to consume after level 1 (may need two more levels when a GPU owns few level-1 bins)
 };
 static int ceil_log2(double x) {
   int b = 0;
@@ -227,10 +228,12 @@ static Plan make_plan(int W, int part_limit, int64_t n_est, double density, bool
   }
   p.l1_bits = std::max(1, std::min(p.l1_bits, std::min(kMaxDigitBits, part_limit)));
   p.l2_bits = std::max(0, std::min({bits - p.l1_bits, kMaxDigitBits, part_limit - p.l1_bits}));
+  p.rest_bits = p.l2_bits;
   if (nseg > 0) {
     // the caller holds only `nseg` of the 2^l1 prefix bins (multi-GPU ownership): size the second level for those
     const int need = ceil_log2((double)std::max<int64_t>(n_est, 1) / ((double)nseg * target));
-    p.l2_bits = std::max(0, std::min({need, kMaxDigitBits, part_limit - p.l1_bits}));
+    p.rest_bits = std::max(0, std::min({need, 2 * kMaxDigitBits, part_limit - p.l1_bits}));
+    p.l2_bits = std::min(p.rest_bits, kMaxDigitBits);
   }
   return p;
 }
@@ -318,7 +321,7 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   MF_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nsl, c.stream));
   // the pageable host vectors above die with this frame: make sure the copies have been consumed
   MF_CUDA(cudaStreamSynchronize(c.stream));
-  LevelArgs a{bit_off, nbits, 0u, (uint32_t)nbins};
+  LevelArgs a{bit_off, nbits, 0u, (uint32_t)nbins, nullptr};
   TileDesc *d_tiles_h = (TileDesc *)alloc(sizeof(TileDesc) * std::max<int64_t>(tb_h[nchunk], 1));
   TileDesc *d_tiles_s = (TileDesc *)alloc(sizeof(TileDesc) * std::max<int64_t>(tb_s[nchunk], 1));
   if (tb_h[nchunk] > 0) {
@@ -351,6 +354,46 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
     kern<<<(unsigned)tb_s[nchunk], C::NT, smem, c.stream>>>(ps, a, d_cur, out);
     MF_LAUNCH_CHECK();
     c.launches++;
+  }
+  return b;
+}
+
+// Consume `rest_bits` more key bits after level 1 with one or two partition levels.  `hc` describes the level-1 chunks
+// (several may feed one segment); on return `*cur` holds the bucketed records and `*bit_off` the bits consumed.
+template <int W, class Alloc>
+static DevBuckets partition_chain(Ctx &c, uint32_t **cur, uint32_t **other, const HostChunks &hc, int *bit_off, int rest_bits,
+                                  Alloc &&alloc, const char *tag) {
+  DevBuckets b;
+  const bool multi = (int)hc.start.size() != hc.nseg;
+  if (rest_bits <= 0 && !multi) {   // level-1 bins are the buckets
+    b.nslots = hc.nseg;
+    b.start = (int64_t *)alloc(sizeof(int64_t) * b.nslots);
+    b.size = (int64_t *)alloc(sizeof(int64_t) * b.nslots);
+    c.h2d(b.start, hc.start.data(), sizeof(int64_t) * b.nslots);
+    c.h2d(b.size, hc.size.data(), sizeof(int64_t) * b.nslots);
+    return b;
+  }
+  rest_bits = std::max(rest_bits, 1);
+  const int first = rest_bits <= kMaxDigitBits ? rest_bits : (rest_bits + 1) / 2;
+  b = partition_level<W>(c, *cur, *other, hc, *bit_off, first, alloc, tag);
+  std::swap(*cur, *other);
+  *bit_off += first;
+  const int second = rest_bits - first;
+  if (second > 0) {
+    std::vector<int64_t> st(b.nslots), sz(b.nslots);
+    c.d2h(st.data(), b.start, sizeof(int64_t) * b.nslots);
+    c.d2h(sz.data(), b.size, sizeof(int64_t) * b.nslots);
+    HostChunks h2;
+    h2.nseg = b.nslots;
+    h2.start.assign(st.begin(), st.end());
+    h2.size.assign(sz.begin(), sz.end());
+    h2.seg.resize(b.nslots);
+    for (int i = 0; i < b.nslots; ++i) h2.seg[i] = i;
+    h2.seg_out_start = h2.start;
+    const std::string tag3 = std::string(tag) + "b";
+    b = partition_level<W>(c, *cur, *other, h2, *bit_off, second, alloc, tag3.c_str());
+    std::swap(*cur, *other);
+    *bit_off += second;
   }
   return b;
 }
@@ -485,20 +528,8 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
   const int key_bits = 2 * (k + 1), We = words_edge(k);
   Plan p = make_plan(W, key_bits, n, 2.0, true, l1_bits, l1.nseg);
   auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
-  DevBuckets b;
   int bit_off = l1_bits;
-  if (p.l2_bits > 0 || (int)l1.start.size() != l1.nseg) {
-    int nb = std::max(1, p.l2_bits);
-    b = partition_level<W>(c, cur, other, l1, l1_bits, nb, salloc, "count_l2");
-    std::swap(cur, other);
-    bit_off += nb;
-  } else {
-    b.nslots = l1.nseg;
-    b.start = c.alloc<int64_t>(b.nslots);
-    b.size = c.alloc<int64_t>(b.nslots);
-    c.h2d(b.start, l1.start.data(), sizeof(int64_t) * b.nslots);
-    c.h2d(b.size, l1.size.data(), sizeof(int64_t) * b.nslots);
-  }
+  DevBuckets b = partition_chain<W>(c, &cur, &other, l1, &bit_off, p.rest_bits, salloc, "count_l2");
   int64_t *d_desc_off = c.alloc<int64_t>(b.nslots), *d_desc_cnt = c.alloc<int64_t>(b.nslots);
   int64_t *d_out_off = c.alloc<int64_t>(b.nslots + 1);
   int32_t *d_bail = c.alloc<int32_t>(b.nslots);
@@ -745,7 +776,7 @@ static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, Edg
   MF_CUDA(cudaMemsetAsync(d_small, 0, sizeof(unsigned long long) * (nb1 + kNumBuckets), c.stream));
   {
     Stage st(c, "reads_hist");
-    launch_reads_hist<W>(c, r, sbits, k, LevelArgs{0, p.l1_bits, 0u, (uint32_t)nb1}, d_hist);
+    launch_reads_hist<W>(c, r, sbits, k, LevelArgs{0, p.l1_bits, 0u, (uint32_t)nb1, nullptr}, d_hist);
   }
   std::vector<unsigned long long> hist(nb1);
   MF_CUDA(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned long long) * nb1, cudaMemcpyDeviceToHost, c.stream));
@@ -799,7 +830,7 @@ static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, Edg
     c.h2d(d_cursor, cursor.data(), sizeof(unsigned long long) * nb1);
     {
       Stage st(c, "reads_scatter");
-      launch_reads_scatter<W>(c, r, sbits, k, LevelArgs{0, p.l1_bits, (uint32_t)lo, (uint32_t)hi}, d_cursor, bufA);
+      launch_reads_scatter<W>(c, r, sbits, k, LevelArgs{0, p.l1_bits, (uint32_t)lo, (uint32_t)hi, nullptr}, d_cursor, bufA);
     }
     count_finish_impl<W>(c, bufA, bufB, acc, l1, k, p.l1_bits, min_count, ri > 0, out, counting_host ? d_counting : nullptr);
   }
@@ -829,7 +860,7 @@ static void dev_count_hist_impl(Ctx &c, const ReadsView &r, int k, int l1_bits, 
   const int nb1 = 1 << l1_bits;
   MF_CUDA(cudaMemsetAsync(hist_dev, 0, sizeof(unsigned long long) * nb1, c.stream));
   Stage st(c, "reads_hist");
-  launch_reads_hist<W>(c, r, sbits, k, LevelArgs{0, l1_bits, 0u, (uint32_t)nb1}, hist_dev);
+  launch_reads_hist<W>(c, r, sbits, k, LevelArgs{0, l1_bits, 0u, (uint32_t)nb1, nullptr}, hist_dev);
 }
 #define MF_DISPATCH_CASE_CHIST(Wn) \
   case Wn: dev_count_hist_impl<Wn>(c, r, k, l1_bits, hist_dev); break;
@@ -852,22 +883,26 @@ __global__ void k_excl_scan_u64_small(const unsigned long long *in, int n, unsig
 }
 template <int W>
 static void dev_count_scatter_impl(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev,
-                                   uint32_t *keys_out) {
+                                   uint32_t *keys_out, const unsigned long long *bin_base) {
   const uint32_t *sbits = c.sbits.as<uint32_t>();
   if (!sbits) sbits = build_start_bits(c, r);
   const int nb1 = 1 << l1_bits;
   c.slab_reserve(1 << 20);
   unsigned long long *d_cursor = c.alloc<unsigned long long>(nb1);
-  k_excl_scan_u64_small<<<1, 1024, 0, c.stream>>>(hist_dev, nb1, d_cursor);
-  MF_LAUNCH_CHECK();
-  c.launches++;
+  if (bin_base) {
+    MF_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long) * nb1, c.stream));   // offsets within each destination
+  } else {
+    k_excl_scan_u64_small<<<1, 1024, 0, c.stream>>>(hist_dev, nb1, d_cursor);
+    MF_LAUNCH_CHECK();
+    c.launches++;
+  }
   Stage st(c, "reads_scatter");
-  launch_reads_scatter<W>(c, r, sbits, k, LevelArgs{0, l1_bits, 0u, (uint32_t)nb1}, d_cursor, keys_out);
+  launch_reads_scatter<W>(c, r, sbits, k, LevelArgs{0, l1_bits, 0u, (uint32_t)nb1, bin_base}, d_cursor, keys_out);
 }
 #define MF_DISPATCH_CASE_CSCAT(Wn) \
-  case Wn: dev_count_scatter_impl<Wn>(c, r, k, l1_bits, hist_dev, keys_out); break;
+  case Wn: dev_count_scatter_impl<Wn>(c, r, k, l1_bits, hist_dev, keys_out, bin_base); break;
 void dev_count_scatter(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev, uint32_t *keys_out,
-                       int64_t) {
+                       const unsigned long long *bin_base) {
   MF_DISPATCH_W(words_key(k), CSCAT)
 }
 template <int W>
@@ -877,7 +912,7 @@ static void dev_count_finish_w(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_
   unsigned long long *d_counting = nullptr;
   MF_CUDA(cudaMalloc(&d_counting, sizeof(unsigned long long) * kNumBuckets));
   MF_CUDA(cudaMemsetAsync(d_counting, 0, sizeof(unsigned long long) * kNumBuckets, c.stream));
-  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)hc.nseg << kMaxDigitBits) * 96 + (size_t)(n_keys / 128);
+  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)hc.nseg << kMaxDigitBits) * 96 + (size_t)(n_keys / 16);
   const size_t arena = (size_t)(min_count > 1 ? n_keys / std::min(min_count, 6) + 1 : n_keys) * We * 4;
   c.slab_reserve(table_bytes + arena + (1 << 20));
   out->n_edges = 0;
@@ -964,20 +999,8 @@ static void sdbg_finish(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n_items,
   unsigned long long *d_bstats = c.sdbg_buckets.as<unsigned long long>();
   Plan p = make_plan(WI, part_limit, n_items, 1.0, false, l1_bits, l1.nseg);
   auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
-  DevBuckets b;
   int bit_off = l1_bits;
-  if (p.l2_bits > 0 || (int)l1.start.size() != l1.nseg) {
-    const int nb = std::max(1, p.l2_bits);
-    b = partition_level<WI>(c, cur, other, l1, l1_bits, nb, salloc, "sdbg_l2");
-    std::swap(cur, other);
-    bit_off += nb;
-  } else {
-    b.nslots = l1.nseg;
-    b.start = c.alloc<int64_t>(b.nslots);
-    b.size = c.alloc<int64_t>(b.nslots);
-    c.h2d(b.start, l1.start.data(), sizeof(int64_t) * b.nslots);
-    c.h2d(b.size, l1.size.data(), sizeof(int64_t) * b.nslots);
-  }
+  DevBuckets b = partition_chain<WI>(c, &cur, &other, l1, &bit_off, p.rest_bits, salloc, "sdbg_l2");
   int64_t *d_items = c.alloc<int64_t>(b.nslots), *d_tips = c.alloc<int64_t>(b.nslots), *d_large = c.alloc<int64_t>(b.nslots);
   int64_t *d_item_src = c.alloc<int64_t>(b.nslots), *d_tip_src = c.alloc<int64_t>(b.nslots);
   int64_t *d_item_off = c.alloc<int64_t>(b.nslots + 1), *d_tip_off = c.alloc<int64_t>(b.nslots + 1),
@@ -1146,12 +1169,13 @@ static void records_hist_impl(Ctx &c, const uint32_t *rec, int64_t n, int l1_bit
   auto kern = k_level_hist<RecordsProducer<W>, W, C::NT, C::IPT_H>;
   set_smem(kern, smem);
   Stage st(c, "records_hist");
-  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ph, LevelArgs{0, l1_bits, 0u, (uint32_t)nb}, hist_dev);
+  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ph, LevelArgs{0, l1_bits, 0u, (uint32_t)nb, nullptr}, hist_dev);
   MF_LAUNCH_CHECK();
   c.launches += 2;
 }
 template <int W>
-static void records_scatter_impl(Ctx &c, const uint32_t *rec, int64_t n, int l1_bits, const unsigned long long *hist_dev, uint32_t *out) {
+static void records_scatter_impl(Ctx &c, const uint32_t *rec, int64_t n, int l1_bits, const unsigned long long *hist_dev, uint32_t *out,
+                                 const unsigned long long *bin_base) {
   using C = TileCfg<W>;
   const int nb = 1 << l1_bits;
   const int64_t tiles = div_ceil64(n, C::TS);
@@ -1166,13 +1190,14 @@ static void records_scatter_impl(Ctx &c, const uint32_t *rec, int64_t n, int l1_
   const int64_t *dp = c.ov[3].as<int64_t>();
   ChunkTable ct{dp, dp + 1, reinterpret_cast<const int32_t *>((const char *)c.ov[3].p + 40), dp + 2, 1};
   k_build_tiles<<<(unsigned)div_ceil64(tiles, 256), 256, 0, c.stream>>>(ct, C::TS, tiles, c.ov[2].as<TileDesc>());
-  k_excl_scan_u64_small<<<1, 1024, 0, c.stream>>>(hist_dev, nb, c.ov[4].as<unsigned long long>());
+  if (bin_base) MF_CUDA(cudaMemsetAsync(c.ov[4].p, 0, sizeof(unsigned long long) * nb, c.stream));
+  else k_excl_scan_u64_small<<<1, 1024, 0, c.stream>>>(hist_dev, nb, c.ov[4].as<unsigned long long>());
   RecordsProducer<W> ps{rec, c.ov[2].as<TileDesc>(), C::TS};
   size_t smem = scatter_smem_bytes<W>(C::NT, C::TS, l1_bits, 4);
   auto kern = k_level_scatter<RecordsProducer<W>, W, C::NT, C::IPT_S>;
   set_smem(kern, smem);
   Stage st(c, "records_scatter");
-  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ps, LevelArgs{0, l1_bits, 0u, (uint32_t)nb}, c.ov[4].as<unsigned long long>(), out);
+  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ps, LevelArgs{0, l1_bits, 0u, (uint32_t)nb, bin_base}, c.ov[4].as<unsigned long long>(), out);
   MF_LAUNCH_CHECK();
   c.launches += 3;
 }
@@ -1183,9 +1208,9 @@ void dev_records_hist(Ctx &c, const uint32_t *rec, int64_t n, int words, int l1_
   MF_DISPATCH_W(words, RHIST)
 }
 #define MF_DISPATCH_CASE_RSCAT(Wn) \
-  case Wn: records_scatter_impl<Wn>(c, rec, n, l1_bits, hist_dev, out); break;
+  case Wn: records_scatter_impl<Wn>(c, rec, n, l1_bits, hist_dev, out, bin_base); break;
 void dev_records_scatter(Ctx &c, const uint32_t *rec, int64_t n, int words, int l1_bits, const unsigned long long *hist_dev,
-                         uint32_t *out) {
+                         uint32_t *out, const unsigned long long *bin_base) {
   if (l1_bits < 1 || l1_bits > kMaxDigitBits) throw std::invalid_argument("l1_bits must be in [1, 11]");
   MF_DISPATCH_W(words, RSCAT)
 }
@@ -1193,7 +1218,7 @@ template <int WI>
 static void dev_sdbg_finish_w(Ctx &c, uint32_t *items, uint32_t *scratch, int64_t n_items, const HostChunks &hc, int k, int l1_bits,
                               int tip_mode, SdbgView *out) {
   if (n_items == 0) return sdbg_empty(c, k, out);
-  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)hc.nseg << kMaxDigitBits) * 96 + (size_t)(n_items / 128);
+  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)hc.nseg << kMaxDigitBits) * 96 + (size_t)(n_items / 16);
   c.slab_reserve(table_bytes + (1 << 20));
   sdbg_finish<WI>(c, items, scratch, n_items, hc, l1_bits, k, tip_mode, out);
 }

@@ -107,7 +107,7 @@ void dev_count(Ctx &c, const ReadsView &r, int k, int min_count, EdgesView *out,
 void dev_seq2sdbg(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &seqs, int k, int tip_mode, SdbgView *out);
 void dev_count_hist(Ctx &c, const ReadsView &r, int k, int l1_bits, unsigned long long *hist_dev);
 void dev_count_scatter(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev, uint32_t *keys_out,
-                       int64_t capacity);
+                       const unsigned long long *bin_base);
 void dev_count_finish(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys, const int64_t *chunk_start,
                       const int64_t *chunk_size, const int32_t *chunk_seg, int n_chunks, int n_segs, int k, int l1_bits,
                       int min_count, EdgesView *out, int64_t *counting_host);
@@ -115,7 +115,7 @@ void dev_count_finish(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys,
 void dev_sdbg_items(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, uint32_t *items_out);
 void dev_records_hist(Ctx &c, const uint32_t *rec, int64_t n, int words, int l1_bits, unsigned long long *hist_dev);
 void dev_records_scatter(Ctx &c, const uint32_t *rec, int64_t n, int words, int l1_bits, const unsigned long long *hist_dev,
-                         uint32_t *out);
+                         uint32_t *out, const unsigned long long *bin_base);
 void dev_sdbg_finish(Ctx &c, uint32_t *items, uint32_t *scratch, int64_t n_items, const int64_t *chunk_start,
                      const int64_t *chunk_size, const int32_t *chunk_seg, int n_chunks, int n_segs, int k, int l1_bits, int tip_mode,
                      SdbgView *out);

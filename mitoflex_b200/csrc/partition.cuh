@@ -27,6 +27,9 @@ struct LevelArgs {
   int bit_off;          // bits already consumed above this digit
   int nbits;            // digit width, 1..kMaxDigitBits
   uint32_t dlo, dhi;    // keep only digits in [dlo, dhi) (out-of-core rounds / multi-GPU ownership)
+  // Fused partition + exchange: when set, bin b is written at byte address bin_base[b] (+ cursor[b] records) instead of
+  // into `out` -- the address may be a peer GPU's buffer mapped over NVLink, so keys go straight to their owner.
+  const unsigned long long *bin_base;
 };
 
 // one tile of a level launch: where its records are and which segment they belong to (built by k_build_tiles so that
@@ -385,14 +388,16 @@ __global__ void __launch_bounds__(NT) k_level_scatter(P prod, LevelArgs a, unsig
       uint2 v = st2[j];
       uint32_t r2[2] = {v.x, v.y};
       uint32_t d = rec_digit<2>(r2, a.bit_off, a.nbits);
-      out2[s_gd[d] + (long long)j] = v;
+      uint2 *dst = a.bin_base ? reinterpret_cast<uint2 *>(a.bin_base[d]) : out2;
+      dst[s_gd[d] + (long long)j] = v;
     }
   } else {
     const uint32_t total_words = total * W;
     for (uint32_t x = tid; x < total_words; x += NT) {
       uint32_t j = x / W, c = x - j * W;
       uint32_t d = rec_digit_mem<W>(stage + (size_t)j * W, a.bit_off, a.nbits);
-      out[(s_gd[d] + (long long)j) * W + c] = stage[x];
+      uint32_t *dst = a.bin_base ? reinterpret_cast<uint32_t *>(a.bin_base[d]) : out;
+      dst[(s_gd[d] + (long long)j) * W + c] = stage[x];
     }
   }
 }

@@ -10,7 +10,9 @@ The planning functions below are pure numpy (tested with gloo on CPU); only Dist
 """
 import numpy as np
 
-L1_BITS = 10
+import os
+
+L1_BITS = int(os.environ.get("MFSDBG_DIST_L1_BITS", "8"))   # 256 bins: runs long enough for efficient NVLink stores
 
 
 def assign_owners(global_hist, world):
@@ -55,6 +57,59 @@ def exchange_plan(all_hists, rank):
                 n_recv=int(recv.sum()))
 
 
+def peer_bin_bases(all_hists, bounds, rank, peer_ptrs, rec_bytes):
+    """Byte address at which this rank's records of every prefix bin must land: bin b belongs to rank r(b), whose receive
+    buffer is laid out source-major with bins ascending (the same layout exchange_plan's chunk table describes)."""
+    H = np.asarray(all_hists, dtype=np.int64)
+    world, nb = H.shape
+    out = np.zeros(nb, dtype=np.uint64)
+    for r in range(world):
+        lo, hi = int(bounds[r]), int(bounds[r + 1])
+        if hi <= lo:
+            continue
+        base = int(H[:rank, lo:hi].sum())                       # lower-ranked sources come first in r's buffer
+        within = np.concatenate([[0], np.cumsum(H[rank, lo:hi])[:-1]])
+        out[lo:hi] = np.uint64(peer_ptrs[r]) + ((base + within) * rec_bytes).astype(np.uint64)
+    return out
+
+
+class PeerBuffer:
+    """A receive buffer in this GPU's HBM that every other rank maps through CUDA IPC (NVLink peer memory)."""
+
+    def __init__(self, ctx, dev):
+        self.ctx, self.dev, self.ptr, self.cap, self.peers = ctx, dev, None, 0, None
+
+    def ensure(self, nbytes):
+        """collective: grow (and re-share) if ANY rank needs more room"""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        flag = torch.tensor([int(nbytes > self.cap or self.ptr is None)], device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()) == 0:
+            return
+        self.release()
+        self.cap = max(int(nbytes * 1.2) + 4096, self.cap)
+        self.ptr = self.ctx.dev_alloc(self.cap)
+        mine = torch.from_numpy(self.ctx.ipc_export(self.ptr)).to(self.dev)
+        allh = torch.empty((world, 64), dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allh, mine)
+        handles = allh.cpu().numpy()
+        self.peers = [self.ptr if r == rank else self.ctx.ipc_open(handles[r]) for r in range(world)]
+
+    def release(self):
+        import torch.distributed as dist
+        if self.ptr is None:
+            return
+        rank = dist.get_rank()
+        for r, p in enumerate(self.peers or []):
+            if r != rank:
+                self.ctx.ipc_close(p)
+        dist.barrier()               # nobody maps the old buffer any more
+        self.ctx.dev_free(self.ptr)
+        self.ptr, self.peers = None, None
+
+
 def all_to_all_records(send_rows, send_splits, recv_splits, group=None):
     """send_rows: [n, W] tensor partitioned by destination rank (splits in rows). Returns the received [m, W] tensor."""
     import torch
@@ -77,7 +132,7 @@ class DistResult:
 class DistRead2Sdbg:
     """read2sdbg over all ranks of the default process group; each rank ends with its prefix range of the graph."""
 
-    def __init__(self, ctx, k, min_count):
+    def __init__(self, ctx, k, min_count, exchange=None):
         import torch
         self.ctx, self.k, self.m = ctx, k, min_count
         self.dev = torch.device("cuda", ctx.device)
@@ -86,6 +141,10 @@ class DistRead2Sdbg:
         self.We = lib.load().mfsdbg_words_per_edge(k)
         self.Wi = lib.load().mfsdbg_words_per_item(k)
         self.profile = {}
+        import os
+        self.mode = exchange or os.environ.get("MFSDBG_EXCHANGE", "p2p")
+        self.key_buf = PeerBuffer(ctx, self.dev)
+        self.item_buf = PeerBuffer(ctx, self.dev)
 
     def _acc(self):
         for name, ms in self.ctx.last_profile().items():
@@ -107,7 +166,8 @@ class DistRead2Sdbg:
         world = dist.get_world_size()
         allh = torch.empty((world, hist.numel()), dtype=torch.int64, device=self.dev)
         dist.all_gather_into_tensor(allh, hist)
-        return allh.cpu().numpy()
+        self._last_hists = allh.cpu().numpy()
+        return self._last_hists
 
     def run(self, reads):
         import torch
@@ -122,20 +182,35 @@ class DistRead2Sdbg:
         ctx.count_hist(reads, k, L1_BITS, hist.data_ptr())
         self._acc()
         plan = exchange_plan(self._gather_hists(hist), rank)
+        allH = self._last_hists
         n_local = int(plan["send"].sum())
-        n_buf = max(n_local, plan["n_recv"], 1)
-        send = torch.empty((n_buf, self.Wk), dtype=torch.int32, device=self.dev)
-        stream.synchronize()
-        ctx.count_scatter(reads, k, L1_BITS, hist.data_ptr(), send.data_ptr(), n_buf)
-        self._acc()
-        recv = self._timed_a2a("a2a_keys", send[:n_local], plan["send"], plan["recv"])
-        stream.synchronize()
-        edges = ctx.count_finish(recv.data_ptr(), send.data_ptr(), plan["n_recv"], plan["chunk_start"], plan["chunk_size"],
-                                 plan["chunk_seg"], plan["n_segs"], k, L1_BITS, self.m)
-        self._acc()
+        if self.mode == "p2p":
+            # fused partition + exchange: the scatter kernel stores every key straight into its owner's HBM over NVLink
+            self.key_buf.ensure(max(plan["n_recv"], 1) * self.Wk * 4)
+            bases = torch.from_numpy(peer_bin_bases(allH, plan["bounds"], rank, self.key_buf.peers, self.Wk * 4).view(np.int64)).to(self.dev)
+            scratch = torch.empty((max(plan["n_recv"], 1), self.Wk), dtype=torch.int32, device=self.dev)
+            stream.synchronize()
+            ctx.count_scatter_peer(reads, k, L1_BITS, bases.data_ptr())
+            self._acc()
+            dist.barrier()            # every rank's stores have landed
+            edges = ctx.count_finish(self.key_buf.ptr, scratch.data_ptr(), plan["n_recv"], plan["chunk_start"], plan["chunk_size"],
+                                     plan["chunk_seg"], plan["n_segs"], k, L1_BITS, self.m)
+            self._acc()
+            del scratch
+        else:
+            n_buf = max(n_local, plan["n_recv"], 1)
+            send = torch.empty((n_buf, self.Wk), dtype=torch.int32, device=self.dev)
+            stream.synchronize()
+            ctx.count_scatter(reads, k, L1_BITS, hist.data_ptr(), send.data_ptr(), n_buf)
+            self._acc()
+            recv = self._timed_a2a("a2a_keys", send[:n_local], plan["send"], plan["recv"])
+            stream.synchronize()
+            edges = ctx.count_finish(recv.data_ptr(), send.data_ptr(), plan["n_recv"], plan["chunk_start"], plan["chunk_size"],
+                                     plan["chunk_seg"], plan["n_segs"], k, L1_BITS, self.m)
+            self._acc()
+            del recv, send
         info = dict(n_keys=plan["n_recv"], n_edges=edges.n, exchanged_keys=n_local - int(plan["send"][rank]),
-                    key_bytes=4 * self.Wk)
-        del recv, send
+                    key_bytes=4 * self.Wk, exchange=self.mode)
         # ---- sdbg: items of the local edges, exchange by item prefix, finish
         n_items = 6 * edges.n
         items = torch.empty((max(n_items, 1), self.Wi), dtype=torch.int32, device=self.dev)
@@ -147,18 +222,38 @@ class DistRead2Sdbg:
         ctx.records_hist(items.data_ptr(), n_items, self.Wi, L1_BITS, ihist.data_ptr())
         self._acc()
         iplan = exchange_plan(self._gather_hists(ihist), rank)
-        ibuf = max(n_items, iplan["n_recv"], 1)
-        isend = torch.empty((ibuf, self.Wi), dtype=torch.int32, device=self.dev)
-        stream.synchronize()
-        ctx.records_scatter(items.data_ptr(), n_items, self.Wi, L1_BITS, ihist.data_ptr(), isend.data_ptr())
-        self._acc()
-        del items
-        irecv = self._timed_a2a("a2a_items", isend[:n_items], iplan["send"], iplan["recv"])
-        stream.synchronize()
-        g = ctx.sdbg_finish(irecv.data_ptr(), isend.data_ptr(), iplan["n_recv"], iplan["chunk_start"], iplan["chunk_size"],
-                            iplan["chunk_seg"], iplan["n_segs"], k, L1_BITS, 1)
-        self._acc()
+        iH = self._last_hists
+        if self.mode == "p2p":
+            self.item_buf.ensure(max(iplan["n_recv"], 1) * self.Wi * 4)
+            ibases = torch.from_numpy(peer_bin_bases(iH, iplan["bounds"], rank, self.item_buf.peers, self.Wi * 4).view(np.int64)).to(self.dev)
+            stream.synchronize()
+            ctx.records_scatter_peer(items.data_ptr(), n_items, self.Wi, L1_BITS, ibases.data_ptr())
+            self._acc()
+            dist.barrier()
+            del items
+            iscratch = torch.empty((max(iplan["n_recv"], 1), self.Wi), dtype=torch.int32, device=self.dev)
+            stream.synchronize()
+            g = ctx.sdbg_finish(self.item_buf.ptr, iscratch.data_ptr(), iplan["n_recv"], iplan["chunk_start"], iplan["chunk_size"],
+                                iplan["chunk_seg"], iplan["n_segs"], k, L1_BITS, 1)
+            self._acc()
+            del iscratch
+        else:
+            ibuf = max(n_items, iplan["n_recv"], 1)
+            isend = torch.empty((ibuf, self.Wi), dtype=torch.int32, device=self.dev)
+            stream.synchronize()
+            ctx.records_scatter(items.data_ptr(), n_items, self.Wi, L1_BITS, ihist.data_ptr(), isend.data_ptr())
+            self._acc()
+            del items
+            irecv = self._timed_a2a("a2a_items", isend[:n_items], iplan["send"], iplan["recv"])
+            stream.synchronize()
+            g = ctx.sdbg_finish(irecv.data_ptr(), isend.data_ptr(), iplan["n_recv"], iplan["chunk_start"], iplan["chunk_size"],
+                                iplan["chunk_seg"], iplan["n_segs"], k, L1_BITS, 1)
+            self._acc()
+            del irecv, isend
         info.update(n_items=iplan["n_recv"], exchanged_items=n_items - int(iplan["send"][rank]), sdbg_items=g.n,
                     item_bytes=4 * self.Wi)
-        del irecv, isend
         return DistResult(g, info)
+
+    def close(self):
+        self.key_buf.release()
+        self.item_buf.release()

@@ -86,6 +86,13 @@ SYMBOLS = {
     "mfsdbg_dev_sdbg_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(DevSdbg)]),
     "mfsdbg_words_per_item": (C.c_int32, [C.c_int32]),
+    "mfsdbg_dev_alloc": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "mfsdbg_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mfsdbg_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mfsdbg_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mfsdbg_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mfsdbg_dev_count_scatter_peer": (C.c_int, [C.c_void_p, C.POINTER(DevReads), C.c_int32, C.c_int32, C.c_void_p]),
+    "mfsdbg_dev_records_scatter_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "mfsdbg_words_per_key": (C.c_int32, [C.c_int32]),
     "mfsdbg_words_per_edge": (C.c_int32, [C.c_int32]),
     "mfsdbg_host_read2sdbg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
@@ -324,6 +331,35 @@ class Context:
                                               counting.ctypes.data if want_counting else None))
         return Edges(self, out, counting)
 
+
+    # -- peer memory (fused partition + exchange)
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        _check(load().mfsdbg_dev_alloc(self._h, int(nbytes), C.byref(p)))
+        return p.value
+
+    def dev_free(self, ptr):
+        _check(load().mfsdbg_dev_free(self._h, ptr))
+
+    def ipc_export(self, ptr):
+        h = np.zeros(64, np.uint8)
+        _check(load().mfsdbg_ipc_export(self._h, ptr, h.ctypes.data))
+        return h
+
+    def ipc_open(self, handle):
+        h = np.ascontiguousarray(handle, dtype=np.uint8)
+        p = C.c_void_p()
+        _check(load().mfsdbg_ipc_open(self._h, h.ctypes.data, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        _check(load().mfsdbg_ipc_close(self._h, ptr))
+
+    def count_scatter_peer(self, reads, k, l1_bits, bin_base_ptr):
+        _check(load().mfsdbg_dev_count_scatter_peer(self._h, C.byref(reads.s), k, l1_bits, bin_base_ptr))
+
+    def records_scatter_peer(self, rec_ptr, n, words, l1_bits, bin_base_ptr):
+        _check(load().mfsdbg_dev_records_scatter_peer(self._h, rec_ptr, n, words, l1_bits, bin_base_ptr))
 
     def sdbg_items(self, edges_ptr, n_edges, k, items_ptr):
         _check(load().mfsdbg_dev_sdbg_items(self._h, edges_ptr, n_edges, k, items_ptr))

@@ -42,6 +42,24 @@ def test_exchange_plan_accounts_for_every_record():
         assert (p["chunk_seg"] >= 0).all() and (p["chunk_seg"] < p["n_segs"]).all()
 
 
+def test_peer_bin_bases_match_the_chunk_table():
+    """fused exchange: the address a source writes bin b to must be where the owner's chunk table expects it"""
+    rng = np.random.default_rng(3)
+    H = rng.integers(0, 40, (3, 1024))
+    H[:, 50:80] = 0
+    ptrs = [10 ** 12, 2 * 10 ** 12, 3 * 10 ** 12]
+    for me in range(3):
+        plan = mdist.exchange_plan(H, me)
+        b = mdist.peer_bin_bases(H, plan["bounds"], me, ptrs, 8)
+        for r in range(3):
+            pr = mdist.exchange_plan(H, r)
+            acc = sum(int(H[s, pr["lo"]:pr["hi"]].sum()) for s in range(me))
+            for bb in range(pr["lo"], pr["hi"]):
+                if H[me, bb] > 0:
+                    assert int(b[bb]) == ptrs[r] + acc * 8
+                acc += int(H[me, bb])
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

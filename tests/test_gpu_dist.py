@@ -15,7 +15,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir, k, m, seed):
+def _worker(rank, world, port, out_dir, k, m, seed, mode):
     import sys
     import torch
     import torch.distributed as dist
@@ -36,25 +36,27 @@ def _worker(rank, world, port, out_dir, k, m, seed):
         sb = bases[starts[lo]:starts[hi]]
         ss = starts[lo:hi + 1] - starts[lo]
         ctx = lib.Context(rank)
-        res = mdist.DistRead2Sdbg(ctx, k, m).run(ctx.upload_reads(sb, ss))
+        runner = mdist.DistRead2Sdbg(ctx, k, m, exchange=mode)
+        res = runner.run(ctx.upload_reads(sb, ss))
         g = res.sdbg.to_numpy()
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), w=g["w"], last=g["last"], tip=g["tip"], mul=g["mul"],
                  tip_labels=g["tip_labels"])
         dist.barrier()
+        runner.close()
         ctx.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,m", [(21, 2), (31, 1)])
-def test_two_gpu_read2sdbg_matches_oracle(oracle, tmp_path, k, m):
+@pytest.mark.parametrize("k,m,mode", [(21, 2, "p2p"), (31, 1, "p2p"), (21, 2, "nccl"), (47, 2, "p2p")])
+def test_two_gpu_read2sdbg_matches_oracle(oracle, tmp_path, k, m, mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from gpu_common import make_reads
     seed, world = 4242 + k, 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), k, m, seed), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), k, m, seed, mode), nprocs=world, join=True)
     bases, starts = make_reads(seed, 60000, k, genome_len=150000, max_len=150, err=0.005)
     g = oracle.read2sdbg(oracle.Reads(bases, starts), k, m, threads=8)
     parts = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
