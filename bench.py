@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--k", type=int, default=21, help="k-mer size (the headline metric is quoted at 21)")
     return ap.parse_args()
 
 
@@ -198,7 +199,9 @@ def run_reference(args):
 
 # ------------------------------------------------------------------ GPU arm
 def main():
+    global K
     args = parse_args()
+    K = args.k
     if args.impl == "reference":
         return run_reference(args)
     import torch

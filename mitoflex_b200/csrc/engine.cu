@@ -18,6 +18,7 @@
 #include "items.cuh"
 #include "local.cuh"
 #include "partition.cuh"
+#include "reads.cuh"
 
 namespace mf {
 
@@ -250,28 +251,27 @@ struct TileCfg {
 
 template <int W>
 static void launch_reads_hist(Ctx &c, const ReadsView &r, const uint32_t *sbits, int k, LevelArgs a, unsigned long long *hist) {
-  using C = TileCfg<W>;
-  ReadsProducer<W> p{r.packed, sbits, r.n_bases, k, C::TH};
-  int64_t tiles = div_ceil64(r.n_bases, C::TH);
+  using C = ReadsTileCfg<W>;
+  const int64_t tiles = div_ceil64(r.n_bases, C::T);
   if (tiles == 0) return;
-  size_t smem = ((size_t)1 << a.nbits) * 4 + (size_t)ReadsProducer<W>::smem_words(C::TH, k) * 4;
-  auto kern = k_level_hist<ReadsProducer<W>, W, C::NT, C::IPT_H>;
+  const size_t smem = (((size_t)1 << a.nbits) + reads_seq_words(C::NT, W) + reads_bit_words(C::NT, k)) * 4;
+  auto kern = k_reads_hist<W, C::NT>;
   set_smem(kern, smem);
-  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(p, a, hist);
+  const int64_t grid = std::min<int64_t>(tiles, (int64_t)c.sm_count * (2048 / C::NT));   // persistent: one flush per CTA
+  kern<<<(unsigned)grid, C::NT, smem, c.stream>>>(ReadsSrc{r.packed, sbits, r.n_bases, k}, a, hist, tiles);
   MF_LAUNCH_CHECK();
   c.launches++;
 }
 template <int W>
 static void launch_reads_scatter(Ctx &c, const ReadsView &r, const uint32_t *sbits, int k, LevelArgs a, unsigned long long *cursor,
                                  uint32_t *out) {
-  using C = TileCfg<W>;
-  ReadsProducer<W> p{r.packed, sbits, r.n_bases, k, C::TS};
-  int64_t tiles = div_ceil64(r.n_bases, C::TS);
+  using C = ReadsTileCfg<W>;
+  const int64_t tiles = div_ceil64(r.n_bases, C::T);
   if (tiles == 0) return;
-  size_t smem = scatter_smem_bytes<W>(C::NT, C::TS, a.nbits, ReadsProducer<W>::smem_words(C::TS, k));
-  auto kern = k_level_scatter<ReadsProducer<W>, W, C::NT, C::IPT_S>;
+  const size_t smem = reads_scatter_smem_bytes<W>(C::NT, a.nbits, k);
+  auto kern = k_reads_scatter<W, C::NT>;
   set_smem(kern, smem);
-  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(p, a, cursor, out);
+  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ReadsSrc{r.packed, sbits, r.n_bases, k}, a, cursor, out);
   MF_LAUNCH_CHECK();
   c.launches++;
 }
@@ -1029,6 +1029,7 @@ static void sdbg_finish(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n_items,
     a.bkt_size = b.size;
     a.bit_off = bit_off;
     a.sort_bits = 32 * WI - 16;   // the walker takes the largest multiplicity of equal (k-mer, b) items itself
+    a.sub_bits = std::max(0, std::min(env_int("MFSDBG_SDBG_SUB", 0), part_limit - bit_off));
     a.cap = p.cap;
     a.k = k;
     a.tip_mode = tip_mode;

@@ -31,6 +31,7 @@ struct LocalArgs {
   const WorkItem *work;      // [grid] explicit work items, or null: blockIdx.x is the slot
   int bit_off;               // leading bits every record of a bucket shares
   int sort_bits;             // bits that take part in the order (count: 2(k+1); sdbg: all 32 W)
+  int sub_bits;              // sdbg fast sort: width of the single in-bucket split (0 = LSD passes only)
   int cap;                   // max records per CTA (shared memory capacity), even
   int k;
   // --- count ---
@@ -117,6 +118,22 @@ __device__ __forceinline__ bool item_diff_km1(const uint32_t *x, const uint32_t 
   for (int i = full - 1; i >= 0; --i)
     if (x[i] != y[i]) return true;
   return false;
+}
+
+// compare two records on their leading `bits` bits only
+template <int W>
+__device__ __forceinline__ int cmp_rec_bits(const uint32_t *a, const uint32_t *b, int bits) {
+  const int full = bits >> 5, rem = bits & 31;
+  for (int i = 0; i < full; ++i) {
+    const uint32_t x = a[i], y = b[i];
+    if (x != y) return x < y ? -1 : 1;
+  }
+  if (rem && full < W) {
+    const uint32_t m = 0xffffffffu << (32 - rem);
+    const uint32_t x = a[full] & m, y = b[full] & m;
+    if (x != y) return x < y ? -1 : 1;
+  }
+  return 0;
 }
 
 // accessors over the sorted order of a range (WR = record stride)
@@ -376,9 +393,48 @@ __global__ void __launch_bounds__(NT) k_local(LocalArgs a) {
   if (tid < 8) s_flag[tid] = 0;
   __syncthreads();
 
-  // LSD sort of the index array over bits [bit_off, sort_bits), least significant digit first
   const uint16_t *cur = nullptr;   // nullptr == identity order
-  {
+  bool sorted = false;
+  if constexpr (MODE == kSdbgEmit) {
+    // sdbg items are almost all distinct: one split on the next sub_bits (shared-atomic ranks, no stability needed) leaves
+    // sub-bins of a few items, which one thread each finishes by insertion.  A crowded sub-bin (repeats) sets the flag and
+    // the bucket takes the general stable-LSD route below.
+    if (a.sub_bits >= 4) {
+      const int nsb = 1 << a.sub_bits;
+      for (int i = tid; i <= nsb; i += NT) bins[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += NT)
+        rk[i] = (uint16_t)atomicAdd(bins + rec_digit_mem<W>(rec + (size_t)i * W, a.bit_off, a.sub_bits), 1u);
+      __syncthreads();
+      block_excl_scan<NT>(bins, nsb + 1, scratch);
+      for (int i = tid; i < n; i += NT)
+        idxA[bins[rec_digit_mem<W>(rec + (size_t)i * W, a.bit_off, a.sub_bits)] + rk[i]] = (uint16_t)i;
+      __syncthreads();
+      int budget = 1024;
+      for (int sb = tid; sb < nsb && budget >= 0; sb += NT) {
+        const int b = (int)bins[sb], e = (int)bins[sb + 1];
+        for (int i = b + 1; i < e && budget >= 0; ++i) {
+          const uint16_t x = idxA[i];
+          const uint32_t *rx = rec + (size_t)x * W;
+          int j = i;
+          while (j > b && cmp_rec_bits<W>(rec + (size_t)idxA[j - 1] * W, rx, a.sort_bits) > 0) {
+            idxA[j] = idxA[j - 1];
+            --j;
+            --budget;
+          }
+          idxA[j] = x;
+        }
+      }
+      if (budget < 0) s_flag[6] = 1;
+      __syncthreads();
+      if (!s_flag[6]) {
+        sorted = true;
+        cur = idxA;
+      }
+    }
+  }
+  // LSD sort of the index array over bits [bit_off, sort_bits), least significant digit first
+  if (!sorted) {
     uint16_t *nxt = idxA;
     int hi = a.sort_bits;
     while (hi > a.bit_off) {
@@ -732,6 +788,17 @@ __global__ void __launch_bounds__(NT) k_count_fast(LocalArgs a) {
   const int64_t start = a.bkt_start[slot];
   const int64_t n = a.bkt_size[slot];
   if (n == 0) return;
+  // the first keys of every thread are requested before the table is cleared, so their DRAM latency hides behind it
+  constexpr int PF = 8;
+  const uint2 *src2 = reinterpret_cast<const uint2 *>(a.in) + start;
+  uint2 pre[PF];
+  if constexpr (W == 2) {
+#pragma unroll
+    for (int q = 0; q < PF; ++q) {
+      const int64_t i = (int64_t)tid + (int64_t)q * NT;
+      pre[q] = i < n ? src2[i] : make_uint2(0u, 0u);
+    }
+  }
   // table size follows the bucket (distinct keys are a fraction of it): fewer slots to clear and to sweep
   int ts_log = 9;
   while ((1 << ts_log) < n && ts_log < 12) ++ts_log;
@@ -764,17 +831,18 @@ __global__ void __launch_bounds__(NT) k_count_fast(LocalArgs a) {
     s_flag[0] = 1;   // table too crowded: this bucket takes the general path
   };
   if constexpr (W == 2) {
-    const uint2 *src = reinterpret_cast<const uint2 *>(a.in) + start;
-    int64_t i = tid;
+    int64_t i = (int64_t)tid + (int64_t)PF * NT;
+    for (int q = 0; q < PF; ++q)
+      if ((int64_t)tid + (int64_t)q * NT < n) insert(((unsigned long long)pre[q].x << 32) | pre[q].y);
     for (; i + 3 * NT < n; i += 4 * NT) {
-      const uint2 v0 = src[i], v1 = src[i + NT], v2 = src[i + 2 * NT], v3 = src[i + 3 * NT];
+      const uint2 v0 = src2[i], v1 = src2[i + NT], v2 = src2[i + 2 * NT], v3 = src2[i + 3 * NT];
       insert(((unsigned long long)v0.x << 32) | v0.y);
       insert(((unsigned long long)v1.x << 32) | v1.y);
       insert(((unsigned long long)v2.x << 32) | v2.y);
       insert(((unsigned long long)v3.x << 32) | v3.y);
     }
     for (; i < n; i += NT) {
-      const uint2 v = src[i];
+      const uint2 v = src2[i];
       insert(((unsigned long long)v.x << 32) | v.y);
     }
   } else {

@@ -12,7 +12,7 @@ import numpy as np
 
 import os
 
-L1_BITS = int(os.environ.get("MFSDBG_DIST_L1_BITS", "8"))   # 256 bins: runs long enough for efficient NVLink stores
+L1_BITS = int(os.environ.get("MFSDBG_DIST_L1_BITS", "7"))   # 128 bins: runs long enough for efficient NVLink stores
 
 
 def assign_owners(global_hist, world):

@@ -142,3 +142,21 @@ def test_synth_generator_and_properties(ctx, oracle):
     g_gpu = ctx.read2sdbg(reads, 21, 2)
     g_orc = oracle.read2sdbg(oracle.Reads(bases, starts), 21, 2, threads=8)
     assert_sdbg_equal(g_gpu, g_orc)
+
+
+def test_count_out_of_core_rounds(oracle):
+    """a small memory budget forces several rounds over prefix-bin ranges (the 30 Gbp-on-one-GPU path, SURVEY config 4)."""
+    from mitoflex_b200 import lib
+    c = lib.Context(0)
+    try:
+        k, m = 21, 2
+        bases, starts = make_reads(99, 150000, k, genome_len=500000, max_len=150, err=0.005)
+        n_keys = int(np.maximum(np.diff(starts) - k, 0).sum())
+        c.set_mem_limit(200 << 20)          # ~9 M keys at 20 B each do not fit next to the tables: at least two rounds
+        e_gpu = c.count(c.upload_reads(bases, starts), k, m, want_counting=True)
+        e_orc = oracle.count(oracle.Reads(bases, starts), k, m, threads=8)
+        assert e_gpu.s.n_keys == n_keys
+        assert_edges_equal(e_gpu, e_orc)
+        assert np.array_equal(e_gpu.counting, e_orc.counting)
+    finally:
+        c.close()
