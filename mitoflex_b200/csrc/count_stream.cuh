@@ -1,0 +1,353 @@
+// count_stream.cuh -- the count finish for keys of 33..64 bits (16 <= k <= 31): persistent CTAs stream CONTIGUOUS runs of
+// buckets out of HBM with TMA bulk copies (cp.async.bulk + mbarrier ring), so DRAM latency never meets the hash loop.
+//
+//   * a CTA owns a contiguous range of buckets == one contiguous key range; thread 0 keeps kCsStages bulk copies in
+//     flight across bucket boundaries, so the next bucket's keys arrive while the current one is being finished;
+//   * keys are grouped in a shared open-addressing table holding the keys themselves (64-bit CAS) + 32-bit counts
+//     (fire-and-forget shared REDs): a bucket of any size fits as long as its DISTINCT keys do;
+//   * bucket end: one sweep over the table collects the solid keys (count >= --min-count), feeds the multiplicity
+//     histogram and clears the slots for the next bucket; the few solid keys are ranked (all pairs, or LSD when many)
+//     and written as edge records (KmerCounter::PackEdge) into arena blocks reserved 4096 edges at a time.
+//   * probe: k_probe_distinct measures distinct/occurrences on a few whole prefix ranges beforehand, so the planner can
+//     size buckets for the table (deep coverage -> large buckets, shallow/erroneous data -> small ones).
+// Buckets whose distinct keys crowd the table or with more than kCsSolidMax solid keys go to the bail list (general path).
+#pragma once
+#include "common.cuh"
+#include "local.cuh"
+
+namespace mf {
+
+constexpr int kCsNT = 512;
+constexpr int kCsSlotsLog = 12;
+constexpr int kCsSlots = 1 << kCsSlotsLog;   // table slots
+constexpr int kCsChunk = 1024;               // keys per ring stage (8 KB bulk copy)
+constexpr int kCsStages = 4;
+constexpr int kCsSolidMax = 1024;            // distinct solid keys of one bucket on this path
+constexpr int kCsWin = 1024;                 // bucket boundaries held in shared memory at a time
+constexpr int kCsProbeLimit = 64;
+constexpr int kCsArenaBlock = 4096;          // edges reserved per global atomic (>= kCsSolidMax)
+constexpr int kCsPairsMax = 256;             // solid keys ranked by all-pairs comparison; more take LSD passes
+
+// ---- mbarrier / bulk-copy primitives (sm_90+ PTX; SASS: UBLKCP + SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+inline size_t count_stream_smem_bytes() {
+  // tkeys u64[4096] | ring u64[stages*chunk] | skeys u64[1024] | mbar u64[4] | tcnt u32[4096] | scnt u32[1024]
+  // | bnd u32[win+2] | bins u32[260] | small u32[64] | scratch u32[36] | flag i32[16] | permA,permB,rk u16[1024]
+  return (size_t)kCsSlots * 8 + (size_t)kCsStages * kCsChunk * 8 + (size_t)kCsSolidMax * 8 + 32 + (size_t)kCsSlots * 4 +
+         (size_t)kCsSolidMax * 4 + (size_t)(kCsWin + 2) * 4 + 260 * 4 + 64 * 4 + 36 * 4 + 16 * 4 + 3 * (size_t)kCsSolidMax * 2;
+}
+
+// cta_first[g] = first bucket slot of CTA g's range: ranges hold equal shares of the keys (bkt_start is monotone)
+__global__ void k_split_ranges(const int64_t *bkt_start, const int64_t *bkt_size, int nslots, int G, int32_t *cta_first) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > G) return;
+  if (g == G) { cta_first[G] = nslots; return; }
+  const int64_t s0 = bkt_start[0], total = bkt_start[nslots - 1] + bkt_size[nslots - 1] - s0;
+  const int64_t target = s0 + (int64_t)(((__int128)total * g) / G);
+  int lo = 0, hi = nslots;   // first slot with bkt_start >= target
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (bkt_start[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  cta_first[g] = g == 0 ? 0 : lo;
+}
+
+__global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const int32_t *__restrict__ cta_first) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  constexpr int NT = kCsNT;
+  unsigned long long *tkeys = reinterpret_cast<unsigned long long *>(smraw);
+  unsigned long long *ring = tkeys + kCsSlots;
+  unsigned long long *skeys = ring + kCsStages * kCsChunk;
+  unsigned long long *mbar = skeys + kCsSolidMax;
+  uint32_t *tcnt = reinterpret_cast<uint32_t *>(mbar + 4);
+  uint32_t *scnt = tcnt + kCsSlots;
+  uint32_t *s_bnd = scnt + kCsSolidMax;
+  uint32_t *bins = s_bnd + kCsWin + 2;
+  uint32_t *s_small = bins + 260;
+  uint32_t *scratch = s_small + 64;
+  int *s_flag = reinterpret_cast<int *>(scratch + 36);   // 0 crowded, 1 ok, 2..3 arena base, 4 ns, 5 blk_left, 6..7 blk_pos
+  uint16_t *permA = reinterpret_cast<uint16_t *>(s_flag + 16);
+  uint16_t *permB = permA + kCsSolidMax, *rk = permB + kCsSolidMax;
+  uint16_t *whist = reinterpret_cast<uint16_t *>(tcnt);   // LSD scratch [NWARP][256] aliases the (swept, empty) counts
+
+  const int tid = threadIdx.x;
+  const int b0 = cta_first[blockIdx.x], b1 = cta_first[blockIdx.x + 1];
+  if (b0 >= b1) return;
+  const int64_t rb = a.bkt_start[b0];
+  const int64_t re = a.bkt_start[b1 - 1] + a.bkt_size[b1 - 1];
+  const uint32_t total = (uint32_t)(re - rb);
+  if (total == 0u) return;
+  const int64_t A = rb & ~(int64_t)1;                    // bulk copies need 16-byte aligned addresses
+  const int64_t re_up = (re + 1) & ~(int64_t)1;
+  const int nchunks = (int)((re_up - A + kCsChunk - 1) / kCsChunk);
+  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(a.in);
+  const uint32_t m = (uint32_t)a.min_count;
+  const int We = a.words_edge;
+
+  auto issue = [&](int c) {   // thread 0 only
+    const int s = c % kCsStages;
+    const int64_t g0 = A + (int64_t)c * kCsChunk;
+    const int64_t left = re_up - g0;
+    const uint32_t bytes = (uint32_t)(left < kCsChunk ? left : kCsChunk) * 8u;
+    mbar_expect_tx(mbar + s, bytes);
+    bulk_g2s(ring + (size_t)s * kCsChunk, src + g0, bytes, mbar + s);
+  };
+  int wb = b0;   // first bucket of the boundary window
+  auto load_window = [&]() {
+    for (int i = tid; i <= kCsWin; i += NT) {
+      const int idx = wb + i;
+      s_bnd[i] = idx < b1 ? (uint32_t)(a.bkt_start[idx] - rb) : total;
+    }
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < kCsStages; ++s) mbar_init(mbar + s, 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < kCsSlots; i += NT) {
+    tkeys[i] = kEmptyKey;
+    tcnt[i] = 0u;
+  }
+  if (tid < 64) s_small[tid] = 0;
+  if (tid < 16) s_flag[tid] = 0;
+  load_window();
+  __syncthreads();
+  if (tid == 0)
+    for (int c = 0; c < kCsStages && c < nchunks; ++c) issue(c);
+
+  auto insert = [&](unsigned long long key) {
+    uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
+    uint32_t h = (x * 0x85EBCA6Bu) >> (32 - kCsSlotsLog);
+    for (int probe = 0; probe < kCsProbeLimit; ++probe) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tkeys + h);
+      if (cur == kEmptyKey) cur = atomicCAS(tkeys + h, kEmptyKey, key);
+      if (cur == kEmptyKey || cur == key) {
+        atomicAdd(tcnt + h, 1u);
+        return;
+      }
+      h = (h + 1) & (kCsSlots - 1);
+    }
+    s_flag[0] = 1;   // table too crowded: this bucket takes the general path
+  };
+
+  // ---- bucket end: sweep + clear, solid keys -> ordered edge records.  Called by all threads, after a __syncthreads.
+  auto finish_bucket = [&](int slot) {
+    const bool crowded = s_flag[0] != 0;
+    for (int h = tid; h < kCsSlots; h += NT) {
+      const uint32_t c = tcnt[h];
+      if (c) {
+        const unsigned long long key = tkeys[h];
+        tkeys[h] = kEmptyKey;
+        tcnt[h] = 0u;
+        if (a.counting && c < 64u) atomicAdd(s_small + c, 1u);
+        if (c >= m) {
+          const int q = atomicAdd(s_flag + 4, 1);
+          if (q < kCsSolidMax) {
+            skeys[q] = key;
+            scnt[q] = c;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int ns_raw = s_flag[4];
+    const bool bail = crowded || ns_raw > kCsSolidMax;
+    const uint32_t ns = bail ? 0u : (uint32_t)ns_raw;
+    if (a.counting) {
+      // multiplicity histogram of the distinct keys (<prefix>.counting): small counts from shared memory, counts >= 64 are
+      // solid keys (the host routes --min-count > 64 with a histogram request to the general kernel).  A bucket that
+      // bails is counted by the general path instead.
+      if (tid < 64) {
+        const uint32_t v = s_small[tid];
+        s_small[tid] = 0;
+        if (v && !bail) atomicAdd(a.counting + tid, (unsigned long long)v);
+      }
+      for (uint32_t q = tid; q < ns; q += NT) {
+        const uint32_t c = scnt[q];
+        if (c >= 64u) atomicAdd(a.counting + (c > (uint32_t)kMaxMul ? (uint32_t)kMaxMul : c), 1ull);
+      }
+    }
+    if (tid == 0) {
+      if (bail) {
+        const int p = atomicAdd(a.bail_count, 1);
+        a.bail_list[p] = slot;
+        s_flag[1] = 0;
+      } else if (ns > 0) {
+        unsigned long long pos = ((unsigned long long)(uint32_t)s_flag[7] << 32) | (uint32_t)s_flag[6];
+        int left = s_flag[5];
+        if ((int)ns > left) {   // next arena block (what is left of the old one is abandoned)
+          pos = atomicAdd(a.arena_cursor, (unsigned long long)kCsArenaBlock);
+          left = kCsArenaBlock;
+        }
+        const int ok = pos + ns <= a.arena_cap;
+        if (!ok) atomicExch(a.overflow_flag, 1);
+        a.desc_off[slot] = (int64_t)pos;
+        a.desc_cnt[slot] = ok ? (int64_t)ns : 0;
+        s_flag[1] = ok;
+        s_flag[2] = (int)(uint32_t)pos;
+        s_flag[3] = (int)(uint32_t)(pos >> 32);
+        pos += ns;
+        left -= (int)ns;
+        s_flag[5] = left;
+        s_flag[6] = (int)(uint32_t)pos;
+        s_flag[7] = (int)(uint32_t)(pos >> 32);
+      } else {
+        s_flag[1] = 0;
+      }
+    }
+    if (ns > 1 && ns <= (uint32_t)kCsPairsMax)
+      for (uint32_t q = tid; q < ns; q += NT) bins[q] = 0;
+    __syncthreads();
+    if (s_flag[1]) {
+      const uint16_t *cur = nullptr;
+      if (ns > 1 && ns <= (uint32_t)kCsPairsMax) {
+        // keys are distinct: rank = number of smaller keys; the comparisons of one key are split over NT / nsp threads
+        uint32_t nsp = 32;
+        while (nsp < ns) nsp <<= 1;
+        const uint32_t parts = NT / nsp, q = tid & (nsp - 1), part = tid / nsp;
+        if (q < ns) {
+          const uint32_t per = (ns + parts - 1) / parts;
+          const uint32_t o0 = part * per, o1 = min(ns, o0 + per);
+          const unsigned long long kq = skeys[q];
+          uint32_t r = 0;
+          for (uint32_t o = o0; o < o1; ++o) r += skeys[o] < kq;
+          if (r) atomicAdd(bins + q, r);
+        }
+        __syncthreads();
+        for (uint32_t q2 = tid; q2 < ns; q2 += NT) permA[bins[q2]] = (uint16_t)q2;
+        __syncthreads();
+        cur = permA;
+      } else if (ns > (uint32_t)kCsPairsMax) {
+        const uint32_t *rec = reinterpret_cast<const uint32_t *>(skeys);   // native u64: word 1 is the high half
+        uint16_t *nxt = permA;
+        int hi = a.sort_bits;
+        while (hi > a.bit_off) {
+          const int nb = min(8, hi - a.bit_off);
+          if (lsd_pass<2, 2, NT, true>(rec, cur, nxt, rk, (int)ns, hi - nb, nb, whist, bins, scratch)) {
+            cur = nxt;
+            nxt = (nxt == permA) ? permB : permA;
+          }
+          hi -= nb;
+        }
+        for (int i = tid; i < (NT / 32) * 256 / 2; i += NT) tcnt[i] = 0u;   // give the counts back clean
+      }
+      const unsigned long long base = ((unsigned long long)(uint32_t)s_flag[3] << 32) | (uint32_t)s_flag[2];
+      for (uint32_t q = tid; q < ns; q += NT) {
+        const uint32_t e = cur ? cur[q] : q;
+        const unsigned long long key = skeys[e];
+        const uint32_t kw[2] = {(uint32_t)(key >> 32), (uint32_t)key};
+        write_edge<2>(a.arena + (base + q) * (unsigned long long)We, kw, We, scnt[e]);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { s_flag[0] = 0; s_flag[4] = 0; }
+    // the barrier the caller issues after advancing publishes the reset
+  };
+
+  // ---- consumer loop over the chunks of the CTA's key range
+  int cur_b = b0;
+  uint32_t p = 0, bend = 0;
+  auto advance = [&]() {   // first bucket at or after cur_b that ends beyond p (all threads, uniform)
+    while (cur_b < b1) {
+      if (cur_b + 1 - wb > kCsWin) {
+        __syncthreads();
+        wb = cur_b;
+        load_window();
+        __syncthreads();
+      }
+      bend = s_bnd[cur_b + 1 - wb];
+      if (bend > p) break;
+      ++cur_b;
+    }
+  };
+  advance();
+  const int off0 = (int)(rb - A);
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c % kCsStages;
+    mbar_wait(mbar + s, (uint32_t)((c / kCsStages) & 1));
+    const int64_t g0 = A + (int64_t)c * kCsChunk;
+    const int64_t ghi = g0 + kCsChunk < re ? g0 + kCsChunk : re;
+    const uint32_t chi = (uint32_t)(ghi - rb);
+    const uint2 *rs = reinterpret_cast<const uint2 *>(ring + (size_t)s * kCsChunk);
+    const int off = off0 - c * kCsChunk;   // ring index of relative position q is q + off
+    while (p < chi) {
+      const uint32_t e = chi < bend ? chi : bend;
+      for (uint32_t q = p + tid; q < e; q += NT) {
+        const uint2 v = rs[(int)q + off];
+        insert(((unsigned long long)v.x << 32) | v.y);
+      }
+      p = e;
+      if (p == bend) {
+        __syncthreads();
+        finish_bucket(cur_b);
+        ++cur_b;
+        advance();
+        __syncthreads();
+      }
+    }
+    __syncthreads();   // everyone is done with stage s
+    if (tid == 0 && c + kCsStages < nchunks) issue(c + kCsStages);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// distinct-ratio probe: for a few whole prefix ranges ("samples", each a list of chunks of one segment) the keys whose
+// next `fbits` bits equal `pattern` form what a final bucket of that range would hold; count them and their distinct keys
+// in a small global table per sample.
+struct ProbeChunk {
+  int64_t start, size;
+  int32_t sample;
+  int32_t fbits;   // filter width
+};
+constexpr int kProbeSlots = 1 << 14;
+__global__ void k_probe_distinct(const uint32_t *__restrict__ keys, const ProbeChunk *__restrict__ chunks, int bit_off, uint32_t pattern,
+                                 unsigned long long *tables /*[samples][kProbeSlots]*/, unsigned long long *stats /*[samples][2]*/) {
+  const ProbeChunk ch = chunks[blockIdx.y];
+  const uint2 *src = reinterpret_cast<const uint2 *>(keys) + ch.start;
+  unsigned long long *tab = tables + (size_t)ch.sample * kProbeSlots;
+  const uint32_t want = ch.fbits ? (pattern & ((1u << ch.fbits) - 1u)) : 0u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ch.size; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint2 v = src[i];
+    const uint32_t r[2] = {v.x, v.y};
+    if (ch.fbits && rec_digit<2>(r, bit_off, ch.fbits) != want) continue;
+    const unsigned long long key = ((unsigned long long)v.x << 32) | v.y;
+    atomicAdd(stats + 2 * ch.sample, 1ull);
+    uint32_t h = (uint32_t)((key * 0x9e3779b97f4a7c15ull) >> (64 - 14));
+    for (int probe = 0; probe < kProbeSlots; ++probe) {
+      unsigned long long cur = tab[h];
+      if (cur == kEmptyKey) cur = atomicCAS(tab + h, kEmptyKey, key);
+      if (cur == kEmptyKey) { atomicAdd(stats + 2 * ch.sample + 1, 1ull); break; }
+      if (cur == key) break;
+      h = (h + 1) & (kProbeSlots - 1);
+    }
+  }
+}
+
+}  // namespace mf

@@ -19,6 +19,8 @@
 #include "local.cuh"
 #include "partition.cuh"
 #include "reads.cuh"
+#include "count_stream.cuh"
+#include "sdbg_local.cuh"
 
 namespace mf {
 
@@ -214,7 +216,7 @@ static Plan make_plan(int W, int part_limit, int64_t n_est, double density, bool
                       int nseg = 0) {
   Plan p;
   p.W = W;
-  p.cap = local_cap(W, hash_family, false);
+  p.cap = hash_family ? local_cap(W, true, false) : (env_int("MFSDBG_SDBG_NEW", 1) ? sdbg_cap(W) : local_cap(W, false, false));
   // buckets of <= 64-bit keys are streamed through a key-resident table (any size, ~10-40 % of it distinct): ~5000 keys
   // on average keeps the densest ones (2x) well inside its 4096 slots; everything else must fit shared memory whole
   const double target = (hash_family && W <= 2) ? 5000.0 : p.cap * 0.65 / density;
@@ -254,11 +256,25 @@ static void launch_reads_hist(Ctx &c, const ReadsView &r, const uint32_t *sbits,
   using C = ReadsTileCfg<W>;
   const int64_t tiles = div_ceil64(r.n_bases, C::T);
   if (tiles == 0) return;
-  const size_t smem = (((size_t)1 << a.nbits) + reads_seq_words(C::NT, W) + reads_bit_words(C::NT, k)) * 4;
-  auto kern = k_reads_hist<W, C::NT>;
+  const size_t smem = (((size_t)1 << a.nbits) + 32 + reads_seq_words(C::NT, W) + reads_bit_words(C::NT, k)) * 4;
+  const bool ranged = a.dlo != 0u || a.dhi != (1u << a.nbits);
+  auto kern = ranged ? k_reads_hist<W, C::NT, true> : k_reads_hist<W, C::NT, false>;
   set_smem(kern, smem);
   const int64_t grid = std::min<int64_t>(tiles, (int64_t)c.sm_count * (2048 / C::NT));   // persistent: one flush per CTA
   kern<<<(unsigned)grid, C::NT, smem, c.stream>>>(ReadsSrc{r.packed, sbits, r.n_bases, k}, a, hist, tiles);
+  MF_LAUNCH_CHECK();
+  c.launches++;
+}
+template <int W, int BPT>
+static void launch_reads_scatter_b(Ctx &c, const ReadsView &r, const uint32_t *sbits, int k, LevelArgs a, unsigned long long *cursor,
+                                   uint32_t *out) {
+  using C = ReadsTileCfg<W>;
+  const int64_t tiles = div_ceil64(r.n_bases, C::T);
+  const size_t smem = reads_scatter_smem_bytes<W>(C::NT, a.nbits, k);
+  const bool ranged = a.dlo != 0u || a.dhi != (1u << a.nbits);
+  auto kern = ranged ? k_reads_scatter<W, C::NT, BPT, true> : k_reads_scatter<W, C::NT, BPT, false>;
+  set_smem(kern, smem);
+  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ReadsSrc{r.packed, sbits, r.n_bases, k}, a, cursor, out);
   MF_LAUNCH_CHECK();
   c.launches++;
 }
@@ -266,14 +282,25 @@ template <int W>
 static void launch_reads_scatter(Ctx &c, const ReadsView &r, const uint32_t *sbits, int k, LevelArgs a, unsigned long long *cursor,
                                  uint32_t *out) {
   using C = ReadsTileCfg<W>;
-  const int64_t tiles = div_ceil64(r.n_bases, C::T);
-  if (tiles == 0) return;
-  const size_t smem = reads_scatter_smem_bytes<W>(C::NT, a.nbits, k);
-  auto kern = k_reads_scatter<W, C::NT>;
-  set_smem(kern, smem);
-  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ReadsSrc{r.packed, sbits, r.n_bases, k}, a, cursor, out);
-  MF_LAUNCH_CHECK();
-  c.launches++;
+  if (r.n_bases == 0) return;
+  const int bpt = std::max(1, (1 << a.nbits) / C::NT);   // bins per thread of the block scan
+  switch (bpt) {
+    case 1: launch_reads_scatter_b<W, 1>(c, r, sbits, k, a, cursor, out); break;
+    case 2: launch_reads_scatter_b<W, 2>(c, r, sbits, k, a, cursor, out); break;
+    case 4: launch_reads_scatter_b<W, 4>(c, r, sbits, k, a, cursor, out); break;
+    case 8: launch_reads_scatter_b<W, 8>(c, r, sbits, k, a, cursor, out); break;
+    default: launch_reads_scatter_b<W, 16>(c, r, sbits, k, a, cursor, out); break;
+  }
+}
+
+// the records-fed scatter kernel for a digit width: bins per thread of its block scan is a template parameter
+template <int W>
+static auto level_scatter_kernel(int nbits) -> void (*)(RecordsProducer<W>, LevelArgs, unsigned long long *, uint32_t *) {
+  using C = TileCfg<W>;
+  const int bpt = std::max(1, (1 << nbits) / C::NT);
+  if (bpt == 1) return k_level_scatter<RecordsProducer<W>, W, C::NT, C::IPT_S, 1>;
+  if (bpt == 2) return k_level_scatter<RecordsProducer<W>, W, C::NT, C::IPT_S, 2>;
+  return k_level_scatter<RecordsProducer<W>, W, C::NT, C::IPT_S, 4>;
 }
 
 struct HostChunks {
@@ -291,7 +318,7 @@ struct DevBuckets {
 // (nseg << nbits slots, slot = seg * nbins + digit) allocated from `alloc`.
 template <int W, class Alloc>
 static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, const HostChunks &hc, int bit_off, int nbits,
-                                  Alloc &&alloc, const char *tag) {
+                                  Alloc &&alloc, const char *tag, const std::vector<uint16_t> *seg_nb = nullptr, int xbits = 0) {
   const std::string tag_h = std::string(tag) + "_hist", tag_s = std::string(tag) + "_scatter";
   using C = TileCfg<W>;
   const int nchunk = (int)hc.start.size(), nseg = hc.nseg, nbins = 1 << nbits;
@@ -321,7 +348,13 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   MF_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nsl, c.stream));
   // the pageable host vectors above die with this frame: make sure the copies have been consumed
   MF_CUDA(cudaStreamSynchronize(c.stream));
-  LevelArgs a{bit_off, nbits, 0u, (uint32_t)nbins, nullptr};
+  LevelArgs a{bit_off, nbits, 0u, (uint32_t)nbins, nullptr, nullptr, 0};
+  if (seg_nb) {   // range partition: per-segment bin counts
+    uint16_t *d_nb = (uint16_t *)alloc(sizeof(uint16_t) * nseg);
+    c.h2d(d_nb, seg_nb->data(), sizeof(uint16_t) * nseg);
+    a.seg_nb = d_nb;
+    a.xbits = xbits;
+  }
   TileDesc *d_tiles_h = (TileDesc *)alloc(sizeof(TileDesc) * std::max<int64_t>(tb_h[nchunk], 1));
   TileDesc *d_tiles_s = (TileDesc *)alloc(sizeof(TileDesc) * std::max<int64_t>(tb_s[nchunk], 1));
   if (tb_h[nchunk] > 0) {
@@ -348,7 +381,7 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   if (tb_s[nchunk] > 0) {
     RecordsProducer<W> ps{in, d_tiles_s, C::TS};
     size_t smem = scatter_smem_bytes<W>(C::NT, C::TS, nbits, 4);
-    auto kern = k_level_scatter<RecordsProducer<W>, W, C::NT, C::IPT_S>;
+    auto kern = level_scatter_kernel<W>(nbits);
     set_smem(kern, smem);
     Stage st(c, tag_s.c_str());
     kern<<<(unsigned)tb_s[nchunk], C::NT, smem, c.stream>>>(ps, a, d_cur, out);
@@ -521,6 +554,106 @@ static std::vector<Range> fetch_bails(Ctx &c, const DevBuckets &b, const int32_t
   return out;
 }
 
+// ------------------------------------------------------------------ count (33..64-bit keys): probe + range partition
+// distinct keys / key occurrences, measured on a few whole level-1 prefix ranges (see k_probe_distinct)
+static double probe_distinct_ratio(Ctx &c, const uint32_t *keys, const HostChunks &l1, int bit_off, int key_bits) {
+  constexpr int S = 8;
+  std::vector<int64_t> seg_total(l1.nseg, 0);
+  for (size_t i = 0; i < l1.start.size(); ++i) seg_total[l1.seg[i]] += l1.size[i];
+  std::vector<int> nonempty;
+  for (int s2 = 0; s2 < l1.nseg; ++s2)
+    if (seg_total[s2] > 0) nonempty.push_back(s2);
+  if (nonempty.empty()) return 1.0;
+  std::vector<int> sample_of(l1.nseg, -1);
+  const int ns = std::min<int>(S, (int)nonempty.size());
+  for (int j = 0; j < ns; ++j) sample_of[nonempty[(size_t)((2 * j + 1) * nonempty.size() / (2 * ns))]] = j;
+  std::vector<ProbeChunk> pcs;
+  for (size_t i = 0; i < l1.start.size(); ++i) {
+    const int sm = sample_of[l1.seg[i]];
+    if (sm < 0 || l1.size[i] == 0) continue;
+    int fb = 0;
+    while (fb < std::min(16, key_bits - bit_off - 8) && (seg_total[l1.seg[i]] >> (fb + 1)) >= 3000) ++fb;
+    pcs.push_back(ProbeChunk{l1.start[i], l1.size[i], sm, fb});
+  }
+  unsigned long long *d_tab = c.alloc<unsigned long long>((size_t)S * kProbeSlots);
+  unsigned long long *d_stats = c.alloc<unsigned long long>(2 * S);
+  ProbeChunk *d_pcs = c.alloc<ProbeChunk>(pcs.size());
+  MF_CUDA(cudaMemsetAsync(d_tab, 0xff, sizeof(unsigned long long) * S * kProbeSlots, c.stream));
+  MF_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 2 * S, c.stream));
+  c.h2d(d_pcs, pcs.data(), sizeof(ProbeChunk) * pcs.size());
+  {
+    Stage st(c, "probe");
+    k_probe_distinct<<<dim3(64, (unsigned)pcs.size()), 256, 0, c.stream>>>(keys, d_pcs, bit_off, 0x5a5au, d_tab, d_stats);
+    MF_LAUNCH_CHECK();
+    c.launches++;
+  }
+  unsigned long long st[2 * S];
+  c.d2h(st, d_stats, sizeof st);
+  double occ = 0, dis = 0;
+  for (int j = 0; j < S; ++j) { occ += (double)st[2 * j]; dis += (double)st[2 * j + 1]; }
+  if (occ < 64) return 1.0;
+  return std::max(dis / occ, 1e-4);
+}
+
+// Level 2 of the streamed count: buckets sized for the shared table from the measured distinct ratio; every level-1
+// segment is cut into its own number of equal key ranges.  *bit_off keeps the bits ALL keys of a bucket share.
+template <int W, class Alloc>
+static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, const HostChunks &l1, int *bit_off, int key_bits,
+                                   Alloc &&alloc) {
+  const double rho = probe_distinct_ratio(c, *cur, l1, *bit_off, key_bits);
+  const double load = env_int("MFSDBG_STREAM_LOAD_PCT", 30) / 100.0;
+  const double B = std::min(60000.0, std::max(1024.0, load * kCsSlots / rho));
+  if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] distinct ratio %.4f -> %.0f keys per bucket\n", rho, B);
+  HostChunks hc = l1;
+  DevBuckets b;
+  for (;;) {
+    std::vector<int64_t> seg_total(hc.nseg, 0);
+    for (size_t i = 0; i < hc.start.size(); ++i) seg_total[hc.seg[i]] += hc.size[i];
+    const int xbits = std::min(16, key_bits - *bit_off);
+    const int64_t nb_cap = std::min<int64_t>(kMaxBins, (int64_t)1 << xbits);
+    int64_t max_need = 1;
+    for (int s2 = 0; s2 < hc.nseg; ++s2) max_need = std::max<int64_t>(max_need, (int64_t)std::ceil((double)seg_total[s2] / B));
+    if (max_need <= nb_cap || xbits < 16) {
+      std::vector<uint16_t> nb(hc.nseg);
+      int mx = 1;
+      for (int s2 = 0; s2 < hc.nseg; ++s2) {
+        nb[s2] = (uint16_t)std::max<int64_t>(1, std::min<int64_t>(nb_cap, (int64_t)std::ceil((double)seg_total[s2] / B)));
+        mx = std::max<int>(mx, nb[s2]);
+      }
+      const int nbits = std::max(1, ceil_log2((double)mx));
+      b = partition_level<W>(c, *cur, *other, hc, *bit_off, nbits, alloc, "count_l2", &nb, xbits);
+      std::swap(*cur, *other);
+      return b;
+    }
+    // a segment needs more than 2048 buckets (shallow data / few segments): one bit-prefix level first
+    const int bits = std::min(kMaxDigitBits, ceil_log2((double)max_need / (double)nb_cap));
+    b = partition_level<W>(c, *cur, *other, hc, *bit_off, bits, alloc, "count_l2a");
+    std::swap(*cur, *other);
+    *bit_off += bits;
+    std::vector<int64_t> st(b.nslots), sz(b.nslots);
+    c.d2h(st.data(), b.start, sizeof(int64_t) * b.nslots);
+    c.d2h(sz.data(), b.size, sizeof(int64_t) * b.nslots);
+    HostChunks h2;
+    h2.nseg = b.nslots;
+    h2.start.assign(st.begin(), st.end());
+    h2.size.assign(sz.begin(), sz.end());
+    h2.seg.resize(b.nslots);
+    for (int i = 0; i < b.nslots; ++i) h2.seg[i] = i;
+    h2.seg_out_start = h2.start;
+    hc = std::move(h2);
+  }
+}
+
+static void launch_count_stream(Ctx &c, const LocalArgs &a, int nslots, int64_t n_keys, int grid, int32_t *d_cta_first) {
+  k_split_ranges<<<div_ceil(grid + 1, 128), 128, 0, c.stream>>>(a.bkt_start, a.bkt_size, nslots, grid, d_cta_first);
+  MF_LAUNCH_CHECK();
+  const size_t smem = count_stream_smem_bytes();
+  set_smem(k_count_stream, smem);
+  k_count_stream<<<grid, kCsNT, smem, c.stream>>>(a, d_cta_first);
+  MF_LAUNCH_CHECK();
+  c.launches += 2;
+}
+
 // ------------------------------------------------------------------ count: finish from l1-partitioned keys
 template <int W>
 static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n, const HostChunks &l1, int k, int l1_bits,
@@ -529,7 +662,15 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
   Plan p = make_plan(W, key_bits, n, 2.0, true, l1_bits, l1.nseg);
   auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
   int bit_off = l1_bits;
-  DevBuckets b = partition_chain<W>(c, &cur, &other, l1, &bit_off, p.rest_bits, salloc, "count_l2");
+  // keys of 33..64 bits take the streamed finish (TMA ring + shared hash table, buckets sized by a distinct-ratio probe)
+  const bool stream = W == 2 && env_int("MFSDBG_COUNT_STREAM", 1) != 0 && !(d_counting && min_count > 64);
+  DevBuckets b;
+  if constexpr (W == 2) {
+    if (stream) b = stream_partition<W>(c, &cur, &other, l1, &bit_off, key_bits, salloc);
+  }
+  if (!stream) b = partition_chain<W>(c, &cur, &other, l1, &bit_off, p.rest_bits, salloc, "count_l2");
+  const int stream_grid = stream ? (int)std::max<int64_t>(1, std::min<int64_t>(2 * c.sm_count, n / 16384)) : 0;
+  int32_t *d_cta_first = stream ? c.alloc<int32_t>(stream_grid + 2) : nullptr;
   int64_t *d_desc_off = c.alloc<int64_t>(b.nslots), *d_desc_cnt = c.alloc<int64_t>(b.nslots);
   int64_t *d_out_off = c.alloc<int64_t>(b.nslots + 1);
   int32_t *d_bail = c.alloc<int32_t>(b.nslots);
@@ -539,7 +680,7 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
   size_t arena_cap;
   {
     const size_t want_max = (size_t)(min_count > 1 ? n / min_count + 1 : n);
-    const size_t guess = std::min(want_max, (size_t)std::max<int64_t>(n / 6 + 1, 1 << 16));
+    const size_t guess = std::min(want_max, (size_t)std::max<int64_t>(n / 6 + 1, 1 << 16)) + (size_t)stream_grid * kCsArenaBlock;
     const size_t room = c.slab_bytes - ((c.slab_off + 255) & ~(size_t)255);
     arena_cap = std::min(guess, room / ((size_t)We * 4));
   }
@@ -574,12 +715,14 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
       // keys of <= 64 bits: stream every bucket through the key-resident hash table (any bucket size)
       {
         Stage st(c, "local_count");
-        launch_count_fast<W>(c, a, b.nslots);
+        if (stream) launch_count_stream(c, a, b.nslots, n, stream_grid, d_cta_first);
+        else launch_count_fast<W>(c, a, b.nslots);
       }
       c.d2h(flags, d_flags, sizeof(int) * 3);
       if (flags[0] > 0) {
         // buckets with too many distinct keys for the table: general path on exactly those slots
         Stage st(c, "local_count_general");
+        if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] count: %d of %d buckets take the general kernel\n", flags[0], b.nslots);
         std::vector<int32_t> slots(flags[0]);
         c.d2h(slots.data(), d_bail, sizeof(int32_t) * flags[0]);
         std::sort(slots.begin(), slots.end());
@@ -1048,12 +1191,45 @@ static void sdbg_finish(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n_items,
     a.bail_list = d_bail;
     a.bail_count = d_flags;
     a.overflow_flag = d_flags + 1;
+    const bool sdbg_new = env_int("MFSDBG_SDBG_NEW", 1) != 0;
     {
       Stage st(c, "local_sdbg");
-      launch_local<WI, kSdbgEmit>(c, a, b.nslots);
+      if (sdbg_new) {
+        a.cap = sdbg_cap(WI);
+        const size_t smem = sdbg_smem_bytes(WI, a.cap);
+        set_smem(k_sdbg_local<WI>, smem);
+        k_sdbg_local<WI><<<b.nslots, kSdNT, smem, c.stream>>>(a);
+        MF_LAUNCH_CHECK();
+        c.launches++;
+      } else {
+        launch_local<WI, kSdbgEmit>(c, a, b.nslots);
+      }
     }
     int flags[2];
     c.d2h(flags, d_flags, sizeof(int) * 2);
+    if (sdbg_new && flags[0] > 0) {
+      // buckets with a crowded sub-bin (low-complexity sequence) or too many items: the general LSD kernel on those slots
+      Stage st(c, "local_sdbg_general");
+      if (getenv("MFSDBG_TRACE")) {
+        int f4[4];
+        c.d2h(f4, d_flags, sizeof f4);
+        fprintf(stderr, "[mfsdbg] sdbg: %d of %d buckets take the general kernel (%d too large, %d crowded; cap %d, %lld items)\n", flags[0],
+                b.nslots, f4[2], f4[3], a.cap, (long long)n_items);
+      }
+      std::vector<int32_t> slots;
+      std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &slots);
+      std::vector<WorkItem> wi(rs.size());
+      for (size_t i = 0; i < rs.size(); ++i) wi[i] = WorkItem{rs[i].start, (int32_t)std::min<int64_t>(rs[i].size, INT32_MAX), slots[i]};
+      c.ov[7].reserve(sizeof(WorkItem) * wi.size());
+      c.h2d(c.ov[7].p, wi.data(), sizeof(WorkItem) * wi.size());
+      MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), c.stream));
+      LocalArgs ga = a;
+      ga.cap = local_cap(WI, false, false);
+      ga.work = c.ov[7].as<WorkItem>();
+      launch_local<WI, kSdbgEmit>(c, ga, (int)wi.size());
+      c.d2h(flags, d_flags, sizeof(int) * 2);
+      a.cap = ga.cap;
+    }
     if (flags[0] > 0) {
       Stage st(c, "fallback");
       std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &bail_slots);
@@ -1195,7 +1371,7 @@ static void records_scatter_impl(Ctx &c, const uint32_t *rec, int64_t n, int l1_
   else k_excl_scan_u64_small<<<1, 1024, 0, c.stream>>>(hist_dev, nb, c.ov[4].as<unsigned long long>());
   RecordsProducer<W> ps{rec, c.ov[2].as<TileDesc>(), C::TS};
   size_t smem = scatter_smem_bytes<W>(C::NT, C::TS, l1_bits, 4);
-  auto kern = k_level_scatter<RecordsProducer<W>, W, C::NT, C::IPT_S>;
+  auto kern = level_scatter_kernel<W>(l1_bits);
   set_smem(kern, smem);
   Stage st(c, "records_scatter");
   kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ps, LevelArgs{0, l1_bits, 0u, (uint32_t)nb, bin_base}, c.ov[4].as<unsigned long long>(), out);

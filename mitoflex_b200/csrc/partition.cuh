@@ -30,7 +30,23 @@ struct LevelArgs {
   // Fused partition + exchange: when set, bin b is written at byte address bin_base[b] (+ cursor[b] records) instead of
   // into `out` -- the address may be a peer GPU's buffer mapped over NVLink, so keys go straight to their owner.
   const unsigned long long *bin_base;
+  // Range partition (count level 2): segment s is cut into seg_nb[s] <= 2^nbits bins of equal key range instead of 2^nbits
+  // bit-prefix bins, digit = (next xbits bits * seg_nb[s]) >> xbits -- monotone in the key, so bins stay key-ordered, and
+  // every segment gets the bin count its size asks for (canonical keys are twice as dense at small prefixes).
+  const uint16_t *seg_nb;
+  int xbits;
 };
+
+template <int W>
+__device__ __forceinline__ uint32_t level_digit(const uint32_t (&r)[W], const LevelArgs &a, uint32_t nb) {
+  if (nb == 0u) return rec_digit<W>(r, a.bit_off, a.nbits);
+  return (rec_digit<W>(r, a.bit_off, a.xbits) * nb) >> a.xbits;
+}
+template <int W>
+__device__ __forceinline__ uint32_t level_digit_mem(const uint32_t *r, const LevelArgs &a, uint32_t nb) {
+  if (nb == 0u) return rec_digit_mem<W>(r, a.bit_off, a.nbits);
+  return (rec_digit_mem<W>(r, a.bit_off, a.xbits) * nb) >> a.xbits;
+}
 
 // one tile of a level launch: where its records are and which segment they belong to (built by k_build_tiles so that
 // no CTA has to walk the chunk table with a chain of dependent loads)
@@ -220,12 +236,13 @@ __global__ void __launch_bounds__(NT) k_level_hist(P prod, LevelArgs a, unsigned
   const int tid = threadIdx.x;
   for (int i = tid; i < nbins; i += NT) s_hist[i] = 0;
   typename P::Tile t = prod.setup(blockIdx.x, psm);   // contains a __syncthreads
+  const uint32_t nb = a.seg_nb ? a.seg_nb[t.seg] : 0u;
 #pragma unroll 4
   for (int i = 0; i < IPT; ++i) {
     uint32_t r[W];
     int j = i * NT + tid;
     bool valid = prod.get(t, psm, j, r);
-    uint32_t d = rec_digit<W>(r, a.bit_off, a.nbits);
+    uint32_t d = level_digit<W>(r, a, nb);
     if (valid && d >= a.dlo && d < a.dhi) atomicAdd(s_hist + d, 1u);
   }
   __syncthreads();
@@ -315,6 +332,61 @@ __global__ void k_level_scan(const unsigned long long *hist, int nbins, const in
   }
 }
 
+// Thread t owns bins [t*BPT, (t+1)*BPT).  In: s_cnt = per-bin record counts of the tile.  Out: s_cnt = exclusive starts
+// (staging offsets); s_gd[b] = global record index reserved for the bin's first staged record minus that start (one global
+// atomicAdd per non-empty bin, all of a thread's in flight together).  Returns the tile's record total.
+template <int NT, int BPT>
+__device__ __forceinline__ uint32_t bins_scan_reserve(uint32_t *s_cnt, long long *s_gd, uint32_t *scratch,
+                                                      unsigned long long *cursor_row, int nbins) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t c[BPT], sum = 0;
+#pragma unroll
+  for (int q = 0; q < BPT; ++q) {
+    const int b = tid * BPT + q;
+    c[q] = b < nbins ? s_cnt[b] : 0u;
+    sum += c[q];
+  }
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t v = lane < NT / 32 ? scratch[lane] : 0u;
+    uint32_t vi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+      if (lane >= o) vi += t;
+    }
+    scratch[lane] = vi - v;
+    if (lane == 31) scratch[32] = vi;
+  }
+  __syncthreads();
+  uint32_t run = scratch[warp] + inc - sum;
+  unsigned long long g[BPT];
+#pragma unroll
+  for (int q = 0; q < BPT; ++q) {
+    const int b = tid * BPT + q;
+    g[q] = c[q] ? atomicAdd(cursor_row + b, (unsigned long long)c[q]) : 0ull;
+  }
+#pragma unroll
+  for (int q = 0; q < BPT; ++q) {
+    const int b = tid * BPT + q;
+    if (b < nbins) {
+      s_cnt[b] = run;
+      s_gd[b] = (long long)g[q] - (long long)run;
+      run += c[q];
+    }
+  }
+  const uint32_t total = scratch[32];
+  __syncthreads();
+  return total;
+}
+
 // ============================================================ scatter
 // dynamic smem layout (uint32 units):
 //   s_cnt   u32 [nbins]      per-bin counters (rank = atomicAdd), then exclusive starts
@@ -329,7 +401,7 @@ __host__ __device__ inline size_t scatter_smem_bytes(int NT, int T, int nbits, i
   return words * 4;
 }
 
-template <class P, int W, int NT, int IPT>
+template <class P, int W, int NT, int IPT, int BPT>
 __global__ void __launch_bounds__(NT) k_level_scatter(P prod, LevelArgs a, unsigned long long *__restrict__ cursor,
                                                       uint32_t *__restrict__ out) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -348,6 +420,7 @@ __global__ void __launch_bounds__(NT) k_level_scatter(P prod, LevelArgs a, unsig
   for (int i = tid; i < nbins; i += NT) s_cnt[i] = 0;
   typename P::Tile t = prod.setup(blockIdx.x, psm);   // contains a __syncthreads
 
+  const uint32_t nb = a.seg_nb ? a.seg_nb[t.seg] : 0u;
   uint32_t rec[IPT][W];
   uint32_t rk[IPT];   // digit << 16 | rank within the bin; 0xffffffff = dropped
   bool ok[IPT];
@@ -355,21 +428,12 @@ __global__ void __launch_bounds__(NT) k_level_scatter(P prod, LevelArgs a, unsig
   for (int i = 0; i < IPT; ++i) ok[i] = prod.get(t, psm, i * NT + tid, rec[i]);   // all loads in flight before any atomic
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
-    const uint32_t d = rec_digit<W>(rec[i], a.bit_off, a.nbits);
+    const uint32_t d = level_digit<W>(rec[i], a, nb);
     const bool valid = ok[i] && d >= a.dlo && d < a.dhi;
     rk[i] = valid ? ((d << 16) | atomicAdd(s_cnt + d, 1u)) : 0xffffffffu;
   }
   __syncthreads();
-  for (int b = tid; b < nbins; b += NT) s_gd[b] = (long long)s_cnt[b];   // stash the counts for the reservation below
-  __syncthreads();
-  const uint32_t total = block_excl_scan<NT>(s_cnt, nbins, scratch);
-  for (int b = tid; b < nbins; b += NT) {
-    long long c = s_gd[b];
-    if (c) {
-      unsigned long long g = atomicAdd(cursor + (size_t)t.seg * nbins + b, (unsigned long long)c);
-      s_gd[b] = (long long)g - (long long)s_cnt[b];
-    }
-  }
+  const uint32_t total = bins_scan_reserve<NT, BPT>(s_cnt, s_gd, scratch, cursor + (size_t)t.seg * nbins, nbins);
   // stage records in bin order
 #pragma unroll
   for (int i = 0; i < IPT; ++i) {
@@ -387,7 +451,7 @@ __global__ void __launch_bounds__(NT) k_level_scatter(P prod, LevelArgs a, unsig
     for (uint32_t j = tid; j < total; j += NT) {
       uint2 v = st2[j];
       uint32_t r2[2] = {v.x, v.y};
-      uint32_t d = rec_digit<2>(r2, a.bit_off, a.nbits);
+      uint32_t d = level_digit<2>(r2, a, nb);
       uint2 *dst = a.bin_base ? reinterpret_cast<uint2 *>(a.bin_base[d]) : out2;
       dst[s_gd[d] + (long long)j] = v;
     }
@@ -395,7 +459,7 @@ __global__ void __launch_bounds__(NT) k_level_scatter(P prod, LevelArgs a, unsig
     const uint32_t total_words = total * W;
     for (uint32_t x = tid; x < total_words; x += NT) {
       uint32_t j = x / W, c = x - j * W;
-      uint32_t d = rec_digit_mem<W>(stage + (size_t)j * W, a.bit_off, a.nbits);
+      uint32_t d = level_digit_mem<W>(stage + (size_t)j * W, a, nb);
       uint32_t *dst = a.bin_base ? reinterpret_cast<uint32_t *>(a.bin_base[d]) : out;
       dst[(s_gd[d] + (long long)j) * W + c] = stage[x];
     }

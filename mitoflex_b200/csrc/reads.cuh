@@ -49,6 +49,16 @@ struct KeyWindow {
     for (int j = 0; j <= W; ++j) rv[j] = __funnelshift_lc(rr[j + 1], rr[j], q2);
     last_mask = 0xffffffffu << (32 * W - 2 * K1);
   }
+  // first word of the canonical key of position I: min(r, c) is decided by the first differing word, so the first word
+  // of the minimum is the minimum of the first words -- all a partition digit needs
+  __device__ __forceinline__ uint32_t head(int I) const {
+    uint32_t c0 = __funnelshift_l(cw[1], cw[0], 2 * I), r0 = __funnelshift_l(rv[1], rv[0], 2 * (15 - I));
+    if constexpr (W == 1) {
+      c0 &= last_mask;
+      r0 &= last_mask;
+    }
+    return min(c0, r0);
+  }
   // canonical key of the thread's position I (0..15)
   __device__ __forceinline__ void key(int I, uint32_t (&out)[W]) const {
     uint32_t c[W], r[W];
@@ -125,18 +135,20 @@ __device__ __forceinline__ int reads_load_tile(const ReadsSrc &src, int64_t tile
 }
 
 // ============================================================ histogram
-template <int W, int NT>
+// invalid positions add to one of 32 per-lane dummy counters behind the bins, so the loop has no branch
+template <int W, int NT, bool RANGED>
 __global__ void __launch_bounds__(NT) k_reads_hist(ReadsSrc src, LevelArgs a, unsigned long long *__restrict__ hist,
                                                    int64_t ntiles) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int nbins = 1 << a.nbits;
-  uint32_t *s_hist = smem;
-  uint32_t *seq = s_hist + nbins;
+  uint32_t *s_hist = smem;                   // [nbins + 32]
+  uint32_t *seq = s_hist + nbins + 32;
   uint32_t *sb = seq + reads_seq_words(NT, W);
   const int tid = threadIdx.x;
   const int dsh = 32 - a.nbits;
   const uint32_t dlo = a.dlo, dspan = a.dhi - a.dlo;
-  for (int i = tid; i < nbins; i += NT) s_hist[i] = 0;
+  const uint32_t dummy = (uint32_t)nbins + (tid & 31);
+  for (int i = tid; i < nbins + 32; i += NT) s_hist[i] = 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     __syncthreads();
     const int lim = reads_load_tile<W, NT>(src, tile, seq, sb);
@@ -147,10 +159,10 @@ __global__ void __launch_bounds__(NT) k_reads_hist(ReadsSrc src, LevelArgs a, un
     kw.init(seq + tid, src.k + 1);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      uint32_t key[W];
-      kw.key(i, key);
-      const uint32_t d = key[0] >> dsh;
-      if (((vm >> i) & 1u) && (d - dlo) < dspan) atomicAdd(s_hist + d, 1u);
+      const uint32_t d = kw.head(i) >> dsh;
+      bool ok = (vm >> i) & 1u;
+      if constexpr (RANGED) ok = ok && (d - dlo) < dspan;
+      atomicAdd(s_hist + (ok ? d : dummy), 1u);
     }
   }
   __syncthreads();
@@ -161,22 +173,22 @@ __global__ void __launch_bounds__(NT) k_reads_hist(ReadsSrc src, LevelArgs a, un
 }
 
 // ============================================================ scatter
-// dynamic smem (uint32 units): s_cnt[nbins] | pad | s_gd i64[nbins] | scratch[36] | stage[T*W] | seq | sb
+// dynamic smem (uint32 units): s_cnt[nbins+32] | pad | s_gd i64[nbins] | scratch[36] | stage[T*W] | seq | sb
 template <int W>
 __host__ __device__ inline size_t reads_scatter_smem_bytes(int NT, int nbits, int k) {
   const size_t nb = (size_t)1 << nbits;
-  return (nb + 2 + 2 * nb + 36 + 2 + (size_t)NT * 16 * W + reads_seq_words(NT, W) + reads_bit_words(NT, k)) * 4;
+  return (nb + 32 + 2 + 2 * nb + 36 + 2 + (size_t)NT * 16 * W + reads_seq_words(NT, W) + reads_bit_words(NT, k)) * 4;
 }
 
-template <int W, int NT>
+template <int W, int NT, int BPT, bool RANGED>
 __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a, unsigned long long *__restrict__ cursor,
                                                       uint32_t *__restrict__ out) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr int T = NT * 16;
   const int nbins = 1 << a.nbits;
   const int tid = threadIdx.x;
-  uint32_t *s_cnt = smem;
-  uint32_t *s_gd32 = s_cnt + nbins;
+  uint32_t *s_cnt = smem;                      // [nbins + 32]: bins, then per-lane dummies for dropped positions
+  uint32_t *s_gd32 = s_cnt + nbins + 32;
   if ((reinterpret_cast<uintptr_t>(s_gd32) & 7) != 0) s_gd32 += 1;
   long long *s_gd = reinterpret_cast<long long *>(s_gd32);
   uint32_t *scratch = s_gd32 + 2 * nbins;
@@ -186,47 +198,37 @@ __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a,
   uint32_t *sb = seq + reads_seq_words(NT, W);
   const int dsh = 32 - a.nbits;
   const uint32_t dlo = a.dlo, dspan = a.dhi - a.dlo;
+  const uint32_t dummy = (uint32_t)nbins + (tid & 31);
 
-  for (int i = tid; i < nbins; i += NT) s_cnt[i] = 0;
+  for (int i = tid; i < nbins + 32; i += NT) s_cnt[i] = 0;
   const int lim = reads_load_tile<W, NT>(src, blockIdx.x, seq, sb);
   __syncthreads();
   const uint32_t vm = valid16(sb, tid * 16, src.k, lim);
   KeyWindow<W> kw;
   kw.init(seq + tid, src.k + 1);
-  // phase A: count
-  uint32_t keep = 0;   // bit i: position i yields a key of this round's digit range
+  // phase A: count (only the first key word matters for the digit)
+  if (vm) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t d = kw.head(i) >> dsh;
+      bool ok = (vm >> i) & 1u;
+      if constexpr (RANGED) ok = ok && (d - dlo) < dspan;
+      atomicAdd(s_cnt + (ok ? d : dummy), 1u);
+    }
+  }
+  __syncthreads();
+  const uint32_t total = bins_scan_reserve<NT, BPT>(s_cnt, s_gd, scratch, cursor, nbins);
+  // phase B: keys again, each takes the next free slot of its bin (the partition need not be stable)
   if (vm) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       uint32_t key[W];
       kw.key(i, key);
       const uint32_t d = key[0] >> dsh;
-      if (((vm >> i) & 1u) && (d - dlo) < dspan) {
-        atomicAdd(s_cnt + d, 1u);
-        keep |= 1u << i;
-      }
-    }
-  }
-  __syncthreads();
-  for (int b = tid; b < nbins; b += NT) s_gd[b] = (long long)s_cnt[b];
-  __syncthreads();
-  const uint32_t total = block_excl_scan<NT>(s_cnt, nbins, scratch);
-  for (int b = tid; b < nbins; b += NT) {
-    const long long c = s_gd[b];
-    if (c) {
-      const unsigned long long g = atomicAdd(cursor + b, (unsigned long long)c);
-      s_gd[b] = (long long)g - (long long)s_cnt[b];
-    }
-  }
-  __syncthreads();
-  // phase B: keys again, each takes the next free slot of its bin (the partition need not be stable)
-  if (keep) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      uint32_t key[W];
-      kw.key(i, key);
-      if ((keep >> i) & 1u) {
-        const uint32_t pos = atomicAdd(s_cnt + (key[0] >> dsh), 1u);
+      bool ok = (vm >> i) & 1u;
+      if constexpr (RANGED) ok = ok && (d - dlo) < dspan;
+      const uint32_t pos = atomicAdd(s_cnt + (ok ? d : dummy), 1u);
+      if (ok) {
         if constexpr (W == 2) {
           *reinterpret_cast<uint2 *>(stage + (size_t)pos * 2) = make_uint2(key[0], key[1]);
         } else {
