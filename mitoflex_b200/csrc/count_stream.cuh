@@ -26,7 +26,7 @@ constexpr int kCsSolidMax = 1024;            // distinct solid keys of one bucke
 constexpr int kCsWin = 1024;                 // bucket boundaries held in shared memory at a time
 constexpr int kCsProbeLimit = 64;
 constexpr int kCsArenaBlock = 4096;          // edges reserved per global atomic (>= kCsSolidMax)
-constexpr int kCsPairsMax = 256;             // solid keys ranked by all-pairs comparison; more take LSD passes
+constexpr int kCsPairsMax = 128;             // solid keys ranked by all-pairs comparison; more take a counting split
 
 // ---- mbarrier / bulk-copy primitives (sm_90+ PTX; SASS: UBLKCP + SYNCS)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,9 +59,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 
 inline size_t count_stream_smem_bytes() {
   // tkeys u64[4096] | ring u64[stages*chunk] | skeys u64[1024] | mbar u64[4] | tcnt u32[4096] | scnt u32[1024]
-  // | bnd u32[win+2] | bins u32[260] | small u32[64] | scratch u32[36] | flag i32[16] | permA,permB,rk u16[1024]
+  // | bnd u32[win+2] | bins u32[260] | small u32[64] | scratch u32[40] | flag i32[16] | permA,permB,rk u16[1024]
   return (size_t)kCsSlots * 8 + (size_t)kCsStages * kCsChunk * 8 + (size_t)kCsSolidMax * 8 + 32 + (size_t)kCsSlots * 4 +
-         (size_t)kCsSolidMax * 4 + (size_t)(kCsWin + 2) * 4 + 260 * 4 + 64 * 4 + 36 * 4 + 16 * 4 + 3 * (size_t)kCsSolidMax * 2;
+         (size_t)kCsSolidMax * 4 + (size_t)(kCsWin + 2) * 4 + 260 * 4 + 64 * 4 + 40 * 4 + 16 * 4 + 3 * (size_t)kCsSolidMax * 2;
 }
 
 // cta_first[g] = first bucket slot of CTA g's range: ranges hold equal shares of the keys (bkt_start is monotone)
@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
   uint32_t *bins = s_bnd + kCsWin + 2;
   uint32_t *s_small = bins + 260;
   uint32_t *scratch = s_small + 64;
-  int *s_flag = reinterpret_cast<int *>(scratch + 36);   // 0 crowded, 1 ok, 2..3 arena base, 4 ns, 5 blk_left, 6..7 blk_pos
+  int *s_flag = reinterpret_cast<int *>(scratch + 40);   // 0 crowded, 1 ok, 2..3 arena base, 4 ns, 5 blk_left, 6..7 blk_pos
   uint16_t *permA = reinterpret_cast<uint16_t *>(s_flag + 16);
   uint16_t *permB = permA + kCsSolidMax, *rk = permB + kCsSolidMax;
-  uint16_t *whist = reinterpret_cast<uint16_t *>(tcnt);   // LSD scratch [NWARP][256] aliases the (swept, empty) counts
+  uint32_t *whist32 = tcnt;   // sub-bin counters [1025] of the many-solid-keys sort alias the (swept, empty) counts
 
   const int tid = threadIdx.x;
   const int b0 = cta_first[blockIdx.x], b1 = cta_first[blockIdx.x + 1];
@@ -245,18 +245,43 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
         __syncthreads();
         cur = permA;
       } else if (ns > (uint32_t)kCsPairsMax) {
-        const uint32_t *rec = reinterpret_cast<const uint32_t *>(skeys);   // native u64: word 1 is the high half
-        uint16_t *nxt = permA;
-        int hi = a.sort_bits;
-        while (hi > a.bit_off) {
-          const int nb = min(8, hi - a.bit_off);
-          if (lsd_pass<2, 2, NT, true>(rec, cur, nxt, rk, (int)ns, hi - nb, nb, whist, bins, scratch)) {
-            cur = nxt;
-            nxt = (nxt == permA) ? permB : permA;
+        // many solid keys (moderate coverage): one counting split on the 10 bits below the keys' common range, then a rank
+        // fix inside each sub-bin (the keys are distinct and spread evenly, so sub-bins hold about one key)
+        unsigned long long *s_mm = reinterpret_cast<unsigned long long *>(scratch);   // [0] min, [1] max (8-byte aligned)
+        if (tid == 0) { s_mm[0] = ~0ull; s_mm[1] = 0ull; }
+        for (int i = tid; i <= 1024; i += NT) whist32[i] = 0u;
+        __syncthreads();
+        {
+          unsigned long long mn = ~0ull, mx = 0ull;
+          for (uint32_t q = tid; q < ns; q += NT) { const unsigned long long kq = skeys[q]; mn = min(mn, kq); mx = max(mx, kq); }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
           }
-          hi -= nb;
+          if ((tid & 31) == 0) { atomicMin(s_mm, mn); atomicMax(s_mm + 1, mx); }
         }
-        for (int i = tid; i < (NT / 32) * 256 / 2; i += NT) tcnt[i] = 0u;   // give the counts back clean
+        __syncthreads();
+        const unsigned long long kmin = s_mm[0];
+        const int span_bits = 64 - __clzll((long long)((s_mm[1] - kmin) | 1ull));
+        const int sh = span_bits > 10 ? span_bits - 10 : 0;
+        for (uint32_t q = tid; q < ns; q += NT) rk[q] = (uint16_t)atomicAdd(whist32 + (uint32_t)((skeys[q] - kmin) >> sh), 1u);
+        __syncthreads();
+        block_excl_scan<NT>(whist32, 1025, scratch + 4);
+        for (uint32_t q = tid; q < ns; q += NT) permB[whist32[(uint32_t)((skeys[q] - kmin) >> sh)] + rk[q]] = (uint16_t)q;
+        __syncthreads();
+        for (uint32_t p2 = tid; p2 < ns; p2 += NT) {
+          const uint32_t q = permB[p2];
+          const unsigned long long kq = skeys[q];
+          const uint32_t d = (uint32_t)((kq - kmin) >> sh);
+          const uint32_t b2 = whist32[d], e2 = whist32[d + 1];
+          uint32_t r = 0;
+          for (uint32_t o = b2; o < e2; ++o) r += skeys[permB[o]] < kq;
+          permA[b2 + r] = (uint16_t)q;
+        }
+        __syncthreads();
+        for (int i = tid; i <= 1024; i += NT) whist32[i] = 0u;   // give the counts back clean
+        cur = permA;
       }
       const unsigned long long base = ((unsigned long long)(uint32_t)s_flag[3] << 32) | (uint32_t)s_flag[2];
       for (uint32_t q = tid; q < ns; q += NT) {

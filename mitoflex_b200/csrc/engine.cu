@@ -66,6 +66,7 @@ Ctx::~Ctx() {
                     &in_words, &in_starts})
     b->release();
   for (DevBuf &b : ov) b.release();
+  for (DevBuf &b : small) b.release();
   out_rec.release();
   out_labels.release();
   if (slab) cudaFree(slab);
@@ -121,7 +122,8 @@ void Ctx::begin_call() {
 }
 void Ctx::end_call() {
   MF_CUDA(cudaStreamSynchronize(stream));
-  if (profiling && getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] call took %.3f ms on the host clock\n", now_ms() - call_t0);
+  if (profiling && getenv("MFSDBG_TRACE"))
+    fprintf(stderr, "[mfsdbg] call took %.3f ms on the host clock (begin %.3f, end %.3f)\n", now_ms() - call_t0, fmod(call_t0, 1e6), fmod(now_ms(), 1e6));
   if (profiling) {
     char buf[128];
     for (auto &s : stages) {
@@ -877,8 +879,8 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
 }
 
 static void edge_bucket_counts(Ctx &c, const EdgesView &e) {
-  unsigned long long *d = nullptr;
-  MF_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * kNumBuckets));
+  c.small[0].reserve(sizeof(unsigned long long) * kNumBuckets);
+  unsigned long long *d = c.small[0].as<unsigned long long>();
   MF_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * kNumBuckets, c.stream));
   if (e.n_edges > 0) {
     k_edge_buckets<<<kNumBuckets / 256, 256, 0, c.stream>>>(e.edges, e.n_edges, e.words, d);
@@ -887,7 +889,6 @@ static void edge_bucket_counts(Ctx &c, const EdgesView &e) {
   }
   MF_CUDA(cudaMemcpyAsync(c.edge_bucket_counts.data(), d, sizeof(int64_t) * kNumBuckets, cudaMemcpyDeviceToHost, c.stream));
   MF_CUDA(cudaStreamSynchronize(c.stream));
-  cudaFree(d);
 }
 
 static const uint32_t *build_start_bits(Ctx &c, const ReadsView &r) {
@@ -913,8 +914,8 @@ static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, Edg
   // the plan needs the key count: it is at most one key per base
   Plan p = make_plan(W, key_bits, std::max<int64_t>(r.n_bases - r.n_reads * (int64_t)k, 1), 2.0, true);   // one key per base minus k per read
   const int nb1 = 1 << p.l1_bits;
-  unsigned long long *d_small = nullptr;   // hist | counting
-  MF_CUDA(cudaMalloc(&d_small, sizeof(unsigned long long) * (nb1 + kNumBuckets)));
+  c.small[1].reserve(sizeof(unsigned long long) * (kMaxBins + kNumBuckets));
+  unsigned long long *d_small = c.small[1].as<unsigned long long>();   // hist | counting
   unsigned long long *d_hist = d_small, *d_counting = d_small + nb1;
   MF_CUDA(cudaMemsetAsync(d_small, 0, sizeof(unsigned long long) * (nb1 + kNumBuckets), c.stream));
   {
@@ -983,7 +984,6 @@ static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, Edg
   }
   if (counting_host)
     c.d2h(counting_host, d_counting, sizeof(int64_t) * kNumBuckets);
-  cudaFree(d_small);
   Stage st(c, "edge_buckets");
   edge_bucket_counts(c, *out);
 }
@@ -1052,8 +1052,8 @@ template <int W>
 static void dev_count_finish_w(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys, const HostChunks &hc, int k, int l1_bits,
                                int min_count, EdgesView *out, int64_t *counting_host) {
   const int We = words_edge(k);
-  unsigned long long *d_counting = nullptr;
-  MF_CUDA(cudaMalloc(&d_counting, sizeof(unsigned long long) * kNumBuckets));
+  c.small[2].reserve(sizeof(unsigned long long) * kNumBuckets);
+  unsigned long long *d_counting = c.small[2].as<unsigned long long>();
   MF_CUDA(cudaMemsetAsync(d_counting, 0, sizeof(unsigned long long) * kNumBuckets, c.stream));
   const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)hc.nseg << kMaxDigitBits) * 96 + (size_t)(n_keys / 16);
   const size_t arena = (size_t)(min_count > 1 ? n_keys / std::min(min_count, 6) + 1 : n_keys) * We * 4;
@@ -1068,7 +1068,6 @@ static void dev_count_finish_w(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_
     out->edges = c.edges.as<uint32_t>();
   }
   if (counting_host) c.d2h(counting_host, d_counting, sizeof(int64_t) * kNumBuckets);
-  cudaFree(d_counting);
   edge_bucket_counts(c, *out);
 }
 #define MF_DISPATCH_CASE_CFIN(Wn) \
@@ -1093,27 +1092,57 @@ void dev_count_finish(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys,
 }
 
 // ------------------------------------------------------------------ seq2sdbg
+// Returns the number of items written.  filter: drop the dummy items Lv2Postprocess would drop anyway (needs the WHOLE edge
+// set in `edges`, so the multi-GPU driver, whose ranks hold key ranges, passes false).
 template <int WI>
-static void sdbg_make_items(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, uint32_t *items) {
+static int64_t sdbg_make_items(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, uint32_t *items, bool filter) {
   const int WK = words_key(k), WE = words_edge(k);
   Stage st(c, "items");
+  int64_t n_edge_items = 6 * n_edges;
   if (n_edges > 0) {
     const unsigned grid = (unsigned)div_ceil64(n_edges, 128);
     // (WK, WE, WI) is one of (w,w,w), (w-1,w-1,w), (w-1,w,w) with w = WI >= 2
     if constexpr (WI >= 2) {
-      if (WK == WI) k_items_from_edges<WI, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
-      else if (WE == WK) k_items_from_edges<WI - 1, WI - 1, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
-      else k_items_from_edges<WI - 1, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
+      if (filter && k <= 31 && WK <= 2 && WI <= 3 && n_edges < ((int64_t)1 << 29)) {
+        if constexpr (WI <= 3) {
+          const int log_slots = std::max(10, std::min(31, ceil_log2(4.0 * (double)n_edges)));
+          const size_t slots = (size_t)1 << log_slots;
+          unsigned long long *d_table = c.alloc<unsigned long long>(slots + 1);
+          unsigned long long *d_cur = d_table + slots;
+          MF_CUDA(cudaMemsetAsync(d_table, 0xff, sizeof(unsigned long long) * slots, c.stream));
+          MF_CUDA(cudaMemsetAsync(d_cur, 0, sizeof(unsigned long long), c.stream));
+          // (WK, WE) for k <= 31: k <= 15 -> (1, 2 or 1); 16..23 -> (2, 2); 24..31 -> (2, 3)
+          auto run = [&](auto wk, auto we) {
+            constexpr int K_ = decltype(wk)::value, E_ = decltype(we)::value;
+            k_kmer_set_insert<K_, E_><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, d_table, log_slots);
+            k_items_from_edges_filtered<K_, E_, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, d_table, log_slots, items, d_cur);
+          };
+          if (WK == 1 && WE == 1) run(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
+          else if (WK == 1) run(std::integral_constant<int, 1>{}, std::integral_constant<int, 2>{});
+          else if (WE == 2) run(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{});
+          else run(std::integral_constant<int, 2>{}, std::integral_constant<int, 3>{});
+          MF_LAUNCH_CHECK();
+          c.launches += 2;
+          unsigned long long got = 0;
+          c.d2h(&got, d_cur, sizeof got);
+          n_edge_items = (int64_t)got;
+        }
+      } else {
+        if (WK == WI) k_items_from_edges<WI, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
+        else if (WE == WK) k_items_from_edges<WI - 1, WI - 1, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
+        else k_items_from_edges<WI - 1, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
+        MF_LAUNCH_CHECK();
+        c.launches++;
+      }
     }
-    MF_LAUNCH_CHECK();
-    c.launches++;
   }
   if (sq.n_items > 0) {
     k_items_from_seqs<WI><<<(unsigned)div_ceil64(sq.n_items, 128), 128, 0, c.stream>>>(
-        sq.packed, sq.starts, sq.mult, sq.item_base, sq.nseq, sq.n_items, k, items + (size_t)6 * n_edges * WI);
+        sq.packed, sq.starts, sq.mult, sq.item_base, sq.nseq, sq.n_items, k, items + (size_t)n_edge_items * WI);
     MF_LAUNCH_CHECK();
     c.launches++;
   }
+  return n_edge_items + sq.n_items;
 }
 static void sdbg_empty(Ctx &c, int k, SdbgView *out) {
   out->k = k;
@@ -1281,14 +1310,18 @@ static void sdbg_finish(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n_items,
 
 template <int WI>
 static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, int tip_mode, SdbgView *out) {
-  const int64_t n_items = 6 * n_edges + sq.n_items;
+  const int64_t n_cap = 6 * n_edges + sq.n_items;   // upper bound: the filtered generator usually writes about a third
+  if (n_cap == 0) return sdbg_empty(c, k, out);
+  const bool filter = env_int("MFSDBG_ITEM_FILTER", 1) != 0 && k <= 31;
+  const size_t set_bytes = filter ? ((size_t)8 << std::max(10, std::min(31, ceil_log2(4.0 * (double)std::max<int64_t>(n_edges, 1))))) + 64 : 0;
+  const int nb1_max = 1 << kMaxDigitBits;
+  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1_max << kMaxDigitBits) * 96 + (size_t)(n_cap / 128);
+  c.slab_reserve((size_t)n_cap * WI * 4 * 2 + table_bytes + set_bytes + (1 << 20));
+  uint32_t *bufA = c.alloc<uint32_t>((size_t)n_cap * WI + 16), *bufB = c.alloc<uint32_t>((size_t)n_cap * WI + 16);
+  const int64_t n_items = sdbg_make_items<WI>(c, edges, n_edges, sq, k, bufA, filter);
   if (n_items == 0) return sdbg_empty(c, k, out);
   Plan p = make_plan(WI, 2 * (k - 1), n_items, 1.0, false);
   const int nb1 = 1 << p.l1_bits;
-  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1 << kMaxDigitBits) * 96 + (size_t)(n_items / 128);
-  c.slab_reserve((size_t)n_items * WI * 4 * 2 + table_bytes + (1 << 20));
-  uint32_t *bufA = c.alloc<uint32_t>((size_t)n_items * WI + 16), *bufB = c.alloc<uint32_t>((size_t)n_items * WI + 16);
-  sdbg_make_items<WI>(c, edges, n_edges, sq, k, bufA);
   auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
   HostChunks whole;   // level 1 over the whole item array
   whole.nseg = 1;
@@ -1319,7 +1352,7 @@ void dev_seq2sdbg(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView
 
 // ---- staged sdbg for the multi-GPU driver: items -> (caller exchanges them by prefix) -> finish
 #define MF_DISPATCH_CASE_SITEMS(Wn) \
-  case Wn: sdbg_make_items<Wn>(c, edges, n_edges, SeqsView{}, k, items_out); break;
+  case Wn: sdbg_make_items<Wn>(c, edges, n_edges, SeqsView{}, k, items_out, false); break;
 void dev_sdbg_items(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, uint32_t *items_out) {
   if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
   MF_DISPATCH_W(words_item(k), SITEMS)

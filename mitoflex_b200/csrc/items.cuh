@@ -89,6 +89,124 @@ __global__ void k_items_from_edges(const uint32_t *__restrict__ edges, int64_t n
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Filtered item generation for k <= 31 (the k-mer fits 62 bits).  Of the 6 items of an edge only the 2 real ones always
+// reach the graph; a "$"-head item survives Lv2Postprocess only if its k-mer has no incoming solid edge, a "$"-tail item
+// only if its k-mer has no outgoing one -- rare at assembly depths.  Both tests are membership queries in the set
+//     PS = { first k bases of e : e in (edges U revcomp(edges)) }
+// ("k-mer has an outgoing edge"; incoming = outgoing of the reverse complement, the edge set is closed under it).
+// PS lives in an open-addressing table in HBM; items that the walker would drop anyway are never generated, sorted or
+// walked.  Dropping them cannot change any other output: they carry no multiplicity, never feed has_solid_a/b or last_a,
+// and whole (a, b) runs of them are skipped together.  The item order is arbitrary (a warp-aggregated append).
+constexpr unsigned long long kKmerEmpty = 0xffffffffffffffffull;   // 2k <= 62 bits used: never a valid entry
+
+__device__ __forceinline__ uint32_t kmer_slot(unsigned long long x, int log_slots) {
+  return (uint32_t)((x * 0x9e3779b97f4a7c15ull) >> (64 - log_slots));
+}
+__device__ __forceinline__ unsigned long long revcomp64(unsigned long long t, int nchars) {   // left-aligned 2*nchars bits
+  unsigned long long x = __brevll(~t);   // complement, reversed bit order: bases reversed with their two bits swapped
+  x = ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
+  return x << (64 - 2 * nchars);         // the reversed string sat right aligned
+}
+template <int WK, int WE>
+__device__ __forceinline__ unsigned long long load_edge64(const uint32_t *src, int k) {
+  unsigned long long t = (unsigned long long)src[0] << 32;
+  if constexpr (WK == 2) t |= src[1];
+  return t & (~0ull << (64 - 2 * (k + 1)));   // drop the multiplicity if it shares the last key word
+}
+
+template <int WK, int WE>
+__global__ void k_kmer_set_insert(const uint32_t *__restrict__ edges, int64_t n_edges, int k, unsigned long long *table, int log_slots) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const unsigned long long fw = load_edge64<WK, WE>(edges + e * WE, k);
+  const unsigned long long rc = revcomp64(fw, k + 1);
+  const unsigned long long mk = ~0ull << (64 - 2 * k);
+  const uint32_t smask = (1u << log_slots) - 1u;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const unsigned long long x = (s ? rc : fw) & mk;
+    uint32_t h = kmer_slot(x, log_slots);
+    for (;;) {
+      unsigned long long cur = table[h];
+      if (cur == kKmerEmpty) cur = atomicCAS(table + h, kKmerEmpty, x);
+      if (cur == kKmerEmpty || cur == x) break;
+      h = (h + 1) & smask;
+    }
+  }
+}
+
+template <int WK, int WE, int WI>
+__global__ void k_items_from_edges_filtered(const uint32_t *__restrict__ edges, int64_t n_edges, int k,
+                                            const unsigned long long *__restrict__ table, int log_slots,
+                                            uint32_t *__restrict__ items, unsigned long long *cursor) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = e < n_edges;
+  uint32_t fwv[WK], rcv[WK];
+  uint32_t mult = 0;
+  bool q[2] = {true, true};   // q[s]: the k-mer t[1..k] of strand s has an outgoing solid edge
+  if (live) {
+    const uint32_t *src = edges + e * WE;
+    const unsigned long long fw = load_edge64<WK, WE>(src, k);
+    const unsigned long long rc = revcomp64(fw, k + 1);
+    mult = src[WE - 1] & 0xffffu;
+    fwv[0] = (uint32_t)(fw >> 32);
+    rcv[0] = (uint32_t)(rc >> 32);
+    if constexpr (WK == 2) { fwv[1] = (uint32_t)fw; rcv[1] = (uint32_t)rc; }
+    const unsigned long long mk = ~0ull << (64 - 2 * k);
+    const uint32_t smask = (1u << log_slots) - 1u;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const unsigned long long x = ((s ? rc : fw) << 2) & mk;
+      uint32_t h = kmer_slot(x, log_slots);
+      for (;;) {
+        const unsigned long long cur = table[h];
+        if (cur == x) break;
+        if (cur == kKmerEmpty) { q[s] = false; break; }
+        h = (h + 1) & smask;
+      }
+    }
+  }
+  // "$"-head of strand s needs no incoming edge = !q[1-s]; "$"-tail of strand s needs no outgoing edge = !q[s]
+  const int extra = live ? 2 * ((q[0] ? 0 : 1) + (q[1] ? 0 : 1)) : 0;
+  const int mine = live ? 2 + extra : 0;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += v;
+  }
+  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long base = 0;
+  if ((threadIdx.x & 31) == 31 && warp_total) base = atomicAdd(cursor, (unsigned long long)warp_total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (!live) return;
+  uint32_t *dst = items + (base + (unsigned long long)(incl - mine)) * WI;
+#pragma unroll
+  for (int strand = 0; strand < 2; ++strand) {
+    const uint32_t(&t)[WK] = strand ? rcv : fwv;
+    const uint32_t c0 = t[0] >> 30, c1 = (t[0] >> 28) & 3;
+    uint32_t it[WI];
+    if (!q[1 - strand]) {
+      window_item<WK, WI>(t, 0, k, 1, kSentinel, 0, it);
+#pragma unroll
+      for (int i = 0; i < WI; ++i) dst[i] = it[i];
+      dst += WI;
+    }
+    window_item<WK, WI>(t, 1, k, 1, c0, mult, it);
+#pragma unroll
+    for (int i = 0; i < WI; ++i) dst[i] = it[i];
+    dst += WI;
+    if (!q[strand]) {
+      window_item<WK, WI>(t, 2, k - 1, 0, c1, 0, it);
+#pragma unroll
+      for (int i = 0; i < WI; ++i) dst[i] = it[i];
+      dst += WI;
+    }
+  }
+}
+
 // General sequences (contigs etc.), stored orientation, 2-bit packed back to back.
 // One thread per item; item -> sequence by binary search over item_base (sequences are long, few).
 template <int WI>
