@@ -106,8 +106,11 @@ def stage_bytes(n_bases, n_keys, n_edges, n_items_gen, k):
         "reads_scatter": n_bases / 4 + n_keys * W,
         "count_l2_hist": n_keys * W,
         "count_l2_scatter": 2 * n_keys * W,
+        "count_l2a_hist": n_keys * W,
+        "count_l2a_scatter": 2 * n_keys * W,
         "local_count": n_keys * W + n_edges * We,
-        "items": n_edges * We + n_items_gen * Wi,
+        # filtered generator: edges read twice (k-mer set build, lookup), 4 random 8-byte table accesses per edge, items out
+        "items": 2 * n_edges * We + 32 * n_edges + n_items_gen * Wi,
         "records_hist": n_items_gen * Wi,
         "records_scatter": 2 * n_items_gen * Wi,
         "local_sdbg": n_items_gen * Wi,
@@ -115,8 +118,6 @@ def stage_bytes(n_bases, n_keys, n_edges, n_items_gen, k):
         "sdbg_l1_scatter": 2 * n_items_gen * Wi,
         "sdbg_l2_hist": n_items_gen * Wi,
         "sdbg_l2_scatter": 2 * n_items_gen * Wi,
-        "local_sdbg_count": n_items_gen * Wi,
-        "local_sdbg_emit": n_items_gen * Wi,
     }
 
 
@@ -312,7 +313,10 @@ def main():
     e_cnt = ctx.count(reads, K, MIN_COUNT) if world == 1 else None
     n_keys = e_cnt.s.n_keys if e_cnt is not None else info.get("n_keys", 0)
     n_edges = e_cnt.n if e_cnt is not None else info.get("n_edges", 0)
-    sb = stage_bytes(n_bases, n_keys, n_edges, 6 * n_edges, K)
+    # generated sdbg items: the filtered generator writes the 2 real items per edge plus the few dummies that survive,
+    # which is what the graph ends up holding (res.n); the multi-GPU driver still generates all 6 per edge
+    n_items_gen = (res.n if res is not None else 2 * n_edges) if world == 1 else 6 * n_edges
+    sb = stage_bytes(n_bases, n_keys, n_edges, n_items_gen, K)
     nvlink = None
     if world > 1:
         # rank 0's share: bytes that left this GPU / time of the all-to-all, against 900 GB/s per direction nominal
@@ -332,10 +336,15 @@ def main():
                     "traffic": None, "peak_source": peak_src, "ms_per_launch": per_step[dom],
                     "algorithmic_bytes_per_launch": sb[dom],
                     "stages_ms": {k2: round(v, 3) for k2, v in sorted(per_step.items(), key=lambda kv: -kv[1])}}
+        # DRAM bytes of that kernel from the committed `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum),
+        # stored per key occurrence because the capture runs a smaller read set; scaled to this launch
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             try:
-                roofline["traffic"] = json.load(open(tr)).get(dom)
+                ent = json.load(open(tr)).get(dom)
+                if ent and "dram_bytes_per_key" in ent:
+                    roofline["traffic"] = ent["dram_bytes_per_key"] * n_keys
+                    roofline["traffic_source"] = ent.get("source")
             except ValueError:
                 pass
     cpu = None

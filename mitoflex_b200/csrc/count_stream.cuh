@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "local.cuh"
+#include "partition.cuh"
 
 namespace mf {
 
@@ -79,7 +80,12 @@ __global__ void k_split_ranges(const int64_t *bkt_start, const int64_t *bkt_size
   cta_first[g] = g == 0 ? 0 : lo;
 }
 
-__global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const int32_t *__restrict__ cta_first) {
+// MULTIPASS = false: the streamed kernel proper.  MULTIPASS = true: one CTA per bucket that bailed there (too many distinct
+// keys for the table): the bucket's key range is cut into 2^passes_log equal sub-ranges and the bucket is re-read once per
+// sub-range and sweep (sweep 1 totals the solid keys so that the arena space is reserved in one piece, sweep 2 emits), keys
+// outside the pass's sub-range are skipped -- the table only ever holds a fraction of the distinct keys, output stays sorted.
+template <bool MULTIPASS>
+__global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const int32_t *__restrict__ cta_first, int passes_log) {
   extern __shared__ __align__(128) unsigned char smraw[];
   constexpr int NT = kCsNT;
   unsigned long long *tkeys = reinterpret_cast<unsigned long long *>(smraw);
@@ -98,12 +104,17 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
   uint32_t *whist32 = tcnt;   // sub-bin counters [1025] of the many-solid-keys sort alias the (swept, empty) counts
 
   const int tid = threadIdx.x;
-  const int b0 = cta_first[blockIdx.x], b1 = cta_first[blockIdx.x + 1];
-  if (b0 >= b1) return;
-  const int64_t rb = a.bkt_start[b0];
-  const int64_t re = a.bkt_start[b1 - 1] + a.bkt_size[b1 - 1];
+  int b0 = 0, b1 = 0;
+  int64_t rb = 0, re = 0;
+  if constexpr (!MULTIPASS) {
+    b0 = cta_first[blockIdx.x];
+    b1 = cta_first[blockIdx.x + 1];
+    if (b0 >= b1) return;
+    rb = a.bkt_start[b0];
+    re = a.bkt_start[b1 - 1] + a.bkt_size[b1 - 1];
+  }
   const uint32_t total = (uint32_t)(re - rb);
-  if (total == 0u) return;
+  if (!MULTIPASS && total == 0u) return;
   const int64_t A = rb & ~(int64_t)1;                    // bulk copies need 16-byte aligned addresses
   const int64_t re_up = (re + 1) & ~(int64_t)1;
   const int nchunks = (int)((re_up - A + kCsChunk - 1) / kCsChunk);
@@ -137,10 +148,12 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
   }
   if (tid < 64) s_small[tid] = 0;
   if (tid < 16) s_flag[tid] = 0;
-  load_window();
+  if constexpr (!MULTIPASS) load_window();
   __syncthreads();
-  if (tid == 0)
-    for (int c = 0; c < kCsStages && c < nchunks; ++c) issue(c);
+  if constexpr (!MULTIPASS) {
+    if (tid == 0)
+      for (int c = 0; c < kCsStages && c < nchunks; ++c) issue(c);
+  }
 
   auto insert = [&](unsigned long long key) {
     uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
@@ -158,7 +171,9 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
   };
 
   // ---- bucket end: sweep + clear, solid keys -> ordered edge records.  Called by all threads, after a __syncthreads.
-  auto finish_bucket = [&](int slot) {
+  // mode 0: streamed bucket (reserve arena space, bail list on failure); mode 1: multi-pass count sweep (only totals the solid
+  // keys in s_flag[9], failure -> s_flag[8]); mode 2: multi-pass emit sweep (writes at the base held in s_flag[2..3] and advances it)
+  auto finish_bucket = [&](int slot, int mode) {
     const bool crowded = s_flag[0] != 0;
     for (int h = tid; h < kCsSlots; h += NT) {
       const uint32_t c = tcnt[h];
@@ -166,7 +181,7 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
         const unsigned long long key = tkeys[h];
         tkeys[h] = kEmptyKey;
         tcnt[h] = 0u;
-        if (a.counting && c < 64u) atomicAdd(s_small + c, 1u);
+        if (a.counting && mode != 1 && c < 64u) atomicAdd(s_small + c, 1u);
         if (c >= m) {
           const int q = atomicAdd(s_flag + 4, 1);
           if (q < kCsSolidMax) {
@@ -180,7 +195,7 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
     const int ns_raw = s_flag[4];
     const bool bail = crowded || ns_raw > kCsSolidMax;
     const uint32_t ns = bail ? 0u : (uint32_t)ns_raw;
-    if (a.counting) {
+    if (a.counting && mode != 1) {
       // multiplicity histogram of the distinct keys (<prefix>.counting): small counts from shared memory, counts >= 64 are
       // solid keys (the host routes --min-count > 64 with a histogram request to the general kernel).  A bucket that
       // bails is counted by the general path instead.
@@ -195,7 +210,13 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
       }
     }
     if (tid == 0) {
-      if (bail) {
+      if (mode == 1) {
+        if (bail) s_flag[8] = 1;
+        s_flag[9] += (int)ns;
+        s_flag[1] = 0;
+      } else if (mode == 2) {
+        s_flag[1] = ns > 0;   // the base in s_flag[2..3] is advanced after the write below
+      } else if (bail) {
         const int p = atomicAdd(a.bail_count, 1);
         a.bail_list[p] = slot;
         s_flag[1] = 0;
@@ -292,10 +313,82 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
       }
     }
     __syncthreads();
-    if (tid == 0) { s_flag[0] = 0; s_flag[4] = 0; }
-    // the barrier the caller issues after advancing publishes the reset
+    if (tid == 0) {
+      if (mode == 2) {
+        const unsigned long long nb2 = (((unsigned long long)(uint32_t)s_flag[3] << 32) | (uint32_t)s_flag[2]) + ns;
+        s_flag[2] = (int)(uint32_t)nb2;
+        s_flag[3] = (int)(uint32_t)(nb2 >> 32);
+      }
+      s_flag[0] = 0;
+      s_flag[4] = 0;
+    }
+    // the barrier the caller issues next publishes the reset
   };
 
+  if constexpr (MULTIPASS) {
+    const WorkItem wi = a.work[blockIdx.x];
+    const int slot = wi.slot;
+    const int64_t n = a.bkt_size[slot];
+    const uint2 *keys = reinterpret_cast<const uint2 *>(a.in) + a.bkt_start[slot];
+    // key range of the bucket
+    unsigned long long *s_mm = reinterpret_cast<unsigned long long *>(scratch);
+    if (tid == 0) { s_mm[0] = ~0ull; s_mm[1] = 0ull; }
+    __syncthreads();
+    {
+      unsigned long long mn = ~0ull, mx = 0ull;
+      for (int64_t i = tid; i < n; i += NT) {
+        const uint2 v = keys[i];
+        const unsigned long long key = ((unsigned long long)v.x << 32) | v.y;
+        mn = min(mn, key);
+        mx = max(mx, key);
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if ((tid & 31) == 0) { atomicMin(s_mm, mn); atomicMax(s_mm + 1, mx); }
+    }
+    __syncthreads();
+    const unsigned long long kmin = s_mm[0];
+    const int span_bits = 64 - __clzll((long long)((s_mm[1] - kmin) | 1ull));
+    const int sh = span_bits > passes_log ? span_bits - passes_log : 0;
+    const uint32_t npass = (uint32_t)((s_mm[1] - kmin) >> sh) + 1u;
+    __syncthreads();
+    for (int sweep = 1; sweep <= 2; ++sweep) {
+      for (uint32_t ps = 0; ps < npass; ++ps) {
+        for (int64_t i = tid; i < n; i += NT) {
+          const uint2 v = keys[i];
+          const unsigned long long key = ((unsigned long long)v.x << 32) | v.y;
+          if ((uint32_t)((key - kmin) >> sh) == ps) insert(key);
+        }
+        __syncthreads();
+        finish_bucket(slot, sweep);
+        __syncthreads();
+      }
+      if (sweep == 1) {
+        if (tid == 0) {
+          if (s_flag[8]) {   // a sub-range still crowds the table: the general path takes the bucket
+            const int p = atomicAdd(a.bail_count, 1);
+            a.bail_list[p] = slot;
+          } else {
+            const unsigned long long tot = (unsigned long long)(uint32_t)s_flag[9];
+            const unsigned long long pos = atomicAdd(a.arena_cursor, tot);
+            const int ok = pos + tot <= a.arena_cap;
+            if (!ok) atomicExch(a.overflow_flag, 1);
+            a.desc_off[slot] = (int64_t)pos;
+            a.desc_cnt[slot] = ok ? (int64_t)tot : 0;
+            s_flag[2] = (int)(uint32_t)pos;
+            s_flag[3] = (int)(uint32_t)(pos >> 32);
+            if (!ok) s_flag[8] = 1;
+          }
+        }
+        __syncthreads();
+        if (s_flag[8]) return;
+      }
+    }
+    return;
+  } else {
   // ---- consumer loop over the chunks of the CTA's key range
   int cur_b = b0;
   uint32_t p = 0, bend = 0;
@@ -331,7 +424,7 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
       p = e;
       if (p == bend) {
         __syncthreads();
-        finish_bucket(cur_b);
+        finish_bucket(cur_b, 0);
         ++cur_b;
         advance();
         __syncthreads();
@@ -339,6 +432,7 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
     }
     __syncthreads();   // everyone is done with stage s
     if (tid == 0 && c + kCsStages < nchunks) issue(c + kCsStages);
+  }
   }
 }
 
@@ -372,6 +466,84 @@ __global__ void k_probe_distinct(const uint32_t *__restrict__ keys, const ProbeC
       if (cur == key) break;
       h = (h + 1) & (kProbeSlots - 1);
     }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-fed scatter of one partition level over 2-word records: the tile arrives in shared memory with one bulk copy (no
+// per-thread loads, no records held in registers), is counted and re-read there, staged in bin order and copied out
+// coalesced.  KPT keys per thread: 12 (6144-key tiles) with up to 1024 bins, 10 with 2048 -- two CTAs per SM either way.
+template <int KPT>
+inline size_t scatter_tma_smem_bytes(int nbits) {
+  const size_t nb = (size_t)1 << nbits, T = (size_t)512 * KPT;
+  return (T + 4) * 8 + T * 8 + (nb + 32) * 4 + nb * 8 + 48 * 4 + 16;
+}
+template <int NT, int KPT, int BPT>
+__global__ void __launch_bounds__(NT, 2) k_scatter_tma(const uint32_t *__restrict__ in, const TileDesc *__restrict__ tiles, LevelArgs a,
+                                                      unsigned long long *__restrict__ cursor, uint32_t *__restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  constexpr int T = NT * KPT;
+  const int nbins = 1 << a.nbits;
+  const int tid = threadIdx.x;
+  uint2 *X = reinterpret_cast<uint2 *>(smraw);                       // [T + 4]
+  uint2 *Y = X + T + 4;                                              // [T]
+  long long *s_gd = reinterpret_cast<long long *>(Y + T);            // [nbins]
+  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_gd + nbins);      // [nbins + 32]
+  uint32_t *scratch = s_cnt + nbins + 32;                            // [48]
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(scratch + 48);
+
+  const TileDesc d = tiles[blockIdx.x];
+  const int n = d.n;
+  const int off = (int)(d.base & 1);
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < nbins + 32; i += NT) s_cnt[i] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)(((n + off) * 8 + 15) & ~15);
+    mbar_expect_tx(mbar, bytes);
+    bulk_g2s(X, reinterpret_cast<const uint2 *>(in) + (d.base - off), bytes, mbar);
+  }
+  const uint32_t nb = a.seg_nb ? a.seg_nb[d.seg] : 0u;
+  const uint32_t dlo = a.dlo, dspan = a.dhi - a.dlo;
+  const uint32_t dummy = (uint32_t)nbins + (tid & 31);
+  mbar_wait(mbar, 0);
+  const uint2 *Xo = X + off;
+  // phase A: count
+#pragma unroll
+  for (int q = 0; q < KPT; ++q) {
+    const int j = q * NT + tid;
+    if (j < n) {
+      const uint2 v = Xo[j];
+      const uint32_t r[2] = {v.x, v.y};
+      const uint32_t dg = level_digit<2>(r, a, nb);
+      atomicAdd(s_cnt + ((dg - dlo) < dspan ? dg : dummy), 1u);
+    }
+  }
+  __syncthreads();
+  const uint32_t total = bins_scan_reserve<NT, BPT>(s_cnt, s_gd, scratch, cursor + (size_t)d.seg * nbins, nbins);
+  // phase B: every record takes the next free slot of its bin
+#pragma unroll
+  for (int q = 0; q < KPT; ++q) {
+    const int j = q * NT + tid;
+    if (j < n) {
+      const uint2 v = Xo[j];
+      const uint32_t r[2] = {v.x, v.y};
+      const uint32_t dg = level_digit<2>(r, a, nb);
+      if ((dg - dlo) < dspan) Y[atomicAdd(s_cnt + dg, 1u)] = v;
+    }
+  }
+  __syncthreads();
+  uint2 *out2 = reinterpret_cast<uint2 *>(out);
+  for (uint32_t j = tid; j < total; j += NT) {
+    const uint2 v = Y[j];
+    const uint32_t r[2] = {v.x, v.y};
+    const uint32_t dg = level_digit<2>(r, a, nb);
+    uint2 *dst = a.bin_base ? reinterpret_cast<uint2 *>(a.bin_base[dg]) : out2;
+    dst[s_gd[dg] + (long long)j] = v;
   }
 }
 

@@ -54,6 +54,8 @@ Ctx::Ctx(int dev) : device(dev) {
   cudaDeviceProp prop;
   MF_CUDA(cudaGetDeviceProperties(&prop, dev));
   sm_count = prop.multiProcessorCount;
+  // the k-mer set of the item generator is read one random 8-byte slot at a time: do not let L2 fetch whole 128-byte lines
+  if (const char *g = getenv("MFSDBG_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
   MF_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
   stream = own_stream;
   edge_bucket_counts.assign(kNumBuckets, 0);
@@ -67,6 +69,7 @@ Ctx::~Ctx() {
     b->release();
   for (DevBuf &b : ov) b.release();
   for (DevBuf &b : small) b.release();
+  for (DevBuf &b : fb) b.release();
   out_rec.release();
   out_labels.release();
   if (slab) cudaFree(slab);
@@ -380,6 +383,31 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   k_level_scan<<<nseg, 1024, 0, c.stream>>>(d_hist, nbins, d_sos, d_cur, b.start, b.size);
   MF_LAUNCH_CHECK();
   c.launches++;
+  if constexpr (W == 2) {
+    if (tb_s[nchunk] > 0 && env_int("MFSDBG_TMA_SCATTER", 1) != 0) {
+      // 2-word records: TMA-fed tiles of 6144 (5120 with 2048 bins) records
+      const int KPT = nbits <= 10 ? 12 : 10, T = 512 * KPT;
+      std::vector<int64_t> tb_t(nchunk + 1);
+      tb_t[0] = 0;
+      for (int i = 0; i < nchunk; ++i) tb_t[i + 1] = tb_t[i] + div_ceil64(hc.size[i], T);
+      int64_t *d_tbt = (int64_t *)alloc(sizeof(int64_t) * (nchunk + 1));
+      c.h2d(d_tbt, tb_t.data(), sizeof(int64_t) * (nchunk + 1));
+      TileDesc *d_tiles_t = (TileDesc *)alloc(sizeof(TileDesc) * std::max<int64_t>(tb_t[nchunk], 1));
+      k_build_tiles<<<(unsigned)div_ceil64(tb_t[nchunk], 256), 256, 0, c.stream>>>(ChunkTable{d_start, d_size, d_seg, d_tbt, nchunk}, T,
+                                                                                tb_t[nchunk], d_tiles_t);
+      MF_LAUNCH_CHECK();
+      const int bpt = std::max(1, (1 << nbits) / 512);
+      void (*kern)(const uint32_t *, const TileDesc *, LevelArgs, unsigned long long *, uint32_t *) =
+          nbits <= 10 ? (bpt == 1 ? k_scatter_tma<512, 12, 1> : k_scatter_tma<512, 12, 2>) : k_scatter_tma<512, 10, 4>;
+      const size_t smem = nbits <= 10 ? scatter_tma_smem_bytes<12>(nbits) : scatter_tma_smem_bytes<10>(nbits);
+      set_smem(kern, smem);
+      Stage st(c, tag_s.c_str());
+      kern<<<(unsigned)tb_t[nchunk], 512, smem, c.stream>>>(in, d_tiles_t, a, d_cur, out);
+      MF_LAUNCH_CHECK();
+      c.launches += 2;
+      return b;
+    }
+  }
   if (tb_s[nchunk] > 0) {
     RecordsProducer<W> ps{in, d_tiles_s, C::TS};
     size_t smem = scatter_smem_bytes<W>(C::NT, C::TS, nbits, 4);
@@ -478,15 +506,22 @@ struct Range {
 // Fully sort the given ranges of `cur` in place (all `sort_bits` leading bits matter); `other` is scratch with the same
 // layout.  Recursive MSD levels; only reached by buckets with more DISTINCT keys than shared memory holds.
 template <int W>
-static void sort_ranges(Ctx &c, uint32_t *cur, uint32_t *other, const std::vector<Range> &ranges, int bit_off, int sort_bits) {
+static void sort_ranges(Ctx &c, uint32_t *cur, uint32_t *other, const std::vector<Range> &ranges, int bit_off, int sort_bits, int depth = 0) {
   if (ranges.empty() || bit_off >= sort_bits) return;
   const int nbits = std::min(kMaxDigitBits, sort_bits - bit_off);
-  std::vector<void *> tmp;
+  // scratch from a grow-only buffer of the context (cudaMalloc / cudaFree stall for 100+ ms at times); recursion levels
+  // take their own buffer so that a parent's tables survive
+  int64_t total_size = 0;
+  for (auto &r : ranges) total_size += r.size;
+  const size_t need = (size_t)ranges.size() * ((size_t)kMaxBins * 40 + 256) + (size_t)(total_size / 128) + (2 << 20);
+  DevBuf &scratch_buf = c.fb[std::min(depth, 3)];
+  scratch_buf.reserve(need);
+  size_t scratch_off = 0;
   auto alloc = [&](size_t bytes) {
-    void *p = nullptr;
-    MF_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
-    tmp.push_back(p);
-    return p;
+    const size_t off = (scratch_off + 255) & ~(size_t)255;
+    if (off + bytes > scratch_buf.cap) throw CudaError("fallback scratch exhausted (internal sizing error)");
+    scratch_off = off + bytes;
+    return (void *)((char *)scratch_buf.p + off);
   };
   HostChunks hc;
   hc.nseg = (int)ranges.size();
@@ -523,12 +558,11 @@ static void sort_ranges(Ctx &c, uint32_t *cur, uint32_t *other, const std::vecto
     c.d2h(sz.data(), b.size, sizeof(int64_t) * b.nslots);
     std::vector<Range> sub;
     for (int s : bl) sub.push_back(Range{st[s], sz[s]});
-    sort_ranges<W>(c, other, cur, sub, bit_off + nbits, sort_bits);
+    sort_ranges<W>(c, other, cur, sub, bit_off + nbits, sort_bits, depth + 1);
     for (auto &r : sub)
       MF_CUDA(cudaMemcpyAsync(cur + r.start * W, other + r.start * W, (size_t)r.size * W * 4, cudaMemcpyDeviceToDevice, c.stream));
   }
   MF_CUDA(cudaStreamSynchronize(c.stream));
-  for (void *p : tmp) cudaFree(p);
 }
 
 // (start, size) of the listed slots, gathered on the device so that the whole table never crosses PCIe
@@ -603,7 +637,7 @@ template <int W, class Alloc>
 static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, const HostChunks &l1, int *bit_off, int key_bits,
                                    Alloc &&alloc) {
   const double rho = probe_distinct_ratio(c, *cur, l1, *bit_off, key_bits);
-  const double load = env_int("MFSDBG_STREAM_LOAD_PCT", 30) / 100.0;
+  const double load = env_int("MFSDBG_STREAM_LOAD_PCT", 45) / 100.0;
   const double B = std::min(60000.0, std::max(1024.0, load * kCsSlots / rho));
   if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] distinct ratio %.4f -> %.0f keys per bucket\n", rho, B);
   HostChunks hc = l1;
@@ -612,7 +646,8 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
     std::vector<int64_t> seg_total(hc.nseg, 0);
     for (size_t i = 0; i < hc.start.size(); ++i) seg_total[hc.seg[i]] += hc.size[i];
     const int xbits = std::min(16, key_bits - *bit_off);
-    const int64_t nb_cap = std::min<int64_t>(kMaxBins, (int64_t)1 << xbits);
+    // 1024 bins keep the scatter's runs long enough (2048-bin levels run at half the speed); more only as a last resort
+    const int64_t nb_cap = std::min<int64_t>(1024, (int64_t)1 << xbits);
     int64_t max_need = 1;
     for (int s2 = 0; s2 < hc.nseg; ++s2) max_need = std::max<int64_t>(max_need, (int64_t)std::ceil((double)seg_total[s2] / B));
     if (max_need <= nb_cap || xbits < 16) {
@@ -650,8 +685,8 @@ static void launch_count_stream(Ctx &c, const LocalArgs &a, int nslots, int64_t 
   k_split_ranges<<<div_ceil(grid + 1, 128), 128, 0, c.stream>>>(a.bkt_start, a.bkt_size, nslots, grid, d_cta_first);
   MF_LAUNCH_CHECK();
   const size_t smem = count_stream_smem_bytes();
-  set_smem(k_count_stream, smem);
-  k_count_stream<<<grid, kCsNT, smem, c.stream>>>(a, d_cta_first);
+  set_smem(k_count_stream<false>, smem);
+  k_count_stream<false><<<grid, kCsNT, smem, c.stream>>>(a, d_cta_first, 0);
   MF_LAUNCH_CHECK();
   c.launches += 2;
 }
@@ -722,7 +757,29 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
       }
       c.d2h(flags, d_flags, sizeof(int) * 3);
       if (flags[0] > 0) {
-        // buckets with too many distinct keys for the table: general path on exactly those slots
+        // buckets with too many distinct keys for the table: the same kernel, one CTA per bucket, in passes over 8 sub-ranges
+        if (stream) {
+          Stage st(c, "local_count_multipass");
+          std::vector<int32_t> slots;
+          std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &slots);
+          std::vector<WorkItem> wi(rs.size());
+          for (size_t i = 0; i < rs.size(); ++i) wi[i] = WorkItem{rs[i].start, (int32_t)std::min<int64_t>(rs[i].size, INT32_MAX), slots[i]};
+          c.ov[7].reserve(sizeof(WorkItem) * wi.size());
+          c.h2d(c.ov[7].p, wi.data(), sizeof(WorkItem) * wi.size());
+          MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), c.stream));
+          LocalArgs ma = a;
+          ma.work = c.ov[7].as<WorkItem>();
+          const size_t smem = count_stream_smem_bytes();
+          set_smem(k_count_stream<true>, smem);
+          k_count_stream<true><<<(unsigned)wi.size(), kCsNT, smem, c.stream>>>(ma, nullptr, 3);
+          MF_LAUNCH_CHECK();
+          c.launches++;
+          if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] count: %d of %d buckets take the multi-pass kernel\n", (int)wi.size(), b.nslots);
+          c.d2h(flags, d_flags, sizeof(int) * 3);
+        }
+      }
+      if (flags[0] > 0) {
+        // buckets that still do not fit: general path on exactly those slots
         Stage st(c, "local_count_general");
         if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] count: %d of %d buckets take the general kernel\n", flags[0], b.nslots);
         std::vector<int32_t> slots(flags[0]);

@@ -50,6 +50,7 @@ struct Ctx {
   DevBuf edges, sdbg_rec, sdbg_labels, sdbg_buckets, sbits, pack_words, pack_starts, synth_words, synth_starts, in_words, in_starts;
   HostBuf out_rec, out_labels;
   DevBuf small[3];   // per-call histograms / counters kept across calls (cudaMalloc and cudaFree stall for 100+ ms at times)
+  DevBuf fb[4];      // scratch of the recursive fallback sort, one per recursion depth
   DevBuf ov[10];   // scratch of the oversized-bucket path, kept across calls (cudaMalloc/cudaFree are slow and synchronise)
   // tables read back by the file-level API
   std::vector<int64_t> edge_bucket_counts;   // 65536
