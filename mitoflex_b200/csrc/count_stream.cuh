@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
         s_flag[9] += (int)ns;
         s_flag[1] = 0;
       } else if (mode == 2) {
-        s_flag[1] = ns > 0;   // the base in s_flag[2..3] is advanced after the write below
+        s_flag[1] = ns > 0 && !s_flag[10];   // the base in s_flag[2..3] is advanced after the write below
       } else if (bail) {
         const int p = atomicAdd(a.bail_count, 1);
         a.bail_list[p] = slot;
@@ -380,11 +380,14 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
             a.desc_cnt[slot] = ok ? (int64_t)tot : 0;
             s_flag[2] = (int)(uint32_t)pos;
             s_flag[3] = (int)(uint32_t)(pos >> 32);
-            if (!ok) s_flag[8] = 1;
+            // arena overflow: the host redoes the finish with a larger arena and WITHOUT the histogram (a retry must not
+            // count twice), so sweep 2 still runs -- for the histogram only
+            if (!ok) s_flag[10] = 1;
           }
         }
         __syncthreads();
         if (s_flag[8]) return;
+        if (s_flag[10] && !a.counting) return;
       }
     }
     return;

@@ -635,10 +635,13 @@ static double probe_distinct_ratio(Ctx &c, const uint32_t *keys, const HostChunk
 // segment is cut into its own number of equal key ranges.  *bit_off keeps the bits ALL keys of a bucket share.
 template <int W, class Alloc>
 static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, const HostChunks &l1, int *bit_off, int key_bits,
-                                   Alloc &&alloc) {
+                                   int min_count, double *rho_out, Alloc &&alloc) {
   const double rho = probe_distinct_ratio(c, *cur, l1, *bit_off, key_bits);
+  *rho_out = rho;
   const double load = env_int("MFSDBG_STREAM_LOAD_PCT", 45) / 100.0;
-  const double B = std::min(60000.0, std::max(1024.0, load * kCsSlots / rho));
+  double B = std::min(60000.0, std::max(1024.0, load * kCsSlots / rho));
+  // --min-count 1 makes every distinct key a solid one: keep them under the per-bucket limit of the streamed kernel
+  if (min_count <= 1 && load <= 1.0) B = std::min(B, std::max(512.0, 0.7 * kCsSolidMax / rho));
   if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] distinct ratio %.4f -> %.0f keys per bucket\n", rho, B);
   HostChunks hc = l1;
   DevBuckets b;
@@ -702,8 +705,9 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
   // keys of 33..64 bits take the streamed finish (TMA ring + shared hash table, buckets sized by a distinct-ratio probe)
   const bool stream = W == 2 && env_int("MFSDBG_COUNT_STREAM", 1) != 0 && !(d_counting && min_count > 64);
   DevBuckets b;
+  double rho = 0.0;   // distinct / occurrences, when the streamed path measured it
   if constexpr (W == 2) {
-    if (stream) b = stream_partition<W>(c, &cur, &other, l1, &bit_off, key_bits, salloc);
+    if (stream) b = stream_partition<W>(c, &cur, &other, l1, &bit_off, key_bits, min_count, &rho, salloc);
   }
   if (!stream) b = partition_chain<W>(c, &cur, &other, l1, &bit_off, p.rest_bits, salloc, "count_l2");
   const int stream_grid = stream ? (int)std::max<int64_t>(1, std::min<int64_t>(2 * c.sm_count, n / 16384)) : 0;
@@ -717,7 +721,9 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
   size_t arena_cap;
   {
     const size_t want_max = (size_t)(min_count > 1 ? n / min_count + 1 : n);
-    const size_t guess = std::min(want_max, (size_t)std::max<int64_t>(n / 6 + 1, 1 << 16)) + (size_t)stream_grid * kCsArenaBlock;
+    size_t guess = std::min(want_max, (size_t)std::max<int64_t>(n / 6 + 1, 1 << 16));
+    if (rho > 0.0 && min_count <= 1) guess = std::max(guess, std::min(want_max, (size_t)(1.15 * rho * (double)n) + 4096));
+    guess += (size_t)stream_grid * kCsArenaBlock;
     const size_t room = c.slab_bytes - ((c.slab_off + 255) & ~(size_t)255);
     arena_cap = std::min(guess, room / ((size_t)We * 4));
   }

@@ -188,7 +188,7 @@ class DistRead2Sdbg:
             # fused partition + exchange: the scatter kernel stores every key straight into its owner's HBM over NVLink
             self.key_buf.ensure(max(plan["n_recv"], 1) * self.Wk * 4)
             bases = torch.from_numpy(peer_bin_bases(allH, plan["bounds"], rank, self.key_buf.peers, self.Wk * 4).view(np.int64)).to(self.dev)
-            scratch = torch.empty((max(plan["n_recv"], 1), self.Wk), dtype=torch.int32, device=self.dev)
+            scratch = torch.empty((max(plan["n_recv"], 1) + 16, self.Wk), dtype=torch.int32, device=self.dev)
             stream.synchronize()
             ctx.count_scatter_peer(reads, k, L1_BITS, bases.data_ptr())
             self._acc()
@@ -231,7 +231,7 @@ class DistRead2Sdbg:
             self._acc()
             dist.barrier()
             del items
-            iscratch = torch.empty((max(iplan["n_recv"], 1), self.Wi), dtype=torch.int32, device=self.dev)
+            iscratch = torch.empty((max(iplan["n_recv"], 1) + 16, self.Wi), dtype=torch.int32, device=self.dev)
             stream.synchronize()
             g = ctx.sdbg_finish(self.item_buf.ptr, iscratch.data_ptr(), iplan["n_recv"], iplan["chunk_start"], iplan["chunk_size"],
                                 iplan["chunk_seg"], iplan["n_segs"], k, L1_BITS, 1)

@@ -160,3 +160,21 @@ def test_count_out_of_core_rounds(oracle):
         assert np.array_equal(e_gpu.counting, e_orc.counting)
     finally:
         c.close()
+
+
+def test_count_crowded_buckets_multipass(ctx, oracle, monkeypatch):
+    """buckets sized far beyond the shared table (every one of them bails) take the multi-pass kernel; shallow, error-rich
+    reads make nearly every key distinct."""
+    monkeypatch.setenv("MFSDBG_STREAM_LOAD_PCT", "400")
+    k, m = 21, 1
+    bases, starts = make_reads(123, 60000, k, genome_len=3000000, max_len=150, err=0.02)
+    ctx.set_profiling(True)
+    try:
+        e_gpu = ctx.count(ctx.upload_reads(bases, starts), k, m, want_counting=True)
+        prof = ctx.last_profile()
+    finally:
+        ctx.set_profiling(False)
+    e_orc = oracle.count(_orc_reads(oracle, bases, starts), k, m, threads=8)
+    assert_edges_equal(e_gpu, e_orc)
+    assert np.array_equal(e_gpu.counting, e_orc.counting)
+    assert "local_count_multipass" in prof, prof
