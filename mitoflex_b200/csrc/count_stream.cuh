@@ -43,6 +43,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
   uint32_t ok;
   do {
@@ -61,7 +64,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 inline size_t count_stream_smem_bytes() {
   // tkeys u64[4096] | ring u64[stages*chunk] | skeys u64[1024] | mbar u64[4] | tcnt u32[4096] | scnt u32[1024]
   // | bnd u32[win+2] | bins u32[260] | small u32[64] | scratch u32[40] | flag i32[16] | permA,permB,rk u16[1024]
-  return (size_t)kCsSlots * 8 + (size_t)kCsStages * kCsChunk * 8 + (size_t)kCsSolidMax * 8 + 32 + (size_t)kCsSlots * 4 +
+  return (size_t)kCsSlots * 8 + (size_t)kCsStages * kCsChunk * 8 + (size_t)kCsSolidMax * 8 + 64 + (size_t)kCsSlots * 4 +
          (size_t)kCsSolidMax * 4 + (size_t)(kCsWin + 2) * 4 + 260 * 4 + 64 * 4 + 40 * 4 + 16 * 4 + 3 * (size_t)kCsSolidMax * 2;
 }
 
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
   unsigned long long *ring = tkeys + kCsSlots;
   unsigned long long *skeys = ring + kCsStages * kCsChunk;
   unsigned long long *mbar = skeys + kCsSolidMax;
-  uint32_t *tcnt = reinterpret_cast<uint32_t *>(mbar + 4);
+  uint32_t *tcnt = reinterpret_cast<uint32_t *>(mbar + 8);   // mbar[0..3] full, mbar[4..7] empty
   uint32_t *scnt = tcnt + kCsSlots;
   uint32_t *s_bnd = scnt + kCsSolidMax;
   uint32_t *bins = s_bnd + kCsWin + 2;
@@ -139,7 +142,10 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
   };
 
   if (tid == 0) {
-    for (int s = 0; s < kCsStages; ++s) mbar_init(mbar + s, 1);
+    for (int s = 0; s < kCsStages; ++s) {
+      mbar_init(mbar + s, 1);              // full: the bulk copy's bytes
+      mbar_init(mbar + 4 + s, NT / 32);    // empty: one arrival per warp
+    }
     mbar_fence_init();
   }
   for (int i = tid; i < kCsSlots; i += NT) {
@@ -433,8 +439,14 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
         __syncthreads();
       }
     }
-    __syncthreads();   // everyone is done with stage s
-    if (tid == 0 && c + kCsStages < nchunks) issue(c + kCsStages);
+    // this warp is done with stage s; thread 0 refills the stage of the PREVIOUS chunk once every warp has released it
+    // (no CTA-wide barrier per chunk: warps drift apart inside a bucket and only meet at bucket ends)
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(mbar + 4 + s);
+    if (tid == 0 && c >= 1 && c - 1 + kCsStages < nchunks) {
+      mbar_wait(mbar + 4 + (c - 1) % kCsStages, (uint32_t)(((c - 1) / kCsStages) & 1));
+      issue(c - 1 + kCsStages);
+    }
   }
   }
 }

@@ -20,6 +20,7 @@
 #include "partition.cuh"
 #include "reads.cuh"
 #include "count_stream.cuh"
+#include "count_stream_w.cuh"
 #include "sdbg_local.cuh"
 
 namespace mf {
@@ -27,9 +28,18 @@ namespace mf {
 // ------------------------------------------------------------------ memory
 void DevBuf::reserve(size_t bytes) {
   if (bytes <= cap) return;
+  // grow geometrically and in whole MiB: cudaMalloc / cudaFree stall for 100-450 ms at times (measured on these boxes), so a
+  // buffer whose demand creeps up by a few per cent from call to call must not be reallocated every time
+  size_t want = std::max(bytes, cap + cap / 2);
+  want = (want + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
   release();
-  MF_CUDA(cudaMalloc(&p, bytes));
-  cap = bytes;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {   // no room for the slack: take exactly what is needed
+    cudaGetLastError();
+    want = bytes;
+    MF_CUDA(cudaMalloc(&p, want));
+  }
+  cap = want;
 }
 void DevBuf::release() {
   if (p) cudaFree(p);
@@ -592,6 +602,7 @@ static std::vector<Range> fetch_bails(Ctx &c, const DevBuckets &b, const int32_t
 
 // ------------------------------------------------------------------ count (33..64-bit keys): probe + range partition
 // distinct keys / key occurrences, measured on a few whole level-1 prefix ranges (see k_probe_distinct)
+template <int W>
 static double probe_distinct_ratio(Ctx &c, const uint32_t *keys, const HostChunks &l1, int bit_off, int key_bits) {
   constexpr int S = 8;
   std::vector<int64_t> seg_total(l1.nseg, 0);
@@ -601,7 +612,11 @@ static double probe_distinct_ratio(Ctx &c, const uint32_t *keys, const HostChunk
     if (seg_total[s2] > 0) nonempty.push_back(s2);
   if (nonempty.empty()) return 1.0;
   std::vector<int> sample_of(l1.nseg, -1);
-  const int ns = std::min<int>(S, (int)nonempty.size());
+  // a sample is a whole segment scan: with the few, huge segments of a multi-GPU owner two of them are plenty
+  int64_t seg_max = 1;
+  for (int s2 : nonempty) seg_max = std::max(seg_max, seg_total[s2]);
+  const int s_cap = (int)std::max<int64_t>(2, std::min<int64_t>(S, ((int64_t)256 << 20) / seg_max));
+  const int ns = std::min<int>(s_cap, (int)nonempty.size());
   for (int j = 0; j < ns; ++j) sample_of[nonempty[(size_t)((2 * j + 1) * nonempty.size() / (2 * ns))]] = j;
   std::vector<ProbeChunk> pcs;
   for (size_t i = 0; i < l1.start.size(); ++i) {
@@ -619,7 +634,8 @@ static double probe_distinct_ratio(Ctx &c, const uint32_t *keys, const HostChunk
   c.h2d(d_pcs, pcs.data(), sizeof(ProbeChunk) * pcs.size());
   {
     Stage st(c, "probe");
-    k_probe_distinct<<<dim3(64, (unsigned)pcs.size()), 256, 0, c.stream>>>(keys, d_pcs, bit_off, 0x5a5au, d_tab, d_stats);
+    if constexpr (W == 2) k_probe_distinct<<<dim3(64, (unsigned)pcs.size()), 256, 0, c.stream>>>(keys, d_pcs, bit_off, 0x5a5au, d_tab, d_stats);
+    else k_probe_distinct_w<W><<<dim3(64, (unsigned)pcs.size()), 256, 0, c.stream>>>(keys, d_pcs, bit_off, 0x5a5au, d_tab, d_stats);
     MF_LAUNCH_CHECK();
     c.launches++;
   }
@@ -636,12 +652,13 @@ static double probe_distinct_ratio(Ctx &c, const uint32_t *keys, const HostChunk
 template <int W, class Alloc>
 static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, const HostChunks &l1, int *bit_off, int key_bits,
                                    int min_count, double *rho_out, Alloc &&alloc) {
-  const double rho = probe_distinct_ratio(c, *cur, l1, *bit_off, key_bits);
+  const double rho = probe_distinct_ratio<W>(c, *cur, l1, *bit_off, key_bits);
   *rho_out = rho;
   const double load = env_int("MFSDBG_STREAM_LOAD_PCT", 45) / 100.0;
   double B = std::min(60000.0, std::max(1024.0, load * kCsSlots / rho));
   // --min-count 1 makes every distinct key a solid one: keep them under the per-bucket limit of the streamed kernel
-  if (min_count <= 1 && load <= 1.0) B = std::min(B, std::max(512.0, 0.7 * kCsSolidMax / rho));
+  const int solid_max = W == 2 ? kCsSolidMax : (W <= 4 ? 1024 : 512);
+  if (min_count <= 1 && load <= 1.0) B = std::min(B, std::max(512.0, 0.7 * solid_max / rho));
   if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] distinct ratio %.4f -> %.0f keys per bucket\n", rho, B);
   HostChunks hc = l1;
   DevBuckets b;
@@ -694,6 +711,19 @@ static void launch_count_stream(Ctx &c, const LocalArgs &a, int nslots, int64_t 
   c.launches += 2;
 }
 
+template <int W>
+static void launch_count_stream_w(Ctx &c, const LocalArgs &a, int nslots, int grid, int32_t *d_cta_first) {
+  if constexpr (W >= 3) {
+    k_split_ranges<<<div_ceil(grid + 1, 128), 128, 0, c.stream>>>(a.bkt_start, a.bkt_size, nslots, grid, d_cta_first);
+    MF_LAUNCH_CHECK();
+    const size_t smem = count_stream_w_smem_bytes<W>();
+    set_smem(k_count_stream_w<W>, smem);
+    k_count_stream_w<W><<<grid, kCwNT, smem, c.stream>>>(a, d_cta_first);
+    MF_LAUNCH_CHECK();
+    c.launches += 2;
+  }
+}
+
 // ------------------------------------------------------------------ count: finish from l1-partitioned keys
 template <int W>
 static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n, const HostChunks &l1, int k, int l1_bits,
@@ -703,10 +733,10 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
   auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
   int bit_off = l1_bits;
   // keys of 33..64 bits take the streamed finish (TMA ring + shared hash table, buckets sized by a distinct-ratio probe)
-  const bool stream = W == 2 && env_int("MFSDBG_COUNT_STREAM", 1) != 0 && !(d_counting && min_count > 64);
+  const bool stream = W >= 2 && env_int(W == 2 ? "MFSDBG_COUNT_STREAM" : "MFSDBG_COUNT_STREAM_W", 1) != 0 && !(d_counting && min_count > 64);
   DevBuckets b;
   double rho = 0.0;   // distinct / occurrences, when the streamed path measured it
-  if constexpr (W == 2) {
+  if constexpr (W >= 2) {
     if (stream) b = stream_partition<W>(c, &cur, &other, l1, &bit_off, key_bits, min_count, &rho, salloc);
   }
   if (!stream) b = partition_chain<W>(c, &cur, &other, l1, &bit_off, p.rest_bits, salloc, "count_l2");
@@ -795,6 +825,28 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
         for (int sl : slots) wi.push_back(WorkItem{0, 0, sl});
         std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &slots);
         for (size_t i = 0; i < rs.size(); ++i) { wi[i].start = rs[i].start; wi[i].n = (int32_t)std::min<int64_t>(rs[i].size, INT32_MAX); }
+        c.ov[7].reserve(sizeof(WorkItem) * wi.size());
+        c.h2d(c.ov[7].p, wi.data(), sizeof(WorkItem) * wi.size());
+        MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), c.stream));
+        LocalArgs ga = a;
+        ga.work = c.ov[7].as<WorkItem>();
+        launch_local<W, kCountEmit>(c, ga, (int)wi.size());
+        c.d2h(flags, d_flags, sizeof(int) * 3);
+      }
+    } else if (stream) {
+      // keys wider than 64 bits: streamed finish with fingerprint + representative slots; what bails takes the general kernel
+      {
+        Stage st(c, "local_count");
+        launch_count_stream_w<W>(c, a, b.nslots, stream_grid, d_cta_first);
+      }
+      c.d2h(flags, d_flags, sizeof(int) * 3);
+      if (flags[0] > 0) {
+        Stage st(c, "local_count_general");
+        if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] count: %d of %d buckets take the general kernel\n", flags[0], b.nslots);
+        std::vector<int32_t> slots;
+        std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &slots);
+        std::vector<WorkItem> wi(rs.size());
+        for (size_t i = 0; i < rs.size(); ++i) wi[i] = WorkItem{rs[i].start, (int32_t)std::min<int64_t>(rs[i].size, INT32_MAX), slots[i]};
         c.ov[7].reserve(sizeof(WorkItem) * wi.size());
         c.h2d(c.ov[7].p, wi.data(), sizeof(WorkItem) * wi.size());
         MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), c.stream));
@@ -1032,7 +1084,7 @@ static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, Edg
       acc += (int64_t)hist[b];
     }
     if (acc == 0) continue;
-    uint32_t *bufA = c.alloc<uint32_t>((size_t)acc * W + 16), *bufB = c.alloc<uint32_t>((size_t)acc * W + 16);
+    uint32_t *bufA = c.alloc<uint32_t>((size_t)acc * W + 64), *bufB = c.alloc<uint32_t>((size_t)acc * W + 64);   // bulk copies round up to 16 bytes
     unsigned long long *d_cursor = c.alloc<unsigned long long>(nb1);
     c.h2d(d_cursor, cursor.data(), sizeof(unsigned long long) * nb1);
     {

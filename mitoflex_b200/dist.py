@@ -12,7 +12,7 @@ import numpy as np
 
 import os
 
-L1_BITS = int(os.environ.get("MFSDBG_DIST_L1_BITS", "7"))   # 128 bins: runs long enough for efficient NVLink stores
+L1_BITS = int(os.environ.get("MFSDBG_DIST_L1_BITS", "6"))   # 64 bins: long runs for the NVLink stores (5-7 bits measured within 3 %)
 
 
 def assign_owners(global_hist, world):
