@@ -322,8 +322,13 @@ def main():
         # rank 0's share: bytes that left this GPU / time of the all-to-all, against 900 GB/s per direction nominal
         kb = info.get("exchanged_keys", 0) * info.get("key_bytes", 8)
         ib = info.get("exchanged_items", 0) * info.get("item_bytes", 8)
-        ak, ai = stage_sum.get("a2a_keys", 0.0) / args.steps, stage_sum.get("a2a_items", 0.0) / args.steps
-        nvlink = {"keys_bytes_sent": kb, "keys_ms": ak, "keys_GBps": kb / ak / 1e6 if ak else None, "items_bytes_sent": ib,
+        # fused mode ("p2p"): the scatter kernels store straight into the owners' HBM, so the exchange time IS the scatter
+        # stage (reads_scatter for keys, records_scatter for items); NCCL mode has separate a2a_* stages
+        fused = info.get("exchange") == "p2p"
+        ak = stage_sum.get("reads_scatter" if fused else "a2a_keys", 0.0) / args.steps
+        ai = stage_sum.get("records_scatter" if fused else "a2a_items", 0.0) / args.steps
+        nvlink = {"exchange": "fused partition+exchange kernel over NVLink peer memory (CUDA IPC)" if fused else "NCCL all_to_all_single",
+                  "keys_bytes_sent": kb, "keys_ms": ak, "keys_GBps": kb / ak / 1e6 if ak else None, "items_bytes_sent": ib,
                   "items_ms": ai, "items_GBps": ib / ai / 1e6 if ai else None, "peak_GBps_per_direction": 900.0,
                   "measured_peer_copy_GBps": 770.0}
     per_step = {k2: v / args.steps for k2, v in stage_sum.items()}
@@ -356,7 +361,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(args.pairs), "bases_per_gpu": n_bases, "keys_per_gpu": n_keys, "solid_edges": n_edges,
                    "sdbg_items": res.n if res is not None else None, "l2_flush": "inputs and key buffers (>= 1 GB) exceed the 126 MB L2",
-                   "parallelism": "reads sharded by GPU, keys routed by 10-bit prefix (NCCL all-to-all)" if world > 1 else "1 GPU"},
+                   "parallelism": "reads sharded by GPU, keys and items stored into the owner GPU of their prefix bin by the partition kernel itself (NVLink peer memory), disjoint key range per GPU" if world > 1 else "1 GPU"},
         "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(out))

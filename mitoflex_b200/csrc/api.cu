@@ -1,4 +1,5 @@
 // api.cu -- the C ABI of libmfsdbg.so (include/mfsdbg.h): argument checking, error convention, no exceptions out.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -336,17 +337,21 @@ int mfsdbg_host_read2sdbg(mfsdbg_ctx *ctx, const uint32_t *packed_host, const in
     mf::Ctx &c = ctx->c;
     c.begin_call();
     const size_t wbytes = (size_t)((n_bases + 15) >> 4) * 4, sbytes = sizeof(int64_t) * (size_t)(n_reads + 1);
-    c.in_words.reserve(wbytes + 64);
-    c.in_starts.reserve(sbytes);
-    {
-      mf::Stage st(c, "h2d");
-      MF_CUDA(cudaMemsetAsync((char *)c.in_words.p + wbytes, 0, 64, c.stream));
-      if (wbytes) MF_CUDA(cudaMemcpyAsync(c.in_words.p, packed_host, wbytes, cudaMemcpyHostToDevice, c.stream));
-      MF_CUDA(cudaMemcpyAsync(c.in_starts.p, starts_host, sbytes, cudaMemcpyHostToDevice, c.stream));
-    }
-    mf::ReadsView r{c.in_words.as<uint32_t>(), c.in_starts.as<int64_t>(), n_reads, n_bases};
     mf::EdgesView e;
-    mf::dev_count(c, r, k, min_count, &e, nullptr);
+    // large inputs: chunked transfer, the reads-fed partition level follows the chunks as they land
+    const char *minb = getenv("MFSDBG_H2D_MIN_BASES");
+    if (!(n_bases >= (minb ? atoll(minb) : (long long)(64 << 20)) && mf::dev_count_host(c, packed_host, starts_host, n_reads, n_bases, k, min_count, &e))) {
+      c.in_words.reserve(wbytes + 64);
+      c.in_starts.reserve(sbytes);
+      {
+        mf::Stage st(c, "h2d");
+        MF_CUDA(cudaMemsetAsync((char *)c.in_words.p + wbytes, 0, 64, c.stream));
+        if (wbytes) MF_CUDA(cudaMemcpyAsync(c.in_words.p, packed_host, wbytes, cudaMemcpyHostToDevice, c.stream));
+        MF_CUDA(cudaMemcpyAsync(c.in_starts.p, starts_host, sbytes, cudaMemcpyHostToDevice, c.stream));
+      }
+      mf::ReadsView r{c.in_words.as<uint32_t>(), c.in_starts.as<int64_t>(), n_reads, n_bases};
+      mf::dev_count(c, r, k, min_count, &e, nullptr);
+    }
     mf::SdbgView g;
     mf::dev_seq2sdbg(c, e.edges, e.n_edges, mf::SeqsView{}, k, 1, &g);
     const size_t rb = (size_t)g.n_items * 4, lb = (size_t)g.n_tips * g.words_tip * 4;

@@ -84,6 +84,8 @@ Ctx::~Ctx() {
   out_labels.release();
   if (slab) cudaFree(slab);
   for (auto &s : stages) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
+  for (auto e : copy_events) cudaEventDestroy(e);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
   if (own_stream) cudaStreamDestroy(own_stream);
 }
 size_t Ctx::budget() {
@@ -266,45 +268,48 @@ struct TileCfg {
   static constexpr int TH = NT * IPT_H;
 };
 
+// tile range [tile0, tile0 + ntiles) of the reads (ntiles < 0: all of them) -- the host-input pipeline runs the reads-fed
+// level chunk by chunk while later chunks are still crossing PCIe
 template <int W>
-static void launch_reads_hist(Ctx &c, const ReadsView &r, const uint32_t *sbits, int k, LevelArgs a, unsigned long long *hist) {
+static void launch_reads_hist(Ctx &c, const ReadsView &r, const uint32_t *sbits, int k, LevelArgs a, unsigned long long *hist,
+                              int64_t tile0 = 0, int64_t ntiles = -1) {
   using C = ReadsTileCfg<W>;
-  const int64_t tiles = div_ceil64(r.n_bases, C::T);
+  const int64_t tiles = ntiles >= 0 ? ntiles : div_ceil64(r.n_bases, C::T);
   if (tiles == 0) return;
   const size_t smem = (((size_t)1 << a.nbits) + 32 + reads_seq_words(C::NT, W) + reads_bit_words(C::NT, k)) * 4;
   const bool ranged = a.dlo != 0u || a.dhi != (1u << a.nbits);
   auto kern = ranged ? k_reads_hist<W, C::NT, true> : k_reads_hist<W, C::NT, false>;
   set_smem(kern, smem);
   const int64_t grid = std::min<int64_t>(tiles, (int64_t)c.sm_count * (2048 / C::NT));   // persistent: one flush per CTA
-  kern<<<(unsigned)grid, C::NT, smem, c.stream>>>(ReadsSrc{r.packed, sbits, r.n_bases, k}, a, hist, tiles);
+  kern<<<(unsigned)grid, C::NT, smem, c.stream>>>(ReadsSrc{r.packed, sbits, r.n_bases, k}, a, hist, tile0, tiles);
   MF_LAUNCH_CHECK();
   c.launches++;
 }
 template <int W, int BPT>
 static void launch_reads_scatter_b(Ctx &c, const ReadsView &r, const uint32_t *sbits, int k, LevelArgs a, unsigned long long *cursor,
-                                   uint32_t *out) {
+                                   uint32_t *out, int64_t tile0, int64_t tiles) {
   using C = ReadsTileCfg<W>;
-  const int64_t tiles = div_ceil64(r.n_bases, C::T);
   const size_t smem = reads_scatter_smem_bytes<W>(C::NT, a.nbits, k);
   const bool ranged = a.dlo != 0u || a.dhi != (1u << a.nbits);
   auto kern = ranged ? k_reads_scatter<W, C::NT, BPT, true> : k_reads_scatter<W, C::NT, BPT, false>;
   set_smem(kern, smem);
-  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ReadsSrc{r.packed, sbits, r.n_bases, k}, a, cursor, out);
+  kern<<<(unsigned)tiles, C::NT, smem, c.stream>>>(ReadsSrc{r.packed, sbits, r.n_bases, k}, a, cursor, out, tile0);
   MF_LAUNCH_CHECK();
   c.launches++;
 }
 template <int W>
 static void launch_reads_scatter(Ctx &c, const ReadsView &r, const uint32_t *sbits, int k, LevelArgs a, unsigned long long *cursor,
-                                 uint32_t *out) {
+                                 uint32_t *out, int64_t tile0 = 0, int64_t ntiles = -1) {
   using C = ReadsTileCfg<W>;
-  if (r.n_bases == 0) return;
+  const int64_t tiles = ntiles >= 0 ? ntiles : div_ceil64(r.n_bases, C::T);
+  if (tiles == 0) return;
   const int bpt = std::max(1, (1 << a.nbits) / C::NT);   // bins per thread of the block scan
   switch (bpt) {
-    case 1: launch_reads_scatter_b<W, 1>(c, r, sbits, k, a, cursor, out); break;
-    case 2: launch_reads_scatter_b<W, 2>(c, r, sbits, k, a, cursor, out); break;
-    case 4: launch_reads_scatter_b<W, 4>(c, r, sbits, k, a, cursor, out); break;
-    case 8: launch_reads_scatter_b<W, 8>(c, r, sbits, k, a, cursor, out); break;
-    default: launch_reads_scatter_b<W, 16>(c, r, sbits, k, a, cursor, out); break;
+    case 1: launch_reads_scatter_b<W, 1>(c, r, sbits, k, a, cursor, out, tile0, tiles); break;
+    case 2: launch_reads_scatter_b<W, 2>(c, r, sbits, k, a, cursor, out, tile0, tiles); break;
+    case 4: launch_reads_scatter_b<W, 4>(c, r, sbits, k, a, cursor, out, tile0, tiles); break;
+    case 8: launch_reads_scatter_b<W, 8>(c, r, sbits, k, a, cursor, out, tile0, tiles); break;
+    default: launch_reads_scatter_b<W, 16>(c, r, sbits, k, a, cursor, out, tile0, tiles); break;
   }
 }
 
@@ -670,7 +675,9 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
     const int64_t nb_cap = std::min<int64_t>(1024, (int64_t)1 << xbits);
     int64_t max_need = 1;
     for (int s2 = 0; s2 < hc.nseg; ++s2) max_need = std::max<int64_t>(max_need, (int64_t)std::ceil((double)seg_total[s2] / B));
-    if (max_need <= nb_cap || xbits < 16) {
+    // up to 1.5x over the bin limit the buckets simply get that much larger (the table runs fuller, what crowds it takes the
+    // multi-pass kernel): cheaper than a whole extra partition level
+    if (max_need <= nb_cap + nb_cap / 2 || xbits < 16) {
       std::vector<uint16_t> nb(hc.nseg);
       int mx = 1;
       for (int s2 = 0; s2 < hc.nseg; ++s2) {
@@ -1018,6 +1025,30 @@ static const uint32_t *build_start_bits(Ctx &c, const ReadsView &r) {
   return c.sbits.as<uint32_t>();
 }
 
+// level-1 digit width of count
+template <int W>
+static Plan count_plan(Ctx &c, int k, int min_count, int64_t n_est) {
+  const int key_bits = 2 * (k + 1);
+  Plan p = make_plan(W, key_bits, n_est, 2.0, true);
+  if (W >= 2 && env_int("MFSDBG_L1_BITS", -1) < 0 && env_int(W == 2 ? "MFSDBG_COUNT_STREAM" : "MFSDBG_COUNT_STREAM_W", 1) != 0) {
+    // streamed finish: level 2 is a range partition into <= 1024 bins of ~16 K keys (45 % table load at the usual distinct
+    // ratio), so level 1 only has to bring the densest segments (2x the average) under ~17-24 M keys -- and the fewer bins the
+    // reads-fed scatter has, the faster it runs (512 bins: 14.9 ms, 1024: 19.4 ms, 2048: 48 ms on the 5 Gbp sample)
+    p.l1_bits = std::max(1, std::min({10, key_bits, ceil_log2((double)n_est / 1.2e7)}));
+    // out-of-core rounds are cut at level-1 bin boundaries: a bin (twice the average at small prefixes) must stay well
+    // inside what one round may hold
+    const size_t bud0 = (size_t)((double)c.budget() * 0.9);
+    const double pk0 = 2.0 * W * 4 + (min_count > 1 ? (double)words_edge(k) * 4 / std::min(min_count, 6) : (double)words_edge(k) * 4);
+    while (p.l1_bits < std::min(kMaxDigitBits, key_bits)) {
+      const size_t tb0 = (size_t)(64 << 20) + (size_t)(((size_t)1 << p.l1_bits) << kMaxDigitBits) * 96;
+      const double mk0 = bud0 > tb0 ? (double)(bud0 - tb0) / pk0 : 0.0;
+      if (mk0 >= (double)n_est || 3.0 * (double)n_est / (double)(1 << p.l1_bits) <= mk0) break;
+      ++p.l1_bits;
+    }
+  }
+  return p;
+}
+
 template <int W>
 static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, EdgesView *out, int64_t *counting_host) {
   const int key_bits = 2 * (k + 1), We = words_edge(k);
@@ -1027,7 +1058,8 @@ static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, Edg
     sbits = build_start_bits(c, r);
   }
   // the plan needs the key count: it is at most one key per base
-  Plan p = make_plan(W, key_bits, std::max<int64_t>(r.n_bases - r.n_reads * (int64_t)k, 1), 2.0, true);   // one key per base minus k per read
+  const int64_t n_est = std::max<int64_t>(r.n_bases - r.n_reads * (int64_t)k, 1);   // one key per base minus k per read
+  Plan p = count_plan<W>(c, k, min_count, n_est);
   const int nb1 = 1 << p.l1_bits;
   c.small[1].reserve(sizeof(unsigned long long) * (kMaxBins + kNumBuckets));
   unsigned long long *d_small = c.small[1].as<unsigned long long>();   // hist | counting
@@ -1109,6 +1141,135 @@ void dev_count(Ctx &c, const ReadsView &r, int k, int min_count, EdgesView *out,
   if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
   if (min_count < 1) throw std::invalid_argument("min_count must be >= 1");
   MF_DISPATCH_W(words_key(k), COUNT)
+}
+
+
+// ------------------------------------------------------------------ count with host-resident reads (pipelined H2D)
+template <int W>
+static bool dev_count_host_impl(Ctx &c, const uint32_t *packed_host, const int64_t *starts_host, int64_t n_reads, int64_t n_bases, int k,
+                                int min_count, EdgesView *out) {
+  using C = ReadsTileCfg<W>;
+  const int We = words_edge(k);
+  const int64_t total_words = (n_bases + 15) >> 4;
+  const int64_t ntiles = div_ceil64(n_bases, C::T);
+  const int n_chunks = (int)std::min<int64_t>(env_int("MFSDBG_H2D_CHUNKS", 8), ntiles / 8);
+  if (n_chunks < 2) return false;
+  const int64_t n_est = std::max<int64_t>(n_bases - n_reads * (int64_t)k, 1);
+  Plan p = count_plan<W>(c, k, min_count, n_est);
+  const int nb1 = 1 << p.l1_bits;
+  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1 << kMaxDigitBits) * 96 + sizeof(int64_t) * 8 * (size_t)nb1 * n_chunks;
+  const size_t budget = (size_t)((double)c.budget() * 0.9);
+  const double per_key = 2.0 * W * 4 + (min_count > 1 ? (double)We * 4 / std::min(min_count, 6) : (double)We * 4);
+  const int64_t n_bound = n_bases;   // a key per base: reads shorter than k make n_est an estimate, not a bound
+  if ((double)n_bound * per_key + (double)table_bytes > (double)budget) return false;   // needs out-of-core rounds
+  const size_t wbytes = (size_t)total_words * 4, sbytes = sizeof(int64_t) * (size_t)(n_reads + 1);
+  c.in_words.reserve(wbytes + 1024);
+  c.in_starts.reserve(sbytes);
+  const size_t sb_words = (size_t)((n_bases + 31) >> 5) + 64;
+  c.sbits.reserve(sb_words * 4);
+  if (!c.copy_stream) MF_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  while ((int)c.copy_events.size() < n_chunks + 1) {
+    cudaEvent_t e;
+    MF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c.copy_events.push_back(e);
+  }
+  c.slab_reserve((size_t)((double)n_bound * per_key) + table_bytes + (1 << 20));
+  c.slab_reset();
+  uint32_t *bufA = c.alloc<uint32_t>((size_t)n_bound * W + 64), *bufB = c.alloc<uint32_t>((size_t)n_bound * W + 64);
+  unsigned long long *d_hist = c.alloc<unsigned long long>((size_t)nb1 * n_chunks);
+  unsigned long long *d_cursor = c.alloc<unsigned long long>((size_t)nb1 * n_chunks);
+  // everything the copy stream overwrites must be idle, and the start bits clean, before the first chunk lands
+  MF_CUDA(cudaMemsetAsync(c.sbits.p, 0, sb_words * 4, c.stream));
+  MF_CUDA(cudaMemsetAsync((char *)c.in_words.p + wbytes, 0, 1024, c.stream));
+  MF_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nb1 * n_chunks, c.stream));
+  MF_CUDA(cudaEventRecord(c.copy_events[n_chunks], c.stream));
+  MF_CUDA(cudaStreamWaitEvent(c.copy_stream, c.copy_events[n_chunks], 0));
+  const int64_t tiles_per = div_ceil64(ntiles, n_chunks);
+  struct Chunk { int64_t t0, t1, r_lo, r_hi; };
+  std::vector<Chunk> chunks;
+  const int64_t margin = k + 256;   // a key near the chunk end looks this far ahead for read starts and bases
+  for (int ci = 0; ci < n_chunks; ++ci) {
+    Chunk ch;
+    ch.t0 = std::min<int64_t>(ntiles, ci * tiles_per);
+    ch.t1 = std::min<int64_t>(ntiles, (ci + 1) * tiles_per);
+    if (ch.t1 <= ch.t0) break;
+    const int64_t b0 = ch.t0 * C::T, b1 = std::min<int64_t>(n_bases, ch.t1 * C::T);
+    const int64_t w0 = b0 >> 4, w1 = std::min<int64_t>(total_words, ((b1 + margin) >> 4) + 2);
+    // words already sent with the previous chunk's margin are sent again (a few hundred bytes)
+    MF_CUDA(cudaMemcpyAsync(c.in_words.as<uint32_t>() + w0, packed_host + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, c.copy_stream));
+    ch.r_lo = std::lower_bound(starts_host, starts_host + n_reads + 1, b0) - starts_host;
+    ch.r_hi = std::upper_bound(starts_host, starts_host + n_reads + 1, b1 + margin) - starts_host;
+    if (ch.r_hi > ch.r_lo)
+      MF_CUDA(cudaMemcpyAsync(c.in_starts.as<int64_t>() + ch.r_lo, starts_host + ch.r_lo, (size_t)(ch.r_hi - ch.r_lo) * 8, cudaMemcpyHostToDevice,
+                              c.copy_stream));
+    MF_CUDA(cudaEventRecord(c.copy_events[chunks.size()], c.copy_stream));
+    chunks.push_back(ch);
+  }
+  ReadsView r{c.in_words.as<uint32_t>(), c.in_starts.as<int64_t>(), n_reads, n_bases};
+  const uint32_t *sbits = c.sbits.as<uint32_t>();
+  HostChunks l1;
+  l1.nseg = nb1;
+  std::vector<int64_t> seg_total(nb1, 0);
+  std::vector<unsigned long long> hist(nb1), cursor(nb1);
+  int64_t acc = 0;
+  for (size_t ci = 0; ci < chunks.size(); ++ci) {
+    const Chunk &ch = chunks[ci];
+    MF_CUDA(cudaStreamWaitEvent(c.stream, c.copy_events[ci], 0));
+    const int64_t nr = std::min<int64_t>(ch.r_hi, n_reads) - ch.r_lo;   // starts[n_reads] is the end sentinel, not a read
+    if (nr > 0) {
+      k_start_bits<<<(unsigned)div_ceil64(nr, 256), 256, 0, c.stream>>>(r.starts + ch.r_lo, nr, c.sbits.as<uint32_t>());
+      MF_LAUNCH_CHECK();
+      c.launches++;
+    }
+    unsigned long long *dh = d_hist + (size_t)ci * nb1, *dc = d_cursor + (size_t)ci * nb1;
+    {
+      Stage st(c, "reads_hist");
+      launch_reads_hist<W>(c, r, sbits, k, LevelArgs{0, p.l1_bits, 0u, (uint32_t)nb1, nullptr}, dh, ch.t0, ch.t1 - ch.t0);
+    }
+    c.d2h(hist.data(), dh, sizeof(unsigned long long) * nb1);
+    for (int b = 0; b < nb1; ++b) {
+      cursor[b] = (unsigned long long)acc;
+      if (hist[b]) {
+        l1.start.push_back(acc);
+        l1.size.push_back((int64_t)hist[b]);
+        l1.seg.push_back(b);
+      }
+      seg_total[b] += (int64_t)hist[b];
+      acc += (int64_t)hist[b];
+    }
+    if (acc > n_bound) throw std::runtime_error("key count exceeds its bound (internal error)");
+    MF_CUDA(cudaMemcpyAsync(dc, cursor.data(), sizeof(unsigned long long) * nb1, cudaMemcpyHostToDevice, c.stream));
+    MF_CUDA(cudaStreamSynchronize(c.stream));   // `cursor` is reused by the next chunk
+    {
+      Stage st(c, "reads_scatter");
+      launch_reads_scatter<W>(c, r, sbits, k, LevelArgs{0, p.l1_bits, 0u, (uint32_t)nb1, nullptr}, dc, bufA, ch.t0, ch.t1 - ch.t0);
+    }
+  }
+  {
+    int64_t run = 0;
+    for (int b = 0; b < nb1; ++b) { l1.seg_out_start.push_back(run); run += seg_total[b]; }
+  }
+  out->n_keys = acc;
+  out->n_edges = 0;
+  out->k = k;
+  out->words = We;
+  if (acc > 0) count_finish_impl<W>(c, bufA, bufB, acc, l1, k, p.l1_bits, min_count, false, out, nullptr);
+  if (out->n_edges == 0) {
+    c.edges.reserve(256);
+    out->edges = c.edges.as<uint32_t>();
+  }
+  Stage st(c, "edge_buckets");
+  edge_bucket_counts(c, *out);
+  return true;
+}
+#define MF_DISPATCH_CASE_COUNTHOST(Wn) \
+  case Wn: return dev_count_host_impl<Wn>(c, packed_host, starts_host, n_reads, n_bases, k, min_count, out);
+bool dev_count_host(Ctx &c, const uint32_t *packed_host, const int64_t *starts_host, int64_t n_reads, int64_t n_bases, int k,
+                    int min_count, EdgesView *out) {
+  if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
+  if (min_count < 1) throw std::invalid_argument("min_count must be >= 1");
+  MF_DISPATCH_W(words_key(k), COUNTHOST)
+  return false;
 }
 
 // staged API for the multi-GPU driver

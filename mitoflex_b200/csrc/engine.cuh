@@ -37,6 +37,8 @@ struct Ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;        // host-input pipeline: chunked H2D runs ahead of the reads-fed kernels
+  std::vector<cudaEvent_t> copy_events;
   char *slab = nullptr;
   size_t slab_bytes = 0, slab_off = 0;
   size_t mem_limit = 0;
@@ -106,6 +108,10 @@ struct SeqsView {          // general sequences (contigs), stored orientation, o
 
 // pipelines
 void dev_count(Ctx &c, const ReadsView &r, int k, int min_count, EdgesView *out, int64_t *counting_host);
+// count with the reads still in (pinned) host memory: the transfer is cut into chunks and the reads-fed partition level runs
+// on chunk i while chunk i+1 crosses PCIe.  Returns false (nothing done) when the job does not fit one in-core round.
+bool dev_count_host(Ctx &c, const uint32_t *packed_host, const int64_t *starts_host, int64_t n_reads, int64_t n_bases, int k,
+                    int min_count, EdgesView *out);
 void dev_seq2sdbg(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &seqs, int k, int tip_mode, SdbgView *out);
 void dev_count_hist(Ctx &c, const ReadsView &r, int k, int l1_bits, unsigned long long *hist_dev);
 void dev_count_scatter(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev, uint32_t *keys_out,

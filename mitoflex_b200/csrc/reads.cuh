@@ -138,7 +138,7 @@ __device__ __forceinline__ int reads_load_tile(const ReadsSrc &src, int64_t tile
 // invalid positions add to one of 32 per-lane dummy counters behind the bins, so the loop has no branch
 template <int W, int NT, bool RANGED>
 __global__ void __launch_bounds__(NT) k_reads_hist(ReadsSrc src, LevelArgs a, unsigned long long *__restrict__ hist,
-                                                   int64_t ntiles) {
+                                                   int64_t tile0, int64_t ntiles) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int nbins = 1 << a.nbits;
   uint32_t *s_hist = smem;                   // [nbins + 32]
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NT) k_reads_hist(ReadsSrc src, LevelArgs a, un
   const uint32_t dlo = a.dlo, dspan = a.dhi - a.dlo;
   const uint32_t dummy = (uint32_t)nbins + (tid & 31);
   for (int i = tid; i < nbins + 32; i += NT) s_hist[i] = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int64_t tile = tile0 + blockIdx.x; tile < tile0 + ntiles; tile += gridDim.x) {
     __syncthreads();
     const int lim = reads_load_tile<W, NT>(src, tile, seq, sb);
     __syncthreads();
@@ -182,7 +182,7 @@ __host__ __device__ inline size_t reads_scatter_smem_bytes(int NT, int nbits, in
 
 template <int W, int NT, int BPT, bool RANGED>
 __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a, unsigned long long *__restrict__ cursor,
-                                                      uint32_t *__restrict__ out) {
+                                                      uint32_t *__restrict__ out, int64_t tile0) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr int T = NT * 16;
   const int nbins = 1 << a.nbits;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a,
   const uint32_t dummy = (uint32_t)nbins + (tid & 31);
 
   for (int i = tid; i < nbins + 32; i += NT) s_cnt[i] = 0;
-  const int lim = reads_load_tile<W, NT>(src, blockIdx.x, seq, sb);
+  const int lim = reads_load_tile<W, NT>(src, tile0 + blockIdx.x, seq, sb);
   __syncthreads();
   const uint32_t vm = valid16(sb, tid * 16, src.k, lim);
   KeyWindow<W> kw;

@@ -178,3 +178,32 @@ def test_count_crowded_buckets_multipass(ctx, oracle, monkeypatch):
     assert_edges_equal(e_gpu, e_orc)
     assert np.array_equal(e_gpu.counting, e_orc.counting)
     assert "local_count_multipass" in prof, prof
+
+
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_host_read2sdbg_matches_oracle(ctx, oracle, monkeypatch, pipelined):
+    """the end-to-end entry point (host buffers in, host buffers out); with MFSDBG_H2D_MIN_BASES=0 the transfer is cut into
+    chunks and the reads-fed partition level runs chunk by chunk behind it (several level-1 chunks per segment)."""
+    import ctypes
+    from mitoflex_b200 import lib
+    if pipelined:
+        monkeypatch.setenv("MFSDBG_H2D_MIN_BASES", "0")
+    k, m = 21, 2
+    bases, starts = make_reads(31, 30000, k, genome_len=120000, max_len=150, err=0.005)
+    words, st = lib.pack_reads(bases, starts)
+    words = np.ascontiguousarray(words)
+    st = np.ascontiguousarray(st)
+    out = ctx.host_read2sdbg(words.ctypes.data, st.ctypes.data, len(st) - 1, int(st[-1]), k, m)
+    g = oracle.read2sdbg(_orc_reads(oracle, bases, starts), k, m, threads=8)
+    assert out.n_items == g.n
+    assert out.n_tips * out.words_per_tip == np.asarray(g.tip_labels).size
+    rec = np.ctypeslib.as_array(ctypes.cast(out.rec, ctypes.POINTER(ctypes.c_uint32)), shape=(out.n_items,)).copy()
+    assert np.array_equal(rec & 0xF, g.w)
+    assert np.array_equal((rec >> 4) & 1, g.last)
+    assert np.array_equal((rec >> 5) & 1, g.tip)
+    assert np.array_equal(rec >> 8, g.mul)
+    if out.n_tips:
+        lab = np.ctypeslib.as_array(ctypes.cast(out.tip_labels, ctypes.POINTER(ctypes.c_uint32)),
+                                    shape=(out.n_tips * out.words_per_tip,)).copy()
+        assert np.array_equal(lab, np.asarray(g.tip_labels).ravel())
+    assert out.n_large == g.n_large
