@@ -78,12 +78,6 @@ __device__ __forceinline__ uint32_t rec_digit_mem(const uint32_t *r, int bit_off
   return __funnelshift_l(lo, hi, sh) >> (32 - nbits);
 }
 
-// Peer mask of lanes holding the same digit (inactive lanes pass valid=false and get 0).
-__device__ __forceinline__ unsigned match_digit(uint32_t d, bool valid) {
-  unsigned m = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
-  return valid ? m : 0u;
-}
-
 // Block-wide exclusive scan of s[0..n) in shared memory (uint32), returns total. All threads must call.
 // scratch: at least 33 uint32 in shared memory.
 template <int NT>

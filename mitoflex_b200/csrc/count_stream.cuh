@@ -494,6 +494,20 @@ inline size_t scatter_tma_smem_bytes(int nbits) {
   const size_t nb = (size_t)1 << nbits, T = (size_t)512 * KPT;
   return (T + 4) * 8 + T * 8 + (nb + 32) * 4 + nb * 8 + 48 * 4 + 16;
 }
+// lean digit of a 2-word record for bit_off < 32: dg = (x * nb) >> xbits with x = the xbits bits at bit_off; the bit-prefix
+// levels pass nb = 2^xbits, so one formula serves both (these kernels are instruction-issue bound: 37 -> ~12 per record)
+struct Digit2 {
+  int sh, shx, xbits;
+  uint32_t nb;
+  __device__ __forceinline__ Digit2(const LevelArgs &a, uint32_t seg_nb) {
+    xbits = seg_nb ? a.xbits : a.nbits;
+    nb = seg_nb ? seg_nb : (1u << a.nbits);
+    sh = a.bit_off;
+    shx = 32 - xbits;
+  }
+  __device__ __forceinline__ uint32_t operator()(uint2 v) const { return ((__funnelshift_l(v.y, v.x, sh) >> shx) * nb) >> xbits; }
+};
+
 template <int NT, int KPT, int BPT>
 __global__ void __launch_bounds__(NT, 2) k_scatter_tma(const uint32_t *__restrict__ in, const TileDesc *__restrict__ tiles, LevelArgs a,
                                                       unsigned long long *__restrict__ cursor, uint32_t *__restrict__ out) {
@@ -522,43 +536,40 @@ __global__ void __launch_bounds__(NT, 2) k_scatter_tma(const uint32_t *__restric
     mbar_expect_tx(mbar, bytes);
     bulk_g2s(X, reinterpret_cast<const uint2 *>(in) + (d.base - off), bytes, mbar);
   }
-  const uint32_t nb = a.seg_nb ? a.seg_nb[d.seg] : 0u;
-  const uint32_t dlo = a.dlo, dspan = a.dhi - a.dlo;
-  const uint32_t dummy = (uint32_t)nbins + (tid & 31);
+  const Digit2 digit(a, a.seg_nb ? a.seg_nb[d.seg] : 0u);
   mbar_wait(mbar, 0);
   const uint2 *Xo = X + off;
-  // phase A: count
+  // phase A: one shared atomic per record; its return value is the record's rank inside its bin, kept with the digit in a
+  // register so that the staging pass needs neither a second atomic nor the digit again
+  uint32_t rk[KPT];
+  if (n == T) {
 #pragma unroll
-  for (int q = 0; q < KPT; ++q) {
-    const int j = q * NT + tid;
-    if (j < n) {
-      const uint2 v = Xo[j];
-      const uint32_t r[2] = {v.x, v.y};
-      const uint32_t dg = level_digit<2>(r, a, nb);
-      atomicAdd(s_cnt + ((dg - dlo) < dspan ? dg : dummy), 1u);
+    for (int q = 0; q < KPT; ++q) {
+      const uint32_t dg = digit(Xo[q * NT + tid]);
+      rk[q] = (dg << 16) | atomicAdd(s_cnt + dg, 1u);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < KPT; ++q) {
+      const int j = q * NT + tid;
+      rk[q] = 0xffffffffu;
+      if (j < n) {
+        const uint32_t dg = digit(Xo[j]);
+        rk[q] = (dg << 16) | atomicAdd(s_cnt + dg, 1u);
+      }
     }
   }
   __syncthreads();
   const uint32_t total = bins_scan_reserve<NT, BPT>(s_cnt, s_gd, scratch, cursor + (size_t)d.seg * nbins, nbins);
-  // phase B: every record takes the next free slot of its bin
+  // phase B: stage every record at its bin's start + rank
 #pragma unroll
-  for (int q = 0; q < KPT; ++q) {
-    const int j = q * NT + tid;
-    if (j < n) {
-      const uint2 v = Xo[j];
-      const uint32_t r[2] = {v.x, v.y};
-      const uint32_t dg = level_digit<2>(r, a, nb);
-      if ((dg - dlo) < dspan) Y[atomicAdd(s_cnt + dg, 1u)] = v;
-    }
-  }
+  for (int q = 0; q < KPT; ++q)
+    if (rk[q] != 0xffffffffu) Y[s_cnt[rk[q] >> 16] + (rk[q] & 0xffffu)] = Xo[q * NT + tid];
   __syncthreads();
   uint2 *out2 = reinterpret_cast<uint2 *>(out);
   for (uint32_t j = tid; j < total; j += NT) {
     const uint2 v = Y[j];
-    const uint32_t r[2] = {v.x, v.y};
-    const uint32_t dg = level_digit<2>(r, a, nb);
-    uint2 *dst = a.bin_base ? reinterpret_cast<uint2 *>(a.bin_base[dg]) : out2;
-    dst[s_gd[dg] + (long long)j] = v;
+    out2[s_gd[digit(v)] + (long long)j] = v;
   }
 }
 

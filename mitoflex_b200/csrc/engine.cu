@@ -1,14 +1,18 @@
 // engine.cu -- device pipelines of libmfsdbg: count, seq2sdbg, read2sdbg (sm_100a).
 //
 // count (megahit_core count, KmerCounter):
-//   P0 k_level_hist<ReadsProducer>    prefix histogram of canonical (k+1)-mers straight from packed reads
-//   P1 k_level_scatter<ReadsProducer> keys computed again and scattered by their top l1 bits (no unsorted key pass)
-//   P2 k_level_hist<RecordsProducer>  per-partition histogram of the next l2 bits
-//   P3 k_level_scatter<RecordsProducer>
-//   P4 k_local<kCountEmit>            bucket in shared memory: sub-split, serial finish, run lengths, -m filter
+//   P0 k_reads_hist                   first key word of every position -> histogram of its top l1 bits       (reads.cuh)
+//   P1 k_reads_scatter                keys recomputed and scattered by their top l1 bits; with LevelArgs::bin_base the
+//                                     bins are peer-GPU buffers (fused partition + exchange)                   (reads.cuh)
+//      k_probe_distinct               distinct / occurrences on a few prefix ranges -> bucket size      (count_stream.cuh)
+//   P2 k_level_hist<RecordsProducer>  per-segment histogram of the range-partition digit                   (partition.cuh)
+//   P3 k_scatter_tma / k_level_scatter  second partition level (TMA-fed tiles for 2-word records)
+//   P4 k_count_stream / k_count_stream_w  persistent CTAs, bulk-copy ring, shared hash table, solid keys -> edge records;
+//      k_count (local.cuh) for what bails and for 32-bit keys
 //   P5 k_gather_edges                 compact per-bucket edge runs into the globally sorted edge array
-// seq2sdbg (SeqToSdbg): k_items_from_edges / k_items_from_seqs, the same partition levels over item words,
-//   k_local<kSdbgEmit> (sort, BOSS emission into arenas) -> k_gather_edges.
+// seq2sdbg (SeqToSdbg): k_kmer_set_insert + k_items_from_edges_filtered (k <= 31) / k_items_from_edges, k_items_from_seqs
+//   (items.cuh), the same partition levels over item words, k_sdbg_local (sdbg_local.cuh; k_local<kSdbgEmit> for crowded
+//   buckets) -> k_gather_edges.
 #include "engine.cuh"
 #include <algorithm>
 #include <cmath>
@@ -386,12 +390,19 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
     c.launches += 2;
   }
   if (tb_h[nchunk] > 0) {
-    RecordsProducer<W> ph{in, d_tiles_h, C::TH};
-    size_t smem = ((size_t)1 << nbits) * 4 + 16;
-    auto kern = k_level_hist<RecordsProducer<W>, W, C::NT, C::IPT_H>;
-    set_smem(kern, smem);
+    const size_t smem = ((size_t)1 << nbits) * 4 + 16;
     Stage st(c, tag_h.c_str());
-    kern<<<(unsigned)tb_h[nchunk], C::NT, smem, c.stream>>>(ph, a, d_hist);
+    if (env_int("MFSDBG_HIST_PERSIST", 1) != 0 && bit_off < 32) {   // the 2-word fast path reads its digit with one funnel shift
+      auto kern = k_level_hist_persist<W, C::NT>;
+      set_smem(kern, smem);
+      const int64_t grid = std::min<int64_t>(tb_h[nchunk], (int64_t)c.sm_count * env_int("MFSDBG_HIST_CTAS", 4));
+      kern<<<(unsigned)grid, C::NT, smem, c.stream>>>(in, d_tiles_h, tb_h[nchunk], a, d_hist);
+    } else {
+      RecordsProducer<W> ph{in, d_tiles_h, C::TH};
+      auto kern = k_level_hist<RecordsProducer<W>, W, C::NT, C::IPT_H>;
+      set_smem(kern, smem);
+      kern<<<(unsigned)tb_h[nchunk], C::NT, smem, c.stream>>>(ph, a, d_hist);
+    }
     MF_LAUNCH_CHECK();
     c.launches++;
   }
@@ -399,7 +410,7 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   MF_LAUNCH_CHECK();
   c.launches++;
   if constexpr (W == 2) {
-    if (tb_s[nchunk] > 0 && env_int("MFSDBG_TMA_SCATTER", 1) != 0) {
+    if (tb_s[nchunk] > 0 && env_int("MFSDBG_TMA_SCATTER", 1) != 0 && bit_off < 32) {
       // 2-word records: TMA-fed tiles of 6144 (5120 with 2048 bins) records
       const int KPT = nbits <= 10 ? 12 : 10, T = 512 * KPT;
       std::vector<int64_t> tb_t(nchunk + 1);
@@ -659,7 +670,7 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
                                    int min_count, double *rho_out, Alloc &&alloc) {
   const double rho = probe_distinct_ratio<W>(c, *cur, l1, *bit_off, key_bits);
   *rho_out = rho;
-  const double load = env_int("MFSDBG_STREAM_LOAD_PCT", 45) / 100.0;
+  const double load = env_int("MFSDBG_STREAM_LOAD_PCT", W == 2 ? 45 : 35) / 100.0;
   double B = std::min(60000.0, std::max(1024.0, load * kCsSlots / rho));
   // --min-count 1 makes every distinct key a solid one: keep them under the per-bucket limit of the streamed kernel
   const int solid_max = W == 2 ? kCsSolidMax : (W <= 4 ? 1024 : 512);
@@ -677,7 +688,8 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
     for (int s2 = 0; s2 < hc.nseg; ++s2) max_need = std::max<int64_t>(max_need, (int64_t)std::ceil((double)seg_total[s2] / B));
     // up to 1.5x over the bin limit the buckets simply get that much larger (the table runs fuller, what crowds it takes the
     // multi-pass kernel): cheaper than a whole extra partition level
-    if (max_need <= nb_cap + nb_cap / 2 || xbits < 16) {
+    // (2-word keys only: wider keys have no multi-pass kernel, their crowded buckets fall to the slow general path)
+    if (max_need <= nb_cap + (W == 2 ? nb_cap / 2 : 0) || xbits < 16) {
       std::vector<uint16_t> nb(hc.nseg);
       int mx = 1;
       for (int s2 = 0; s2 < hc.nseg; ++s2) {
@@ -952,7 +964,9 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
         c.h2d(d_hw.p, hw.data(), sizeof(WorkItem) * hw.size());
         LocalArgs sa = a;
         sa.work = d_hw.as<WorkItem>();
-        launch_serial<W, kCountEmit>(c, sa, (int)hw.size());
+        k_sorted_runs<W, 256><<<(unsigned)hw.size(), 256, 0, c.stream>>>(sa, (int)hw.size());
+        MF_LAUNCH_CHECK();
+        c.launches++;
         int sf[3];
         c.d2h(sf, d_flags, sizeof(int) * 3);
         flags[1] |= sf[1];
@@ -1034,7 +1048,7 @@ static Plan count_plan(Ctx &c, int k, int min_count, int64_t n_est) {
     // streamed finish: level 2 is a range partition into <= 1024 bins of ~16 K keys (45 % table load at the usual distinct
     // ratio), so level 1 only has to bring the densest segments (2x the average) under ~17-24 M keys -- and the fewer bins the
     // reads-fed scatter has, the faster it runs (512 bins: 14.9 ms, 1024: 19.4 ms, 2048: 48 ms on the 5 Gbp sample)
-    p.l1_bits = std::max(1, std::min({10, key_bits, ceil_log2((double)n_est / 1.2e7)}));
+    p.l1_bits = std::max(1, std::min({10, key_bits, ceil_log2((double)n_est / (W == 2 ? 1.2e7 : 4.0e6))}));
     // out-of-core rounds are cut at level-1 bin boundaries: a bin (twice the average at small prefixes) must stay well
     // inside what one round may hold
     const size_t bud0 = (size_t)((double)c.budget() * 0.9);

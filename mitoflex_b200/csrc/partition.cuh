@@ -4,9 +4,8 @@
 //   k_level_hist    : digit histogram per output segment          (read only)
 //   k_level_scan    : histogram -> absolute cursors + bucket table (tiny)
 //   k_level_scatter : rank in shared memory, stage, coalesced copy-out
-// A Producer feeds a tile of records: ReadsProducer computes canonical (k+1)-mer keys straight from
-// 2-bit packed reads (so unsorted keys are never written to HBM), RecordsProducer re-reads records that
-// an earlier level wrote.  Ranking is one shared-memory atomicAdd per record on a CTA-wide counter array (keys only, so
+// A Producer feeds a tile of records: RecordsProducer re-reads records that an earlier level wrote (the reads-fed level,
+// which computes canonical (k+1)-mer keys straight from 2-bit packed reads, has its own kernels in reads.cuh).  Ranking is one shared-memory atomicAdd per record on a CTA-wide counter array (keys only, so
 // the partition need not be stable; on B200 that is ~20x cheaper than match.any, see tools/ubench.cu).
 #pragma once
 #include "common.cuh"
@@ -112,117 +111,6 @@ struct RecordsProducer {
   }
 };
 
-// Canonical (k+1)-mer keys of the REVERSED read, computed per base position from true-orientation packed
-// reads: stored edge = reverse(e), its reverse complement = complement(e); key = min of the two
-// (megahit KmerCounter reads the library with is_reverse=true; strand tie -> the edge itself).
-template <int W>
-struct ReadsProducer {
-  const uint32_t *packed;   // 16 bases / word, first base in the top bits, reads back to back
-  const uint32_t *sbits;    // bit g (LSB-first within word) set iff a read starts at base g
-  int64_t n_bases;
-  int k;
-  int T;
-  static constexpr bool kNeedsSmem = true;
-  __host__ __device__ static int n_seq_words(int T) { return T / 16 + W + 2; }
-  __host__ __device__ static int n_bit_words(int T, int k) { return T / 32 + (k + 31) / 32 + 2; }
-  __host__ __device__ static int smem_words(int T, int k) { return n_seq_words(T) + n_bit_words(T, k); }
-
-  struct Tile {
-    int64_t base;  // first base position of the tile
-    int n;
-    int seg;
-  };
-  __device__ __forceinline__ Tile setup(int64_t tile, uint32_t *sm) const {
-    Tile t;
-    t.base = tile * (int64_t)T;
-    int64_t rem = n_bases - t.base;
-    t.n = (int)(rem < T ? rem : T);
-    t.seg = 0;
-    const int64_t total_words = (n_bases + 15) >> 4;
-    const int64_t w0 = t.base >> 4;  // T is a multiple of 32 so tiles are word aligned
-    const int nsw = n_seq_words(T);
-    for (int i = threadIdx.x; i < nsw; i += blockDim.x) sm[i] = (w0 + i < total_words) ? packed[w0 + i] : 0u;
-    const int64_t total_bw = (n_bases + 31) >> 5;
-    const int64_t b0 = t.base >> 5;
-    const int nbw = n_bit_words(T, k);
-    uint32_t *sb = sm + nsw;
-    for (int i = threadIdx.x; i < nbw; i += blockDim.x) sb[i] = (b0 + i < total_bw) ? sbits[b0 + i] : 0u;
-    __syncthreads();
-    return t;
-  }
-  __device__ __forceinline__ bool get(const Tile &t, const uint32_t *sm, int j, uint32_t (&key)[W]) const {
-    const int K1 = k + 1;
-    if constexpr (W <= 2) {
-      // the whole (k+1)-mer fits 64 bits (k <= 31): one 64-bit window, one validity funnel shift
-      const uint32_t *sb = sm + n_seq_words(T);
-      const int bit = j + 1;
-      uint32_t v = __funnelshift_r(sb[bit >> 5], sb[(bit >> 5) + 1], bit & 31);
-      v &= (1u << k) - 1u;                                   // k <= 31
-      const bool valid = j < t.n && (t.base + j + K1 <= n_bases) && v == 0;
-      const int wi = j >> 4, sh = (j & 15) * 2;
-      const uint32_t w0 = sm[wi], w1 = sm[wi + 1], w2 = sm[wi + 2];
-      const unsigned long long raw0 =
-          ((unsigned long long)__funnelshift_l(w1, w0, sh) << 32) | __funnelshift_l(w2, w1, sh);
-      const int bits = 2 * K1;
-      const unsigned long long mask = ~0ull << (64 - bits);
-      const unsigned long long raw = raw0 & mask;
-      const unsigned long long cmpl = ~raw0 & mask;
-      unsigned long long rv = __brevll(raw);                 // reversed bit string, right aligned
-      rv = ((rv & 0x5555555555555555ull) << 1) | ((rv >> 1) & 0x5555555555555555ull);
-      rv <<= (64 - bits);
-      const unsigned long long kk = rv < cmpl ? rv : cmpl;
-      key[0] = (uint32_t)(kk >> 32);
-      if constexpr (W == 2) key[1] = (uint32_t)kk;
-      return valid;
-    }
-    bool valid = j < t.n && (t.base + j + K1 <= n_bases);
-    // no read may start inside (j, j+k]
-    const uint32_t *sb = sm + n_seq_words(T);
-    {
-      int bit = j + 1, left = k;
-      while (left > 0) {
-        int wi = bit >> 5, sh = bit & 31;
-        uint32_t v = __funnelshift_r(sb[wi], sb[wi + 1], sh);
-        if (left < 32) v &= (1u << left) - 1u;
-        valid = valid && (v == 0);
-        bit += 32;
-        left -= 32;
-      }
-    }
-    // raw = 2*K1 bits at base j, left aligned
-    const int wi = j >> 4, sh = (j & 15) * 2;
-    uint32_t raw[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) raw[i] = __funnelshift_l(sm[wi + i + 1], sm[wi + i], sh);
-    const int pad = 32 * W - 2 * K1;  // 0..30
-    raw[W - 1] &= 0xffffffffu << pad;
-    // complement(e): same direction, bases 3-c
-    uint32_t cmpl[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) cmpl[i] = ~raw[i];
-    cmpl[W - 1] &= 0xffffffffu << pad;
-    // reverse(e): reverse base order (bit reverse, then swap the two bits of every base back)
-    uint32_t rr[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-      uint32_t x = __brev(raw[W - 1 - i]);
-      rr[i] = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
-    }
-    uint32_t rev[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) rev[i] = __funnelshift_l(i + 1 < W ? rr[i + 1] : 0u, rr[i], pad);
-    // min(rev, cmpl)
-    int c = 0;
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-      if (c == 0 && rev[i] != cmpl[i]) c = rev[i] < cmpl[i] ? -1 : 1;
-    }
-#pragma unroll
-    for (int i = 0; i < W; ++i) key[i] = c <= 0 ? rev[i] : cmpl[i];
-    return valid;
-  }
-};
-
 // ============================================================ histogram
 // grid.x = number of tiles; dynamic smem = CTA histogram (u32 [nbins]) + producer words.
 // Shared-memory atomics are the ranking primitive: measured on B200 (tools/ubench.cu) a warp-wide shared atomicAdd on
@@ -251,6 +139,110 @@ __global__ void __launch_bounds__(NT) k_level_hist(P prod, LevelArgs a, unsigned
     uint32_t c = s_hist[b];
     if (c) atomicAdd(h + b, (unsigned long long)c);
   }
+}
+
+
+// Persistent variant for records: a CTA walks a contiguous range of tiles, keeps its shared histogram across the tiles of
+// one segment (tiles are segment-major, so it flushes a handful of times instead of once per tile) and has all the loads
+// of a round in flight before the first shared atomic.  The per-tile kernel above waits on a chain of dependent loads
+// (tile descriptor -> records) at the start of every short-lived CTA (long_scoreboard 73 % under ncu).
+template <int W, int NT>
+__global__ void __launch_bounds__(NT) k_level_hist_persist(const uint32_t *__restrict__ in, const TileDesc *__restrict__ tiles, int64_t ntiles,
+                                                           LevelArgs a, unsigned long long *__restrict__ hist) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int IPT = W <= 2 ? 16 : (W <= 4 ? 8 : 4);   // records held in registers per round
+  const int nbins = 1 << a.nbits;
+  uint32_t *s_hist = smem;
+  const int tid = threadIdx.x;
+  const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
+  if (t0 >= t1) return;
+  for (int i = tid; i < nbins; i += NT) s_hist[i] = 0;
+  int cur_seg = -1;
+  uint32_t nb = 0;
+  TileDesc d = tiles[t0];
+  auto flush = [&]() {
+    __syncthreads();
+    if (cur_seg >= 0) {
+      unsigned long long *h = hist + (size_t)cur_seg * nbins;
+      for (int b = tid; b < nbins; b += NT) {
+        const uint32_t c = s_hist[b];
+        if (c) {
+          atomicAdd(h + b, (unsigned long long)c);
+          s_hist[b] = 0;
+        }
+      }
+    }
+    __syncthreads();
+  };
+  for (int64_t t = t0; t < t1; ++t) {
+    const TileDesc nd = t + 1 < t1 ? tiles[t + 1] : d;   // the next descriptor is on its way while this tile is read
+    if (d.seg != cur_seg) {
+      flush();
+      cur_seg = d.seg;
+      nb = a.seg_nb ? a.seg_nb[cur_seg] : 0u;
+    }
+    if constexpr (W == 2) {
+      // 16-byte loads: two records per lane; the tile is read from the 16-byte boundary at or below its first record.
+      // Lean digit (bit_off < 32, checked by the host): (x * nb) >> xbits, bit-prefix levels pass nb = 2^xbits.
+      const int off = (int)(d.base & 1);
+      const uint4 *p4 = reinterpret_cast<const uint4 *>(in + (d.base - off) * 2);
+      const int npair = (d.n + off + 1) >> 1;
+      const int xb = nb ? a.xbits : a.nbits, shx = 32 - xb;
+      const uint32_t mul = nb ? nb : (1u << a.nbits);
+      const bool whole = off == 0 && (d.n & 1) == 0 && npair % (NT * 8) == 0;
+      for (int e0 = 0; e0 < npair; e0 += NT * 8) {
+        uint4 v[8];
+        if (whole) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = p4[e0 + i * NT + tid];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            atomicAdd(s_hist + (((__funnelshift_l(v[i].y, v[i].x, a.bit_off) >> shx) * mul) >> xb), 1u);
+            atomicAdd(s_hist + (((__funnelshift_l(v[i].w, v[i].z, a.bit_off) >> shx) * mul) >> xb), 1u);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = p4[min(e0 + i * NT + tid, npair - 1)];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int e = e0 + i * NT + tid;
+            const int j = 2 * e - off;   // record index of v[i].xy within the tile; .zw is j + 1
+            const uint32_t d0 = ((__funnelshift_l(v[i].y, v[i].x, a.bit_off) >> shx) * mul) >> xb;
+            const uint32_t d1 = ((__funnelshift_l(v[i].w, v[i].z, a.bit_off) >> shx) * mul) >> xb;
+            if (e < npair && j >= 0) atomicAdd(s_hist + d0, 1u);
+            if (e < npair && j + 1 < d.n) atomicAdd(s_hist + d1, 1u);
+          }
+        }
+      }
+    } else {
+    const uint32_t *base = in + d.base * (int64_t)W;
+    for (int j0 = 0; j0 < d.n; j0 += NT * IPT) {
+      uint32_t r[IPT][W];
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const int j = min(j0 + i * NT + tid, d.n - 1);   // clamped: a duplicate load instead of a branch, dropped below
+        if constexpr (W == 2) {
+          const uint2 v = *reinterpret_cast<const uint2 *>(base + (size_t)j * 2);
+          r[i][0] = v.x; r[i][1] = v.y;
+        } else if constexpr (W == 4) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(base + (size_t)j * 4);
+          r[i][0] = v.x; r[i][1] = v.y; r[i][2] = v.z; r[i][3] = v.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < W; ++c) r[i][c] = base[(size_t)j * W + c];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const uint32_t dg = level_digit<W>(r[i], a, nb);
+        if (j0 + i * NT + tid < d.n && dg >= a.dlo && dg < a.dhi) atomicAdd(s_hist + dg, 1u);
+      }
+    }
+    }
+    d = nd;
+  }
+  flush();
 }
 
 // ============================================================ scan: hist -> cursors + bucket table
