@@ -47,8 +47,10 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  // a warp that finds the stage not ready backs off for a few dozen ns instead of spinning at full issue rate: under ncu the
+  // spin loop alone was 8 % of all instructions the count kernel executed
   uint32_t ok;
-  do {
+  for (;;) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -58,7 +60,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
-  } while (!ok);
+    if (ok) break;
+    __nanosleep(40);
+  }
 }
 
 inline size_t count_stream_smem_bytes() {
@@ -161,31 +165,22 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
       for (int c = 0; c < kCsStages && c < nchunks; ++c) issue(c);
   }
 
-  // hi:lo = the key.  The hit path (the key is already in its slot: 9 of 10 inserts at assembly depths) is one shared load,
-  // two logic ops, a compare and the count RED; these kernels are bound by instruction issue, not by shared memory.
-  auto insert = [&](uint32_t hi, uint32_t lo) {
-    const uint32_t x = lo ^ (hi * 0x9E3779B1u);
+  auto insert = [&](unsigned long long key) {
+    uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
     uint32_t h = (x * 0x85EBCA6Bu) >> (32 - kCsSlotsLog);
     for (int probe = 0; probe < kCsProbeLimit; ++probe) {
-      const unsigned long long cur64 = *reinterpret_cast<volatile unsigned long long *>(tkeys + h);
-      const uint2 cur = make_uint2((uint32_t)cur64, (uint32_t)(cur64 >> 32));   // .x = low word, .y = high word
-      if (((cur.x ^ lo) | (cur.y ^ hi)) == 0u) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tkeys + h);
+      if (cur == kEmptyKey) cur = atomicCAS(tkeys + h, kEmptyKey, key);
+      if (cur == kEmptyKey || cur == key) {
         atomicAdd(tcnt + h, 1u);
         return;
       }
-      if ((cur.x & cur.y) == 0xffffffffu) {   // empty (a key never has both words all ones)
-        const unsigned long long key = ((unsigned long long)hi << 32) | lo;
-        const unsigned long long old = atomicCAS(tkeys + h, kEmptyKey, key);
-        if (old == kEmptyKey || old == key) {
-          atomicAdd(tcnt + h, 1u);
-          return;
-        }
-      }
-      h = (h + 1) & (kCsSlots - 1);
+      h = (h + probe + 1) & (kCsSlots - 1);   // triangular steps: every slot once, without linear probing's clusters
     }
-    s_flag[0] = 1;   // table too crowded: this bucket takes the multi-pass / general path
+    s_flag[0] = 1;   // table too crowded: this bucket takes the general path
   };
 
+  // ---- bucket end: sweep + clear, solid keys -> ordered edge records.  Called by all threads, after a __syncthreads.
   // mode 0: streamed bucket (reserve arena space, bail list on failure); mode 1: multi-pass count sweep (only totals the solid
   // keys in s_flag[9], failure -> s_flag[8]); mode 2: multi-pass emit sweep (writes at the base held in s_flag[2..3] and advances it)
   auto finish_bucket = [&](int slot, int mode) {
@@ -375,7 +370,7 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
         for (int64_t i = tid; i < n; i += NT) {
           const uint2 v = keys[i];
           const unsigned long long key = ((unsigned long long)v.x << 32) | v.y;
-          if ((uint32_t)((key - kmin) >> sh) == ps) insert(v.x, v.y);
+          if ((uint32_t)((key - kmin) >> sh) == ps) insert(key);
         }
         __syncthreads();
         finish_bucket(slot, sweep);
@@ -428,16 +423,14 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
   for (int c = 0; c < nchunks; ++c) {
     const int s = c % kCsStages;
     mbar_wait(mbar + s, (uint32_t)((c / kCsStages) & 1));
-    const int64_t g0 = A + (int64_t)c * kCsChunk;
-    const int64_t ghi = g0 + kCsChunk < re ? g0 + kCsChunk : re;
-    const uint32_t chi = (uint32_t)(ghi - rb);
-    const uint2 *rs = reinterpret_cast<const uint2 *>(ring + (size_t)s * kCsChunk);
     const int off = off0 - c * kCsChunk;   // ring index of relative position q is q + off
+    const uint32_t chi = min((uint32_t)(kCsChunk - off), total);   // relative end of the chunk (32-bit: a CTA's range is < 4 G keys)
+    const uint2 *rs = reinterpret_cast<const uint2 *>(ring + (size_t)s * kCsChunk);
     while (p < chi) {
       const uint32_t e = chi < bend ? chi : bend;
       for (uint32_t q = p + tid; q < e; q += NT) {
         const uint2 v = rs[(int)q + off];
-        insert(v.x, v.y);
+        insert(((unsigned long long)v.x << 32) | v.y);
       }
       p = e;
       if (p == bend) {
@@ -518,8 +511,8 @@ struct Digit2 {
 };
 
 template <int NT, int KPT, int BPT>
-__global__ void __launch_bounds__(NT, 2) k_scatter_tma(const uint32_t *__restrict__ in, const TileDesc *__restrict__ tiles, LevelArgs a,
-                                                      unsigned long long *__restrict__ cursor, uint32_t *__restrict__ out) {
+__global__ void __launch_bounds__(NT, 2) k_scatter_tma(const uint32_t *__restrict__ in, const TileDesc *__restrict__ tiles, int64_t ntiles,
+                                                      LevelArgs a, unsigned long long *__restrict__ cursor, uint32_t *__restrict__ out) {
   extern __shared__ __align__(128) unsigned char smraw[];
   constexpr int T = NT * KPT;
   const int nbins = 1 << a.nbits;
@@ -531,58 +524,75 @@ __global__ void __launch_bounds__(NT, 2) k_scatter_tma(const uint32_t *__restric
   uint32_t *scratch = s_cnt + nbins + 32;                            // [48]
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(scratch + 48);
 
-  const TileDesc d = tiles[blockIdx.x];
-  const int n = d.n;
-  const int off = (int)(d.base & 1);
+  // persistent: CTA b takes tiles b, b + grid, ...; the bulk copy of the next tile is issued as soon as the staging pass
+  // has emptied X, so it flies behind the copy-out of the current tile
+  int64_t t = blockIdx.x;
+  if (t >= ntiles) return;
+  TileDesc d = tiles[t];
+  auto issue = [&](const TileDesc &td) {   // thread 0 only
+    const int o = (int)(td.base & 1);
+    const uint32_t bytes = (uint32_t)(((td.n + o) * 8 + 15) & ~15);
+    mbar_expect_tx(mbar, bytes);
+    bulk_g2s(X, reinterpret_cast<const uint2 *>(in) + (td.base - o), bytes, mbar);
+  };
   if (tid == 0) {
     mbar_init(mbar, 1);
     mbar_fence_init();
   }
   for (int i = tid; i < nbins + 32; i += NT) s_cnt[i] = 0;
   __syncthreads();
-  if (tid == 0) {
-    const uint32_t bytes = (uint32_t)(((n + off) * 8 + 15) & ~15);
-    mbar_expect_tx(mbar, bytes);
-    bulk_g2s(X, reinterpret_cast<const uint2 *>(in) + (d.base - off), bytes, mbar);
-  }
-  const Digit2 digit(a, a.seg_nb ? a.seg_nb[d.seg] : 0u);
-  mbar_wait(mbar, 0);
-  const uint2 *Xo = X + off;
-  // phase A: one shared atomic per record; its return value is the record's rank inside its bin, kept with the digit in a
-  // register so that the staging pass needs neither a second atomic nor the digit again
-  uint32_t rk[KPT];
-  if (n == T) {
+  if (tid == 0) issue(d);
+  for (uint32_t it = 0;; ++it) {
+    const int64_t tn = t + gridDim.x;
+    const bool more = tn < ntiles;
+    TileDesc dn = d;
+    if (more) dn = tiles[tn];   // on its way while this tile is processed
+    const int n = d.n;
+    const Digit2 digit(a, a.seg_nb ? a.seg_nb[d.seg] : 0u);
+    const uint2 *Xo = X + (int)(d.base & 1);
+    mbar_wait(mbar, it & 1u);
+    // phase A: one shared atomic per record; its return value is the record's rank inside its bin, kept with the digit in a
+    // register so that the staging pass needs neither a second atomic nor the digit again
+    uint32_t rk[KPT];
+    if (n == T) {
 #pragma unroll
-    for (int q = 0; q < KPT; ++q) {
-      const uint32_t dg = digit(Xo[q * NT + tid]);
-      rk[q] = (dg << 16) | atomicAdd(s_cnt + dg, 1u);
-    }
-  } else {
-#pragma unroll
-    for (int q = 0; q < KPT; ++q) {
-      const int j = q * NT + tid;
-      rk[q] = 0xffffffffu;
-      if (j < n) {
-        const uint32_t dg = digit(Xo[j]);
+      for (int q = 0; q < KPT; ++q) {
+        const uint32_t dg = digit(Xo[q * NT + tid]);
         rk[q] = (dg << 16) | atomicAdd(s_cnt + dg, 1u);
       }
-    }
-  }
-  __syncthreads();
-  const uint32_t total = bins_scan_reserve<NT, BPT>(s_cnt, s_gd, scratch, cursor + (size_t)d.seg * nbins, nbins);
-  // phase B: stage every record at its bin's start + rank
+    } else {
 #pragma unroll
-  for (int q = 0; q < KPT; ++q)
-    if (rk[q] != 0xffffffffu) Y[s_cnt[rk[q] >> 16] + (rk[q] & 0xffffu)] = Xo[q * NT + tid];
-  __syncthreads();
-  uint2 *out2 = reinterpret_cast<uint2 *>(out);
-#pragma unroll
-  for (int q = 0; q < KPT; ++q) {   // fully unrolled: all the shared loads of a thread are in flight together
-    const uint32_t j = (uint32_t)(q * NT + tid);
-    if (j < total) {
-      const uint2 v = Y[j];
-      out2[s_gd[digit(v)] + (long long)j] = v;
+      for (int q = 0; q < KPT; ++q) {
+        const int j = q * NT + tid;
+        rk[q] = 0xffffffffu;
+        if (j < n) {
+          const uint32_t dg = digit(Xo[j]);
+          rk[q] = (dg << 16) | atomicAdd(s_cnt + dg, 1u);
+        }
+      }
     }
+    __syncthreads();
+    const uint32_t total = bins_scan_reserve<NT, BPT>(s_cnt, s_gd, scratch, cursor + (size_t)d.seg * nbins, nbins);
+    // phase B: stage every record at its bin's start + rank
+#pragma unroll
+    for (int q = 0; q < KPT; ++q)
+      if (rk[q] != 0xffffffffu) Y[s_cnt[rk[q] >> 16] + (rk[q] & 0xffffu)] = Xo[q * NT + tid];
+    __syncthreads();   // X is free, Y is complete, the bin starts in s_cnt are dead
+    if (tid == 0 && more) issue(dn);
+    for (int i = tid; i < nbins + 32; i += NT) s_cnt[i] = 0;
+    uint2 *out2 = reinterpret_cast<uint2 *>(out);
+#pragma unroll
+    for (int q = 0; q < KPT; ++q) {   // fully unrolled: all the shared loads of a thread are in flight together
+      const uint32_t j = (uint32_t)(q * NT + tid);
+      if (j < total) {
+        const uint2 v = Y[j];
+        out2[s_gd[digit(v)] + (long long)j] = v;
+      }
+    }
+    if (!more) break;
+    __syncthreads();   // Y and s_gd are free, the cleared counters are visible
+    t = tn;
+    d = dn;
   }
 }
 

@@ -423,12 +423,13 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
                                                                                 tb_t[nchunk], d_tiles_t);
       MF_LAUNCH_CHECK();
       const int bpt = std::max(1, (1 << nbits) / 512);
-      void (*kern)(const uint32_t *, const TileDesc *, LevelArgs, unsigned long long *, uint32_t *) =
+      void (*kern)(const uint32_t *, const TileDesc *, int64_t, LevelArgs, unsigned long long *, uint32_t *) =
           nbits <= 10 ? (bpt == 1 ? k_scatter_tma<512, 12, 1> : k_scatter_tma<512, 12, 2>) : k_scatter_tma<512, 10, 4>;
       const size_t smem = nbits <= 10 ? scatter_tma_smem_bytes<12>(nbits) : scatter_tma_smem_bytes<10>(nbits);
       set_smem(kern, smem);
       Stage st(c, tag_s.c_str());
-      kern<<<(unsigned)tb_t[nchunk], 512, smem, c.stream>>>(in, d_tiles_t, a, d_cur, out);
+      const int64_t grid_t = std::min<int64_t>(tb_t[nchunk], (int64_t)c.sm_count * env_int("MFSDBG_SCATTER_CTAS", 2));
+      kern<<<(unsigned)grid_t, 512, smem, c.stream>>>(in, d_tiles_t, tb_t[nchunk], a, d_cur, out);
       MF_LAUNCH_CHECK();
       c.launches += 2;
       return b;
