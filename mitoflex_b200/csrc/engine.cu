@@ -651,8 +651,10 @@ static double probe_distinct_ratio(Ctx &c, const uint32_t *keys, const HostChunk
   c.h2d(d_pcs, pcs.data(), sizeof(ProbeChunk) * pcs.size());
   {
     Stage st(c, "probe");
-    if constexpr (W == 2) k_probe_distinct<<<dim3(64, (unsigned)pcs.size()), 256, 0, c.stream>>>(keys, d_pcs, bit_off, 0x5a5au, d_tab, d_stats);
-    else k_probe_distinct_w<W><<<dim3(64, (unsigned)pcs.size()), 256, 0, c.stream>>>(keys, d_pcs, bit_off, 0x5a5au, d_tab, d_stats);
+    // enough CTAs to stream the sampled segments at full bandwidth whatever the number of chunks
+    const unsigned probe_gx = (unsigned)std::max<size_t>(16, std::min<size_t>(1024, (size_t)8 * c.sm_count / std::max<size_t>(pcs.size(), 1)));
+    if constexpr (W == 2) k_probe_distinct<<<dim3(probe_gx, (unsigned)pcs.size()), 256, 0, c.stream>>>(keys, d_pcs, bit_off, 0x5a5au, d_tab, d_stats);
+    else k_probe_distinct_w<W><<<dim3(probe_gx, (unsigned)pcs.size()), 256, 0, c.stream>>>(keys, d_pcs, bit_off, 0x5a5au, d_tab, d_stats);
     MF_LAUNCH_CHECK();
     c.launches++;
   }

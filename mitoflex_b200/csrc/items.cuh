@@ -124,16 +124,18 @@ __global__ void k_kmer_set_insert(const uint32_t *__restrict__ edges, int64_t n_
   const unsigned long long rc = revcomp64(fw, k + 1);
   const unsigned long long mk = ~0ull << (64 - 2 * k);
   const uint32_t smask = (1u << log_slots) - 1u;
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const unsigned long long x = (s ? rc : fw) & mk;
-    uint32_t h = kmer_slot(x, log_slots);
-    for (;;) {
-      unsigned long long cur = table[h];
-      if (cur == kKmerEmpty) cur = atomicCAS(table + h, kKmerEmpty, x);
-      if (cur == kKmerEmpty || cur == x) break;
-      h = (h + 1) & smask;
-    }
+  // both first probes are in flight together (these kernels wait on random DRAM accesses and nothing else)
+  const unsigned long long x0 = fw & mk, x1 = rc & mk;
+  uint32_t h0 = kmer_slot(x0, log_slots), h1 = kmer_slot(x1, log_slots);
+  // straight to the CAS (one round trip to L2 instead of a load and then the CAS); both are in flight together
+  unsigned long long c0 = atomicCAS(table + h0, kKmerEmpty, x0), c1 = atomicCAS(table + h1, kKmerEmpty, x1);
+  while (c0 != kKmerEmpty && c0 != x0) {
+    h0 = (h0 + 1) & smask;
+    c0 = atomicCAS(table + h0, kKmerEmpty, x0);
+  }
+  while (c1 != kKmerEmpty && c1 != x1) {
+    h1 = (h1 + 1) & smask;
+    c1 = atomicCAS(table + h1, kKmerEmpty, x1);
   }
 }
 
@@ -156,16 +158,20 @@ __global__ void k_items_from_edges_filtered(const uint32_t *__restrict__ edges, 
     if constexpr (WK == 2) { fwv[1] = (uint32_t)fw; rcv[1] = (uint32_t)rc; }
     const unsigned long long mk = ~0ull << (64 - 2 * k);
     const uint32_t smask = (1u << log_slots) - 1u;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const unsigned long long x = ((s ? rc : fw) << 2) & mk;
-      uint32_t h = kmer_slot(x, log_slots);
-      for (;;) {
-        const unsigned long long cur = table[h];
-        if (cur == x) break;
-        if (cur == kKmerEmpty) { q[s] = false; break; }
-        h = (h + 1) & smask;
-      }
+    const unsigned long long x0 = (fw << 2) & mk, x1 = (rc << 2) & mk;
+    uint32_t h0 = kmer_slot(x0, log_slots), h1 = kmer_slot(x1, log_slots);
+    unsigned long long c0 = table[h0], c1 = table[h1];   // both first probes in flight together
+    for (;;) {
+      if (c0 == x0) break;
+      if (c0 == kKmerEmpty) { q[0] = false; break; }
+      h0 = (h0 + 1) & smask;
+      c0 = table[h0];
+    }
+    for (;;) {
+      if (c1 == x1) break;
+      if (c1 == kKmerEmpty) { q[1] = false; break; }
+      h1 = (h1 + 1) & smask;
+      c1 = table[h1];
     }
   }
   // "$"-head of strand s needs no incoming edge = !q[1-s]; "$"-tail of strand s needs no outgoing edge = !q[s]
