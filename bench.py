@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--k", type=int, default=21, help="k-mer size (the headline metric is quoted at 21)")
+    ap.add_argument("--min-count", type=int, default=2, help="solidity threshold -m (headline: 2)")
+    ap.add_argument("--error-rate", type=float, default=0.005, help="substitution error rate of the synthetic reads (headline: 0.005)")
+    ap.add_argument("--nuclear-len", type=int, default=50_000_000, help="nuclear background length (headline: 50 Mb)")
     return ap.parse_args()
 
 
@@ -200,9 +203,10 @@ def run_reference(args):
 
 # ------------------------------------------------------------------ GPU arm
 def main():
-    global K
+    global K, MIN_COUNT
     args = parse_args()
     K = args.k
+    MIN_COUNT = args.min_count
     if args.impl == "reference":
         return run_reference(args)
     import torch
@@ -225,7 +229,7 @@ def main():
     torch.cuda.set_stream(stream)              # CUDA events bracket exactly the kernels the library launches
     ctx.set_stream(stream.cuda_stream)
     ctx.set_profiling(True)
-    reads = ctx.synth(n_pairs=args.pairs, seed=1002 + 7919 * rank)
+    reads = ctx.synth(n_pairs=args.pairs, seed=1002 + 7919 * rank, error_rate=args.error_rate, nuclear_len=args.nuclear_len)
     n_bases = reads.n_bases
 
     if world > 1:
