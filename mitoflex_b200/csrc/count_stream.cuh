@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
         atomicAdd(tcnt + h, 1u);
         return;
       }
-      h = (h + probe + 1) & (kCsSlots - 1);   // triangular steps: every slot once, without linear probing's clusters
+      h = (h + 1) & (kCsSlots - 1);
     }
     s_flag[0] = 1;   // table too crowded: this bucket takes the general path
   };

@@ -243,11 +243,21 @@ __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a,
   if constexpr (W == 2) {
     const uint2 *st2 = reinterpret_cast<const uint2 *>(stage);
     uint2 *out2 = reinterpret_cast<uint2 *>(out);
-    for (uint32_t j = tid; j < total; j += NT) {
-      const uint2 v = st2[j];
-      const uint32_t d = v.x >> dsh;
-      uint2 *dst = a.bin_base ? reinterpret_cast<uint2 *>(a.bin_base[d]) : out2;
-      dst[s_gd[d] + (long long)j] = v;
+    if (a.bin_base) {   // fused exchange: bin b lives at its own (possibly peer-GPU) address
+      for (uint32_t j = tid; j < total; j += NT) {
+        const uint2 v = st2[j];
+        const uint32_t d = v.x >> dsh;
+        reinterpret_cast<uint2 *>(a.bin_base[d])[s_gd[d] + (long long)j] = v;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {   // a tile stages at most 16 keys per thread: unrolled, all shared loads in flight
+        const uint32_t j = (uint32_t)(q * NT + tid);
+        if (j < total) {
+          const uint2 v = st2[j];
+          out2[s_gd[v.x >> dsh] + (long long)j] = v;
+        }
+      }
     }
   } else {
     const uint32_t total_words = total * W;
