@@ -21,10 +21,10 @@ namespace mf {
 constexpr int kCsNT = 512;
 constexpr int kCsSlotsLog = 12;
 constexpr int kCsSlots = 1 << kCsSlotsLog;   // table slots
-constexpr int kCsChunk = 1024;               // keys per ring stage (8 KB bulk copy)
-constexpr int kCsStages = 4;
-constexpr int kCsSolidMax = 1024;            // distinct solid keys of one bucket on this path
-constexpr int kCsWin = 1024;                 // bucket boundaries held in shared memory at a time
+constexpr int kCsChunk = 2048;               // keys per ring stage (16 KB bulk copy): 4 keys per thread and chunk
+constexpr int kCsStages = 3;
+constexpr int kCsSolidMax = 768;             // distinct solid keys of one bucket on this path
+constexpr int kCsWin = 256;                  // bucket boundaries held in shared memory at a time
 constexpr int kCsProbeLimit = 64;
 constexpr int kCsArenaBlock = 4096;          // edges reserved per global atomic (>= kCsSolidMax)
 constexpr int kCsPairsMax = 128;             // solid keys ranked by all-pairs comparison; more take a counting split
@@ -591,6 +591,106 @@ __global__ void __launch_bounds__(NT, 2) k_scatter_tma(const uint32_t *__restric
     }
     if (!more) break;
     __syncthreads();   // Y and s_gd are free, the cleared counters are visible
+    t = tn;
+    d = dn;
+  }
+}
+
+
+// The same kernel for records of W = 3..10 words (keys of k >= 32, sdbg items of k >= 23): the tile lives in shared memory,
+// so its size no longer depends on how many records a thread can hold in registers (the register-staged k_level_scatter
+// gets 1024-2048 records per tile at these widths -- one or two records per bin and run).  T = NT * KPT records, X and Y of
+// 48 KB each; the digit comes from the first two words (bit_off < 32).
+template <int W>
+struct ScatterWCfg {
+  static constexpr int NT = 512;
+  static constexpr int KPT = (48 * 1024 / (4 * W)) / NT < 1 ? 1 : (48 * 1024 / (4 * W)) / NT;   // 8, 6, 4, 4, 3, 3, 2, 2
+  static constexpr int T = NT * KPT;
+  static constexpr int AL = (W % 4 == 0) ? 1 : ((W % 2 == 0) ? 2 : 4);   // records per 16-byte boundary
+};
+template <int W>
+inline size_t scatter_tma_w_smem_bytes(int nbits) {
+  using C = ScatterWCfg<W>;
+  const size_t nb = (size_t)1 << nbits;
+  return ((size_t)(C::T + 4) * W * 4 + 15) / 16 * 16 + (size_t)C::T * W * 4 + nb * 8 + (nb + 32) * 4 + 48 * 4 + 16 + 16;
+}
+template <int W, int BPT>
+__global__ void __launch_bounds__(512, 2) k_scatter_tma_w(const uint32_t *__restrict__ in, const TileDesc *__restrict__ tiles, int64_t ntiles,
+                                                         LevelArgs a, unsigned long long *__restrict__ cursor, uint32_t *__restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  using C = ScatterWCfg<W>;
+  constexpr int NT = C::NT, KPT = C::KPT, T = C::T, AL = C::AL;
+  const int nbins = 1 << a.nbits;
+  const int tid = threadIdx.x;
+  uint32_t *X = reinterpret_cast<uint32_t *>(smraw);                                                   // [(T + 4) * W]
+  uint32_t *Y = X + (((size_t)(T + 4) * W + 3) & ~(size_t)3);                                          // [T * W]
+  long long *s_gd = reinterpret_cast<long long *>(Y + (size_t)T * W + (((size_t)T * W) & 1));          // [nbins]
+  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_gd + nbins);                                        // [nbins + 32]
+  uint32_t *scratch = s_cnt + nbins + 32;                                                              // [48]
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(scratch + 48 + ((nbins + 32 + 48) & 1));
+
+  int64_t t = blockIdx.x;
+  if (t >= ntiles) return;
+  TileDesc d = tiles[t];
+  auto issue = [&](const TileDesc &td) {   // thread 0 only
+    const int o = (int)(td.base % AL);
+    const uint32_t bytes = (uint32_t)((((td.n + o) * W * 4) + 15) & ~15);
+    mbar_expect_tx(mbar, bytes);
+    bulk_g2s(X, in + (td.base - o) * W, bytes, mbar);
+  };
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < nbins + 32; i += NT) s_cnt[i] = 0;
+  __syncthreads();
+  if (tid == 0) issue(d);
+  for (uint32_t it = 0;; ++it) {
+    const int64_t tn = t + gridDim.x;
+    const bool more = tn < ntiles;
+    TileDesc dn = d;
+    if (more) dn = tiles[tn];
+    const int n = d.n;
+    const Digit2 digit(a, a.seg_nb ? a.seg_nb[d.seg] : 0u);
+    const uint32_t *Xo = X + (size_t)(d.base % AL) * W;
+    mbar_wait(mbar, it & 1u);
+    uint32_t rk[KPT];
+#pragma unroll
+    for (int q = 0; q < KPT; ++q) {
+      const int j = q * NT + tid;
+      rk[q] = 0xffffffffu;
+      if (j < n) {
+        const uint32_t dg = digit(make_uint2(Xo[(size_t)j * W], Xo[(size_t)j * W + 1]));
+        rk[q] = (dg << 16) | atomicAdd(s_cnt + dg, 1u);
+      }
+    }
+    __syncthreads();
+    const uint32_t total = bins_scan_reserve<NT, BPT>(s_cnt, s_gd, scratch, cursor + (size_t)d.seg * nbins, nbins);
+#pragma unroll
+    for (int q = 0; q < KPT; ++q) {
+      if (rk[q] != 0xffffffffu) {
+        const uint32_t *src = Xo + (size_t)(q * NT + tid) * W;
+        uint32_t *dst = Y + (size_t)(s_cnt[rk[q] >> 16] + (rk[q] & 0xffffu)) * W;
+#pragma unroll
+        for (int c = 0; c < W; ++c) dst[c] = src[c];
+      }
+    }
+    __syncthreads();   // X is free, Y is complete
+    if (tid == 0 && more) issue(dn);
+    for (int i = tid; i < nbins + 32; i += NT) s_cnt[i] = 0;
+#pragma unroll
+    for (int q = 0; q < KPT; ++q) {
+      const uint32_t j = (uint32_t)(q * NT + tid);
+      if (j < total) {
+        const uint32_t *src = Y + (size_t)j * W;
+        const uint32_t dg = digit(make_uint2(src[0], src[1]));
+        uint32_t *dst = out + (s_gd[dg] + (long long)j) * W;
+#pragma unroll
+        for (int c = 0; c < W; ++c) dst[c] = src[c];
+      }
+    }
+    if (!more) break;
+    __syncthreads();
     t = tn;
     d = dn;
   }

@@ -435,6 +435,32 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
       return b;
     }
   }
+  if constexpr (W >= 3) {
+    if (tb_s[nchunk] > 0 && env_int("MFSDBG_TMA_SCATTER_W", 1) != 0 && bit_off < 32) {
+      // wide records: the shared-memory staged kernel (tiles of 48 KB whatever the width)
+      using SC = ScatterWCfg<W>;
+      std::vector<int64_t> tb_t(nchunk + 1);
+      tb_t[0] = 0;
+      for (int i = 0; i < nchunk; ++i) tb_t[i + 1] = tb_t[i] + div_ceil64(hc.size[i], SC::T);
+      int64_t *d_tbt = (int64_t *)alloc(sizeof(int64_t) * (nchunk + 1));
+      c.h2d(d_tbt, tb_t.data(), sizeof(int64_t) * (nchunk + 1));
+      TileDesc *d_tiles_t = (TileDesc *)alloc(sizeof(TileDesc) * std::max<int64_t>(tb_t[nchunk], 1));
+      k_build_tiles<<<(unsigned)div_ceil64(tb_t[nchunk], 256), 256, 0, c.stream>>>(ChunkTable{d_start, d_size, d_seg, d_tbt, nchunk}, SC::T,
+                                                                                tb_t[nchunk], d_tiles_t);
+      MF_LAUNCH_CHECK();
+      const int bpt = std::max(1, (1 << nbits) / 512);
+      void (*kern)(const uint32_t *, const TileDesc *, int64_t, LevelArgs, unsigned long long *, uint32_t *) =
+          bpt == 1 ? k_scatter_tma_w<W, 1> : (bpt == 2 ? k_scatter_tma_w<W, 2> : k_scatter_tma_w<W, 4>);
+      const size_t smem = scatter_tma_w_smem_bytes<W>(nbits);
+      set_smem(kern, smem);
+      Stage st(c, tag_s.c_str());
+      const int64_t grid_t = std::min<int64_t>(tb_t[nchunk], (int64_t)c.sm_count * 2);
+      kern<<<(unsigned)grid_t, 512, smem, c.stream>>>(in, d_tiles_t, tb_t[nchunk], a, d_cur, out);
+      MF_LAUNCH_CHECK();
+      c.launches += 2;
+      return b;
+    }
+  }
   if (tb_s[nchunk] > 0) {
     RecordsProducer<W> ps{in, d_tiles_s, C::TS};
     size_t smem = scatter_smem_bytes<W>(C::NT, C::TS, nbits, 4);

@@ -207,3 +207,29 @@ def test_host_read2sdbg_matches_oracle(ctx, oracle, monkeypatch, pipelined):
                                     shape=(out.n_tips * out.words_per_tip,)).copy()
         assert np.array_equal(lab, np.asarray(g.tip_labels).ravel())
     assert out.n_large == g.n_large
+
+
+@pytest.mark.parametrize("k", [21, 47])
+def test_count_general_and_fallback_paths(ctx, oracle, monkeypatch, k):
+    """with the streamed kernels switched off every bucket takes the general kernel, and the skewed input (one read 70 000
+    times, 20 000 distinct keys behind one stem) drives it through the chunk / merge / sorted-run fallbacks."""
+    monkeypatch.setenv("MFSDBG_COUNT_STREAM", "0")
+    monkeypatch.setenv("MFSDBG_COUNT_STREAM_W", "0")
+    bases, starts = make_reads(6, 1500, k, dup_boost=70000, max_len=max(150, k + 40))
+    rng = np.random.default_rng(10)
+    stem = rng.integers(0, 4, k + 30, dtype=np.uint8)
+    extra = [np.concatenate([stem, rng.integers(0, 4, 40, dtype=np.uint8)]) for _ in range(20000)]
+    seqs = [bases[starts[i]:starts[i + 1]] for i in range(len(starts) - 1)] + extra
+    starts2 = np.zeros(len(seqs) + 1, np.int64)
+    starts2[1:] = np.cumsum([len(s) for s in seqs])
+    bases2 = np.concatenate(seqs).astype(np.uint8)
+    ctx.set_profiling(True)
+    try:
+        e_gpu = ctx.count(ctx.upload_reads(bases2, starts2), k, 2, want_counting=True)
+        prof = ctx.last_profile()
+    finally:
+        ctx.set_profiling(False)
+    e_orc = oracle.count(_orc_reads(oracle, bases2, starts2), k, 2, threads=8)
+    assert_edges_equal(e_gpu, e_orc)
+    assert np.array_equal(e_gpu.counting, e_orc.counting)
+    assert "oversized" in prof, prof
