@@ -435,7 +435,7 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
       return b;
     }
   }
-  if constexpr (W >= 3) {
+  if constexpr (W >= 3 && W <= 5) {   // beyond 5 words a tile is under 2048 records and the register-staged kernel wins (measured at k=141)
     if (tb_s[nchunk] > 0 && env_int("MFSDBG_TMA_SCATTER_W", 1) != 0 && bit_off < 32) {
       // wide records: the shared-memory staged kernel (tiles of 48 KB whatever the width)
       using SC = ScatterWCfg<W>;
