@@ -233,3 +233,41 @@ def test_count_general_and_fallback_paths(ctx, oracle, monkeypatch, k):
     assert_edges_equal(e_gpu, e_orc)
     assert np.array_equal(e_gpu.counting, e_orc.counting)
     assert "oversized" in prof, prof
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] read set (16 666 667 x PE150, 5 Gbp): too large for the oracle, so size-independent properties:
+    the multiplicity histogram accounts for every (k+1)-mer occurrence, the edge stream is strictly increasing (sorted and
+    distinct), edge multiplicities add up to the solid part of the histogram, the graph's bucket statistics add up to its
+    totals, and read2sdbg equals count followed by seq2sdbg."""
+    from mitoflex_b200 import lib
+    c = lib.Context(0)
+    try:
+        k, m = 21, 2
+        reads = c.synth(n_pairs=16_666_667, seed=1002)
+        e = c.count(reads, k, m, want_counting=True)
+        cnt = e.counting.astype(np.int64)
+        idx = np.arange(65536, dtype=np.int64)
+        assert cnt[65535] == 0                                   # nothing reaches the multiplicity cap on this sample
+        assert int((cnt * idx).sum()) == e.s.n_keys              # every key occurrence is in exactly one run
+        assert int(cnt[m:].sum()) == e.n                         # one edge per solid distinct key
+        ed = e.to_numpy()                                        # [n, 2] words: key (44 bits) | multiplicity (16 bits)
+        key = (ed[:, 0].astype(np.uint64) << np.uint64(32)) | (ed[:, 1].astype(np.uint64) & np.uint64(0xFFF00000))
+        assert bool((key[1:] > key[:-1]).all())                  # globally sorted, no duplicates
+        mult = (ed[:, 1] & 0xFFFF).astype(np.int64)
+        assert int(mult.min()) >= m
+        assert int(mult.sum()) == int((cnt[m:] * idx[m:]).sum())
+        assert int(e.bucket_counts().sum()) == e.n
+        del ed, key, mult
+        g1 = c.seq2sdbg(e, k)
+        n1, st1 = g1.n, g1.bucket_stats().sum(axis=0)
+        rec1 = g1.to_numpy()
+        g2 = c.read2sdbg(reads, k, m)
+        rec2 = g2.to_numpy()
+        assert g2.n == n1 and n1 > 2 * e.n                      # two real items per edge plus the surviving dummies
+        assert int(st1[0]) == n1 and int(st1[1]) == int(rec1["tip"].sum()) and int(st1[2]) == rec1["n_large"]
+        for f in ("w", "last", "tip", "mul"):
+            assert np.array_equal(rec1[f], rec2[f]), f
+        assert int(rec2["last"].sum()) > 0
+    finally:
+        c.close()
