@@ -216,6 +216,26 @@ __global__ void k_edge_buckets(const uint32_t *edges, int64_t n, int We, unsigne
   counts[b] = (unsigned long long)((b + 1 < kNumBuckets ? lower((uint32_t)b + 1) : n) - lower((uint32_t)b));
 }
 
+// exclusive scan of int64 v[0..n) -> out[0..n] (out[n] = total): block sums, scan of the sums, fix-up (kernels in synth.cu);
+// the scratch comes from the slab.  The single-block k_scan_i64 took 1.3 ms for the 524 288 bucket slots of the 5 Gbp sample.
+__global__ void k_block_sums(const int64_t *v, int64_t n, int64_t *sums);
+__global__ void k_block_scan_fix(const int64_t *v, int64_t n, const int64_t *sum_off, int64_t *out);
+static void scan_slots(Ctx &c, const int64_t *v, int64_t n, int64_t *out) {
+  if (n <= 4096) {
+    k_scan_i64<<<1, 1024, 0, c.stream>>>(v, n, 0, out);
+    MF_LAUNCH_CHECK();
+    c.launches++;
+    return;
+  }
+  const int64_t nb = div_ceil64(n, 1024);
+  int64_t *sums = c.alloc<int64_t>((size_t)(2 * nb + 2));
+  k_block_sums<<<(unsigned)nb, 1024, 0, c.stream>>>(v, n, sums);
+  k_scan_i64<<<1, 1024, 0, c.stream>>>(sums, nb, 0, sums + nb + 1);
+  k_block_scan_fix<<<(unsigned)nb, 1024, 0, c.stream>>>(v, n, sums + nb + 1, out);
+  MF_LAUNCH_CHECK();
+  c.launches += 3;
+}
+
 // ------------------------------------------------------------------ plan
 struct Plan {
   int W, l1_bits, l2_bits, cap;
@@ -412,7 +432,8 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   if constexpr (W == 2) {
     if (tb_s[nchunk] > 0 && env_int("MFSDBG_TMA_SCATTER", 1) != 0 && bit_off < 32) {
       // 2-word records: TMA-fed tiles of 6144 (5120 with 2048 bins) records
-      const int KPT = nbits <= 10 ? 12 : 10, T = 512 * KPT;
+      const int kpt_env = env_int("MFSDBG_SCATTER_KPT", 0);
+      const int KPT = kpt_env == 7 ? 7 : (nbits <= 10 ? 12 : 10), T = 512 * KPT;
       std::vector<int64_t> tb_t(nchunk + 1);
       tb_t[0] = 0;
       for (int i = 0; i < nchunk; ++i) tb_t[i + 1] = tb_t[i] + div_ceil64(hc.size[i], T);
@@ -424,11 +445,12 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
       MF_LAUNCH_CHECK();
       const int bpt = std::max(1, (1 << nbits) / 512);
       void (*kern)(const uint32_t *, const TileDesc *, int64_t, LevelArgs, unsigned long long *, uint32_t *) =
-          nbits <= 10 ? (bpt == 1 ? k_scatter_tma<512, 12, 1> : k_scatter_tma<512, 12, 2>) : k_scatter_tma<512, 10, 4>;
-      const size_t smem = nbits <= 10 ? scatter_tma_smem_bytes<12>(nbits) : scatter_tma_smem_bytes<10>(nbits);
+          KPT == 7 ? (bpt == 1 ? k_scatter_tma<512, 7, 1> : (bpt == 2 ? k_scatter_tma<512, 7, 2> : k_scatter_tma<512, 7, 4>))
+                   : (nbits <= 10 ? (bpt == 1 ? k_scatter_tma<512, 12, 1> : k_scatter_tma<512, 12, 2>) : k_scatter_tma<512, 10, 4>);
+      const size_t smem = KPT == 7 ? scatter_tma_smem_bytes<7>(nbits) : (nbits <= 10 ? scatter_tma_smem_bytes<12>(nbits) : scatter_tma_smem_bytes<10>(nbits));
       set_smem(kern, smem);
       Stage st(c, tag_s.c_str());
-      const int64_t grid_t = std::min<int64_t>(tb_t[nchunk], (int64_t)c.sm_count * env_int("MFSDBG_SCATTER_CTAS", 2));
+      const int64_t grid_t = std::min<int64_t>(tb_t[nchunk], (int64_t)c.sm_count * env_int("MFSDBG_SCATTER_CTAS", KPT == 7 ? 3 : 2));
       kern<<<(unsigned)grid_t, 512, smem, c.stream>>>(in, d_tiles_t, tb_t[nchunk], a, d_cur, out);
       MF_LAUNCH_CHECK();
       c.launches += 2;
@@ -1012,9 +1034,7 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
   }
   // gather
   Stage st(c, "gather");
-  k_scan_i64<<<1, 1024, 0, c.stream>>>(d_desc_cnt, b.nslots, 0, d_out_off);
-  MF_LAUNCH_CHECK();
-  c.launches++;
+  scan_slots(c, d_desc_cnt, b.nslots, d_out_off);
   int64_t E = 0;
   MF_CUDA(cudaMemcpyAsync(&E, d_out_off + b.nslots, sizeof E, cudaMemcpyDeviceToHost, c.stream));
   MF_CUDA(cudaStreamSynchronize(c.stream));
@@ -1598,11 +1618,9 @@ static void sdbg_finish(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n_items,
     tip_cap = std::max<size_t>(tip_cap, (size_t)need[1]);
   }
   Stage st(c, "sdbg_gather");
-  k_scan_i64<<<1, 1024, 0, c.stream>>>(d_items, b.nslots, 0, d_item_off);
-  k_scan_i64<<<1, 1024, 0, c.stream>>>(d_tips, b.nslots, 0, d_tip_off);
-  k_scan_i64<<<1, 1024, 0, c.stream>>>(d_large, b.nslots, 0, d_large_off);
-  MF_LAUNCH_CHECK();
-  c.launches += 3;
+  scan_slots(c, d_items, b.nslots, d_item_off);
+  scan_slots(c, d_tips, b.nslots, d_tip_off);
+  scan_slots(c, d_large, b.nslots, d_large_off);
   int64_t tot[3];
   MF_CUDA(cudaMemcpyAsync(&tot[0], d_item_off + b.nslots, 8, cudaMemcpyDeviceToHost, c.stream));
   MF_CUDA(cudaMemcpyAsync(&tot[1], d_tip_off + b.nslots, 8, cudaMemcpyDeviceToHost, c.stream));
