@@ -101,8 +101,13 @@ __global__ void k_items_from_edges(const uint32_t *__restrict__ edges, int64_t n
 // and whole (a, b) runs of them are skipped together.  The item order is arbitrary (a warp-aggregated append).
 constexpr unsigned long long kKmerEmpty = 0xffffffffffffffffull;   // 2k <= 62 bits used: never a valid entry
 
+// Slot = the k-mer's own top bits (k-mers of a genome are spread evenly over them), scrambled only inside a 64-slot window
+// by its low bits.  The edges arrive sorted, so the prefix k-mers of the forward strand and -- per first base -- the suffix
+// k-mers it looks up walk the table front to back: half of the accesses become sequential instead of random DRAM rows.
 __device__ __forceinline__ uint32_t kmer_slot(unsigned long long x, int log_slots) {
-  return (uint32_t)((x * 0x9e3779b97f4a7c15ull) >> (64 - log_slots));
+  const uint32_t top = (uint32_t)(x >> (64 - log_slots));
+  const uint32_t mix = (uint32_t)((x * 0x9e3779b97f4a7c15ull) >> 58);   // 6 bits
+  return top ^ mix;
 }
 __device__ __forceinline__ unsigned long long revcomp64(unsigned long long t, int nchars) {   // left-aligned 2*nchars bits
   unsigned long long x = __brevll(~t);   // complement, reversed bit order: bases reversed with their two bits swapped
