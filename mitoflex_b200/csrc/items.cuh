@@ -109,6 +109,13 @@ __device__ __forceinline__ uint32_t kmer_slot(unsigned long long x, int log_slot
   const uint32_t mix = (uint32_t)((x * 0x9e3779b97f4a7c15ull) >> 58);   // 6 bits
   return top ^ mix;
 }
+// probe sequence of a k-mer: 64 linear steps from its ordered slot, then it moves to a fully hashed slot and goes on linearly
+// from there (a genome with a huge family of k-mers behind one 14-base prefix must not turn the ordered slots into one long
+// chain); insert and lookup walk the same sequence, entries never move.
+__device__ __forceinline__ uint32_t kmer_next(unsigned long long x, uint32_t h, int &probe, int log_slots) {
+  if (++probe == 64) return (uint32_t)((x * 0xbf58476d1ce4e5b9ull) >> (64 - log_slots));
+  return (h + 1) & ((1u << log_slots) - 1u);
+}
 __device__ __forceinline__ unsigned long long revcomp64(unsigned long long t, int nchars) {   // left-aligned 2*nchars bits
   unsigned long long x = __brevll(~t);   // complement, reversed bit order: bases reversed with their two bits swapped
   x = ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
@@ -128,18 +135,18 @@ __global__ void k_kmer_set_insert(const uint32_t *__restrict__ edges, int64_t n_
   const unsigned long long fw = load_edge64<WK, WE>(edges + e * WE, k);
   const unsigned long long rc = revcomp64(fw, k + 1);
   const unsigned long long mk = ~0ull << (64 - 2 * k);
-  const uint32_t smask = (1u << log_slots) - 1u;
   // both first probes are in flight together (these kernels wait on random DRAM accesses and nothing else)
   const unsigned long long x0 = fw & mk, x1 = rc & mk;
   uint32_t h0 = kmer_slot(x0, log_slots), h1 = kmer_slot(x1, log_slots);
   // straight to the CAS (one round trip to L2 instead of a load and then the CAS); both are in flight together
   unsigned long long c0 = atomicCAS(table + h0, kKmerEmpty, x0), c1 = atomicCAS(table + h1, kKmerEmpty, x1);
+  int p0 = 0, p1 = 0;
   while (c0 != kKmerEmpty && c0 != x0) {
-    h0 = (h0 + 1) & smask;
+    h0 = kmer_next(x0, h0, p0, log_slots);
     c0 = atomicCAS(table + h0, kKmerEmpty, x0);
   }
   while (c1 != kKmerEmpty && c1 != x1) {
-    h1 = (h1 + 1) & smask;
+    h1 = kmer_next(x1, h1, p1, log_slots);
     c1 = atomicCAS(table + h1, kKmerEmpty, x1);
   }
 }
@@ -162,20 +169,20 @@ __global__ void k_items_from_edges_filtered(const uint32_t *__restrict__ edges, 
     rcv[0] = (uint32_t)(rc >> 32);
     if constexpr (WK == 2) { fwv[1] = (uint32_t)fw; rcv[1] = (uint32_t)rc; }
     const unsigned long long mk = ~0ull << (64 - 2 * k);
-    const uint32_t smask = (1u << log_slots) - 1u;
     const unsigned long long x0 = (fw << 2) & mk, x1 = (rc << 2) & mk;
     uint32_t h0 = kmer_slot(x0, log_slots), h1 = kmer_slot(x1, log_slots);
     unsigned long long c0 = table[h0], c1 = table[h1];   // both first probes in flight together
+    int p0 = 0, p1 = 0;
     for (;;) {
       if (c0 == x0) break;
       if (c0 == kKmerEmpty) { q[0] = false; break; }
-      h0 = (h0 + 1) & smask;
+      h0 = kmer_next(x0, h0, p0, log_slots);
       c0 = table[h0];
     }
     for (;;) {
       if (c1 == x1) break;
       if (c1 == kKmerEmpty) { q[1] = false; break; }
-      h1 = (h1 + 1) & smask;
+      h1 = kmer_next(x1, h1, p1, log_slots);
       c1 = table[h1];
     }
   }
