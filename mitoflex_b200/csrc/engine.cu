@@ -1466,6 +1466,31 @@ static int64_t sdbg_make_items(Ctx &c, const uint32_t *edges, int64_t n_edges, c
           c.d2h(&got, d_cur, sizeof got);
           n_edge_items = (int64_t)got;
         }
+      } else if (filter && k >= 32 && k <= 63 && WI >= 3 && WI <= 5 && n_edges < ((int64_t)1 << 29)) {
+        // 32 <= k <= 63: the same filter with 16-byte slots (128-bit CAS)
+        if constexpr (WI >= 3 && WI <= 5) {
+          const int log_slots = std::max(10, std::min(31, ceil_log2(4.0 * (double)n_edges)));
+          const size_t slots = (size_t)1 << log_slots;
+          unsigned __int128 *d_table = c.alloc<unsigned __int128>(slots + 1);
+          unsigned long long *d_cur = reinterpret_cast<unsigned long long *>(d_table + slots);
+          MF_CUDA(cudaMemsetAsync(d_table, 0xff, sizeof(unsigned __int128) * slots, c.stream));
+          MF_CUDA(cudaMemsetAsync(d_cur, 0, sizeof(unsigned long long), c.stream));
+          auto run = [&](auto wk, auto we) {
+            constexpr int K_ = decltype(wk)::value, E_ = decltype(we)::value;
+            k_kmer_set_insert128<K_, E_><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, d_table, log_slots);
+            k_items_from_edges_filtered128<K_, E_, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, d_table, log_slots, items, d_cur);
+          };
+          // (WK, WE): k 32..39 -> (3, 3); 40..47 -> (3, 4); 48..55 -> (4, 4); 56..63 -> (4, 5)
+          if (WK == 3 && WE == 3) run(std::integral_constant<int, 3>{}, std::integral_constant<int, 3>{});
+          else if (WK == 3) run(std::integral_constant<int, 3>{}, std::integral_constant<int, 4>{});
+          else if (WE == 4) run(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
+          else run(std::integral_constant<int, 4>{}, std::integral_constant<int, 5>{});
+          MF_LAUNCH_CHECK();
+          c.launches += 2;
+          unsigned long long got = 0;
+          c.d2h(&got, d_cur, sizeof got);
+          n_edge_items = (int64_t)got;
+        }
       } else {
         if (WK == WI) k_items_from_edges<WI, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
         else if (WE == WK) k_items_from_edges<WI - 1, WI - 1, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
@@ -1649,8 +1674,9 @@ template <int WI>
 static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, int tip_mode, SdbgView *out) {
   const int64_t n_cap = 6 * n_edges + sq.n_items;   // upper bound: the filtered generator usually writes about a third
   if (n_cap == 0) return sdbg_empty(c, k, out);
-  const bool filter = env_int("MFSDBG_ITEM_FILTER", 1) != 0 && k <= 31;
-  const size_t set_bytes = filter ? ((size_t)8 << std::max(10, std::min(31, ceil_log2(4.0 * (double)std::max<int64_t>(n_edges, 1))))) + 64 : 0;
+  const bool filter = env_int("MFSDBG_ITEM_FILTER", 1) != 0 && k <= 63;
+  const size_t set_bytes =
+      filter ? ((size_t)(k <= 31 ? 8 : 16) << std::max(10, std::min(31, ceil_log2(4.0 * (double)std::max<int64_t>(n_edges, 1))))) + 1024 : 0;
   const int nb1_max = 1 << kMaxDigitBits;
   const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1_max << kMaxDigitBits) * 96 + (size_t)(n_cap / 128);
   c.slab_reserve((size_t)n_cap * WI * 4 * 2 + table_bytes + set_bytes + (1 << 20));

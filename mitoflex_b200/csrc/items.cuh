@@ -225,6 +225,138 @@ __global__ void k_items_from_edges_filtered(const uint32_t *__restrict__ edges, 
   }
 }
 
+// ---- the same for 32 <= k <= 63: the k-mer takes up to 126 bits, the table holds 16-byte slots (ATOMG.CAS.128 on sm_100a)
+struct K128 {
+  unsigned long long hi, lo;
+};
+__device__ __forceinline__ K128 shl128(K128 a, int s) {   // 0 <= s < 128
+  if (s == 0) return a;
+  if (s >= 64) return K128{a.lo << (s - 64), 0ull};
+  return K128{(a.hi << s) | (a.lo >> (64 - s)), a.lo << s};
+}
+__device__ __forceinline__ K128 mask_top128(K128 a, int bits) {   // keep the top `bits` bits, 0 < bits <= 128
+  if (bits >= 128) return a;
+  if (bits >= 64) return K128{a.hi, bits == 64 ? 0ull : (a.lo & (~0ull << (128 - bits)))};
+  return K128{a.hi & (~0ull << (64 - bits)), 0ull};
+}
+__device__ __forceinline__ unsigned long long rev_bases64(unsigned long long x) {
+  x = __brevll(x);
+  return ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
+}
+__device__ __forceinline__ K128 revcomp128(K128 t, int nchars) {   // left-aligned 2*nchars bits
+  const K128 r{rev_bases64(~t.lo), rev_bases64(~t.hi)};             // whole register reversed: the string sits right aligned
+  return shl128(r, 128 - 2 * nchars);
+}
+template <int WK, int WE>
+__device__ __forceinline__ K128 load_edge128(const uint32_t *src, int k) {
+  K128 t;
+  t.hi = ((unsigned long long)src[0] << 32) | src[1];
+  t.lo = (unsigned long long)src[2] << 32;
+  if constexpr (WK >= 4) t.lo |= src[3];
+  return mask_top128(t, 2 * (k + 1));   // drop the multiplicity if it shares the last key word
+}
+__device__ __forceinline__ unsigned __int128 pack128(K128 a) { return ((unsigned __int128)a.hi << 64) | a.lo; }
+__device__ __forceinline__ uint32_t kmer_slot128(K128 x, int log_slots) {
+  const uint32_t top = (uint32_t)(x.hi >> (64 - log_slots));
+  const uint32_t mix = (uint32_t)(((x.hi ^ (x.lo * 0xbf58476d1ce4e5b9ull)) * 0x9e3779b97f4a7c15ull) >> 58);
+  return top ^ mix;
+}
+__device__ __forceinline__ uint32_t kmer_next128(K128 x, uint32_t h, int &probe, int log_slots) {
+  if (++probe == 64) return (uint32_t)(((x.hi ^ (x.lo * 0x94d049bb133111ebull)) * 0xbf58476d1ce4e5b9ull) >> (64 - log_slots));
+  return (h + 1) & ((1u << log_slots) - 1u);
+}
+
+template <int WK, int WE>
+__global__ void k_kmer_set_insert128(const uint32_t *__restrict__ edges, int64_t n_edges, int k, unsigned __int128 *table, int log_slots) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const K128 fw = load_edge128<WK, WE>(edges + e * WE, k);
+  const K128 rc = revcomp128(fw, k + 1);
+  const unsigned __int128 empty = ~(unsigned __int128)0;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const K128 xk = mask_top128(s ? rc : fw, 2 * k);
+    const unsigned __int128 x = pack128(xk);
+    uint32_t h = kmer_slot128(xk, log_slots);
+    int probe = 0;
+    unsigned __int128 c = atomicCAS(table + h, empty, x);
+    while (c != empty && c != x) {
+      h = kmer_next128(xk, h, probe, log_slots);
+      c = atomicCAS(table + h, empty, x);
+    }
+  }
+}
+
+template <int WK, int WE, int WI>
+__global__ void k_items_from_edges_filtered128(const uint32_t *__restrict__ edges, int64_t n_edges, int k,
+                                               const unsigned __int128 *__restrict__ table, int log_slots, uint32_t *__restrict__ items,
+                                               unsigned long long *cursor) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = e < n_edges;
+  uint32_t fwv[WK], rcv[WK];
+  uint32_t mult = 0;
+  bool q[2] = {true, true};   // q[s]: the k-mer t[1..k] of strand s has an outgoing solid edge
+  if (live) {
+    const uint32_t *src = edges + e * WE;
+    const K128 fw = load_edge128<WK, WE>(src, k);
+    const K128 rc = revcomp128(fw, k + 1);
+    mult = src[WE - 1] & 0xffffu;
+    fwv[0] = (uint32_t)(fw.hi >> 32); fwv[1] = (uint32_t)fw.hi; fwv[2] = (uint32_t)(fw.lo >> 32);
+    rcv[0] = (uint32_t)(rc.hi >> 32); rcv[1] = (uint32_t)rc.hi; rcv[2] = (uint32_t)(rc.lo >> 32);
+    if constexpr (WK >= 4) { fwv[3] = (uint32_t)fw.lo; rcv[3] = (uint32_t)rc.lo; }
+    const unsigned __int128 empty = ~(unsigned __int128)0;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const K128 xk = mask_top128(shl128(s ? rc : fw, 2), 2 * k);
+      const unsigned __int128 x = pack128(xk);
+      uint32_t h = kmer_slot128(xk, log_slots);
+      int probe = 0;
+      for (;;) {
+        const unsigned __int128 cur = table[h];
+        if (cur == x) break;
+        if (cur == empty) { q[s] = false; break; }
+        h = kmer_next128(xk, h, probe, log_slots);
+      }
+    }
+  }
+  const int extra = live ? 2 * ((q[0] ? 0 : 1) + (q[1] ? 0 : 1)) : 0;
+  const int mine = live ? 2 + extra : 0;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += v;
+  }
+  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long base = 0;
+  if ((threadIdx.x & 31) == 31 && warp_total) base = atomicAdd(cursor, (unsigned long long)warp_total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (!live) return;
+  uint32_t *dst = items + (base + (unsigned long long)(incl - mine)) * WI;
+#pragma unroll
+  for (int strand = 0; strand < 2; ++strand) {
+    const uint32_t(&t)[WK] = strand ? rcv : fwv;
+    const uint32_t c0 = t[0] >> 30, c1 = (t[0] >> 28) & 3;
+    uint32_t it[WI];
+    if (!q[1 - strand]) {
+      window_item<WK, WI>(t, 0, k, 1, kSentinel, 0, it);
+#pragma unroll
+      for (int i = 0; i < WI; ++i) dst[i] = it[i];
+      dst += WI;
+    }
+    window_item<WK, WI>(t, 1, k, 1, c0, mult, it);
+#pragma unroll
+    for (int i = 0; i < WI; ++i) dst[i] = it[i];
+    dst += WI;
+    if (!q[strand]) {
+      window_item<WK, WI>(t, 2, k - 1, 0, c1, 0, it);
+#pragma unroll
+      for (int i = 0; i < WI; ++i) dst[i] = it[i];
+      dst += WI;
+    }
+  }
+}
+
 // General sequences (contigs etc.), stored orientation, 2-bit packed back to back.
 // One thread per item; item -> sequence by binary search over item_base (sequences are long, few).
 template <int WI>

@@ -78,8 +78,8 @@ def test_count_skewed_buckets(ctx, oracle):
         assert np.array_equal(e_gpu.counting, e_orc.counting)
 
 
-@pytest.mark.parametrize("k,m", [(9, 1), (13, 2), (15, 2), (16, 2), (21, 2), (24, 1), (31, 2), (32, 2), (47, 2), (63, 2), (79, 2),
-                                 (141, 2)])
+@pytest.mark.parametrize("k,m", [(9, 1), (13, 2), (15, 2), (16, 2), (21, 2), (24, 1), (31, 2), (32, 2), (39, 2), (40, 1), (47, 2), (48, 2),
+                                 (55, 2), (56, 2), (63, 2), (64, 2), (79, 2), (141, 2)])
 def test_seq2sdbg_parity(ctx, oracle, k, m):
     bases, starts = make_reads(300 + k, 2500, k, genome_len=5000, max_len=max(150, k + 40))
     e_gpu = ctx.count(ctx.upload_reads(bases, starts), k, m)
