@@ -25,8 +25,10 @@ constexpr int kCwProbeLimit = 64;
 constexpr int kCwPairsMax = 96;
 template <int W>
 struct CwCfg {
-  static constexpr int kChunk = W <= 4 ? 512 : 256;        // keys per ring stage
-  static constexpr int kSolidMax = W <= 4 ? 1024 : 512;    // distinct solid keys of one bucket on this path
+  // keys per ring stage: as many as two CTAs per SM allow (a thread's per-chunk bookkeeping is ~50 instructions, so one key
+  // per thread and chunk doubles the cost of a key)
+  static constexpr int kChunk = W == 3 ? 1024 : (W == 4 ? 768 : (W <= 6 ? 512 : 256));
+  static constexpr int kSolidMax = W == 3 ? 768 : 512;     // distinct solid keys of one bucket on this path
   static constexpr int kAlign = (W % 4 == 0) ? 1 : ((W % 2 == 0) ? 2 : 4);   // records per 16-byte boundary
 };
 template <int W>

@@ -724,7 +724,7 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
   const double load = env_int("MFSDBG_STREAM_LOAD_PCT", W == 2 ? 45 : 35) / 100.0;
   double B = std::min(60000.0, std::max(1024.0, load * kCsSlots / rho));
   // --min-count 1 makes every distinct key a solid one: keep them under the per-bucket limit of the streamed kernel
-  const int solid_max = W == 2 ? kCsSolidMax : (W <= 4 ? 1024 : 512);
+  const int solid_max = W == 2 ? kCsSolidMax : (W == 3 ? 768 : 512);
   if (min_count <= 1 && load <= 1.0) B = std::min(B, std::max(512.0, 0.7 * solid_max / rho));
   if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] distinct ratio %.4f -> %.0f keys per bucket\n", rho, B);
   HostChunks hc = l1;
