@@ -34,7 +34,11 @@ struct LevelArgs {
   // every segment gets the bin count its size asks for (canonical keys are twice as dense at small prefixes).
   const uint16_t *seg_nb;
   int xbits;
+  // Sampled-histogram mode of the reads-fed level: bin b owns [its start, limit[b]) and a tile's run that would cross the
+  // limit is dropped (the host sees cursor > limit afterwards and redoes the level with an exact histogram).
+  const unsigned long long *limit;
 };
+constexpr long long kDropRun = (long long)0x8000000000000000ull;
 
 template <int W>
 __device__ __forceinline__ uint32_t level_digit(const uint32_t (&r)[W], const LevelArgs &a, uint32_t nb) {
@@ -329,7 +333,8 @@ __global__ void k_level_scan(const unsigned long long *hist, int nbins, const in
 // atomicAdd per non-empty bin, all of a thread's in flight together).  Returns the tile's record total.
 template <int NT, int BPT>
 __device__ __forceinline__ uint32_t bins_scan_reserve(uint32_t *s_cnt, long long *s_gd, uint32_t *scratch,
-                                                      unsigned long long *cursor_row, int nbins) {
+                                                      unsigned long long *cursor_row, int nbins,
+                                                      const unsigned long long *limit = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t c[BPT], sum = 0;
 #pragma unroll
@@ -370,7 +375,7 @@ __device__ __forceinline__ uint32_t bins_scan_reserve(uint32_t *s_cnt, long long
     const int b = tid * BPT + q;
     if (b < nbins) {
       s_cnt[b] = run;
-      s_gd[b] = (long long)g[q] - (long long)run;
+      s_gd[b] = (limit && c[q] && g[q] + c[q] > limit[b]) ? kDropRun : (long long)g[q] - (long long)run;
       run += c[q];
     }
   }

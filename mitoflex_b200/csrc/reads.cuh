@@ -138,7 +138,7 @@ __device__ __forceinline__ int reads_load_tile(const ReadsSrc &src, int64_t tile
 // invalid positions add to one of 32 per-lane dummy counters behind the bins, so the loop has no branch
 template <int W, int NT, bool RANGED>
 __global__ void __launch_bounds__(NT) k_reads_hist(ReadsSrc src, LevelArgs a, unsigned long long *__restrict__ hist,
-                                                   int64_t tile0, int64_t ntiles) {
+                                                   int64_t tile0, int64_t ntiles, int64_t tstride) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int nbins = 1 << a.nbits;
   uint32_t *s_hist = smem;                   // [nbins + 32]
@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(NT) k_reads_hist(ReadsSrc src, LevelArgs a, un
   const uint32_t dlo = a.dlo, dspan = a.dhi - a.dlo;
   const uint32_t dummy = (uint32_t)nbins + (tid & 31);
   for (int i = tid; i < nbins + 32; i += NT) s_hist[i] = 0;
-  for (int64_t tile = tile0 + blockIdx.x; tile < tile0 + ntiles; tile += gridDim.x) {
+  for (int64_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {   // tiles tile0, tile0 + tstride, ... (a strided sample when tstride > 1)
+    const int64_t tile = tile0 + ti * tstride;
     __syncthreads();
     const int lim = reads_load_tile<W, NT>(src, tile, seq, sb);
     __syncthreads();
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a,
     }
   }
   __syncthreads();
-  const uint32_t total = bins_scan_reserve<NT, BPT>(s_cnt, s_gd, scratch, cursor, nbins);
+  const uint32_t total = bins_scan_reserve<NT, BPT>(s_cnt, s_gd, scratch, cursor, nbins, a.limit);
   // phase B: keys again, each takes the next free slot of its bin (the partition need not be stable)
   if (vm) {
 #pragma unroll
@@ -255,7 +256,8 @@ __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a,
         const uint32_t j = (uint32_t)(q * NT + tid);
         if (j < total) {
           const uint2 v = st2[j];
-          out2[s_gd[v.x >> dsh] + (long long)j] = v;
+          const long long gd = s_gd[v.x >> dsh];
+          if (gd != kDropRun) out2[gd + (long long)j] = v;
         }
       }
     }
@@ -265,7 +267,8 @@ __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a,
       const uint32_t j = x / W, c = x - j * W;
       const uint32_t d = stage[(size_t)j * W] >> dsh;
       uint32_t *dst = a.bin_base ? reinterpret_cast<uint32_t *>(a.bin_base[d]) : out;
-      dst[(s_gd[d] + (long long)j) * W + c] = stage[x];
+      const long long gd = s_gd[d];
+      if (gd != kDropRun) dst[(gd + (long long)j) * W + c] = stage[x];
     }
   }
 }

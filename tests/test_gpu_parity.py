@@ -271,3 +271,22 @@ def test_full_size_properties():
         assert int(rec2["last"].sum()) > 0
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("stride", [2, 64])
+def test_count_sampled_histogram(ctx, oracle, monkeypatch, stride):
+    """level 1 sized from a strided sample of the tiles: stride 2 estimates well (bins keep their slack), stride 64 on an
+    input of a few hundred tiles does not (a bin outgrows its region and the exact pass takes over); equal results."""
+    monkeypatch.setenv("MFSDBG_SAMPLED_MIN_TILES", "0")
+    monkeypatch.setenv("MFSDBG_SAMPLED_STRIDE", str(stride))
+    k, m = 21, 2
+    bases, starts = make_reads(77, 40000, k, genome_len=200000, max_len=150, err=0.005)
+    ctx.set_profiling(True)
+    try:
+        e_gpu = ctx.count(ctx.upload_reads(bases, starts), k, m, want_counting=True)
+    finally:
+        ctx.set_profiling(False)
+    e_orc = oracle.count(_orc_reads(oracle, bases, starts), k, m, threads=8)
+    assert e_gpu.s.n_keys == int(np.maximum(np.diff(starts) - k, 0).sum())
+    assert_edges_equal(e_gpu, e_orc)
+    assert np.array_equal(e_gpu.counting, e_orc.counting)
