@@ -273,19 +273,22 @@ def test_full_size_properties():
         c.close()
 
 
-@pytest.mark.parametrize("stride", [2, 64])
-def test_count_sampled_histogram(ctx, oracle, monkeypatch, stride):
-    """level 1 sized from a strided sample of the tiles: stride 2 estimates well (bins keep their slack), stride 64 on an
-    input of a few hundred tiles does not (a bin outgrows its region and the exact pass takes over); equal results."""
+@pytest.mark.parametrize("stride,slack", [(2, 10), (64, 10), (4, -60)])
+def test_count_sampled_histogram(ctx, oracle, monkeypatch, stride, slack):
+    """level 1 sized from a strided sample of the tiles; with a negative slack the bins outgrow their regions (runs that
+    would cross a limit are dropped) and the exact pass takes over; equal results either way."""
     monkeypatch.setenv("MFSDBG_SAMPLED_MIN_TILES", "0")
     monkeypatch.setenv("MFSDBG_SAMPLED_STRIDE", str(stride))
+    monkeypatch.setenv("MFSDBG_SAMPLED_SLACK_PCT", str(slack))
     k, m = 21, 2
     bases, starts = make_reads(77, 40000, k, genome_len=200000, max_len=150, err=0.005)
     ctx.set_profiling(True)
     try:
         e_gpu = ctx.count(ctx.upload_reads(bases, starts), k, m, want_counting=True)
+        prof = ctx.last_profile()
     finally:
         ctx.set_profiling(False)
+    assert ("sampled_overflow" in prof) == (slack < 0), prof
     e_orc = oracle.count(_orc_reads(oracle, bases, starts), k, m, threads=8)
     assert e_gpu.s.n_keys == int(np.maximum(np.diff(starts) - k, 0).sum())
     assert_edges_equal(e_gpu, e_orc)
