@@ -48,9 +48,11 @@ def parse_args():
     return ap.parse_args()
 
 
-def workload_name(pairs):
+def workload_name(pairs, error_rate=0.005, nuclear_len=50_000_000):
+    headline = error_rate == 0.005 and nuclear_len == 50_000_000
     return (f"read2sdbg k={K} -m {MIN_COUNT} on synthetic {pairs}xPE{READ_LEN} ({2 * pairs * READ_LEN / 1e9:.2f} Gbp/GPU): "
-            "16.5 kb mitogenome at 5% of pairs + 50 Mb nuclear background, 0.5% errors (BASELINE configs[1] read set)")
+            f"16.5 kb mitogenome at 5% of pairs + {nuclear_len / 1e6:.0f} Mb nuclear background, {100 * error_rate:g}% errors "
+            + ("(BASELINE configs[1] read set)" if headline else "(non-headline read set)"))
 
 
 # ------------------------------------------------------------------ clocks
@@ -194,7 +196,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(args.pairs), "sample": sample},
+        "config": {"workload": workload_name(args.pairs, args.error_rate, args.nuclear_len), "sample": sample},
         "cpu_baseline": {"value": v, "unit": "bases/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -363,7 +365,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.pairs), "bases_per_gpu": n_bases, "keys_per_gpu": n_keys, "solid_edges": n_edges,
+        "config": {"workload": workload_name(args.pairs, args.error_rate, args.nuclear_len), "bases_per_gpu": n_bases, "keys_per_gpu": n_keys, "solid_edges": n_edges,
                    "sdbg_items": res.n if res is not None else None, "l2_flush": "inputs and key buffers (>= 1 GB) exceed the 126 MB L2",
                    "parallelism": "reads sharded by GPU, keys and items stored into the owner GPU of their prefix bin by the partition kernel itself (NVLink peer memory), disjoint key range per GPU" if world > 1 else "1 GPU"},
         "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

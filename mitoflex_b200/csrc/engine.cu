@@ -1746,10 +1746,169 @@ static void sdbg_finish(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n_items,
   out->n_large = tot[2];
 }
 
+// ---- memory-bounded sdbg: rounds over contiguous ranges of the level-1 prefix bins ------------------------------
+// When the item buffers of the whole input do not fit the budget (config 5: -m 1 on error-rich reads, E ~ a third of the key
+// occurrences) the stage runs like megahit's --host_mem-bounded lv1 passes: a histogram pass counts the items of every
+// level-1 bin, contiguous bin ranges of at most `round_items` items are generated (ranged generators, items.cuh), sorted
+// and walked one after the other, and their outputs are appended -- bin order is key order, so the concatenation is the
+// global stream.  A (k-1)-prefix group never straddles a bin (l1_bits <= 11 < 2(k-1)), 16-bit buckets never do either.
+template <int WI, bool HIST>
+static void launch_items_ranged(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, int bin_bits, uint32_t lo,
+                                uint32_t hi, uint32_t *items, unsigned long long *cursor, unsigned long long *hist) {
+  if constexpr (WI >= 2) {
+    const int WK = words_key(k), WE = words_edge(k);
+    const size_t smem = HIST ? sizeof(uint32_t) << bin_bits : 0;
+    if (n_edges > 0) {
+      const unsigned grid = (unsigned)std::min<int64_t>(div_ceil64(n_edges, kRangedNT), (int64_t)c.sm_count * 8);
+      if (WK == WI)
+        k_items_from_edges_ranged<WI, WI, WI, HIST><<<grid, kRangedNT, smem, c.stream>>>(edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
+      else if (WE == WK)
+        k_items_from_edges_ranged<WI - 1, WI - 1, WI, HIST><<<grid, kRangedNT, smem, c.stream>>>(edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
+      else
+        k_items_from_edges_ranged<WI - 1, WI, WI, HIST><<<grid, kRangedNT, smem, c.stream>>>(edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
+      MF_LAUNCH_CHECK();
+      c.launches++;
+    }
+    if (sq.n_items > 0) {
+      const unsigned grid = (unsigned)std::min<int64_t>(div_ceil64(sq.n_items, kRangedNT), (int64_t)c.sm_count * 8);
+      k_items_from_seqs_ranged<WI, HIST><<<grid, kRangedNT, smem, c.stream>>>(sq.packed, sq.starts, sq.mult, sq.item_base, sq.nseq, sq.n_items,
+                                                                            k, bin_bits, lo, hi, items, cursor, hist);
+      MF_LAUNCH_CHECK();
+      c.launches++;
+    }
+  }
+}
+template <int WI>
+static void sdbg_rounds(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, int tip_mode, int64_t round_items,
+                        size_t table_bytes, SdbgView *out) {
+  const int64_t n_cap = 6 * n_edges + sq.n_items;
+  const int Wt = words_tip(k);
+  Plan p = make_plan(WI, 2 * (k - 1), n_cap, 1.0, false);
+  const int nb1 = 1 << p.l1_bits;
+  // per-bin item counts of the whole input
+  std::vector<unsigned long long> hist(nb1);
+  {
+    Stage st(c, "items_hist");
+    c.small[2].reserve(sizeof(unsigned long long) * ((size_t)1 << kMaxDigitBits));
+    unsigned long long *d_hist = c.small[2].as<unsigned long long>();
+    MF_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nb1, c.stream));
+    launch_items_ranged<WI, true>(c, edges, n_edges, sq, k, p.l1_bits, 0u, (uint32_t)nb1, nullptr, nullptr, d_hist);
+    c.d2h(hist.data(), d_hist, sizeof(unsigned long long) * nb1);
+  }
+  // contiguous bin ranges of at most round_items items (a single bin may exceed it: it then is a round of its own)
+  std::vector<std::pair<int, int>> rounds;
+  int64_t biggest = 0;
+  for (int b0 = 0; b0 < nb1;) {
+    int b1 = b0;
+    int64_t acc = 0;
+    while (b1 < nb1 && (b1 == b0 || acc + (int64_t)hist[b1] <= round_items)) acc += (int64_t)hist[b1++];
+    if (acc > 0) rounds.push_back({b0, b1});
+    biggest = std::max(biggest, acc);
+    b0 = b1;
+  }
+  if (getenv("MFSDBG_TRACE"))
+    fprintf(stderr, "[mfsdbg] sdbg: %lld items in %d rounds of <= %lld (largest %lld), %d level-1 bins\n", (long long)n_cap,
+            (int)rounds.size(), (long long)round_items, (long long)biggest, nb1);
+  if (rounds.empty()) return sdbg_empty(c, k, out);
+  c.slab_reserve((size_t)biggest * WI * 4 * 2 + 64 + table_bytes + (size_t)(biggest / 16) + (1 << 20));
+  DevBuf acc_rec, acc_lab;
+  int64_t n_rec = 0, n_tip = 0, n_large = 0, items_done = 0;
+  std::vector<int64_t> stats((size_t)kNumBuckets * 3, 0);
+  auto append = [&](DevBuf &acc, int64_t have, const uint32_t *src, int64_t add, int words, int64_t est_total) {
+    const size_t need = (size_t)(have + add) * words * 4 + 256;
+    if (need > acc.cap) {
+      DevBuf grown;
+      grown.reserve(std::max(need, (size_t)est_total * words * 4 + 256));
+      if (have > 0) MF_CUDA(cudaMemcpyAsync(grown.p, acc.p, (size_t)have * words * 4, cudaMemcpyDeviceToDevice, c.stream));
+      MF_CUDA(cudaStreamSynchronize(c.stream));
+      acc.release();
+      acc = grown;
+    }
+    if (add > 0)
+      MF_CUDA(cudaMemcpyAsync(acc.as<uint32_t>() + (size_t)have * words, src, (size_t)add * words * 4, cudaMemcpyDeviceToDevice, c.stream));
+  };
+  for (const auto &rd : rounds) {
+    int64_t n_r = 0;
+    for (int b = rd.first; b < rd.second; ++b) n_r += (int64_t)hist[b];
+    c.slab_reset();
+    uint32_t *bufA = c.alloc<uint32_t>((size_t)n_r * WI + 16), *bufB = c.alloc<uint32_t>((size_t)n_r * WI + 16);
+    unsigned long long *d_cur = c.alloc<unsigned long long>(1);
+    {
+      Stage st(c, "items");
+      MF_CUDA(cudaMemsetAsync(d_cur, 0, sizeof(unsigned long long), c.stream));
+      launch_items_ranged<WI, false>(c, edges, n_edges, sq, k, p.l1_bits, (uint32_t)rd.first, (uint32_t)rd.second, bufA, d_cur, nullptr);
+      unsigned long long got = 0;
+      c.d2h(&got, d_cur, sizeof got);
+      if ((int64_t)got != n_r) throw std::runtime_error("sdbg rounds: generated items disagree with the histogram");
+    }
+    auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
+    HostChunks whole;
+    whole.nseg = 1;
+    whole.start = {0};
+    whole.size = {n_r};
+    whole.seg = {0};
+    whole.seg_out_start = {0};
+    DevBuckets b1 = partition_level<WI>(c, bufA, bufB, whole, 0, p.l1_bits, salloc, "sdbg_l1");
+    std::vector<int64_t> st(nb1), sz(nb1);
+    c.d2h(st.data(), b1.start, sizeof(int64_t) * nb1);
+    c.d2h(sz.data(), b1.size, sizeof(int64_t) * nb1);
+    HostChunks l1;
+    l1.nseg = rd.second - rd.first;
+    for (int i = rd.first; i < rd.second; ++i) {
+      l1.start.push_back(st[i]);
+      l1.size.push_back(sz[i]);
+      l1.seg.push_back(i - rd.first);
+      l1.seg_out_start.push_back(st[i]);
+    }
+    SdbgView g;
+    sdbg_finish<WI>(c, bufB, bufA, n_r, l1, p.l1_bits, k, tip_mode, &g);
+    items_done += n_r;
+    // size the accumulators once, from the first round's yield
+    const double scale = 1.1 * (double)n_cap / (double)std::max<int64_t>(items_done, 1);
+    append(acc_rec, n_rec, g.rec, g.n_items, 1, (int64_t)((double)(n_rec + g.n_items) * scale) + 4096);
+    append(acc_lab, n_tip, g.labels, g.n_tips, Wt, (int64_t)((double)(n_tip + g.n_tips) * scale) + 4096);
+    MF_CUDA(cudaStreamSynchronize(c.stream));
+    n_rec += g.n_items;
+    n_tip += g.n_tips;
+    n_large += g.n_large;
+    for (size_t i = 0; i < stats.size(); ++i) stats[i] += c.sdbg_bucket_stats[i];
+  }
+  c.sdbg_rec.release();
+  c.sdbg_labels.release();
+  c.sdbg_rec = acc_rec;
+  c.sdbg_labels = acc_lab;
+  if (!c.sdbg_labels.p) c.sdbg_labels.reserve(256);
+  c.sdbg_bucket_stats = stats;
+  out->k = k;
+  out->words_tip = Wt;
+  out->bucket_items = nullptr;
+  out->rec = c.sdbg_rec.as<uint32_t>();
+  out->labels = c.sdbg_labels.as<uint32_t>();
+  out->n_items = n_rec;
+  out->n_tips = n_tip;
+  out->n_large = n_large;
+}
+
 template <int WI>
 static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, int tip_mode, SdbgView *out) {
   const int64_t n_cap = 6 * n_edges + sq.n_items;   // upper bound: the filtered generator usually writes about a third
   if (n_cap == 0) return sdbg_empty(c, k, out);
+  {
+    // does the whole item set fit?  per item: two partition buffers, the record arena and the gathered records, tip labels
+    const size_t per_item = (size_t)WI * 8 + 8 + (size_t)words_tip(k) / 2 + 1;
+    const size_t tables = (size_t)(64 << 20) + (size_t)((size_t)(1 << kMaxDigitBits) << kMaxDigitBits) * 96;
+    const size_t held = (size_t)n_edges * words_edge(k) * 4;
+    const size_t budget = c.budget();
+    const size_t avail = budget > held + tables ? budget - held - tables : 0;
+    int64_t round_items = env_int("MFSDBG_SDBG_ROUND_ITEMS", 0);
+    if (round_items <= 0 && (size_t)n_cap * per_item > avail) {
+      // keep half a record per generated item for the accumulated output (grown if the data yields more)
+      const size_t acc = (size_t)n_cap * 2;
+      round_items = (int64_t)((avail > acc ? avail - acc : avail / 2) / per_item * 9 / 10);
+      round_items = std::max<int64_t>(round_items, 1 << 20);
+    }
+    if (round_items > 0) return sdbg_rounds<WI>(c, edges, n_edges, sq, k, tip_mode, round_items, tables, out);
+  }
   const bool filter = env_int("MFSDBG_ITEM_FILTER", 1) != 0 && k <= 63;
   const size_t set_bytes =
       filter ? ((size_t)(k <= 31 ? 8 : 16) << std::max(10, std::min(31, ceil_log2(4.0 * (double)std::max<int64_t>(n_edges, 1))))) + 1024 : 0;

@@ -360,11 +360,9 @@ __global__ void k_items_from_edges_filtered128(const uint32_t *__restrict__ edge
 // General sequences (contigs etc.), stored orientation, 2-bit packed back to back.
 // One thread per item; item -> sequence by binary search over item_base (sequences are long, few).
 template <int WI>
-__global__ void k_items_from_seqs(const uint32_t *__restrict__ packed, const int64_t *__restrict__ seq_start,
-                                  const uint16_t *__restrict__ seq_mult, const int64_t *__restrict__ item_base, int nseq,
-                                  int64_t n_items, int k, uint32_t *__restrict__ items) {
-  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= n_items) return;
+__device__ __forceinline__ void seq_item(const uint32_t *__restrict__ packed, const int64_t *__restrict__ seq_start,
+                                         const uint16_t *__restrict__ seq_mult, const int64_t *__restrict__ item_base, int nseq,
+                                         int64_t x, int k, uint32_t (&w)[WI]) {
   int lo = 0, hi = nseq;
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;
@@ -390,7 +388,6 @@ __global__ void k_items_from_seqs(const uint32_t *__restrict__ packed, const int
     for (int i = 0; i < WI; ++i) raw[i] = __funnelshift_l(packed[wi + i + 1], packed[wi + i], sh);
   }
   const int nb = 2 * nchars, wm = nb >> 5, rem = nb & 31;
-  uint32_t w[WI];
 #pragma unroll
   for (int i = 0; i < WI; ++i) {
     w[i] = raw[i];
@@ -408,9 +405,132 @@ __global__ void k_items_from_seqs(const uint32_t *__restrict__ packed, const int
     prev = of == 0 ? (uint32_t)kSentinel : base_at(s0 + of - 1);
   }
   w[WI - 1] |= ((uint32_t)(nchars == k) << 19) | (prev << 16) | (uint32_t)(kMaxMul - (int)cnt);
+}
+template <int WI>
+__global__ void k_items_from_seqs(const uint32_t *__restrict__ packed, const int64_t *__restrict__ seq_start,
+                                  const uint16_t *__restrict__ seq_mult, const int64_t *__restrict__ item_base, int nseq,
+                                  int64_t n_items, int k, uint32_t *__restrict__ items) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n_items) return;
+  uint32_t w[WI];
+  seq_item<WI>(packed, seq_start, seq_mult, item_base, nseq, x, k, w);
   uint32_t *dst = items + x * WI;
 #pragma unroll
   for (int i = 0; i < WI; ++i) dst[i] = w[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Ranged generation for the memory-bounded sdbg rounds (megahit bounds SeqToSdbg by --host_mem the same way: lv1 passes
+// over bucket ranges).  An item belongs to a round if its top `bin_bits` bits fall into [lo, hi).  HIST = true: nothing is
+// written, the per-bin item counts of the whole input go to hist[1 << bin_bits] (shared histogram per CTA, flushed once);
+// HIST = false: items of the range are appended through a warp-aggregated cursor (arbitrary order, like the filtered path).
+constexpr int kRangedNT = 256;
+template <int WI, int N>
+__device__ __forceinline__ void ranged_sink(const uint32_t (&it)[N][WI], const bool (&in)[N], uint32_t *__restrict__ items,
+                                            unsigned long long *cursor) {
+  int mine = 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+    if (in[j]) ++mine;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += v;
+  }
+  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long base = 0;
+  if ((threadIdx.x & 31) == 31 && warp_total) base = atomicAdd(cursor, (unsigned long long)warp_total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  uint32_t *dst = items + (base + (unsigned long long)(incl - mine)) * WI;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    if (in[j]) {
+#pragma unroll
+      for (int i = 0; i < WI; ++i) dst[i] = it[j][i];
+      dst += WI;
+    }
+  }
+}
+template <int WK, int WE, int WI, bool HIST>
+__global__ void __launch_bounds__(kRangedNT) k_items_from_edges_ranged(const uint32_t *__restrict__ edges, int64_t n_edges, int k,
+                                                                        int bin_bits, uint32_t lo, uint32_t hi,
+                                                                        uint32_t *__restrict__ items, unsigned long long *cursor,
+                                                                        unsigned long long *__restrict__ hist) {
+  extern __shared__ uint32_t sh_hist[];
+  const int nbins = 1 << bin_bits;
+  if constexpr (HIST) {
+    for (int i = threadIdx.x; i < nbins; i += kRangedNT) sh_hist[i] = 0;
+    __syncthreads();
+  }
+  for (int64_t base = (int64_t)blockIdx.x * kRangedNT; base < n_edges; base += (int64_t)gridDim.x * kRangedNT) {
+    const int64_t e = base + threadIdx.x;
+    const bool live = e < n_edges;
+    uint32_t it[6][WI];
+    bool in[6] = {false, false, false, false, false, false};
+    if (live) {
+      uint32_t fw[WK], rc[WK];
+      const uint32_t *src = edges + e * WE;
+#pragma unroll
+      for (int i = 0; i < WK; ++i) fw[i] = src[i];
+      const uint32_t mult = src[WE - 1] & 0xffffu;
+      const int pad = 32 * WK - 2 * (k + 1);
+      fw[WK - 1] &= 0xffffffffu << pad;        // drop the multiplicity if it shares the last key word
+      revcomp_words<WK>(fw, k + 1, rc);
+#pragma unroll
+      for (int strand = 0; strand < 2; ++strand) {
+        const uint32_t(&t)[WK] = strand ? rc : fw;
+        const uint32_t c0 = t[0] >> 30, c1 = (t[0] >> 28) & 3;
+        window_item<WK, WI>(t, 0, k, 1, kSentinel, 0, it[3 * strand]);
+        window_item<WK, WI>(t, 1, k, 1, c0, mult, it[3 * strand + 1]);
+        window_item<WK, WI>(t, 2, k - 1, 0, c1, 0, it[3 * strand + 2]);
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const uint32_t bin = it[j][0] >> (32 - bin_bits);
+        if constexpr (HIST) atomicAdd(&sh_hist[bin], 1u);
+        else in[j] = bin >= lo && bin < hi;
+      }
+    }
+    if constexpr (!HIST) ranged_sink<WI, 6>(it, in, items, cursor);
+  }
+  if constexpr (HIST) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += kRangedNT)
+      if (sh_hist[i]) atomicAdd(hist + i, (unsigned long long)sh_hist[i]);
+  }
+}
+template <int WI, bool HIST>
+__global__ void __launch_bounds__(kRangedNT) k_items_from_seqs_ranged(const uint32_t *__restrict__ packed,
+                                                                       const int64_t *__restrict__ seq_start,
+                                                                       const uint16_t *__restrict__ seq_mult,
+                                                                       const int64_t *__restrict__ item_base, int nseq, int64_t n_items,
+                                                                       int k, int bin_bits, uint32_t lo, uint32_t hi,
+                                                                       uint32_t *__restrict__ items, unsigned long long *cursor,
+                                                                       unsigned long long *__restrict__ hist) {
+  extern __shared__ uint32_t sh_hist[];
+  const int nbins = 1 << bin_bits;
+  if constexpr (HIST) {
+    for (int i = threadIdx.x; i < nbins; i += kRangedNT) sh_hist[i] = 0;
+    __syncthreads();
+  }
+  for (int64_t base = (int64_t)blockIdx.x * kRangedNT; base < n_items; base += (int64_t)gridDim.x * kRangedNT) {
+    const int64_t x = base + threadIdx.x;
+    uint32_t it[1][WI];
+    bool in[1] = {false};
+    if (x < n_items) {
+      seq_item<WI>(packed, seq_start, seq_mult, item_base, nseq, x, k, it[0]);
+      const uint32_t bin = it[0][0] >> (32 - bin_bits);
+      if constexpr (HIST) atomicAdd(&sh_hist[bin], 1u);
+      else in[0] = bin >= lo && bin < hi;
+    }
+    if constexpr (!HIST) ranged_sink<WI, 1>(it, in, items, cursor);
+  }
+  if constexpr (HIST) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += kRangedNT)
+      if (sh_hist[i]) atomicAdd(hist + i, (unsigned long long)sh_hist[i]);
+  }
 }
 
 }  // namespace mf

@@ -77,9 +77,13 @@ def test_count_seq2sdbg_read2sdbg_files(oracle, tmp_path):
     _same_files(g1, o1, ".sdbg*")
 
 
-def test_next_k_with_contigs(oracle, tmp_path):
-    """k > k_min: unsorted iterative edges + contig / bubble / addi / local FASTA of the previous k (loop contigs extended)."""
+@pytest.mark.parametrize("rounds", [False, True])
+def test_next_k_with_contigs(oracle, tmp_path, monkeypatch, rounds):
+    """k > k_min: unsorted iterative edges + contig / bubble / addi / local FASTA of the previous k (loop contigs extended);
+    once in one pass, once through the memory-bounded rounds (ranged edge and contig item generators)."""
     from mitoflex_b200 import lib
+    if rounds:
+        monkeypatch.setenv("MFSDBG_SDBG_ROUND_ITEMS", "20000")
     k_from, k = 21, 29
     rng = np.random.default_rng(5)
     genome = rng.integers(0, 4, 30000, dtype=np.uint8)

@@ -293,3 +293,21 @@ def test_count_sampled_histogram(ctx, oracle, monkeypatch, stride, slack):
     assert e_gpu.s.n_keys == int(np.maximum(np.diff(starts) - k, 0).sum())
     assert_edges_equal(e_gpu, e_orc)
     assert np.array_equal(e_gpu.counting, e_orc.counting)
+
+
+@pytest.mark.parametrize("k,m,round_items", [(9, 1, 700), (15, 2, 3000), (21, 1, 2000), (21, 2, 50000), (31, 2, 3000), (47, 2, 4000),
+                                             (79, 2, 2500), (141, 2, 1500)])
+def test_sdbg_memory_bounded_rounds(ctx, oracle, monkeypatch, k, m, round_items):
+    """the sdbg stage in rounds over level-1 bin ranges (what an item set larger than the HBM budget takes: SURVEY config 5,
+    -m 1 on error-rich reads); a tiny round size forces many rounds, the appended outputs must equal the one-pass graph."""
+    monkeypatch.setenv("MFSDBG_SDBG_ROUND_ITEMS", str(round_items))
+    bases, starts = make_reads(900 + k, 4000, k, genome_len=8000, max_len=max(150, k + 40), err=0.02)
+    ctx.set_profiling(True)
+    try:
+        g_gpu = ctx.read2sdbg(ctx.upload_reads(bases, starts), k, m)
+        prof = ctx.last_profile()
+    finally:
+        ctx.set_profiling(False)
+    g_orc = oracle.read2sdbg(_orc_reads(oracle, bases, starts), k, m, threads=4)
+    assert_sdbg_equal(g_gpu, g_orc)
+    assert "items_hist" in prof, prof
