@@ -622,9 +622,15 @@ static void sort_ranges(Ctx &c, uint32_t *cur, uint32_t *other, const std::vecto
   a.bail_list = d_bail;
   a.bail_count = d_flags;
   a.overflow_flag = d_flags + 1;
-  launch_local<W, kSortOnly>(c, a, b.nslots);
+  {
+    Stage st(c, "fallback_local");
+    launch_local<W, kSortOnly>(c, a, b.nslots);
+  }
   int nbail = 0;
   c.d2h(&nbail, d_flags, sizeof(int));
+  if (getenv("MFSDBG_TRACE"))
+    fprintf(stderr, "[mfsdbg] fallback sort depth %d: %d ranges, %lld records, %d slots, %d bail\n", depth, (int)ranges.size(),
+            (long long)total_size, b.nslots, nbail);
   if (nbail > 0) {
     std::vector<int32_t> bl(nbail);
     std::vector<int64_t> st(b.nslots), sz(b.nslots);
@@ -937,10 +943,13 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
       std::vector<int32_t> slots;
       std::vector<Range> rs = fetch_bails(c, b, d_bail, flags[0], &slots);
       std::vector<WorkItem> chunks, merges;
+      // one CTA per SM for these few launches: larger chunks leave fewer (key, count) pairs for the merge, which in turn
+      // holds more of them (W = 8: 5100-key chunks and 3600 pairs instead of 1600 and 520)
+      const int big_cap = env_int("MFSDBG_OVERSIZED_BIG", 1) ? local_cap(W, true, false, kLocalBigSmem) : p.cap;
       for (size_t i = 0; i < rs.size(); ++i) {
         WorkItem m{(int64_t)chunks.size(), 0, slots[i]};
-        for (int64_t off = 0; off < rs[i].size; off += p.cap) {
-          chunks.push_back(WorkItem{rs[i].start + off, (int32_t)std::min<int64_t>(p.cap, rs[i].size - off), slots[i]});
+        for (int64_t off = 0; off < rs[i].size; off += big_cap) {
+          chunks.push_back(WorkItem{rs[i].start + off, (int32_t)std::min<int64_t>(big_cap, rs[i].size - off), slots[i]});
           m.n++;
         }
         merges.push_back(m);
@@ -964,6 +973,7 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
         MF_CUDA(cudaMemsetAsync(d_pcur.p, 0, 64, c.stream));
         MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, c.stream));
         LocalArgs pa = a;
+        pa.cap = big_cap;
         pa.work = d_chunks.as<WorkItem>();
         pa.counting = nullptr;
         pa.pair_arena = d_pairs.as<uint32_t>();
@@ -984,7 +994,7 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
         }
         LocalArgs ma = pa;
         ma.work = d_merges.as<WorkItem>();
-        ma.cap = local_cap(W + 1, true, true);
+        ma.cap = env_int("MFSDBG_OVERSIZED_BIG", 1) ? local_cap(W + 1, true, true, kLocalBigSmem) : local_cap(W + 1, true, true);
         ma.counting = a.counting;
         ma.bail_list = d_bail2.as<int32_t>();
         {
@@ -1008,16 +1018,28 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
             hr.push_back(rs[i]);
             hw.push_back(WorkItem{rs[i].start, 0, slots[i]});
           }
-        if (!fallback_sorted) sort_ranges<W>(c, cur, other, hr, bit_off, key_bits);
+        if (getenv("MFSDBG_TRACE")) {
+          int64_t tot = 0, mx = 0;
+          for (auto &r : hr) { tot += r.size; mx = std::max(mx, r.size); }
+          fprintf(stderr, "[mfsdbg] count: %d of %d oversized buckets take the sorted-run path (%lld keys, largest %lld)\n", (int)hr.size(),
+                  (int)rs.size(), (long long)tot, (long long)mx);
+        }
+        if (!fallback_sorted) {
+          Stage st2(c, "oversized_sort");
+          sort_ranges<W>(c, cur, other, hr, bit_off, key_bits);
+        }
         fallback_sorted = true;
         DevBuf &d_hw = c.ov[7];
         d_hw.reserve(sizeof(WorkItem) * hw.size());
         c.h2d(d_hw.p, hw.data(), sizeof(WorkItem) * hw.size());
         LocalArgs sa = a;
         sa.work = d_hw.as<WorkItem>();
-        k_sorted_runs<W, 256><<<(unsigned)hw.size(), 256, 0, c.stream>>>(sa, (int)hw.size());
-        MF_LAUNCH_CHECK();
-        c.launches++;
+        {
+          Stage st2(c, "oversized_runs");
+          k_sorted_runs<W, 256><<<(unsigned)hw.size(), 256, 0, c.stream>>>(sa, (int)hw.size());
+          MF_LAUNCH_CHECK();
+          c.launches++;
+        }
         int sf[3];
         c.d2h(sf, d_flags, sizeof(int) * 3);
         flags[1] |= sf[1];

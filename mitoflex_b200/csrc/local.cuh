@@ -89,9 +89,11 @@ inline size_t local_smem_bytes(int WR, int cap, bool hash, bool weighted) {
   size_t words = (size_t)cap * WR + local_fixed_words(hash, weighted) + (hash ? 0 : 3 * ((size_t)cap / 2));
   return words * 4;
 }
-// records per CTA such that two CTAs fit an SM (110 KB each)
-inline int local_cap(int WR, bool hash, bool weighted) {
-  const int budget = 110 * 1024 - (int)local_fixed_words(hash, weighted) * 4;
+// records per CTA such that two CTAs fit an SM (110 KB each); the rare pair / merge launches of oversized buckets take a
+// whole SM (kLocalBigSmem) so that far fewer of them fall through to the sorted-run path
+constexpr int kLocalBigSmem = 220 * 1024;
+inline int local_cap(int WR, bool hash, bool weighted, int smem_budget = 110 * 1024) {
+  const int budget = smem_budget - (int)local_fixed_words(hash, weighted) * 4;
   int cap = budget / (WR * 4 + (hash ? 0 : 6));
   cap &= ~1;
   if (hash && cap > kHashSlots - 256) cap = kHashSlots - 256;   // the table must keep free slots
