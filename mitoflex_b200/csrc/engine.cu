@@ -1119,7 +1119,11 @@ static Plan count_plan(Ctx &c, int k, int min_count, int64_t n_est) {
     // streamed finish: level 2 is a range partition into <= 1024 bins of ~16 K keys (45 % table load at the usual distinct
     // ratio), so level 1 only has to bring the densest segments (2x the average) under ~17-24 M keys -- and the fewer bins the
     // reads-fed scatter has, the faster it runs (512 bins: 14.9 ms, 1024: 19.4 ms, 2048: 48 ms on the 5 Gbp sample)
-    p.l1_bits = std::max(1, std::min({10, key_bits, ceil_log2((double)n_est / (W == 2 ? 1.2e7 : 4.0e6))}));
+    // keys of 4+ words are staged in small tiles (ReadsTileCfg: 256 / 128 threads, 4096 / 2048 positions, and only (L-k)/L
+    // of the positions start a key): beyond 256 bins a tile holds less than a key or two per bin and the reads-fed scatter
+    // falls off a cliff (k=79: 51 ms at 8 bits, 96 ms at 9); the extra bits go to the prefix level that follows anyway
+    const int l1_cap = W >= 4 ? 8 : 10;
+    p.l1_bits = std::max(1, std::min({l1_cap, key_bits, ceil_log2((double)n_est / (W == 2 ? 1.2e7 : 4.0e6))}));
     // out-of-core rounds are cut at level-1 bin boundaries: a bin (twice the average at small prefixes) must stay well
     // inside what one round may hold
     const size_t bud0 = (size_t)((double)c.budget() * 0.9);
