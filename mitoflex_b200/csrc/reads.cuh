@@ -113,7 +113,8 @@ __device__ __forceinline__ uint32_t valid16(const uint32_t *sb, int p0, int k, i
 
 template <int W>
 struct ReadsTileCfg {
-  static constexpr int NT = W <= 3 ? 512 : (W <= 4 ? 256 : 128);   // W = 3: 8192 keys x 12 B = 96 KB of staging, still two CTAs per SM
+  // W = 3: 8192 keys x 12 B = 96 KB of staging, still two CTAs per SM; W = 5, 6: 4096 keys x 20 / 24 B = 80 / 96 KB, likewise
+  static constexpr int NT = W <= 3 ? 512 : (W <= 6 ? 256 : 128);
   static constexpr int T = NT * 16;   // base positions per tile
 };
 __host__ __device__ inline int reads_seq_words(int NT, int W) { return NT + W + 1; }

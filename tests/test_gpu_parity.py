@@ -22,9 +22,9 @@ def _orc_reads(oracle, bases, starts):
     return oracle.Reads(bases, starts)
 
 
-# k values cover every key width class: 1 word (k<=15), 2 (<=31), 3, 4, 5 (k=79), 7 (k=99), 8 (k=119), 9 (k=141)
+# k values cover every key width class: 1 word (k<=15), 2 (<=31), 3, 4, 5 (k=79), 6 (k=90), 7 (k=99), 8 (k=119), 9 (k=141)
 COUNT_CASES = [(9, 1), (9, 2), (15, 2), (16, 1), (21, 1), (21, 2), (21, 3), (31, 2), (32, 2), (47, 1), (59, 2), (63, 2),
-               (79, 2), (99, 2), (119, 2), (141, 2)]
+               (79, 2), (90, 2), (99, 2), (119, 2), (141, 2)]
 
 
 @pytest.mark.parametrize("k,m", COUNT_CASES)
