@@ -1853,6 +1853,7 @@ static void sdbg_rounds(Ctx &c, const uint32_t *edges, int64_t n_edges, const Se
     if (add > 0)
       MF_CUDA(cudaMemcpyAsync(acc.as<uint32_t>() + (size_t)have * words, src, (size_t)add * words * 4, cudaMemcpyDeviceToDevice, c.stream));
   };
+  try {
   for (const auto &rd : rounds) {
     int64_t n_r = 0;
     for (int b = rd.first; b < rd.second; ++b) n_r += (int64_t)hist[b];
@@ -1898,6 +1899,11 @@ static void sdbg_rounds(Ctx &c, const uint32_t *edges, int64_t n_edges, const Se
     n_tip += g.n_tips;
     n_large += g.n_large;
     for (size_t i = 0; i < stats.size(); ++i) stats[i] += c.sdbg_bucket_stats[i];
+  }
+  } catch (...) {   // DevBuf has no destructor: a failed round must not leak the accumulated output
+    acc_rec.release();
+    acc_lab.release();
+    throw;
   }
   c.sdbg_rec.release();
   c.sdbg_labels.release();
