@@ -311,3 +311,54 @@ def test_sdbg_memory_bounded_rounds(ctx, oracle, monkeypatch, k, m, round_items)
     g_orc = oracle.read2sdbg(_orc_reads(oracle, bases, starts), k, m, threads=4)
     assert_sdbg_equal(g_gpu, g_orc)
     assert "items_hist" in prof, prof
+
+
+def test_config1_full_size_vs_oracle(oracle):
+    """BASELINE configs[0] as SURVEY.md 8d defines it (2 000 000 x PE150 pairs = 600 Mbp, seed 1001, 5 % mitogenome, 0.5 %
+    errors): `count`, `seq2sdbg` and `read2sdbg` at k=21, -m 2 and -m 3, default planner, no environment overrides, every
+    output bit-exact against the oracle.  The planner takes its full-size branches here (sampled level-1 histogram, range
+    partition digit, distinct-ratio probe), which the small tests only reach through overrides."""
+    from mitoflex_b200 import lib
+    c = lib.Context(0)
+    try:
+        k = 21
+        reads = c.synth(n_pairs=2_000_000, seed=1001)
+        bases, starts = c.download_reads(reads)
+        assert reads.n_reads == 4_000_000 and 590e6 < reads.n_bases < 600e6
+        o_reads = oracle.Reads(bases, starts)
+        threads = os.cpu_count() or 8
+        for m in (2, 3):
+            e_gpu = c.count(reads, k, m, want_counting=True)
+            e_orc = oracle.count(o_reads, k, m, threads=threads)
+            assert_edges_equal(e_gpu, e_orc)
+            assert np.array_equal(e_gpu.counting, e_orc.counting)
+            s = oracle.Seqs()
+            s.add_edges(e_orc)
+            g_orc = oracle.seq2sdbg(s, k, threads=threads)
+            assert_sdbg_equal(c.seq2sdbg(e_gpu, k), g_orc)
+            g_gpu = c.read2sdbg(reads, k, m)
+            if m == 2:   # the oracle's one-pass route sorts an item per solid read position (minutes): once is enough
+                g_orc = oracle.read2sdbg(o_reads, k, m, threads=threads)
+            assert_sdbg_equal(g_gpu, g_orc)
+            assert g_gpu.n > 2 * e_gpu.n > 0
+    finally:
+        c.close()
+
+
+def test_synth_port_matches_device(ctx):
+    """oracle/synth_np.py (what the CPU arm of bench.py generates its sample with, so that it never loads libmfsdbg.so) is
+    the same generator as csrc/synth.cu: same hash, geometry, error and N model.  libm rounding may move an insert size or
+    a trim point on a vanishing fraction of reads, so the bar is: identical read count, > 99.9 % of reads byte-identical."""
+    from oracle import synth_np
+    for kw in (dict(n_pairs=30000, nuclear_len=300_000, seed=1001), dict(n_pairs=20000, nuclear_len=100_000, seed=5, error_rate=0.02)):
+        reads = ctx.synth(**kw)
+        gb, gs = ctx.download_reads(reads)
+        nb, ns = synth_np.synth_reads(**kw, workers=1)
+        assert len(ns) == len(gs)
+        same_len = np.diff(ns) == np.diff(gs)
+        assert same_len.mean() > 0.999
+        if same_len.all():
+            assert (nb == gb).mean() > 0.999
+        idx = np.nonzero(same_len)[0][:5000]
+        ok = sum(np.array_equal(nb[ns[i]:ns[i + 1]], gb[gs[i]:gs[i + 1]]) for i in idx)
+        assert ok > 0.999 * len(idx)
