@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--min-count", type=int, default=2, help="solidity threshold -m (headline: 2)")
     ap.add_argument("--error-rate", type=float, default=0.005, help="substitution error rate of the synthetic reads (headline: 0.005)")
     ap.add_argument("--nuclear-len", type=int, default=50_000_000, help="nuclear background length (headline: 50 Mb)")
+    ap.add_argument("--verify-pairs", type=int, default=250_000,
+                    help="N>1: read pairs per GPU of the correctness pass run before the timed region (0 = skip)")
     return ap.parse_args()
 
 
@@ -145,62 +147,166 @@ def cpu_run(bases, starts, threads):
     return dt, g.n
 
 
-def cpu_sample(ctx, reads, n_sample_reads):
-    """first n reads of the device-resident workload, on the host as 1 byte/base."""
-    from mitoflex_b200 import lib
-    n = min(n_sample_reads, reads.n_reads)
-    starts = ctx.d2h(reads.s.starts, (n + 1) * 8, np.int64)
-    nb = int(starts[-1])
-    words = ctx.d2h(reads.s.packed, ((nb + 15) // 16) * 4, np.uint32)
-    return lib.unpack_reads(words, nb), starts
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
-def cpu_baseline(ctx, reads, target_seconds):
-    threads = os.cpu_count() or 1
-    pilot_reads = 200_000
-    b, s = cpu_sample(ctx, reads, pilot_reads)
+def max_rss_gb():
+    import resource
+    return resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6   # Linux reports KiB
+
+
+def cpu_sample(full_pairs, sample_pairs, error_rate, nuclear_len, seed=1002):
+    """A depth-preserving sample of the workload for the CPU arm, generated on the host by the numpy port of the generator
+    (oracle/synth_np.py) -- libmfsdbg.so is never loaded on this path.  The nuclear background is scaled with the pair count
+    so that its depth (95x on the headline read set) and with it the solid fraction stay those of the full workload; the
+    mitogenome keeps its 16.5 kb."""
+    from oracle import synth_np
+    scale = sample_pairs / float(full_pairs)
+    nuc = max(int(nuclear_len * scale), 20_000)
+    b, s = synth_np.synth_reads(sample_pairs, read_len=READ_LEN, nuclear_len=nuc, error_rate=error_rate, seed=seed)
+    depth = 0.95 * 2 * READ_LEN * sample_pairs / nuc
+    desc = (f"{sample_pairs} pairs ({len(b) / 1e6:.1f} Mbp) of the same generator, nuclear background scaled "
+            f"{nuclear_len / 1e6:g} Mb -> {nuc / 1e6:.3f} Mb so its depth stays {depth:.0f}x (same solid fraction as the full workload)")
+    return b, s, desc
+
+
+def sized_cpu_sample(args, target_seconds, threads):
+    """pilot on 100 000 pairs, then the sample the oracle finishes in about target_seconds"""
+    pilot_pairs = min(100_000, args.pairs)
+    b, s, desc = cpu_sample(args.pairs, pilot_pairs, args.error_rate, args.nuclear_len)
     dt, _ = cpu_run(b, s, threads)
-    rate = len(b) / dt
-    n = int(min(reads.n_reads, max(pilot_reads, rate * target_seconds / READ_LEN)))
-    n = min(n, 8_000_000)
-    if n > pilot_reads * 1.5:
-        b, s = cpu_sample(ctx, reads, n)
+    want = int(min(args.pairs, 4_000_000, pilot_pairs * target_seconds / max(dt, 1e-3)))
+    if want > pilot_pairs * 1.5:
+        b, s, desc = cpu_sample(args.pairs, want, args.error_rate, args.nuclear_len)
+        dt = None
+    return b, s, desc, dt
+
+
+def cpu_baseline(args, target_seconds):
+    threads = os.cpu_count() or 1
+    b, s, desc, dt = sized_cpu_sample(args, target_seconds, threads)
+    if dt is None:
         dt, _ = cpu_run(b, s, threads)
     return {"value": len(b) / dt, "unit": "bases/s", "cores": threads, "kind": "port",
-            "sample": f"first {len(s) - 1} reads ({len(b) / 1e6:.1f} Mbp) of the same synthetic read set, oracle read2sdbg "
-                      f"(CPU restatement of megahit_core, OpenMP) in {dt:.2f} s; megahit itself is not vendored"}
+            "sample": f"{desc}; oracle read2sdbg (CPU restatement of megahit_core, OpenMP) in {dt:.2f} s; megahit itself is not vendored",
+            "cpu_model": cpu_model(), "max_rss_gb": round(max_rss_gb(), 2)}
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement on host cores, bounded sample per step (rank 0 only)."""
+    """--impl reference: the CPU restatement on host cores, bounded sample per step (rank 0 only).  Loads oracle/ only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from mitoflex_b200 import lib
     threads = os.cpu_count() or 1
-    ctx = lib.Context(0)
-    pairs = min(args.pairs, 1_000_000)
-    reads = ctx.synth(n_pairs=pairs, seed=1002)
-    pilot_b, pilot_s = cpu_sample(ctx, reads, 200_000)
-    dt, _ = cpu_run(pilot_b, pilot_s, threads)
-    n = int(min(reads.n_reads, max(200_000, (len(pilot_b) / dt) * 6.0 / READ_LEN)))
-    b, s = cpu_sample(ctx, reads, n)
-    ctx.close()
+    per_step = max(1.0, min(6.0, 150.0 / max(args.steps + args.warmup, 1)))
+    b, s, desc, _ = sized_cpu_sample(args, per_step, threads)
     for _ in range(args.warmup):
         cpu_run(b, s, threads)
     times = [cpu_run(b, s, threads)[0] for _ in range(args.steps)]
     tot = sum(times)
     v = len(b) * args.steps / tot
-    sample = f"first {len(s) - 1} reads ({len(b) / 1e6:.1f} Mbp) of the synthetic read set per step"
+    sample = desc + " per step"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(args.pairs, args.error_rate, args.nuclear_len), "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "bases/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "bases/s", "cores": threads, "kind": "port", "sample": sample,
+                         "cpu_model": cpu_model(), "max_rss_gb": round(max_rss_gb(), 2)},
         "e2e": {"value": v, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# ------------------------------------------------------------------ N>1 correctness (outside the timed region)
+def stream_checksum(values, offset):
+    """position-dependent 64-bit checksum of a uint32 stream that starts at global position `offset`: the sum over the
+    concatenated rank outputs equals the checksum of the single-GPU stream iff both hold the same values in the same order
+    (up to 2^-64 collisions)."""
+    v = np.asarray(values).astype(np.uint64).ravel()
+    with np.errstate(over="ignore"):
+        x = v * np.uint64(0x9E3779B97F4A7C15) + (np.arange(len(v), dtype=np.uint64) + np.uint64(offset)) * np.uint64(0xD1342543DE82EF95)
+        x ^= x >> np.uint64(29)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(32)
+        return int(x.sum(dtype=np.uint64))
+
+
+def graph_stats(g, item_off, tip_off):
+    """what rank-local pieces of a graph contribute to the global figures"""
+    rec = g.ctx.d2h(g.s.rec, g.s.n_items * 4, np.uint32)
+    lab = g.ctx.d2h(g.s.tip_labels, g.s.n_tips * g.s.words_per_tip * 4, np.uint32)
+    return np.array([g.s.n_items, g.s.n_tips, g.s.n_large, int((rec >> 8).astype(np.int64).sum()),
+                     stream_checksum(rec, item_off) & 0x7FFFFFFFFFFFFFFF,
+                     stream_checksum(lab, tip_off * g.s.words_per_tip) & 0x7FFFFFFFFFFFFFFF], dtype=np.int64)
+
+
+def verify_multi_gpu(ctx, runner, args, rank, world, dev):
+    """Every rank runs the sharded path on a small shard; rank 0 then runs the single-GPU path on the CONCATENATED reads of all
+    shards and the global figures must agree: item / tip / large-multiplicity counts, the sum of multiplicities and
+    position-dependent checksums of the concatenated record and tip-label streams (rank order = key order)."""
+    import torch
+    import torch.distributed as dist
+    from mitoflex_b200 import lib
+    seeds = [424_242 + 7919 * r for r in range(world)]
+    kw = dict(n_pairs=args.verify_pairs, error_rate=args.error_rate, nuclear_len=max(args.nuclear_len // 50, 100_000))
+    reads = ctx.synth(seed=seeds[rank], **kw)
+    res = runner.run(reads)
+    g = res.sdbg
+    mine = torch.tensor([g.s.n_items, g.s.n_tips, res.info["n_edges"]], dtype=torch.int64, device=dev)
+    allc = torch.empty((world, 3), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc, mine)
+    allc = allc.cpu().numpy()
+    st = torch.from_numpy(graph_stats(g, int(allc[:rank, 0].sum()), int(allc[:rank, 1].sum()))).to(dev)
+    alls = torch.empty((world, 6), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(alls, st)
+    alls = alls.cpu().numpy()
+    out = None
+    if rank == 0:
+        parts, lens = [], []
+        for sd in seeds:
+            b, s0 = ctx.download_reads(ctx.synth(seed=sd, **kw))
+            parts.append(b)
+            lens.append(np.diff(s0))
+        starts = np.concatenate([[0], np.cumsum(np.concatenate(lens))]).astype(np.int64)
+        whole = ctx.upload_reads(np.concatenate(parts), starts)
+        e1 = ctx.count(whole, K, MIN_COUNT)
+        n_edges_1 = e1.n
+        g1 = ctx.read2sdbg(whole, K, MIN_COUNT)
+        ref = graph_stats(g1, 0, 0)
+        got = alls[:, :4].sum(axis=0).tolist()
+        ok = got == ref[:4].tolist() and int(allc[:, 2].sum()) == n_edges_1
+        # checksums: every rank's value was masked to 63 bits for the int64 transport, so the reference is built the same
+        # way -- piecewise over the ranks' item / tip ranges of the single-GPU streams -- and both are summed modulo 2^63
+        M = (1 << 63) - 1
+        got_cs = [sum(int(x) for x in alls[:, 4]) & M, sum(int(x) for x in alls[:, 5]) & M]
+        rec1 = ctx.d2h(g1.s.rec, g1.s.n_items * 4, np.uint32)
+        wt = g1.s.words_per_tip
+        lab1 = ctx.d2h(g1.s.tip_labels, g1.s.n_tips * wt * 4, np.uint32)
+        ref_cs = [0, 0]
+        io = to = 0
+        for r in range(world):
+            ni, nt = int(allc[r, 0]), int(allc[r, 1])
+            ref_cs[0] += stream_checksum(rec1[io:io + ni], io) & M
+            ref_cs[1] += stream_checksum(lab1[to * wt:(to + nt) * wt], to * wt) & M
+            io += ni
+            to += nt
+        ok = ok and io == g1.s.n_items and to == g1.s.n_tips and got_cs == [ref_cs[0] & M, ref_cs[1] & M]
+        out = {"verified": bool(ok), "pairs_per_gpu": args.verify_pairs, "n_edges": int(allc[:, 2].sum()), "n_items": int(got[0]),
+               "n_tips": int(got[1]), "sum_mult": int(got[3]), "checksum_items": f"{got_cs[0]:016x}", "checksum_tips": f"{got_cs[1]:016x}",
+               "single_gpu": {"n_edges": int(n_edges_1), "n_items": int(ref[0]), "n_tips": int(ref[1]), "sum_mult": int(ref[3]),
+                              "checksum_items": f"{ref_cs[0] & M:016x}", "checksum_tips": f"{ref_cs[1] & M:016x}"},
+               "how": "sharded run on all ranks vs single-GPU run of the concatenated reads on rank 0, outside the timed region"}
+        del whole
+    dist.barrier()
+    return out
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -231,12 +337,17 @@ def main():
     torch.cuda.set_stream(stream)              # CUDA events bracket exactly the kernels the library launches
     ctx.set_stream(stream.cuda_stream)
     ctx.set_profiling(True)
-    reads = ctx.synth(n_pairs=args.pairs, seed=1002 + 7919 * rank, error_rate=args.error_rate, nuclear_len=args.nuclear_len)
-    n_bases = reads.n_bases
-
+    verify = None
+    runner = None
     if world > 1:
         from mitoflex_b200 import dist as mdist
         runner = mdist.DistRead2Sdbg(ctx, K, MIN_COUNT)
+        if args.verify_pairs > 0:
+            # correctness of the sharded path, before (and outside) the timed region; the synth buffers are reused below
+            verify = verify_multi_gpu(ctx, runner, args, rank, world, dev)
+    reads = ctx.synth(n_pairs=args.pairs, seed=1002 + 7919 * rank, error_rate=args.error_rate, nuclear_len=args.nuclear_len)
+    n_bases = reads.n_bases
+    if world > 1:
         step = lambda: runner.run(reads)   # noqa: E731
     else:
         step = lambda: ctx.read2sdbg(reads, K, MIN_COUNT)   # noqa: E731
@@ -307,6 +418,44 @@ def main():
         e2e = {"value": n_bases * args.steps / te, "unit": "bases/s", "h2d_bytes_per_step": int(out.h2d_bytes),
                "d2h_bytes_per_step": int(out.d2h_bytes), "ms_per_step": 1e3 * te / args.steps,
                "api": "mfsdbg_host_read2sdbg (pinned host packed reads in, sdbg arrays out)"}
+    elif not args.no_e2e:
+        # N > 1: every rank's shard starts in pinned host memory and its piece of the graph ends there; the copies are inside
+        # the timed region, the time is the wall clock between two barriers, max over ranks
+        nw = (n_bases + 15) // 16
+        hw = torch.empty(nw + 16, dtype=torch.int32, pin_memory=True)
+        hs = torch.empty(reads.n_reads + 1, dtype=torch.int64, pin_memory=True)
+        from ctypes import c_void_p
+        L = lib.load()
+        lib._check(L.mfsdbg_dev_copy(ctx._h, c_void_p(hw.data_ptr()), reads.s.packed, nw * 4, 0))
+        lib._check(L.mfsdbg_dev_copy(ctx._h, c_void_p(hs.data_ptr()), reads.s.starts, (reads.n_reads + 1) * 8, 0))
+        dw = torch.zeros(nw + 16, dtype=torch.int32, device=dev)
+        ds = torch.empty(reads.n_reads + 1, dtype=torch.int64, device=dev)
+        cap_items = int(res.n * 1.2) + 1024
+        out_rec = torch.empty(cap_items, dtype=torch.int32, pin_memory=True)
+        out_lab = torch.empty(int(res.sdbg.s.n_tips * res.sdbg.s.words_per_tip * 1.5) + 1024, dtype=torch.int32, pin_memory=True)
+
+        def e2e_step():
+            dw[:nw + 16].copy_(hw, non_blocking=True)
+            ds.copy_(hs, non_blocking=True)
+            r2 = runner.run(ctx.reads_from_tensors(dw, ds, n_bases))
+            g2 = r2.sdbg
+            lib._check(L.mfsdbg_dev_copy(ctx._h, c_void_p(out_rec.data_ptr()), g2.s.rec, g2.s.n_items * 4, 0))
+            lib._check(L.mfsdbg_dev_copy(ctx._h, c_void_p(out_lab.data_ptr()), g2.s.tip_labels, g2.s.n_tips * g2.s.words_per_tip * 4, 0))
+            return g2
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 5))
+        for _ in range(n_e2e):
+            g2 = e2e_step()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        byts = torch.tensor([nw * 4 + (reads.n_reads + 1) * 8, g2.s.n_items * 4 + g2.s.n_tips * g2.s.words_per_tip * 4], device=dev, dtype=torch.int64)
+        dist.all_reduce(byts)
+        e2e = {"value": total_bases * n_e2e / float(te.item()), "unit": "bases/s", "h2d_bytes_per_step": int(byts[0].item()),
+               "d2h_bytes_per_step": int(byts[1].item()), "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e,
+               "api": "per rank: pinned host packed reads -> HBM, DistRead2Sdbg.run (C-ABI staged calls), sdbg arrays -> pinned host; bytes summed over ranks"}
 
     if rank != 0:
         if world > 1:
@@ -360,7 +509,7 @@ def main():
                 pass
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cpu = cpu_baseline(ctx, reads, args.cpu_seconds)
+        cpu = cpu_baseline(args, args.cpu_seconds)
     out = {
         "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
@@ -370,6 +519,11 @@ def main():
                    "parallelism": "reads sharded by GPU, keys and items stored into the owner GPU of their prefix bin by the partition kernel itself (NVLink peer memory), disjoint key range per GPU" if world > 1 else "1 GPU"},
         "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
+    if world > 1:
+        out["verified"] = bool(verify and verify.get("verified"))
+        out["config"]["verified"] = out["verified"]
+        out["config"]["verify"] = verify
+        out["config"]["nvlink"] = nvlink
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -58,3 +58,30 @@ def test_reference_arm_is_silent_on_other_ranks():
                         "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip() == ""
+
+
+def test_stream_checksum_is_position_dependent_and_additive():
+    """the N>1 verification sums per-rank checksums of the ranks' pieces: pieces at their global offsets add up to the
+    checksum of the whole stream, and a swap or a shifted boundary changes it"""
+    import numpy as np
+    b = _bench()
+    rng = np.random.default_rng(1)
+    v = rng.integers(0, 2**32, 10000, dtype=np.uint64).astype(np.uint32)
+    whole = b.stream_checksum(v, 0)
+    M = (1 << 64) - 1
+    assert (b.stream_checksum(v[:3000], 0) + b.stream_checksum(v[3000:], 3000)) & M == whole
+    assert (b.stream_checksum(v[:3000], 0) + b.stream_checksum(v[3000:], 2999)) & M != whole
+    w = v.copy()
+    w[[10, 11]] = w[[11, 10]]
+    assert b.stream_checksum(w, 0) != whole
+    assert b.stream_checksum(np.zeros(0, np.uint32), 5) == 0
+
+
+def test_cpu_sample_keeps_the_depth():
+    """the CPU arm's sample scales the nuclear background with the pair count (same depth, same solid fraction) and comes
+    from the numpy port of the generator -- it must not load libmfsdbg.so"""
+    b = _bench()
+    bases, starts, desc = b.cpu_sample(16_666_667, 2000, 0.005, 50_000_000)
+    assert len(starts) - 1 == 4000 and bases.max() <= 3 and "95x" in desc
+    maps = open("/proc/self/maps").read()
+    assert "libmfsdbg" not in maps
