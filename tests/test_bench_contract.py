@@ -81,7 +81,7 @@ def test_cpu_sample_keeps_the_depth():
     """the CPU arm's sample scales the nuclear background with the pair count (same depth, same solid fraction) and comes
     from the numpy port of the generator -- it must not load libmfsdbg.so"""
     b = _bench()
-    bases, starts, desc = b.cpu_sample(16_666_667, 2000, 0.005, 50_000_000)
-    assert len(starts) - 1 == 4000 and bases.max() <= 3 and "95x" in desc
+    bases, starts, desc = b.cpu_sample(16_666_667, 20_000, 0.005, 50_000_000)
+    assert len(starts) - 1 == 40_000 and bases.max() <= 3 and "95x" in desc
     maps = open("/proc/self/maps").read()
     assert "libmfsdbg" not in maps
