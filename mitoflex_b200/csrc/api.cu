@@ -181,13 +181,12 @@ int mfsdbg_dev_count_hist(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int32_
 }
 int mfsdbg_dev_count_scatter(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int32_t k, int32_t l1_bits, const uint64_t *hist_dev,
                              uint32_t *keys_out, int64_t capacity) {
-  if (!ctx || !hist_dev || (!keys_out && capacity > 0)) return MFSDBG_EINVAL;
+  if (!ctx || !hist_dev || capacity < 0 || (!keys_out && capacity > 0)) return MFSDBG_EINVAL;
   std::lock_guard<std::mutex> lk(g_job_mutex);
   return guarded([&] {
     ctx->c.begin_call();
-    (void)capacity;
     mf::dev_count_scatter(ctx->c, view(reads), k, l1_bits, reinterpret_cast<const unsigned long long *>(hist_dev), keys_out,
-                          nullptr);
+                          capacity, nullptr);
     ctx->c.end_call();
   });
 }
@@ -300,7 +299,7 @@ int mfsdbg_dev_count_scatter_peer(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads
   std::lock_guard<std::mutex> lk(g_job_mutex);
   return guarded([&] {
     ctx->c.begin_call();
-    mf::dev_count_scatter(ctx->c, view(reads), k, l1_bits, nullptr, nullptr, reinterpret_cast<const unsigned long long *>(bin_base_dev));
+    mf::dev_count_scatter(ctx->c, view(reads), k, l1_bits, nullptr, nullptr, -1, reinterpret_cast<const unsigned long long *>(bin_base_dev));
     ctx->c.end_call();
   });
 }

@@ -1465,28 +1465,46 @@ __global__ void k_excl_scan_u64_small(const unsigned long long *in, int n, unsig
   __syncthreads();
   for (int t = threadIdx.x; t < n; t += blockDim.x) out[t] = s[t];
 }
+__global__ void k_sum_u64(const unsigned long long *in, int n, unsigned long long *out) {
+  unsigned long long v = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += in[i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
 template <int W>
 static void dev_count_scatter_impl(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev,
-                                   uint32_t *keys_out, const unsigned long long *bin_base) {
-  const uint32_t *sbits = c.sbits.as<uint32_t>();
-  if (!sbits) sbits = build_start_bits(c, r);
+                                   uint32_t *keys_out, int64_t capacity, const unsigned long long *bin_base) {
+  // the start bitmap is rebuilt for THESE reads: a cached one may belong to another reads object or an earlier call
+  const uint32_t *sbits = build_start_bits(c, r);
   const int nb1 = 1 << l1_bits;
   c.slab_reserve(1 << 20);
-  unsigned long long *d_cursor = c.alloc<unsigned long long>(nb1);
+  unsigned long long *d_cursor = c.alloc<unsigned long long>(nb1 + 1);
   if (bin_base) {
     MF_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long) * nb1, c.stream));   // offsets within each destination
   } else {
+    // the histogram decides how much is written: it must fit what the caller allocated
+    MF_CUDA(cudaMemsetAsync(d_cursor + nb1, 0, sizeof(unsigned long long), c.stream));
+    k_sum_u64<<<1, 256, 0, c.stream>>>(hist_dev, nb1, d_cursor + nb1);
     k_excl_scan_u64_small<<<1, 1024, 0, c.stream>>>(hist_dev, nb1, d_cursor);
     MF_LAUNCH_CHECK();
-    c.launches++;
+    c.launches += 2;
+    unsigned long long total = 0;
+    c.d2h(&total, d_cursor + nb1, sizeof total);
+    if (capacity >= 0 && total > (unsigned long long)capacity)
+      throw std::invalid_argument("count_scatter: the histogram holds " + std::to_string(total) + " keys, keys_out has room for " +
+                                  std::to_string(capacity));
   }
   Stage st(c, "reads_scatter");
   launch_reads_scatter<W>(c, r, sbits, k, LevelArgs{0, l1_bits, 0u, (uint32_t)nb1, bin_base}, d_cursor, keys_out);
 }
 #define MF_DISPATCH_CASE_CSCAT(Wn) \
-  case Wn: dev_count_scatter_impl<Wn>(c, r, k, l1_bits, hist_dev, keys_out, bin_base); break;
+  case Wn: dev_count_scatter_impl<Wn>(c, r, k, l1_bits, hist_dev, keys_out, capacity, bin_base); break;
 void dev_count_scatter(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev, uint32_t *keys_out,
-                       const unsigned long long *bin_base) {
+                       int64_t capacity, const unsigned long long *bin_base) {
+  if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
+  if (l1_bits < 1 || l1_bits > kMaxDigitBits) throw std::invalid_argument("l1_bits must be in [1, 11]");
+  if (!bin_base && !hist_dev) throw std::invalid_argument("count_scatter needs a histogram or peer bin bases");
   MF_DISPATCH_W(words_key(k), CSCAT)
 }
 template <int W>

@@ -114,8 +114,9 @@ bool dev_count_host(Ctx &c, const uint32_t *packed_host, const int64_t *starts_h
                     int min_count, EdgesView *out);
 void dev_seq2sdbg(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &seqs, int k, int tip_mode, SdbgView *out);
 void dev_count_hist(Ctx &c, const ReadsView &r, int k, int l1_bits, unsigned long long *hist_dev);
+// capacity: records keys_out can hold (checked against the histogram total; < 0 = unchecked, peer mode ignores it)
 void dev_count_scatter(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev, uint32_t *keys_out,
-                       const unsigned long long *bin_base);
+                       int64_t capacity, const unsigned long long *bin_base);
 void dev_count_finish(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys, const int64_t *chunk_start,
                       const int64_t *chunk_size, const int32_t *chunk_seg, int n_chunks, int n_segs, int k, int l1_bits,
                       int min_count, EdgesView *out, int64_t *counting_host);

@@ -19,7 +19,28 @@ namespace {
 std::string errno_msg(const std::string &what, const std::string &path) {
   return what + " " + path + ": " + strerror(errno);
 }
-// whole file (plain, gzip or FIFO) into memory
+// whole BINARY file into memory: never through zlib, whose gzopen switches to gzip decoding on the magic bytes 1f 8b -- an edge
+// word or a read length may well start with them
+std::vector<uint8_t> slurp_binary(const std::string &path) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) throw IoError(errno_msg("cannot open", path));
+  std::vector<uint8_t> buf;
+  size_t cap = 1 << 22, len = 0;
+  buf.resize(cap);
+  for (;;) {
+    if (len == cap) { cap *= 2; buf.resize(cap); }
+    const size_t got = fread(buf.data() + len, 1, cap - len, f);
+    len += got;
+    if (got == 0) {
+      if (ferror(f)) { fclose(f); throw IoError("read error on " + path); }
+      break;
+    }
+  }
+  fclose(f);
+  buf.resize(len);
+  return buf;
+}
+// whole TEXT file (FASTA / FASTQ: plain, gzip or FIFO) into memory
 std::vector<uint8_t> slurp(const std::string &path) {
   gzFile f = gzopen(path.c_str(), "rb");
   if (!f) throw IoError(errno_msg("cannot open", path));
@@ -128,7 +149,7 @@ void file_buildlib(Ctx &c, const char *lib_file, const char *out_prefix, int n_p
 }
 
 static void load_read_lib(Ctx &c, const char *read_lib_file, ReadsView *r) {
-  std::vector<uint8_t> raw = slurp(std::string(read_lib_file) + ".bin");
+  std::vector<uint8_t> raw = slurp_binary(std::string(read_lib_file) + ".bin");
   if (raw.size() % 4) throw IoError("read library .bin is not a whole number of words");
   bin_stream_to_reads(c, reinterpret_cast<const uint32_t *>(raw.data()), (int64_t)(raw.size() / 4), r);
 }
@@ -180,11 +201,15 @@ static HostEdges read_edges(const std::string &prefix) {
   expect_field(is, "num_buckets", &nbuckets);
   expect_field(is, "num_edges", &nedges);
   expect_field(is, "is_sorted", &sorted);
+  // a mismatched or corrupt meta file must end in a clean EIO, not in a wrong stride on the device or a huge allocation
+  if (k < 1 || k > 255 || words != words_edge((int)k)) throw IoError("edges.info: words_per_edge does not belong to kmer_size");
+  if (nbuckets != kNumBuckets) throw IoError("edges.info: num_buckets must be 65536");
+  if (nfiles < 1 || nfiles > 65536 || nedges < 0 || nedges > ((long long)1 << 40)) throw IoError("edges.info: implausible num_files / num_edges");
   HostEdges e;
   e.k = (int)k; e.words = (int)words; e.sorted = sorted != 0; e.n = nedges;
   e.data.resize((size_t)nedges * words);
   std::vector<std::vector<uint8_t>> fdata(nfiles);
-  for (int f = 0; f < nfiles; ++f) fdata[f] = slurp(prefix + ".edges." + std::to_string(f));
+  for (int f = 0; f < nfiles; ++f) fdata[f] = slurp_binary(prefix + ".edges." + std::to_string(f));
   int64_t pos = 0;
   const size_t rec = (size_t)words * 4;
   if (e.sorted) {
@@ -192,6 +217,7 @@ static HostEdges read_edges(const std::string &prefix) {
       long long bid, fid, off, cnt;
       if (!(is >> bid >> fid >> off >> cnt) || bid != b) throw IoError("Invalid format: bucket id not matched!");
       if (fid < 0 || cnt == 0) continue;
+      if (off < 0 || cnt < 0) throw IoError("edges.info: negative offset or count");
       if (fid >= nfiles || (size_t)(off + cnt) * rec > fdata[fid].size() || pos + cnt > nedges) throw IoError("edge file shorter than its meta says");
       memcpy(e.data.data() + pos * words, fdata[fid].data() + (size_t)off * rec, (size_t)cnt * rec);
       pos += cnt;
@@ -311,11 +337,14 @@ static void write_sdbg(Ctx &c, const SdbgView &g, const std::string &prefix, int
   info << "k " << g.k << "\nwords_per_tip_label " << g.words_tip << "\nnum_buckets " << kNumBuckets << "\nnum_files " << n_files << '\n';
   std::vector<int64_t> foff(n_files, 0);
   std::vector<uint8_t> buf;
-  int64_t pos = 0, tpos = 0, large = 0;
+  // SdbgMeta: a bucket record nobody wrote to keeps bucket_id = kUninitializedBucketID = size_t(-1) and zeros elsewhere, and
+  // the records are sorted by bucket_id before they are serialised -- the unused ones come LAST (recollection shared by the
+  // oracle; the first run against a real megahit_core decides it)
+  int64_t pos = 0, tpos = 0, large = 0, n_empty = 0;
   for (int b = 0; b < kNumBuckets; ++b) {
     const int64_t items = c.sdbg_bucket_stats[(size_t)b * 3], tips = c.sdbg_bucket_stats[(size_t)b * 3 + 1],
                   lg = c.sdbg_bucket_stats[(size_t)b * 3 + 2];
-    if (!items) { info << b << " -1 0 0 0 0\n"; continue; }
+    if (!items) { ++n_empty; continue; }
     const int f = bucket_file(b, n_files);
     buf.clear();
     for (int64_t i = pos; i < pos + items; ++i) {
@@ -336,6 +365,7 @@ static void write_sdbg(Ctx &c, const SdbgView &g, const std::string &prefix, int
     pos += items;
   }
   if (pos != g.n_items || tpos != g.n_tips) throw std::runtime_error("sdbg bucket statistics do not add up");
+  for (int64_t i = 0; i < n_empty; ++i) info << "18446744073709551615 0 0 0 0 0\n";
   info << "item_count " << g.n_items << "\ntip_count " << g.n_tips << "\nlarge_mul_count " << large << '\n';
   for (auto &f : files) f->close();
   File fi(prefix + ".sdbg_info", "w");

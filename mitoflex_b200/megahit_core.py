@@ -44,19 +44,36 @@ def parse(argv):
     return opts
 
 
-def forward(argv):
+REAL_NAMES = ("megahit_core", "megahit_core_popcnt", "megahit_core_no_hw_accel", "megahit_core_no_hwaccel")
+
+
+def find_real(invoked=None):
+    """The real megahit_core behind this shim: $MFSDBG_REAL_MEGAHIT_CORE, else the first non-shim binary on PATH -- the variant
+    the shim was invoked as first (MitoFlex picks megahit_core / _popcnt / _no_hwaccel from the CPU probes,
+    assemble_wrapper.py:101-125, and spells the last one without the underscore megahit installs it with: both are tried)."""
     real = os.environ.get("MFSDBG_REAL_MEGAHIT_CORE")
-    if not real:
-        me = os.path.realpath(sys.argv[0])
+    if real:
+        return real
+    me = os.path.realpath(sys.argv[0])
+    base = os.path.basename(invoked or sys.argv[0])
+    names = [n for n in REAL_NAMES if n == base]
+    if base in ("megahit_core_no_hwaccel", "megahit_core_no_hw_accel"):
+        names = ["megahit_core_no_hw_accel", "megahit_core_no_hwaccel"]
+    names += [n for n in REAL_NAMES if n not in names]
+    for name in names:
         for d in os.environ.get("PATH", "").split(os.pathsep):
-            for name in ("megahit_core", "megahit_core_popcnt", "megahit_core_no_hw_accel"):
-                cand = os.path.join(d, name)
+            cand = os.path.join(d, name)
+            try:
                 if os.path.isfile(cand) and os.access(cand, os.X_OK) and os.path.realpath(cand) != me \
                         and b"mitoflex_b200" not in open(cand, "rb").read(4096):
-                    real = cand
-                    break
-            if real:
-                break
+                    return cand
+            except OSError:
+                continue
+    return None
+
+
+def forward(argv):
+    real = find_real()
     if not real:
         sys.stderr.write(f"megahit_core shim: sub-command '{argv[0] if argv else ''}' is not part of libmfsdbg and no real "
                          "megahit_core was found (set MFSDBG_REAL_MEGAHIT_CORE)\n")
@@ -70,6 +87,18 @@ def main(argv=None):
         return forward(argv)
     cmd, rest = argv[0], argv[1:]
     if cmd in ("checkcpu", "checkpopcnt"):
+        # the answers select the binary variant MitoFlex runs the FORWARDED stages with (assemble / local / iterate): when a
+        # real megahit_core is there its probe of this CPU decides; the sDBG sub-commands themselves need neither BMI2 nor POPCNT
+        real = find_real("megahit_core")
+        if real:
+            import subprocess
+            try:
+                out = subprocess.run([real, cmd], capture_output=True, text=True, timeout=30).stdout.strip()
+                if out in ("0", "1"):
+                    print(out)
+                    return 0
+            except (OSError, subprocess.SubprocessError):
+                pass
         print(1)
         return 0
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

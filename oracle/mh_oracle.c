@@ -1004,11 +1004,13 @@ int orc_sdbg_write(const orc_sdbg *g, const char *prefix, int n_files) {
   FILE *fi = fopen(path, "w");
   if (!fi) return fail("cannot create %s", path);
   fprintf(fi, "k %d\nwords_per_tip_label %d\nnum_buckets %d\nnum_files %d\n", g->k, g->words_per_tip, ORC_NUM_BUCKETS, n_files);
-  int64_t pos = 0, tpos = 0;
+  /* SdbgMeta (src/sdbg/sdbg_meta.h): a bucket record nobody wrote to keeps bucket_id = kUninitializedBucketID = size_t(-1)
+   * and zeros elsewhere; the records are sorted by bucket_id before they are serialised, so the unused ones come LAST. */
+  int64_t pos = 0, tpos = 0, n_empty = 0;
   for (int b = 0; b < ORC_NUM_BUCKETS; ++b) {
     int f = (int)((int64_t)b * n_files / ORC_NUM_BUCKETS);
     int64_t c = g->bucket_items[b];
-    if (!c) { fprintf(fi, "%d -1 0 0 0 0\n", b); continue; }
+    if (!c) { ++n_empty; continue; }
     int64_t start = foff[f];
     for (int64_t i = pos; i < pos + c; ++i) {
       int m = g->mul[i];
@@ -1021,6 +1023,7 @@ int orc_sdbg_write(const orc_sdbg *g, const char *prefix, int n_files) {
             (long long)g->bucket_tips[b], (long long)g->bucket_large[b]);
     pos += c;
   }
+  for (int64_t i = 0; i < n_empty; ++i) fprintf(fi, "18446744073709551615 0 0 0 0 0\n");
   fprintf(fi, "item_count %lld\ntip_count %lld\nlarge_mul_count %lld\n", (long long)g->n, (long long)g->n_tips, (long long)g->n_large);
   fclose(fi);
   for (int f = 0; f < n_files; ++f) fclose(fps[f]);
@@ -1047,9 +1050,11 @@ orc_sdbg *orc_sdbg_read(const char *prefix) {
     fclose(fp);
   }
   for (int b = 0; b < nb; ++b) {
-    long long bid, fid, off, items, tips, large;
-    if (fscanf(fi, "%lld %lld %lld %lld %lld %lld", &bid, &fid, &off, &items, &tips, &large) != 6) { fail("bad bucket line"); return NULL; }
-    if (fid < 0) continue;
+    unsigned long long bid;
+    long long fid, off, items, tips, large;
+    if (fscanf(fi, "%llu %lld %lld %lld %lld %lld", &bid, &fid, &off, &items, &tips, &large) != 6) { fail("bad bucket line"); return NULL; }
+    if (bid >= (unsigned long long)ORC_NUM_BUCKETS || fid < 0 || items == 0) continue;   /* unused record */
+    if (fid >= nf) { fail("bucket record names file %lld of %lld", fid, nf); return NULL; }
     const uint8_t *p = fdata[fid] + off;
     for (long long i = 0; i < items; ++i) {
       uint16_t rec; memcpy(&rec, p, 2); p += 2;

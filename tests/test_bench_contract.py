@@ -79,9 +79,15 @@ def test_stream_checksum_is_position_dependent_and_additive():
 
 def test_cpu_sample_keeps_the_depth():
     """the CPU arm's sample scales the nuclear background with the pair count (same depth, same solid fraction) and comes
-    from the numpy port of the generator -- it must not load libmfsdbg.so"""
-    b = _bench()
-    bases, starts, desc = b.cpu_sample(16_666_667, 20_000, 0.005, 50_000_000)
-    assert len(starts) - 1 == 40_000 and bases.max() <= 3 and "95x" in desc
-    maps = open("/proc/self/maps").read()
-    assert "libmfsdbg" not in maps
+    from the numpy port of the generator -- in a fresh process it must not map libmfsdbg.so"""
+    code = ("import importlib.util, sys\n"
+            f"spec = importlib.util.spec_from_file_location('b', {os.path.join(ROOT, 'bench.py')!r})\n"
+            "b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)\n"
+            "bases, starts, desc = b.cpu_sample(16_666_667, 20_000, 0.005, 50_000_000)\n"
+            "assert len(starts) - 1 == 40_000 and bases.max() <= 3 and '95x' in desc, desc\n"
+            "dt, n = b.cpu_run(bases, starts, 2)\n"
+            "assert n > 0\n"
+            "assert 'libmfsdbg' not in open('/proc/self/maps').read()\n"
+            "assert 'libmhoracle' in open('/proc/self/maps').read()\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr

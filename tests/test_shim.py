@@ -67,3 +67,24 @@ def test_bad_option_is_an_error(tmp_path):
     exe = os.path.join(ROOT, "mitoflex_b200", "bin", "megahit_core")
     p = subprocess.run([sys.executable, exe, "count", "--no_such_flag", "1"], capture_output=True)
     assert p.returncode == 1
+
+
+def test_probes_and_forwarding_follow_the_real_binary(tmp_path):
+    """with a real megahit_core on PATH its answer to checkcpu / checkpopcnt is passed through (it selects the variant MitoFlex
+    runs the forwarded stages with), and a forwarded sub-command goes to the variant the shim was invoked as -- including
+    MitoFlex's `megahit_core_no_hwaccel` spelling (assemble_wrapper.py:101) of megahit's `megahit_core_no_hw_accel`."""
+    real_dir = tmp_path / "real"
+    real_dir.mkdir()
+    for name, ans in (("megahit_core", "0"), ("megahit_core_no_hw_accel", "1")):
+        f = real_dir / name
+        f.write_text(f"#!/bin/sh\nif [ \"$1\" = checkcpu ] || [ \"$1\" = checkpopcnt ]; then echo {ans}; else echo {name} \"$@\"; fi\n")
+        f.chmod(0o755)
+    shim_dir = os.path.join(ROOT, "mitoflex_b200", "bin")
+    env = dict(os.environ, PATH=shim_dir + os.pathsep + str(real_dir) + os.pathsep + os.environ.get("PATH", ""))
+    env.pop("MFSDBG_REAL_MEGAHIT_CORE", None)
+    out = subprocess.check_output([sys.executable, os.path.join(shim_dir, "megahit_core"), "checkcpu"], env=env).decode()
+    assert out.strip() == "0"
+    out = subprocess.check_output([sys.executable, os.path.join(shim_dir, "megahit_core_no_hwaccel"), "assemble", "-s", "p"], env=env).decode()
+    assert out.strip() == "megahit_core_no_hw_accel assemble -s p"
+    out = subprocess.check_output([sys.executable, os.path.join(shim_dir, "megahit_core"), "iterate", "-k", "21"], env=env).decode()
+    assert out.strip() == "megahit_core iterate -k 21"
