@@ -1,0 +1,453 @@
+// count_stream2.cuh -- the streamed count finish for keys of 33..64 bits (16 <= k <= 31), second generation.
+//
+// Same contract as k_count_stream<false> (count_stream.cuh): persistent CTAs own contiguous runs of buckets, the keys arrive
+// through a cp.async.bulk + mbarrier ring, a shared hash table groups them, the bucket end turns the solid keys into ordered
+// edge records (KmerCounter::PackEdge).  What changed, and why (ncu r1i/r2a: the old kernel issued ~120 thread-instructions per
+// key, 0.68 issue/cycle, stalls wait / barrier / branch_resolving):
+//
+//   * LANES NEVER WAIT FOR THE SLOWEST PROBE.  The old loop handed every lane one key and looped until the longest linear
+//     probe of the warp was done (5-8 rounds at 45 % load although the AVERAGE probe is 1.6 slots).  Now a lane that is done
+//     takes the next key of its warp at once (ballot + popc hand out consecutive keys), so a warp iteration is one probe step
+//     for 32 keys in different stages of their probe sequences: iterations = total probes / 32.
+//   * ONE 64-BIT SLOT HOLDS KEY AND COUNT.  All keys of a bucket lie in a narrow range (level 1 fixed their top bits, the range
+//     partition of level 2 their next ~10), so a slot stores the low RB bits of the right-aligned key above a CB-bit count
+//     (RB + CB = 64): claiming is one CAS, counting one RED on the same word, the probe compares one shifted word.  The table
+//     has 8192 slots in the memory the 4096 separate key / count slots took: half the load, ~1.15 probes per key.  A reference
+//     key per bucket restores the full key (delta sign-extended in RB bits).  The host picks RB from the plan; when the range
+//     does not fit (small inputs with few level-1 bits) the FULL variant keeps 64-bit keys and separate counts.
+//   * A PRODUCER WARP owns the ring (waits for a stage to be released by all consumer warps, issues the next bulk copy), so the
+//     next bucket's keys stream in during a bucket end; the 512 consumers synchronise on a named barrier.
+#pragma once
+#include "common.cuh"
+#include "count_stream.cuh"
+
+namespace mf {
+
+constexpr int kC2NC = 512;              // consumer threads
+constexpr int kC2NW = kC2NC / 32;       // consumer warps
+constexpr int kC2NT = kC2NC + 32;       // + the producer warp
+constexpr int kC2RelSlotsLog = 13;      // REL: 8192 slots of 8 bytes (key | count)
+constexpr int kC2FullSlotsLog = 12;     // FULL: 4096 keys + 4096 counts
+constexpr int kC2ChunkLog = 11;         // 2048 keys (16 KB) per ring stage
+constexpr int kC2Chunk = 1 << kC2ChunkLog;
+constexpr int kC2StagesRel = 2;         // ring stages (a power of two: the ring is addressed modulo stages * chunk)
+constexpr int kC2StagesFull = 2;
+constexpr int kC2MinCountBits = 17;     // REL needs room for counts up to 65535 and then some
+
+template <bool REL>
+struct C2Cfg {
+  static constexpr int SlotsLog = REL ? kC2RelSlotsLog : kC2FullSlotsLog;
+  static constexpr int Slots = 1 << SlotsLog;
+  static constexpr int Stages = REL ? kC2StagesRel : kC2StagesFull;
+  static constexpr int RingKeys = Stages * kC2Chunk;
+  static constexpr size_t TableBytes = REL ? (size_t)Slots * 8 : (size_t)Slots * 12;
+};
+template <bool REL>
+inline size_t count_stream2_smem_bytes() {
+  using C = C2Cfg<REL>;
+  // table | ring u64 | skeys u64[768] | mbar u64[8] | scnt u32[768] | bnd u32[win+2] | bins u32[260] | small u32[64]
+  // | scratch u32[40] | flag i32[16] | ref u64[2] | permA,permB,rk u16[768]
+  return C::TableBytes + (size_t)C::RingKeys * 8 + (size_t)kCsSolidMax * 8 + 64 + (size_t)kCsSolidMax * 4 + (size_t)(kCsWin + 2) * 4 +
+         260 * 4 + 64 * 4 + 40 * 4 + 16 * 4 + 16 + 3 * (size_t)kCsSolidMax * 2;
+}
+
+__device__ __forceinline__ void c2_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kC2NC) : "memory"); }
+
+// block_excl_scan for the 512 consumers (named barrier 1)
+__device__ __forceinline__ uint32_t c2_excl_scan(uint32_t *s, int n, uint32_t *scratch) {
+  constexpr int NT = kC2NC;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + NT - 1) / NT;
+  const int b = tid * per, e = min(n, b + per);
+  uint32_t sum = 0;
+  for (int i = b; i < e; ++i) sum += s[i];
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  c2_sync();
+  if (warp == 0) {
+    uint32_t v = lane < NT / 32 ? scratch[lane] : 0;
+    uint32_t vi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, vi, o);
+      if (lane >= o) vi += t;
+    }
+    scratch[lane] = vi - v;
+    if (lane == 31) scratch[32] = vi;
+  }
+  c2_sync();
+  uint32_t run = scratch[warp] + inc - sum;
+  for (int i = b; i < e; ++i) {
+    uint32_t v = s[i];
+    s[i] = run;
+    run += v;
+  }
+  uint32_t total = scratch[32];
+  c2_sync();
+  return total;
+}
+
+// key_shift = 64 - 2(k+1) (keys are left-aligned in 64 bits); REL: count_bits = CB, a slot is (rel << CB) | count with rel =
+// the low 64 - CB bits of the right-aligned key; every bucket's key range must span < 2^(63 - CB) (the host guarantees it).
+template <bool REL>
+__global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const int32_t *__restrict__ cta_first, int key_shift, int count_bits) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  using C = C2Cfg<REL>;
+  constexpr int NC = kC2NC, NW = kC2NW, Slots = C::Slots, Stages = C::Stages, RingKeys = C::RingKeys;
+  unsigned long long *tab = reinterpret_cast<unsigned long long *>(smraw);                 // REL: [8192] slots; FULL: [4096] keys
+  uint32_t *tcnt = reinterpret_cast<uint32_t *>(tab + (REL ? 0 : Slots));                  // FULL: [4096] counts
+  unsigned long long *ring = reinterpret_cast<unsigned long long *>(smraw + C::TableBytes);
+  unsigned long long *skeys = ring + RingKeys;
+  unsigned long long *mbar = skeys + kCsSolidMax;                                          // [0..3] full, [4..7] empty
+  uint32_t *scnt = reinterpret_cast<uint32_t *>(mbar + 8);
+  uint32_t *s_bnd = scnt + kCsSolidMax;
+  uint32_t *bins = s_bnd + kCsWin + 2;
+  uint32_t *s_small = bins + 260;
+  uint32_t *scratch = s_small + 64;
+  int *s_flag = reinterpret_cast<int *>(scratch + 40);   // 0 crowded, 1 ok, 2..3 arena base, 4 ns, 5 blk_left, 6..7 blk_pos
+  unsigned long long *s_ref = reinterpret_cast<unsigned long long *>(s_flag + 16);         // [0] reference key of the bucket
+  uint16_t *permA = reinterpret_cast<uint16_t *>(s_ref + 2);
+  uint16_t *permB = permA + kCsSolidMax, *rk = permB + kCsSolidMax;
+  uint32_t *whist32 = reinterpret_cast<uint32_t *>(tab);   // sub-bin counters [1025] of the many-solid-keys sort alias the swept table
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b0 = cta_first[blockIdx.x], b1 = cta_first[blockIdx.x + 1];
+  if (b0 >= b1) return;
+  const int64_t rb = a.bkt_start[b0], re = a.bkt_start[b1 - 1] + a.bkt_size[b1 - 1];
+  const uint32_t total = (uint32_t)(re - rb);
+  if (total == 0u) return;
+  const int64_t A = rb & ~(int64_t)1;                    // bulk copies need 16-byte aligned addresses
+  const int64_t re_up = (re + 1) & ~(int64_t)1;
+  const int nchunks = (int)((re_up - A + kC2Chunk - 1) >> kC2ChunkLog);
+  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(a.in);
+
+  if (tid == 0) {
+    for (int s = 0; s < Stages; ++s) {
+      mbar_init(mbar + s, 1);          // full: the bulk copy's bytes
+      mbar_init(mbar + 4 + s, NW);     // empty: one arrival per consumer warp
+    }
+    mbar_fence_init();
+  }
+  for (int i = tid; i < (int)(C::TableBytes / 8); i += kC2NT) tab[i] = REL ? 0ull : (i < Slots ? kEmptyKey : 0ull);
+  if (tid < 64) s_small[tid] = 0;
+  if (tid < 16) s_flag[tid] = 0;
+  __syncthreads();   // the only CTA-wide barrier: the producer warp leaves after this
+
+  // ---------------------------------------------------------------- producer warp
+  if (warp == NW) {
+    if (lane == 0) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c & (Stages - 1);
+        if (c >= Stages) mbar_wait(mbar + 4 + s, (uint32_t)(((c / Stages) - 1) & 1));
+        const int64_t g0 = A + ((int64_t)c << kC2ChunkLog);
+        const int64_t left = re_up - g0;
+        const uint32_t bytes = (uint32_t)(left < kC2Chunk ? left : kC2Chunk) * 8u;
+        mbar_expect_tx(mbar + s, bytes);
+        bulk_g2s(ring + (size_t)s * kC2Chunk, src + g0, bytes, mbar + s);
+      }
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------- consumers
+  const uint32_t m = (uint32_t)a.min_count;
+  const int We = a.words_edge;
+  const uint32_t off0 = (uint32_t)(rb - A);               // ring / chunk coordinates of relative position q: q + off0
+  const int CB = count_bits;
+  const unsigned long long cmask = REL ? ((1ull << CB) - 1ull) : 0ull;
+  const unsigned lt = lanemask_lt();
+
+  int wb = b0;   // first bucket of the boundary window
+  auto load_window = [&]() {
+    for (int i = tid; i <= kCsWin; i += NC) {
+      const int idx = wb + i;
+      s_bnd[i] = idx < b1 ? (uint32_t)(a.bkt_start[idx] - rb) : total;
+    }
+  };
+  load_window();
+  c2_sync();
+
+  // ---- bucket end: sweep + clear, solid keys -> ordered edge records.  All consumers, after a c2_sync.
+  auto finish_bucket = [&](int slot) {
+    const bool crowded = s_flag[0] != 0;
+    if constexpr (REL) {
+      const unsigned long long ref = s_ref[0] >> key_shift;   // right-aligned reference key
+      const int RB = 64 - CB;
+      for (int h = tid; h < Slots; h += NC) {
+        const unsigned long long s = tab[h];
+        if (s) {
+          tab[h] = 0ull;
+          const uint32_t c = (uint32_t)(s & cmask);
+          if (a.counting && c < 64u) atomicAdd(s_small + c, 1u);
+          if (c >= m) {
+            const int q = atomicAdd(s_flag + 4, 1);
+            if (q < kCsSolidMax) {
+              // full key = ref + (rel - ref) sign-extended in RB bits
+              const long long d = ((long long)(((s >> CB) - ref) << CB)) >> CB;
+              skeys[q] = (unsigned long long)((long long)ref + d) << key_shift;
+              scnt[q] = c;
+            }
+          }
+        }
+      }
+    } else {
+      for (int h = tid; h < Slots; h += NC) {
+        const uint32_t c = tcnt[h];
+        if (c) {
+          const unsigned long long key = tab[h];
+          tab[h] = kEmptyKey;
+          tcnt[h] = 0u;
+          if (a.counting && c < 64u) atomicAdd(s_small + c, 1u);
+          if (c >= m) {
+            const int q = atomicAdd(s_flag + 4, 1);
+            if (q < kCsSolidMax) {
+              skeys[q] = key;
+              scnt[q] = c;
+            }
+          }
+        }
+      }
+    }
+    c2_sync();
+    const int ns_raw = s_flag[4];
+    const bool bail = crowded || ns_raw > kCsSolidMax;
+    const uint32_t ns = bail ? 0u : (uint32_t)ns_raw;
+    if (a.counting) {
+      // multiplicity histogram of the distinct keys (<prefix>.counting): small counts from shared memory, counts >= 64 are
+      // solid keys (the host routes --min-count > 64 with a histogram request to the general kernel).  A bucket that
+      // bails is counted by the path that takes it instead.
+      if (tid < 64) {
+        const uint32_t v = s_small[tid];
+        s_small[tid] = 0;
+        if (v && !bail) atomicAdd(a.counting + tid, (unsigned long long)v);
+      }
+      for (uint32_t q = tid; q < ns; q += NC) {
+        const uint32_t c = scnt[q];
+        if (c >= 64u) atomicAdd(a.counting + (c > (uint32_t)kMaxMul ? (uint32_t)kMaxMul : c), 1ull);
+      }
+    }
+    if (tid == 0) {
+      if (bail) {
+        const int p = atomicAdd(a.bail_count, 1);
+        a.bail_list[p] = slot;
+        s_flag[1] = 0;
+      } else if (ns > 0) {
+        unsigned long long pos = ((unsigned long long)(uint32_t)s_flag[7] << 32) | (uint32_t)s_flag[6];
+        int left = s_flag[5];
+        if ((int)ns > left) {   // next arena block (what is left of the old one is abandoned)
+          pos = atomicAdd(a.arena_cursor, (unsigned long long)kCsArenaBlock);
+          left = kCsArenaBlock;
+        }
+        const int ok = pos + ns <= a.arena_cap;
+        if (!ok) atomicExch(a.overflow_flag, 1);
+        a.desc_off[slot] = (int64_t)pos;
+        a.desc_cnt[slot] = ok ? (int64_t)ns : 0;
+        s_flag[1] = ok;
+        s_flag[2] = (int)(uint32_t)pos;
+        s_flag[3] = (int)(uint32_t)(pos >> 32);
+        pos += ns;
+        left -= (int)ns;
+        s_flag[5] = left;
+        s_flag[6] = (int)(uint32_t)pos;
+        s_flag[7] = (int)(uint32_t)(pos >> 32);
+      } else {
+        s_flag[1] = 0;
+      }
+    }
+    if (ns > 1 && ns <= (uint32_t)kCsPairsMax)
+      for (uint32_t q = tid; q < ns; q += NC) bins[q] = 0;
+    c2_sync();
+    if (s_flag[1]) {
+      const uint16_t *cur = nullptr;
+      if (ns > 1 && ns <= (uint32_t)kCsPairsMax) {
+        // keys are distinct: rank = number of smaller keys; the comparisons of one key are split over NC / nsp threads
+        uint32_t nsp = 32;
+        while (nsp < ns) nsp <<= 1;
+        const uint32_t parts = NC / nsp, q = tid & (nsp - 1), part = tid / nsp;
+        if (q < ns) {
+          const uint32_t per = (ns + parts - 1) / parts;
+          const uint32_t o0 = part * per, o1 = min(ns, o0 + per);
+          const unsigned long long kq = skeys[q];
+          uint32_t r = 0;
+          for (uint32_t o = o0; o < o1; ++o) r += skeys[o] < kq;
+          if (r) atomicAdd(bins + q, r);
+        }
+        c2_sync();
+        for (uint32_t q2 = tid; q2 < ns; q2 += NC) permA[bins[q2]] = (uint16_t)q2;
+        c2_sync();
+        cur = permA;
+      } else if (ns > (uint32_t)kCsPairsMax) {
+        // many solid keys (moderate coverage): one counting split on the 10 bits below the keys' common range, then a rank
+        // fix inside each sub-bin (the keys are distinct and spread evenly, so sub-bins hold about one key)
+        unsigned long long *s_mm = reinterpret_cast<unsigned long long *>(scratch);   // [0] min, [1] max (8-byte aligned)
+        if (tid == 0) { s_mm[0] = ~0ull; s_mm[1] = 0ull; }
+        for (int i = tid; i <= 1024; i += NC) whist32[i] = 0u;
+        c2_sync();
+        {
+          unsigned long long mn = ~0ull, mx = 0ull;
+          for (uint32_t q = tid; q < ns; q += NC) { const unsigned long long kq = skeys[q]; mn = min(mn, kq); mx = max(mx, kq); }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          }
+          if (lane == 0) { atomicMin(s_mm, mn); atomicMax(s_mm + 1, mx); }
+        }
+        c2_sync();
+        const unsigned long long kmin = s_mm[0];
+        const int span_bits = 64 - __clzll((long long)((s_mm[1] - kmin) | 1ull));
+        const int sh = span_bits > 10 ? span_bits - 10 : 0;
+        for (uint32_t q = tid; q < ns; q += NC) rk[q] = (uint16_t)atomicAdd(whist32 + (uint32_t)((skeys[q] - kmin) >> sh), 1u);
+        c2_sync();
+        c2_excl_scan(whist32, 1025, scratch);
+        for (uint32_t q = tid; q < ns; q += NC) permB[whist32[(uint32_t)((skeys[q] - kmin) >> sh)] + rk[q]] = (uint16_t)q;
+        c2_sync();
+        for (uint32_t p2 = tid; p2 < ns; p2 += NC) {
+          const uint32_t q = permB[p2];
+          const unsigned long long kq = skeys[q];
+          const uint32_t d = (uint32_t)((kq - kmin) >> sh);
+          const uint32_t b2 = whist32[d], e2 = whist32[d + 1];
+          uint32_t r = 0;
+          for (uint32_t o = b2; o < e2; ++o) r += skeys[permB[o]] < kq;
+          permA[b2 + r] = (uint16_t)q;
+        }
+        c2_sync();
+        for (int i = tid; i <= 1024; i += NC) whist32[i] = REL ? 0u : 0xffffffffu;   // give the table back clean
+        cur = permA;
+      }
+      const unsigned long long base = ((unsigned long long)(uint32_t)s_flag[3] << 32) | (uint32_t)s_flag[2];
+      for (uint32_t q = tid; q < ns; q += NC) {
+        const uint32_t e = cur ? cur[q] : q;
+        const unsigned long long key = skeys[e];
+        const uint32_t kw[2] = {(uint32_t)(key >> 32), (uint32_t)key};
+        write_edge<2>(a.arena + (base + q) * (unsigned long long)We, kw, We, scnt[e]);
+      }
+    }
+    c2_sync();
+    if (tid == 0) {
+      s_flag[0] = 0;
+      s_flag[4] = 0;
+    }
+    // the barrier the caller issues next publishes the reset
+  };
+
+  // ---- consumer loop
+  int cur_b = b0;
+  uint32_t p = 0, bend = 0;      // [p, bend) = relative key range of bucket cur_b
+  auto advance = [&]() {         // first bucket at or after cur_b that ends beyond p (all consumers, uniform)
+    while (cur_b < b1) {
+      if (cur_b + 1 - wb > kCsWin) {
+        c2_sync();
+        wb = cur_b;
+        load_window();
+        c2_sync();
+      }
+      bend = s_bnd[cur_b + 1 - wb];
+      if (bend > p) break;
+      ++cur_b;
+    }
+  };
+  advance();
+  int c_ready = 0;   // chunks [0, c_ready) are known to have landed (warp-uniform)
+  int c_rel = 0;     // chunks [0, c_rel) have been released by this warp
+  auto need_chunk = [&](int c) {   // warp-uniform
+    while (c_ready <= c) {
+      mbar_wait(mbar + (c_ready & (Stages - 1)), (uint32_t)((c_ready / Stages) & 1));
+      ++c_ready;
+    }
+  };
+  auto release_below = [&](int c) {   // this warp never reads chunks < c again
+    while (c_rel < c) {
+      need_chunk(c_rel);              // a stage is only handed back after its copy has landed (phase order of the barriers)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mbar + 4 + (c_rel & (Stages - 1)));
+      ++c_rel;
+    }
+  };
+
+  while (cur_b < b1) {
+    // warp w takes the 32-key groups w, w + NW, ... of the bucket; t = next warp-local key index to hand out
+    const uint32_t blen = bend - p;
+    // REL: a count must stay inside its CB-bit field, so a bucket with 2^CB or more keys is not taken here at all
+    // (nor one of 2^30 keys or more: the position arithmetic below is 32-bit); it goes to the bail list
+    const bool skip = blen >= (1u << 30) || (REL && CB < 32 && blen >= (1u << CB));
+    if (skip && tid == 0) s_flag[0] = 1;
+    bool exhausted = skip;   // warp-uniform: every key of the bucket that belongs to this warp has been handed out
+    uint32_t t = 0;
+    bool have = false;
+    unsigned long long key = 0;
+    uint32_t h = 0;
+    int probe = 0;
+    auto pos_of = [&](uint32_t tt) -> uint32_t { return (((tt >> 5) * NW + (uint32_t)warp) << 5) + (tt & 31u); };   // offset in the bucket
+    for (;;) {
+      const unsigned need = __ballot_sync(0xffffffffu, !have);
+      if (need && !exhausted && pos_of(t) >= blen) exhausted = true;
+      if (need && !exhausted) {
+        const uint32_t nn = (uint32_t)__popc(need);
+        const uint32_t o_mine = pos_of(t + (uint32_t)__popc(need & lt));
+        const uint32_t o_last = min(pos_of(t + nn - 1u), blen - 1u);
+        need_chunk((int)((p + o_last + off0) >> kC2ChunkLog));
+        if (!have && o_mine < blen) {
+          const uint32_t q = p + o_mine + off0;
+          key = ring[q & (uint32_t)(RingKeys - 1)];
+          have = true;
+          probe = 0;
+          if (o_mine == 0u) s_ref[0] = key;   // the bucket's first key is its reference (REL)
+          if constexpr (REL) {
+            const uint32_t v = (uint32_t)(key >> key_shift);
+            h = (v * 0x9E3779B1u) >> (32 - C::SlotsLog);
+          } else {
+            const uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
+            h = (x * 0x85EBCA6Bu) >> (32 - C::SlotsLog);
+          }
+        }
+        t += nn;
+        // chunks below the warp's next key (or the bucket end) are done with for this warp
+        release_below((int)((p + min(pos_of(t), blen) + off0) >> kC2ChunkLog));
+      }
+      if (!__any_sync(0xffffffffu, have)) break;
+      if (have) {
+        if constexpr (REL) {
+          const unsigned long long v = (key >> key_shift) & (~0ull >> CB);
+          unsigned long long s = *reinterpret_cast<volatile unsigned long long *>(tab + h);
+          if (s == 0ull) s = atomicCAS(tab + h, 0ull, (v << CB) | 1ull);
+          if (s == 0ull) {
+            have = false;                                          // claimed, count = 1
+          } else if ((s >> CB) == v) {
+            atomicAdd(reinterpret_cast<uint32_t *>(tab + h), 1u);   // the count is the low word (CB <= 32 bits of it)
+            have = false;
+          } else {
+            h = (h + 1) & (Slots - 1);
+            if (++probe >= kCsProbeLimit) { s_flag[0] = 1; have = false; }   // table too crowded: the bucket bails
+          }
+        } else {
+          unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tab + h);
+          if (cur == kEmptyKey) cur = atomicCAS(tab + h, kEmptyKey, key);
+          if (cur == kEmptyKey || cur == key) {
+            atomicAdd(tcnt + h, 1u);
+            have = false;
+          } else {
+            h = (h + 1) & (Slots - 1);
+            if (++probe >= kCsProbeLimit) { s_flag[0] = 1; have = false; }
+          }
+        }
+      }
+    }
+    // whatever this warp handed out (or skipped) of the bucket is fetched: chunks below the next bucket's first key may go
+    release_below((int)((bend + off0) >> kC2ChunkLog));
+    p = bend;
+    c2_sync();
+    finish_bucket(cur_b);
+    ++cur_b;
+    advance();
+    c2_sync();
+  }
+  release_below(nchunks);
+}
+
+}  // namespace mf

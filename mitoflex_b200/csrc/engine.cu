@@ -24,6 +24,7 @@
 #include "partition.cuh"
 #include "reads.cuh"
 #include "count_stream.cuh"
+#include "count_stream2.cuh"
 #include "count_stream_w.cuh"
 #include "sdbg_local.cuh"
 
@@ -724,11 +725,12 @@ static double probe_distinct_ratio(Ctx &c, const uint32_t *keys, const HostChunk
 // segment is cut into its own number of equal key ranges.  *bit_off keeps the bits ALL keys of a bucket share.
 template <int W, class Alloc>
 static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, const HostChunks &l1, int *bit_off, int key_bits,
-                                   int min_count, double *rho_out, Alloc &&alloc) {
+                                   int min_count, double *rho_out, int *rel_count_bits, Alloc &&alloc) {
   const double rho = probe_distinct_ratio<W>(c, *cur, l1, *bit_off, key_bits);
   *rho_out = rho;
   const double load = env_int("MFSDBG_STREAM_LOAD_PCT", W == 2 ? 45 : 35) / 100.0;
   double B = std::min(60000.0, std::max(1024.0, load * kCsSlots / rho));
+  *rel_count_bits = 0;
   // --min-count 1 makes every distinct key a solid one: keep them under the per-bucket limit of the streamed kernel
   const int solid_max = W == 2 ? kCsSolidMax : (W == 3 ? 768 : 512);
   if (min_count <= 1 && load <= 1.0) B = std::min(B, std::max(512.0, 0.7 * solid_max / rho));
@@ -747,10 +749,28 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
     // multi-pass kernel): cheaper than a whole extra partition level
     // (2-word keys only: wider keys have no multi-pass kernel, their crowded buckets fall to the slow general path)
     if (max_need <= nb_cap + (W == 2 ? nb_cap / 2 : 0) || xbits < 16) {
+      // 2-word keys: can a slot of the streamed kernel hold "low RB bits of the key | CB-bit count" (k_count_stream2<REL>)?  The
+      // keys of a bucket span at most 2^(key_bits - bit_off) / nb of the key space; RB must cover twice that, CB >= 17.
+      int64_t nb_min = 1;
+      if (W == 2 && env_int("MFSDBG_COUNT_REL", 1) != 0) {
+        const int rest = key_bits - *bit_off;                       // bits the keys of a segment may differ in
+        const int over = rest - (63 - kC2MinCountBits);             // > 0: the segment must be cut into >= 2^over ranges
+        int64_t tot = 0;
+        for (int64_t v : seg_total) tot += v;
+        const double avg_need = (double)tot / ((double)std::max(hc.nseg, 1) * B);
+        if (over <= 0) {
+          *rel_count_bits = 64 - (rest + 1);
+        } else if (over <= 10 && xbits == 16 && ((int64_t)1 << over) <= nb_cap &&
+                   (avg_need >= (double)((int64_t)1 << over) * 0.5 || env_int("MFSDBG_COUNT_REL", 1) == 2)) {
+          nb_min = (int64_t)1 << over;
+          *rel_count_bits = kC2MinCountBits;
+        }
+        *rel_count_bits = std::min(*rel_count_bits, 32);
+      }
       std::vector<uint16_t> nb(hc.nseg);
       int mx = 1;
       for (int s2 = 0; s2 < hc.nseg; ++s2) {
-        nb[s2] = (uint16_t)std::max<int64_t>(1, std::min<int64_t>(nb_cap, (int64_t)std::ceil((double)seg_total[s2] / B)));
+        nb[s2] = (uint16_t)std::max<int64_t>(nb_min, std::min<int64_t>(nb_cap, (int64_t)std::ceil((double)seg_total[s2] / B)));
         mx = std::max<int>(mx, nb[s2]);
       }
       const int nbits = std::max(1, ceil_log2((double)mx));
@@ -777,12 +797,20 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
   }
 }
 
-static void launch_count_stream(Ctx &c, const LocalArgs &a, int nslots, int64_t n_keys, int grid, int32_t *d_cta_first) {
+// rel_count_bits > 0: slots hold "key low bits | count" (stream_partition guarantees the buckets' key ranges fit)
+static void launch_count_stream(Ctx &c, const LocalArgs &a, int nslots, int64_t n_keys, int grid, int32_t *d_cta_first, int key_bits,
+                                int rel_count_bits) {
   k_split_ranges<<<div_ceil(grid + 1, 128), 128, 0, c.stream>>>(a.bkt_start, a.bkt_size, nslots, grid, d_cta_first);
   MF_LAUNCH_CHECK();
-  const size_t smem = count_stream_smem_bytes();
-  set_smem(k_count_stream<false>, smem);
-  k_count_stream<false><<<grid, kCsNT, smem, c.stream>>>(a, d_cta_first, 0);
+  if (rel_count_bits > 0) {
+    const size_t smem = count_stream2_smem_bytes<true>();
+    set_smem(k_count_stream2<true>, smem);
+    k_count_stream2<true><<<grid, kC2NT, smem, c.stream>>>(a, d_cta_first, 64 - key_bits, rel_count_bits);
+  } else {
+    const size_t smem = count_stream2_smem_bytes<false>();
+    set_smem(k_count_stream2<false>, smem);
+    k_count_stream2<false><<<grid, kC2NT, smem, c.stream>>>(a, d_cta_first, 64 - key_bits, 0);
+  }
   MF_LAUNCH_CHECK();
   c.launches += 2;
 }
@@ -812,8 +840,9 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
   const bool stream = W >= 2 && env_int(W == 2 ? "MFSDBG_COUNT_STREAM" : "MFSDBG_COUNT_STREAM_W", 1) != 0 && !(d_counting && min_count > 64);
   DevBuckets b;
   double rho = 0.0;   // distinct / occurrences, when the streamed path measured it
+  int rel_count_bits = 0;
   if constexpr (W >= 2) {
-    if (stream) b = stream_partition<W>(c, &cur, &other, l1, &bit_off, key_bits, min_count, &rho, salloc);
+    if (stream) b = stream_partition<W>(c, &cur, &other, l1, &bit_off, key_bits, min_count, &rho, &rel_count_bits, salloc);
   }
   if (!stream) b = partition_chain<W>(c, &cur, &other, l1, &bit_off, p.rest_bits, salloc, "count_l2");
   const int stream_grid = stream ? (int)std::max<int64_t>(1, std::min<int64_t>(2 * c.sm_count, n / 16384)) : 0;
@@ -864,7 +893,7 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
       // keys of <= 64 bits: stream every bucket through the key-resident hash table (any bucket size)
       {
         Stage st(c, "local_count");
-        if (stream) launch_count_stream(c, a, b.nslots, n, stream_grid, d_cta_first);
+        if (stream) launch_count_stream(c, a, b.nslots, n, stream_grid, d_cta_first, key_bits, rel_count_bits);
         else launch_count_fast<W>(c, a, b.nslots);
       }
       c.d2h(flags, d_flags, sizeof(int) * 3);

@@ -203,7 +203,8 @@ static HostEdges read_edges(const std::string &prefix) {
   expect_field(is, "is_sorted", &sorted);
   // a mismatched or corrupt meta file must end in a clean EIO, not in a wrong stride on the device or a huge allocation
   if (k < 1 || k > 255 || words != words_edge((int)k)) throw IoError("edges.info: words_per_edge does not belong to kmer_size");
-  if (nbuckets != kNumBuckets) throw IoError("edges.info: num_buckets must be 65536");
+  if (sorted ? nbuckets != kNumBuckets : (nbuckets < 0 || nbuckets > kNumBuckets))   // unsorted (iterate) files carry no bucket table
+    throw IoError("edges.info: num_buckets must be 65536 for sorted edges");
   if (nfiles < 1 || nfiles > 65536 || nedges < 0 || nedges > ((long long)1 << 40)) throw IoError("edges.info: implausible num_files / num_edges");
   HostEdges e;
   e.k = (int)k; e.words = (int)words; e.sorted = sorted != 0; e.n = nedges;

@@ -362,3 +362,28 @@ def test_synth_port_matches_device(ctx):
         idx = np.nonzero(same_len)[0][:5000]
         ok = sum(np.array_equal(nb[ns[i]:ns[i + 1]], gb[gs[i]:gs[i + 1]]) for i in idx)
         assert ok > 0.999 * len(idx)
+
+
+@pytest.mark.parametrize("k,env", [(21, {}), (21, {"MFSDBG_COUNT_REL": "0"}), (23, {}), (24, {}), (31, {}),
+                                   (31, {"MFSDBG_COUNT_REL": "2", "MFSDBG_L1_BITS": "11"}),
+                                   (29, {"MFSDBG_COUNT_REL": "2", "MFSDBG_L1_BITS": "10"}),
+                                   (21, {"MFSDBG_L1_BITS": "3"})])
+def test_count_stream2_slot_layouts(ctx, oracle, monkeypatch, k, env):
+    """k_count_stream2: slots that hold "key low bits | count" (REL, chosen from the plan), the full-key variant
+    (MFSDBG_COUNT_REL=0 / few level-1 bits), and REL with a forced minimum number of level-2 ranges per segment (k >= 24 at full
+    size; forced here with MFSDBG_COUNT_REL=2).  Deep coverage plus skew: 3000 copies of a read, a low-complexity family."""
+    for name, v in env.items():
+        monkeypatch.setenv(name, v)
+    bases, starts = make_reads(8800 + k, 40000, k, genome_len=60000, max_len=150, err=0.01, dup_boost=3000)
+    rng = np.random.default_rng(k)
+    stem = rng.integers(0, 4, k + 20, dtype=np.uint8)
+    extra = [np.concatenate([stem, rng.integers(0, 4, 40, dtype=np.uint8)]) for _ in range(3000)] + [np.zeros(150, np.uint8)] * 50
+    seqs = [bases[starts[i]:starts[i + 1]] for i in range(len(starts) - 1)] + extra
+    starts2 = np.zeros(len(seqs) + 1, np.int64)
+    starts2[1:] = np.cumsum([len(s) for s in seqs])
+    bases2 = np.concatenate(seqs).astype(np.uint8)
+    for m in (1, 2):
+        e_gpu = ctx.count(ctx.upload_reads(bases2, starts2), k, m, want_counting=True)
+        e_orc = oracle.count(_orc_reads(oracle, bases2, starts2), k, m, threads=8)
+        assert_edges_equal(e_gpu, e_orc)
+        assert np.array_equal(e_gpu.counting, e_orc.counting)
