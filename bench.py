@@ -116,8 +116,10 @@ def stage_bytes(n_bases, n_keys, n_edges, n_items_gen, k):
         "count_l2a_hist": n_keys * W,
         "count_l2a_scatter": 2 * n_keys * W,
         "local_count": n_keys * W + n_edges * We,
-        # filtered generator: edges read twice (k-mer set build, lookup), 4 random 8-byte table accesses per edge, items out
-        "items": 2 * n_edges * We + 32 * n_edges + n_items_gen * Wi,
+        # item filter (kmerset.cuh): two passes over the edges, 4 k-mer records per edge written once and read once
+        "items_filter": 2 * n_edges * We + 2 * 4 * n_edges * (8 if k <= 31 else 16),
+        # generator: edges in, items out
+        "items": n_edges * We + n_items_gen * Wi,
         "records_hist": n_items_gen * Wi,
         "records_scatter": 2 * n_items_gen * Wi,
         "local_sdbg": n_items_gen * Wi,

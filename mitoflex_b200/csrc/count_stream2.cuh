@@ -177,7 +177,6 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
     const bool crowded = s_flag[0] != 0;
     if constexpr (REL) {
       const unsigned long long ref = s_ref[0] >> key_shift;   // right-aligned reference key
-      const int RB = 64 - CB;
       for (int h = tid; h < Slots; h += NC) {
         const unsigned long long s = tab[h];
         if (s) {
@@ -394,7 +393,9 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
         need_chunk((int)((p + o_last + off0) >> kC2ChunkLog));
         if (!have && o_mine < blen) {
           const uint32_t q = p + o_mine + off0;
-          key = ring[q & (uint32_t)(RingKeys - 1)];
+          // records are two big-endian u32 words: word 0 (the key's high half) is the low half of the 8-byte load
+          const unsigned long long raw = ring[q & (uint32_t)(RingKeys - 1)];
+          key = (raw << 32) | (raw >> 32);
           have = true;
           probe = 0;
           if (o_mine == 0u) s_ref[0] = key;   // the bucket's first key is its reference (REL)

@@ -10,7 +10,7 @@
 //   P4 k_count_stream / k_count_stream_w  persistent CTAs, bulk-copy ring, shared hash table, solid keys -> edge records;
 //      k_count (local.cuh) for what bails and for 32-bit keys
 //   P5 k_gather_edges                 compact per-bucket edge runs into the globally sorted edge array
-// seq2sdbg (SeqToSdbg): k_kmer_set_insert + k_items_from_edges_filtered (k <= 31) / k_items_from_edges, k_items_from_seqs
+// seq2sdbg (SeqToSdbg): item filter k_ks_* + k_items_real / k_items_miss (kmerset.cuh, k <= 63) / k_items_from_edges, k_items_from_seqs
 //   (items.cuh), the same partition levels over item words, k_sdbg_local (sdbg_local.cuh; k_local<kSdbgEmit> for crowded
 //   buckets) -> k_gather_edges.
 #include "engine.cuh"
@@ -25,6 +25,7 @@
 #include "reads.cuh"
 #include "count_stream.cuh"
 #include "count_stream2.cuh"
+#include "kmerset.cuh"
 #include "count_stream_w.cuh"
 #include "sdbg_local.cuh"
 
@@ -83,6 +84,7 @@ Ctx::~Ctx() {
                     &in_words, &in_starts})
     b->release();
   for (DevBuf &b : ov) b.release();
+  miss.release();
   for (DevBuf &b : small) b.release();
   for (DevBuf &b : fb) b.release();
   out_rec.release();
@@ -1580,82 +1582,139 @@ void dev_count_finish(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys,
 }
 
 // ------------------------------------------------------------------ seq2sdbg
-// Returns the number of items written.  filter: drop the dummy items Lv2Postprocess would drop anyway (needs the WHOLE edge
-// set in `edges`, so the multi-GPU driver, whose ranks hold key ranges, passes false).
-template <int WI>
-static int64_t sdbg_make_items(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, uint32_t *items, bool filter) {
+// ---- the item filter (kmerset.cuh): the k-mers whose "$" dummies reach the graph
+// Where the items of an input come from: every sequence of `seqs` yields all its items; the edges yield either all 6 per
+// edge (unfiltered: k > 63, the multi-GPU driver whose ranks hold key ranges, or no room for the set) or their 2 real items
+// plus 2 dummies per k-mer of the miss list.
+struct ItemSource {
+  const uint32_t *edges = nullptr;
+  int64_t n_edges = 0;
+  SeqsView seqs;
+  bool filtered = false;
+  const void *miss = nullptr;   // k-mers (8 bytes for k <= 31, 16 for k <= 63)
+  int64_t n_miss = 0;
+  int64_t n_items() const { return (filtered ? 2 * n_edges + 2 * n_miss : 6 * n_edges) + seqs.n_items; }
+};
+static KsGeom ks_geometry(int64_t n_edges) {
+  KsGeom g;
+  g.log_slots = std::max(10, ceil_log2(3.0 * (double)std::max<int64_t>(n_edges, 1)));   // >= 1.5 x the 2E entries
+  g.slice_log = std::min(g.log_slots, std::max(kKsSliceLog, g.log_slots - 10));         // at most 1024 slices
+  g.nslices = 1 << (g.log_slots - g.slice_log);
+  return g;
+}
+static size_t ks_bytes(int64_t n_edges, int k) {   // records + table + small tables
+  const size_t kb = k <= 31 ? 8 : 16;
+  return (size_t)4 * n_edges * kb + ((size_t)kb << ks_geometry(n_edges).log_slots) + (1 << 20);
+}
+// Runs the filter on the slab (reset by the caller); the miss list is copied into c.miss so that it survives the slab.
+template <int KW>
+static void sdbg_filter(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, ItemSource *src) {
+  using Slot = typename KsKey<KW>::Slot;
   const int WK = words_key(k), WE = words_edge(k);
-  Stage st(c, "items");
-  int64_t n_edge_items = 6 * n_edges;
-  if (n_edges > 0) {
-    const unsigned grid = (unsigned)div_ceil64(n_edges, 128);
-    // (WK, WE, WI) is one of (w,w,w), (w-1,w-1,w), (w-1,w,w) with w = WI >= 2
-    if constexpr (WI >= 2) {
-      if (filter && k <= 31 && WK <= 2 && WI <= 3 && n_edges < ((int64_t)1 << 29)) {
-        if constexpr (WI <= 3) {
-          const int log_slots = std::max(10, std::min(31, ceil_log2(4.0 * (double)n_edges)));
-          const size_t slots = (size_t)1 << log_slots;
-          unsigned long long *d_table = c.alloc<unsigned long long>(slots + 1);
-          unsigned long long *d_cur = d_table + slots;
-          MF_CUDA(cudaMemsetAsync(d_table, 0xff, sizeof(unsigned long long) * slots, c.stream));
-          MF_CUDA(cudaMemsetAsync(d_cur, 0, sizeof(unsigned long long), c.stream));
-          // (WK, WE) for k <= 31: k <= 15 -> (1, 2 or 1); 16..23 -> (2, 2); 24..31 -> (2, 3)
-          auto run = [&](auto wk, auto we) {
-            constexpr int K_ = decltype(wk)::value, E_ = decltype(we)::value;
-            k_kmer_set_insert<K_, E_><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, d_table, log_slots);
-            k_items_from_edges_filtered<K_, E_, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, d_table, log_slots, items, d_cur);
-          };
-          if (WK == 1 && WE == 1) run(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{});
-          else if (WK == 1) run(std::integral_constant<int, 1>{}, std::integral_constant<int, 2>{});
-          else if (WE == 2) run(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{});
-          else run(std::integral_constant<int, 2>{}, std::integral_constant<int, 3>{});
-          MF_LAUNCH_CHECK();
-          c.launches += 2;
-          unsigned long long got = 0;
-          c.d2h(&got, d_cur, sizeof got);
-          n_edge_items = (int64_t)got;
+  const KsGeom g = ks_geometry(n_edges);
+  const int nbins = 2 * g.nslices;
+  Stage st(c, "items_filter");
+  Slot *rec = c.alloc<Slot>((size_t)4 * n_edges);
+  Slot *table = c.alloc<Slot>((size_t)1 << g.log_slots);
+  unsigned long long *hist = c.alloc<unsigned long long>(nbins), *cursor = c.alloc<unsigned long long>(nbins + 1);
+  MF_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * nbins, c.stream));
+  MF_CUDA(cudaMemsetAsync(cursor + nbins, 0, sizeof(unsigned long long), c.stream));
+  MF_CUDA(cudaMemsetAsync(table, 0xff, sizeof(Slot) << g.log_slots, c.stream));
+  const unsigned hgrid = (unsigned)std::min<int64_t>(div_ceil64(n_edges, kKsNT), (int64_t)c.sm_count * 4);
+  k_ks_hist<KW><<<hgrid, kKsNT, sizeof(uint32_t) * nbins, c.stream>>>(edges, n_edges, WK, WE, k, g, hist);
+  k_excl_scan_u64_small<<<1, 1024, 0, c.stream>>>(hist, nbins, cursor);
+  using SC = KsScatterCfg<KW>;
+  const unsigned sgrid = (unsigned)div_ceil64(n_edges, kKsNT * SC::EPT);
+  const size_t ssm = ks_scatter_smem_bytes<KW>(nbins);
+  if (nbins <= kKsNT) {
+    set_smem(k_ks_scatter<KW, 1>, ssm);
+    k_ks_scatter<KW, 1><<<sgrid, kKsNT, ssm, c.stream>>>(edges, n_edges, WK, WE, k, g, cursor, rec);
+  } else {
+    set_smem(k_ks_scatter<KW, 4>, ssm);
+    k_ks_scatter<KW, 4><<<sgrid, kKsNT, ssm, c.stream>>>(edges, n_edges, WK, WE, k, g, cursor, rec);
+  }
+  // inserts are the first 2E records, queries the last 2E, both in slice order; the misses overwrite the (dead) inserts
+  const unsigned wgrid = (unsigned)std::min<int64_t>(div_ceil64(2 * n_edges, 256), (int64_t)c.sm_count * 8);
+  k_ks_insert<KW><<<wgrid, 256, 0, c.stream>>>(rec, 2 * n_edges, g, table);
+  k_ks_query<KW><<<wgrid, 256, 0, c.stream>>>(rec + 2 * n_edges, 2 * n_edges, g, table, rec, cursor + nbins);
+  MF_LAUNCH_CHECK();
+  c.launches += 5;
+  unsigned long long n_miss = 0;
+  c.d2h(&n_miss, cursor + nbins, sizeof n_miss);
+  c.miss.reserve((size_t)n_miss * sizeof(Slot) + 256);
+  if (n_miss) MF_CUDA(cudaMemcpyAsync(c.miss.p, rec, (size_t)n_miss * sizeof(Slot), cudaMemcpyDeviceToDevice, c.stream));
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  src->filtered = true;
+  src->miss = c.miss.p;
+  src->n_miss = (int64_t)n_miss;
+}
+
+// MODE 0: all items of `src` into items[0 .. n_items) (returns the count); MODE 1: per-bin counts of the items' top bin_bits
+// bits into hist; MODE 2: the items whose bin lies in [lo, hi) appended at *cursor.
+template <int WI, int MODE>
+static int64_t sdbg_generate(Ctx &c, const ItemSource &src, int k, uint32_t *items, int bin_bits, uint32_t lo, uint32_t hi,
+                             unsigned long long *cursor, unsigned long long *hist) {
+  if constexpr (WI >= 2) {
+    const int WK = words_key(k), WE = words_edge(k);
+    const size_t smem = MODE == 1 ? sizeof(uint32_t) << bin_bits : 0;
+    const int64_t n_edges = src.n_edges;
+    int64_t written = 0;
+    // (WK, WE, WI) is one of (w,w,w), (w-1,w-1,w), (w-1,w,w) with w = WI
+    if (n_edges > 0 && src.filtered) {
+      const unsigned grid = (unsigned)std::min<int64_t>(div_ceil64(n_edges, kRangedNT), (int64_t)c.sm_count * 16);
+      if (WK == WI) k_items_real<WI, WI, WI, MODE><<<grid, kRangedNT, smem, c.stream>>>(src.edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
+      else if (WE == WK) k_items_real<WI - 1, WI - 1, WI, MODE><<<grid, kRangedNT, smem, c.stream>>>(src.edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
+      else k_items_real<WI - 1, WI, WI, MODE><<<grid, kRangedNT, smem, c.stream>>>(src.edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
+      c.launches++;
+      written = 2 * n_edges;
+      if (src.n_miss > 0) {
+        const unsigned mgrid = (unsigned)std::min<int64_t>(div_ceil64(src.n_miss, kRangedNT), (int64_t)c.sm_count * 16);
+        uint32_t *dst = MODE == 0 ? items + (size_t)written * WI : items;
+        if (k <= 31) {
+          k_items_miss<1, WI, MODE><<<mgrid, kRangedNT, smem, c.stream>>>(reinterpret_cast<const unsigned long long *>(src.miss), src.n_miss, k,
+                                                                         bin_bits, lo, hi, dst, cursor, hist);
+        } else {
+          if constexpr (WI >= 3)
+            k_items_miss<2, WI, MODE><<<mgrid, kRangedNT, smem, c.stream>>>(reinterpret_cast<const unsigned __int128 *>(src.miss), src.n_miss,
+                                                                           k, bin_bits, lo, hi, dst, cursor, hist);
         }
-      } else if (filter && k >= 32 && k <= 63 && WI >= 3 && WI <= 5 && n_edges < ((int64_t)1 << 29)) {
-        // 32 <= k <= 63: the same filter with 16-byte slots (128-bit CAS)
-        if constexpr (WI >= 3 && WI <= 5) {
-          const int log_slots = std::max(10, std::min(31, ceil_log2(4.0 * (double)n_edges)));
-          const size_t slots = (size_t)1 << log_slots;
-          unsigned __int128 *d_table = c.alloc<unsigned __int128>(slots + 1);
-          unsigned long long *d_cur = reinterpret_cast<unsigned long long *>(d_table + slots);
-          MF_CUDA(cudaMemsetAsync(d_table, 0xff, sizeof(unsigned __int128) * slots, c.stream));
-          MF_CUDA(cudaMemsetAsync(d_cur, 0, sizeof(unsigned long long), c.stream));
-          auto run = [&](auto wk, auto we) {
-            constexpr int K_ = decltype(wk)::value, E_ = decltype(we)::value;
-            k_kmer_set_insert128<K_, E_><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, d_table, log_slots);
-            k_items_from_edges_filtered128<K_, E_, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, d_table, log_slots, items, d_cur);
-          };
-          // (WK, WE): k 32..39 -> (3, 3); 40..47 -> (3, 4); 48..55 -> (4, 4); 56..63 -> (4, 5)
-          if (WK == 3 && WE == 3) run(std::integral_constant<int, 3>{}, std::integral_constant<int, 3>{});
-          else if (WK == 3) run(std::integral_constant<int, 3>{}, std::integral_constant<int, 4>{});
-          else if (WE == 4) run(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
-          else run(std::integral_constant<int, 4>{}, std::integral_constant<int, 5>{});
-          MF_LAUNCH_CHECK();
-          c.launches += 2;
-          unsigned long long got = 0;
-          c.d2h(&got, d_cur, sizeof got);
-          n_edge_items = (int64_t)got;
-        }
-      } else {
-        if (WK == WI) k_items_from_edges<WI, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
-        else if (WE == WK) k_items_from_edges<WI - 1, WI - 1, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
-        else k_items_from_edges<WI - 1, WI, WI><<<grid, 128, 0, c.stream>>>(edges, n_edges, k, items);
-        MF_LAUNCH_CHECK();
         c.launches++;
+        written += 2 * src.n_miss;
       }
+    } else if (n_edges > 0) {
+      if constexpr (MODE == 0) {
+        const unsigned grid = (unsigned)div_ceil64(n_edges, 128);
+        if (WK == WI) k_items_from_edges<WI, WI, WI><<<grid, 128, 0, c.stream>>>(src.edges, n_edges, k, items);
+        else if (WE == WK) k_items_from_edges<WI - 1, WI - 1, WI><<<grid, 128, 0, c.stream>>>(src.edges, n_edges, k, items);
+        else k_items_from_edges<WI - 1, WI, WI><<<grid, 128, 0, c.stream>>>(src.edges, n_edges, k, items);
+      } else {
+        const unsigned grid = (unsigned)std::min<int64_t>(div_ceil64(n_edges, kRangedNT), (int64_t)c.sm_count * 8);
+        constexpr bool H = MODE == 1;
+        if (WK == WI) k_items_from_edges_ranged<WI, WI, WI, H><<<grid, kRangedNT, smem, c.stream>>>(src.edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
+        else if (WE == WK) k_items_from_edges_ranged<WI - 1, WI - 1, WI, H><<<grid, kRangedNT, smem, c.stream>>>(src.edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
+        else k_items_from_edges_ranged<WI - 1, WI, WI, H><<<grid, kRangedNT, smem, c.stream>>>(src.edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
+      }
+      c.launches++;
+      written = 6 * n_edges;
     }
-  }
-  if (sq.n_items > 0) {
-    k_items_from_seqs<WI><<<(unsigned)div_ceil64(sq.n_items, 128), 128, 0, c.stream>>>(
-        sq.packed, sq.starts, sq.mult, sq.item_base, sq.nseq, sq.n_items, k, items + (size_t)n_edge_items * WI);
+    const SeqsView &sq = src.seqs;
+    if (sq.n_items > 0) {
+      if constexpr (MODE == 0) {
+        k_items_from_seqs<WI><<<(unsigned)div_ceil64(sq.n_items, 128), 128, 0, c.stream>>>(sq.packed, sq.starts, sq.mult, sq.item_base, sq.nseq,
+                                                                                        sq.n_items, k, items + (size_t)written * WI);
+      } else {
+        const unsigned grid = (unsigned)std::min<int64_t>(div_ceil64(sq.n_items, kRangedNT), (int64_t)c.sm_count * 8);
+        k_items_from_seqs_ranged<WI, MODE == 1><<<grid, kRangedNT, smem, c.stream>>>(sq.packed, sq.starts, sq.mult, sq.item_base, sq.nseq,
+                                                                                    sq.n_items, k, bin_bits, lo, hi, items, cursor, hist);
+      }
+      c.launches++;
+      written += sq.n_items;
+    }
     MF_LAUNCH_CHECK();
-    c.launches++;
+    return written;
+  } else {
+    return 0;
   }
-  return n_edge_items + sq.n_items;
 }
 static void sdbg_empty(Ctx &c, int k, SdbgView *out) {
   out->k = k;
@@ -1825,36 +1884,9 @@ static void sdbg_finish(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n_items,
 // level-1 bin, contiguous bin ranges of at most `round_items` items are generated (ranged generators, items.cuh), sorted
 // and walked one after the other, and their outputs are appended -- bin order is key order, so the concatenation is the
 // global stream.  A (k-1)-prefix group never straddles a bin (l1_bits <= 11 < 2(k-1)), 16-bit buckets never do either.
-template <int WI, bool HIST>
-static void launch_items_ranged(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, int bin_bits, uint32_t lo,
-                                uint32_t hi, uint32_t *items, unsigned long long *cursor, unsigned long long *hist) {
-  if constexpr (WI >= 2) {
-    const int WK = words_key(k), WE = words_edge(k);
-    const size_t smem = HIST ? sizeof(uint32_t) << bin_bits : 0;
-    if (n_edges > 0) {
-      const unsigned grid = (unsigned)std::min<int64_t>(div_ceil64(n_edges, kRangedNT), (int64_t)c.sm_count * 8);
-      if (WK == WI)
-        k_items_from_edges_ranged<WI, WI, WI, HIST><<<grid, kRangedNT, smem, c.stream>>>(edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
-      else if (WE == WK)
-        k_items_from_edges_ranged<WI - 1, WI - 1, WI, HIST><<<grid, kRangedNT, smem, c.stream>>>(edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
-      else
-        k_items_from_edges_ranged<WI - 1, WI, WI, HIST><<<grid, kRangedNT, smem, c.stream>>>(edges, n_edges, k, bin_bits, lo, hi, items, cursor, hist);
-      MF_LAUNCH_CHECK();
-      c.launches++;
-    }
-    if (sq.n_items > 0) {
-      const unsigned grid = (unsigned)std::min<int64_t>(div_ceil64(sq.n_items, kRangedNT), (int64_t)c.sm_count * 8);
-      k_items_from_seqs_ranged<WI, HIST><<<grid, kRangedNT, smem, c.stream>>>(sq.packed, sq.starts, sq.mult, sq.item_base, sq.nseq, sq.n_items,
-                                                                            k, bin_bits, lo, hi, items, cursor, hist);
-      MF_LAUNCH_CHECK();
-      c.launches++;
-    }
-  }
-}
 template <int WI>
-static void sdbg_rounds(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, int tip_mode, int64_t round_items,
-                        size_t table_bytes, SdbgView *out) {
-  const int64_t n_cap = 6 * n_edges + sq.n_items;
+static void sdbg_rounds(Ctx &c, const ItemSource &src, int k, int tip_mode, int64_t round_items, size_t table_bytes, SdbgView *out) {
+  const int64_t n_cap = src.n_items();
   const int Wt = words_tip(k);
   Plan p = make_plan(WI, 2 * (k - 1), n_cap, 1.0, false);
   const int nb1 = 1 << p.l1_bits;
@@ -1865,7 +1897,7 @@ static void sdbg_rounds(Ctx &c, const uint32_t *edges, int64_t n_edges, const Se
     c.small[2].reserve(sizeof(unsigned long long) * ((size_t)1 << kMaxDigitBits));
     unsigned long long *d_hist = c.small[2].as<unsigned long long>();
     MF_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nb1, c.stream));
-    launch_items_ranged<WI, true>(c, edges, n_edges, sq, k, p.l1_bits, 0u, (uint32_t)nb1, nullptr, nullptr, d_hist);
+    sdbg_generate<WI, 1>(c, src, k, nullptr, p.l1_bits, 0u, (uint32_t)nb1, nullptr, d_hist);
     c.d2h(hist.data(), d_hist, sizeof(unsigned long long) * nb1);
   }
   // contiguous bin ranges of at most round_items items (a single bin may exceed it: it then is a round of its own)
@@ -1910,7 +1942,7 @@ static void sdbg_rounds(Ctx &c, const uint32_t *edges, int64_t n_edges, const Se
     {
       Stage st(c, "items");
       MF_CUDA(cudaMemsetAsync(d_cur, 0, sizeof(unsigned long long), c.stream));
-      launch_items_ranged<WI, false>(c, edges, n_edges, sq, k, p.l1_bits, (uint32_t)rd.first, (uint32_t)rd.second, bufA, d_cur, nullptr);
+      sdbg_generate<WI, 2>(c, src, k, bufA, p.l1_bits, (uint32_t)rd.first, (uint32_t)rd.second, d_cur, nullptr);
       unsigned long long got = 0;
       c.d2h(&got, d_cur, sizeof got);
       if ((int64_t)got != n_r) throw std::runtime_error("sdbg rounds: generated items disagree with the histogram");
@@ -1970,33 +2002,44 @@ static void sdbg_rounds(Ctx &c, const uint32_t *edges, int64_t n_edges, const Se
 
 template <int WI>
 static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &sq, int k, int tip_mode, SdbgView *out) {
-  const int64_t n_cap = 6 * n_edges + sq.n_items;   // upper bound: the filtered generator usually writes about a third
-  if (n_cap == 0) return sdbg_empty(c, k, out);
+  ItemSource src;
+  src.edges = edges;
+  src.n_edges = n_edges;
+  src.seqs = sq;
+  if (src.n_items() == 0) return sdbg_empty(c, k, out);
+  const size_t held = (size_t)n_edges * words_edge(k) * 4;
+  const size_t budget = c.budget();
+  // ---- which dummies reach the graph (k <= 63): afterwards the item count is exact
+  if (env_int("MFSDBG_ITEM_FILTER", 1) != 0 && k <= 63 && n_edges > 0 && ks_bytes(n_edges, k) + held < budget) {
+    c.slab_reserve(ks_bytes(n_edges, k) + (1 << 20));
+    c.slab_reset();
+    if (k <= 31) sdbg_filter<1>(c, edges, n_edges, k, &src);
+    else sdbg_filter<2>(c, edges, n_edges, k, &src);
+  }
+  const int64_t n_items = src.n_items();
+  const int nb1_max = 1 << kMaxDigitBits;
+  const size_t tables = (size_t)(64 << 20) + (size_t)((size_t)nb1_max << kMaxDigitBits) * 96 + (size_t)(n_items / 128);
   {
     // does the whole item set fit?  per item: two partition buffers, the record arena and the gathered records, tip labels
     const size_t per_item = (size_t)WI * 8 + 8 + (size_t)words_tip(k) / 2 + 1;
-    const size_t tables = (size_t)(64 << 20) + (size_t)((size_t)(1 << kMaxDigitBits) << kMaxDigitBits) * 96;
-    const size_t held = (size_t)n_edges * words_edge(k) * 4;
-    const size_t budget = c.budget();
     const size_t avail = budget > held + tables ? budget - held - tables : 0;
     int64_t round_items = env_int("MFSDBG_SDBG_ROUND_ITEMS", 0);
-    if (round_items <= 0 && (size_t)n_cap * per_item > avail) {
+    if (round_items <= 0 && (size_t)n_items * per_item > avail) {
       // keep half a record per generated item for the accumulated output (grown if the data yields more)
-      const size_t acc = (size_t)n_cap * 2;
+      const size_t acc = (size_t)n_items * 2;
       round_items = (int64_t)((avail > acc ? avail - acc : avail / 2) / per_item * 9 / 10);
       round_items = std::max<int64_t>(round_items, 1 << 20);
     }
-    if (round_items > 0) return sdbg_rounds<WI>(c, edges, n_edges, sq, k, tip_mode, round_items, tables, out);
+    if (round_items > 0) return sdbg_rounds<WI>(c, src, k, tip_mode, round_items, tables, out);
   }
-  const bool filter = env_int("MFSDBG_ITEM_FILTER", 1) != 0 && k <= 63;
-  const size_t set_bytes =
-      filter ? ((size_t)(k <= 31 ? 8 : 16) << std::max(10, std::min(31, ceil_log2(4.0 * (double)std::max<int64_t>(n_edges, 1))))) + 1024 : 0;
-  const int nb1_max = 1 << kMaxDigitBits;
-  const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1_max << kMaxDigitBits) * 96 + (size_t)(n_cap / 128);
-  c.slab_reserve((size_t)n_cap * WI * 4 * 2 + table_bytes + set_bytes + (1 << 20));
-  uint32_t *bufA = c.alloc<uint32_t>((size_t)n_cap * WI + 16), *bufB = c.alloc<uint32_t>((size_t)n_cap * WI + 16);
-  const int64_t n_items = sdbg_make_items<WI>(c, edges, n_edges, sq, k, bufA, filter);
-  if (n_items == 0) return sdbg_empty(c, k, out);
+  c.slab_reserve((size_t)n_items * WI * 4 * 2 + tables + (1 << 20));
+  c.slab_reset();
+  uint32_t *bufA = c.alloc<uint32_t>((size_t)n_items * WI + 16), *bufB = c.alloc<uint32_t>((size_t)n_items * WI + 16);
+  {
+    Stage st(c, "items");
+    const int64_t got = sdbg_generate<WI, 0>(c, src, k, bufA, 0, 0u, 0u, nullptr, nullptr);
+    if (got != n_items) throw std::runtime_error("sdbg: generated items disagree with their count");
+  }
   Plan p = make_plan(WI, 2 * (k - 1), n_items, 1.0, false);
   const int nb1 = 1 << p.l1_bits;
   auto salloc = [&](size_t bytes) { return c.slab_alloc(bytes); };
@@ -2028,8 +2071,14 @@ void dev_seq2sdbg(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView
 }
 
 // ---- staged sdbg for the multi-GPU driver: items -> (caller exchanges them by prefix) -> finish
-#define MF_DISPATCH_CASE_SITEMS(Wn) \
-  case Wn: sdbg_make_items<Wn>(c, edges, n_edges, SeqsView{}, k, items_out, false); break;
+#define MF_DISPATCH_CASE_SITEMS(Wn)                                                  \
+  case Wn: {                                                                          \
+    ItemSource src;                                                                   \
+    src.edges = edges;                                                                \
+    src.n_edges = n_edges;                                                            \
+    Stage st(c, "items");                                                             \
+    sdbg_generate<Wn, 0>(c, src, k, items_out, 0, 0u, 0u, nullptr, nullptr);          \
+  } break;
 void dev_sdbg_items(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, uint32_t *items_out) {
   if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
   MF_DISPATCH_W(words_item(k), SITEMS)

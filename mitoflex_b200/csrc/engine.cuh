@@ -53,6 +53,7 @@ struct Ctx {
   HostBuf out_rec, out_labels;
   DevBuf small[3];   // per-call histograms / counters kept across calls (cudaMalloc and cudaFree stall for 100+ ms at times)
   DevBuf fb[4];      // scratch of the recursive fallback sort, one per recursion depth
+  DevBuf miss;     // miss list of the sdbg item filter (kmerset.cuh): outlives the slab across the rounds of a call
   DevBuf ov[10];   // scratch of the oversized-bucket path, kept across calls (cudaMalloc/cudaFree are slow and synchronise)
   // tables read back by the file-level API
   std::vector<int64_t> edge_bucket_counts;   // 65536

@@ -91,141 +91,17 @@ __global__ void k_items_from_edges(const uint32_t *__restrict__ edges, int64_t n
 
 
 // ---------------------------------------------------------------------------------------------------------
-// Filtered item generation for k <= 31 (the k-mer fits 62 bits).  Of the 6 items of an edge only the 2 real ones always
-// reach the graph; a "$"-head item survives Lv2Postprocess only if its k-mer has no incoming solid edge, a "$"-tail item
-// only if its k-mer has no outgoing one -- rare at assembly depths.  Both tests are membership queries in the set
-//     PS = { first k bases of e : e in (edges U revcomp(edges)) }
-// ("k-mer has an outgoing edge"; incoming = outgoing of the reverse complement, the edge set is closed under it).
-// PS lives in an open-addressing table in HBM; items that the walker would drop anyway are never generated, sorted or
-// walked.  Dropping them cannot change any other output: they carry no multiplicity, never feed has_solid_a/b or last_a,
-// and whole (a, b) runs of them are skipped together.  The item order is arbitrary (a warp-aggregated append).
-constexpr unsigned long long kKmerEmpty = 0xffffffffffffffffull;   // 2k <= 62 bits used: never a valid entry
-
-// Slot = the k-mer's own top bits (k-mers of a genome are spread evenly over them), scrambled only inside a 64-slot window
-// by its low bits.  The edges arrive sorted, so the prefix k-mers of the forward strand and -- per first base -- the suffix
-// k-mers it looks up walk the table front to back: half of the accesses become sequential instead of random DRAM rows.
-__device__ __forceinline__ uint32_t kmer_slot(unsigned long long x, int log_slots) {
-  const uint32_t top = (uint32_t)(x >> (64 - log_slots));
-  const uint32_t mix = (uint32_t)((x * 0x9e3779b97f4a7c15ull) >> 58);   // 6 bits
-  return top ^ mix;
-}
-// probe sequence of a k-mer: 64 linear steps from its ordered slot, then it moves to a fully hashed slot and goes on linearly
-// from there (a genome with a huge family of k-mers behind one 14-base prefix must not turn the ordered slots into one long
-// chain); insert and lookup walk the same sequence, entries never move.
-__device__ __forceinline__ uint32_t kmer_next(unsigned long long x, uint32_t h, int &probe, int log_slots) {
-  if (++probe == 64) return (uint32_t)((x * 0xbf58476d1ce4e5b9ull) >> (64 - log_slots));
-  return (h + 1) & ((1u << log_slots) - 1u);
-}
+// Helpers of the item filter (kmerset.cuh): k-mers of up to 64 / 128 bits, left aligned.  Of the 6 items of an edge only the 2
+// real ones always reach the graph; a "$"-head item survives Lv2Postprocess only if its k-mer has no incoming solid edge, a
+// "$"-tail item only if its k-mer has no outgoing one -- rare at assembly depths.  Items that the walker would drop anyway
+// are never generated, sorted or walked.  Dropping them cannot change any other output: they carry no multiplicity, never
+// feed has_solid_a/b or last_a, and whole (a, b) runs of them are skipped together.
 __device__ __forceinline__ unsigned long long revcomp64(unsigned long long t, int nchars) {   // left-aligned 2*nchars bits
   unsigned long long x = __brevll(~t);   // complement, reversed bit order: bases reversed with their two bits swapped
   x = ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
   return x << (64 - 2 * nchars);         // the reversed string sat right aligned
 }
-template <int WK, int WE>
-__device__ __forceinline__ unsigned long long load_edge64(const uint32_t *src, int k) {
-  unsigned long long t = (unsigned long long)src[0] << 32;
-  if constexpr (WK == 2) t |= src[1];
-  return t & (~0ull << (64 - 2 * (k + 1)));   // drop the multiplicity if it shares the last key word
-}
-
-template <int WK, int WE>
-__global__ void k_kmer_set_insert(const uint32_t *__restrict__ edges, int64_t n_edges, int k, unsigned long long *table, int log_slots) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_edges) return;
-  const unsigned long long fw = load_edge64<WK, WE>(edges + e * WE, k);
-  const unsigned long long rc = revcomp64(fw, k + 1);
-  const unsigned long long mk = ~0ull << (64 - 2 * k);
-  // both first probes are in flight together (these kernels wait on random DRAM accesses and nothing else)
-  const unsigned long long x0 = fw & mk, x1 = rc & mk;
-  uint32_t h0 = kmer_slot(x0, log_slots), h1 = kmer_slot(x1, log_slots);
-  // straight to the CAS (one round trip to L2 instead of a load and then the CAS); both are in flight together
-  unsigned long long c0 = atomicCAS(table + h0, kKmerEmpty, x0), c1 = atomicCAS(table + h1, kKmerEmpty, x1);
-  int p0 = 0, p1 = 0;
-  while (c0 != kKmerEmpty && c0 != x0) {
-    h0 = kmer_next(x0, h0, p0, log_slots);
-    c0 = atomicCAS(table + h0, kKmerEmpty, x0);
-  }
-  while (c1 != kKmerEmpty && c1 != x1) {
-    h1 = kmer_next(x1, h1, p1, log_slots);
-    c1 = atomicCAS(table + h1, kKmerEmpty, x1);
-  }
-}
-
-template <int WK, int WE, int WI>
-__global__ void k_items_from_edges_filtered(const uint32_t *__restrict__ edges, int64_t n_edges, int k,
-                                            const unsigned long long *__restrict__ table, int log_slots,
-                                            uint32_t *__restrict__ items, unsigned long long *cursor) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = e < n_edges;
-  uint32_t fwv[WK], rcv[WK];
-  uint32_t mult = 0;
-  bool q[2] = {true, true};   // q[s]: the k-mer t[1..k] of strand s has an outgoing solid edge
-  if (live) {
-    const uint32_t *src = edges + e * WE;
-    const unsigned long long fw = load_edge64<WK, WE>(src, k);
-    const unsigned long long rc = revcomp64(fw, k + 1);
-    mult = src[WE - 1] & 0xffffu;
-    fwv[0] = (uint32_t)(fw >> 32);
-    rcv[0] = (uint32_t)(rc >> 32);
-    if constexpr (WK == 2) { fwv[1] = (uint32_t)fw; rcv[1] = (uint32_t)rc; }
-    const unsigned long long mk = ~0ull << (64 - 2 * k);
-    const unsigned long long x0 = (fw << 2) & mk, x1 = (rc << 2) & mk;
-    uint32_t h0 = kmer_slot(x0, log_slots), h1 = kmer_slot(x1, log_slots);
-    unsigned long long c0 = table[h0], c1 = table[h1];   // both first probes in flight together
-    int p0 = 0, p1 = 0;
-    for (;;) {
-      if (c0 == x0) break;
-      if (c0 == kKmerEmpty) { q[0] = false; break; }
-      h0 = kmer_next(x0, h0, p0, log_slots);
-      c0 = table[h0];
-    }
-    for (;;) {
-      if (c1 == x1) break;
-      if (c1 == kKmerEmpty) { q[1] = false; break; }
-      h1 = kmer_next(x1, h1, p1, log_slots);
-      c1 = table[h1];
-    }
-  }
-  // "$"-head of strand s needs no incoming edge = !q[1-s]; "$"-tail of strand s needs no outgoing edge = !q[s]
-  const int extra = live ? 2 * ((q[0] ? 0 : 1) + (q[1] ? 0 : 1)) : 0;
-  const int mine = live ? 2 + extra : 0;
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((threadIdx.x & 31) >= o) incl += v;
-  }
-  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-  unsigned long long base = 0;
-  if ((threadIdx.x & 31) == 31 && warp_total) base = atomicAdd(cursor, (unsigned long long)warp_total);
-  base = __shfl_sync(0xffffffffu, base, 31);
-  if (!live) return;
-  uint32_t *dst = items + (base + (unsigned long long)(incl - mine)) * WI;
-#pragma unroll
-  for (int strand = 0; strand < 2; ++strand) {
-    const uint32_t(&t)[WK] = strand ? rcv : fwv;
-    const uint32_t c0 = t[0] >> 30, c1 = (t[0] >> 28) & 3;
-    uint32_t it[WI];
-    if (!q[1 - strand]) {
-      window_item<WK, WI>(t, 0, k, 1, kSentinel, 0, it);
-#pragma unroll
-      for (int i = 0; i < WI; ++i) dst[i] = it[i];
-      dst += WI;
-    }
-    window_item<WK, WI>(t, 1, k, 1, c0, mult, it);
-#pragma unroll
-    for (int i = 0; i < WI; ++i) dst[i] = it[i];
-    dst += WI;
-    if (!q[strand]) {
-      window_item<WK, WI>(t, 2, k - 1, 0, c1, 0, it);
-#pragma unroll
-      for (int i = 0; i < WI; ++i) dst[i] = it[i];
-      dst += WI;
-    }
-  }
-}
-
-// ---- the same for 32 <= k <= 63: the k-mer takes up to 126 bits, the table holds 16-byte slots (ATOMG.CAS.128 on sm_100a)
+// ---- 32 <= k <= 63: the k-mer takes up to 126 bits, the table holds 16-byte slots (ATOMG.CAS.128 on sm_100a)
 struct K128 {
   unsigned long long hi, lo;
 };
@@ -247,115 +123,7 @@ __device__ __forceinline__ K128 revcomp128(K128 t, int nchars) {   // left-align
   const K128 r{rev_bases64(~t.lo), rev_bases64(~t.hi)};             // whole register reversed: the string sits right aligned
   return shl128(r, 128 - 2 * nchars);
 }
-template <int WK, int WE>
-__device__ __forceinline__ K128 load_edge128(const uint32_t *src, int k) {
-  K128 t;
-  t.hi = ((unsigned long long)src[0] << 32) | src[1];
-  t.lo = (unsigned long long)src[2] << 32;
-  if constexpr (WK >= 4) t.lo |= src[3];
-  return mask_top128(t, 2 * (k + 1));   // drop the multiplicity if it shares the last key word
-}
 __device__ __forceinline__ unsigned __int128 pack128(K128 a) { return ((unsigned __int128)a.hi << 64) | a.lo; }
-__device__ __forceinline__ uint32_t kmer_slot128(K128 x, int log_slots) {
-  const uint32_t top = (uint32_t)(x.hi >> (64 - log_slots));
-  const uint32_t mix = (uint32_t)(((x.hi ^ (x.lo * 0xbf58476d1ce4e5b9ull)) * 0x9e3779b97f4a7c15ull) >> 58);
-  return top ^ mix;
-}
-__device__ __forceinline__ uint32_t kmer_next128(K128 x, uint32_t h, int &probe, int log_slots) {
-  if (++probe == 64) return (uint32_t)(((x.hi ^ (x.lo * 0x94d049bb133111ebull)) * 0xbf58476d1ce4e5b9ull) >> (64 - log_slots));
-  return (h + 1) & ((1u << log_slots) - 1u);
-}
-
-template <int WK, int WE>
-__global__ void k_kmer_set_insert128(const uint32_t *__restrict__ edges, int64_t n_edges, int k, unsigned __int128 *table, int log_slots) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_edges) return;
-  const K128 fw = load_edge128<WK, WE>(edges + e * WE, k);
-  const K128 rc = revcomp128(fw, k + 1);
-  const unsigned __int128 empty = ~(unsigned __int128)0;
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const K128 xk = mask_top128(s ? rc : fw, 2 * k);
-    const unsigned __int128 x = pack128(xk);
-    uint32_t h = kmer_slot128(xk, log_slots);
-    int probe = 0;
-    unsigned __int128 c = atomicCAS(table + h, empty, x);
-    while (c != empty && c != x) {
-      h = kmer_next128(xk, h, probe, log_slots);
-      c = atomicCAS(table + h, empty, x);
-    }
-  }
-}
-
-template <int WK, int WE, int WI>
-__global__ void k_items_from_edges_filtered128(const uint32_t *__restrict__ edges, int64_t n_edges, int k,
-                                               const unsigned __int128 *__restrict__ table, int log_slots, uint32_t *__restrict__ items,
-                                               unsigned long long *cursor) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = e < n_edges;
-  uint32_t fwv[WK], rcv[WK];
-  uint32_t mult = 0;
-  bool q[2] = {true, true};   // q[s]: the k-mer t[1..k] of strand s has an outgoing solid edge
-  if (live) {
-    const uint32_t *src = edges + e * WE;
-    const K128 fw = load_edge128<WK, WE>(src, k);
-    const K128 rc = revcomp128(fw, k + 1);
-    mult = src[WE - 1] & 0xffffu;
-    fwv[0] = (uint32_t)(fw.hi >> 32); fwv[1] = (uint32_t)fw.hi; fwv[2] = (uint32_t)(fw.lo >> 32);
-    rcv[0] = (uint32_t)(rc.hi >> 32); rcv[1] = (uint32_t)rc.hi; rcv[2] = (uint32_t)(rc.lo >> 32);
-    if constexpr (WK >= 4) { fwv[3] = (uint32_t)fw.lo; rcv[3] = (uint32_t)rc.lo; }
-    const unsigned __int128 empty = ~(unsigned __int128)0;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const K128 xk = mask_top128(shl128(s ? rc : fw, 2), 2 * k);
-      const unsigned __int128 x = pack128(xk);
-      uint32_t h = kmer_slot128(xk, log_slots);
-      int probe = 0;
-      for (;;) {
-        const unsigned __int128 cur = table[h];
-        if (cur == x) break;
-        if (cur == empty) { q[s] = false; break; }
-        h = kmer_next128(xk, h, probe, log_slots);
-      }
-    }
-  }
-  const int extra = live ? 2 * ((q[0] ? 0 : 1) + (q[1] ? 0 : 1)) : 0;
-  const int mine = live ? 2 + extra : 0;
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((threadIdx.x & 31) >= o) incl += v;
-  }
-  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-  unsigned long long base = 0;
-  if ((threadIdx.x & 31) == 31 && warp_total) base = atomicAdd(cursor, (unsigned long long)warp_total);
-  base = __shfl_sync(0xffffffffu, base, 31);
-  if (!live) return;
-  uint32_t *dst = items + (base + (unsigned long long)(incl - mine)) * WI;
-#pragma unroll
-  for (int strand = 0; strand < 2; ++strand) {
-    const uint32_t(&t)[WK] = strand ? rcv : fwv;
-    const uint32_t c0 = t[0] >> 30, c1 = (t[0] >> 28) & 3;
-    uint32_t it[WI];
-    if (!q[1 - strand]) {
-      window_item<WK, WI>(t, 0, k, 1, kSentinel, 0, it);
-#pragma unroll
-      for (int i = 0; i < WI; ++i) dst[i] = it[i];
-      dst += WI;
-    }
-    window_item<WK, WI>(t, 1, k, 1, c0, mult, it);
-#pragma unroll
-    for (int i = 0; i < WI; ++i) dst[i] = it[i];
-    dst += WI;
-    if (!q[strand]) {
-      window_item<WK, WI>(t, 2, k - 1, 0, c1, 0, it);
-#pragma unroll
-      for (int i = 0; i < WI; ++i) dst[i] = it[i];
-      dst += WI;
-    }
-  }
-}
 
 // General sequences (contigs etc.), stored orientation, 2-bit packed back to back.
 // One thread per item; item -> sequence by binary search over item_base (sequences are long, few).
