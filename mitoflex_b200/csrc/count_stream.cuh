@@ -491,9 +491,9 @@ __global__ void k_probe_distinct(const uint32_t *__restrict__ keys, const ProbeC
 // TMA-fed scatter of one partition level over 2-word records: the tile arrives in shared memory with one bulk copy (no
 // per-thread loads, no records held in registers), is counted and re-read there, staged in bin order and copied out
 // coalesced.  KPT keys per thread: 12 (6144-key tiles) with up to 1024 bins, 10 with 2048 -- two CTAs per SM either way.
-template <int KPT>
+template <int KPT, int NT = 512>
 inline size_t scatter_tma_smem_bytes(int nbits) {
-  const size_t nb = (size_t)1 << nbits, T = (size_t)512 * KPT;
+  const size_t nb = (size_t)1 << nbits, T = (size_t)NT * KPT;
   return (T + 4) * 8 + T * 8 + (nb + 32) * 4 + nb * 8 + 48 * 4 + 16;
 }
 // lean digit of a 2-word record for bit_off < 32: dg = (x * nb) >> xbits with x = the xbits bits at bit_off; the bit-prefix
@@ -511,7 +511,7 @@ struct Digit2 {
 };
 
 template <int NT, int KPT, int BPT>
-__global__ void __launch_bounds__(NT, KPT <= 7 ? 3 : 2) k_scatter_tma(const uint32_t *__restrict__ in, const TileDesc *__restrict__ tiles, int64_t ntiles,
+__global__ void __launch_bounds__(NT, (NT == 512 && KPT <= 7) ? 3 : 2) k_scatter_tma(const uint32_t *__restrict__ in, const TileDesc *__restrict__ tiles, int64_t ntiles,
                                                       LevelArgs a, unsigned long long *__restrict__ cursor, uint32_t *__restrict__ out) {
   extern __shared__ __align__(128) unsigned char smraw[];
   constexpr int T = NT * KPT;

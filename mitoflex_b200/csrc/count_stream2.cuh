@@ -5,10 +5,12 @@
 // edge records (KmerCounter::PackEdge).  What changed, and why (ncu r1i/r2a: the old kernel issued ~120 thread-instructions per
 // key, 0.68 issue/cycle, stalls wait / barrier / branch_resolving):
 //
-//   * LANES NEVER WAIT FOR THE SLOWEST PROBE.  The old loop handed every lane one key and looped until the longest linear
-//     probe of the warp was done (5-8 rounds at 45 % load although the AVERAGE probe is 1.6 slots).  Now a lane that is done
-//     takes the next key of its warp at once (ballot + popc hand out consecutive keys), so a warp iteration is one probe step
-//     for 32 keys in different stages of their probe sequences: iterations = total probes / 32.
+//   * THE FIRST PROBE IS STRAIGHT-LINE CODE.  The old loop handed every lane one key and looped until the longest linear
+//     probe of the warp was done (5-8 rounds at 45 % load although the AVERAGE probe is 1.6 slots).  Now a thread takes 4 keys
+//     per round, has their 4 ring loads and 4 slot loads in flight together, settles what the first slot decides (a hit or a
+//     claim: ~85 % at 22 % load) without a loop, and only the few keys left over probe on.  (A first attempt that handed out
+//     keys to idle lanes with ballot + popc packed the lanes perfectly but spent ~150 instructions per warp iteration on the
+//     bookkeeping: 12.5 ms against 8.0 ms of the old kernel on the 1.8 Gbp sample, ncu r2d.)
 //   * ONE 64-BIT SLOT HOLDS KEY AND COUNT.  All keys of a bucket lie in a narrow range (level 1 fixed their top bits, the range
 //     partition of level 2 their next ~10), so a slot stores the low RB bits of the right-aligned key above a CB-bit count
 //     (RB + CB = 64): claiming is one CAS, counting one RED on the same word, the probe compares one shifted word.  The table
@@ -94,7 +96,8 @@ __device__ __forceinline__ uint32_t c2_excl_scan(uint32_t *s, int n, uint32_t *s
 
 // key_shift = 64 - 2(k+1) (keys are left-aligned in 64 bits); REL: count_bits = CB, a slot is (rel << CB) | count with rel =
 // the low 64 - CB bits of the right-aligned key; every bucket's key range must span < 2^(63 - CB) (the host guarantees it).
-template <bool REL>
+// CBT: compile-time count width (32: the slot's high word IS the key part -- one compare, no shifts), 0 = count_bits at run time.
+template <bool REL, int CBT>
 __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const int32_t *__restrict__ cta_first, int key_shift, int count_bits) {
   extern __shared__ __align__(128) unsigned char smraw[];
   using C = C2Cfg<REL>;
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
   const uint32_t m = (uint32_t)a.min_count;
   const int We = a.words_edge;
   const uint32_t off0 = (uint32_t)(rb - A);               // ring / chunk coordinates of relative position q: q + off0
-  const int CB = count_bits;
+  const int CB = CBT ? CBT : count_bits;
   const unsigned long long cmask = REL ? ((1ull << CB) - 1ull) : 0ull;
   const unsigned lt = lanemask_lt();
 
@@ -335,9 +338,10 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
     // the barrier the caller issues next publishes the reset
   };
 
-  // ---- consumer loop
+  uint32_t pbeg = 0;             // relative start of the current bucket (its first key is the REL reference)
+  // ---- consumer loop: chunk by chunk in lockstep (every warp waits for the chunk, takes its share, hands the stage back)
   int cur_b = b0;
-  uint32_t p = 0, bend = 0;      // [p, bend) = relative key range of bucket cur_b
+  uint32_t p = 0, bend = 0;      // p = relative position processed so far, bend = relative end of bucket cur_b
   auto advance = [&]() {         // first bucket at or after cur_b that ends beyond p (all consumers, uniform)
     while (cur_b < b1) {
       if (cur_b + 1 - wb > kCsWin) {
@@ -352,103 +356,120 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
     }
   };
   advance();
-  int c_ready = 0;   // chunks [0, c_ready) are known to have landed (warp-uniform)
-  int c_rel = 0;     // chunks [0, c_rel) have been released by this warp
-  auto need_chunk = [&](int c) {   // warp-uniform
-    while (c_ready <= c) {
-      mbar_wait(mbar + (c_ready & (Stages - 1)), (uint32_t)((c_ready / Stages) & 1));
-      ++c_ready;
-    }
-  };
-  auto release_below = [&](int c) {   // this warp never reads chunks < c again
-    while (c_rel < c) {
-      need_chunk(c_rel);              // a stage is only handed back after its copy has landed (phase order of the barriers)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(mbar + 4 + (c_rel & (Stages - 1)));
-      ++c_rel;
-    }
-  };
-
-  while (cur_b < b1) {
-    // warp w takes the 32-key groups w, w + NW, ... of the bucket; t = next warp-local key index to hand out
-    const uint32_t blen = bend - p;
-    // REL: a count must stay inside its CB-bit field, so a bucket with 2^CB or more keys is not taken here at all
-    // (nor one of 2^30 keys or more: the position arithmetic below is 32-bit); it goes to the bail list
-    const bool skip = blen >= (1u << 30) || (REL && CB < 32 && blen >= (1u << CB));
+  bool skip = false;             // the current bucket is not taken here (see below); set when a bucket starts
+  auto bucket_begin = [&](uint32_t blen) {
+    // REL: a count must stay inside its CB-bit field, so a bucket with 2^CB or more keys goes to the bail list untouched
+    skip = REL && CB < 32 && blen >= (1u << CB);
     if (skip && tid == 0) s_flag[0] = 1;
-    bool exhausted = skip;   // warp-uniform: every key of the bucket that belongs to this warp has been handed out
-    uint32_t t = 0;
-    bool have = false;
-    unsigned long long key = 0;
-    uint32_t h = 0;
-    int probe = 0;
-    auto pos_of = [&](uint32_t tt) -> uint32_t { return (((tt >> 5) * NW + (uint32_t)warp) << 5) + (tt & 31u); };   // offset in the bucket
-    for (;;) {
-      const unsigned need = __ballot_sync(0xffffffffu, !have);
-      if (need && !exhausted && pos_of(t) >= blen) exhausted = true;
-      if (need && !exhausted) {
-        const uint32_t nn = (uint32_t)__popc(need);
-        const uint32_t o_mine = pos_of(t + (uint32_t)__popc(need & lt));
-        const uint32_t o_last = min(pos_of(t + nn - 1u), blen - 1u);
-        need_chunk((int)((p + o_last + off0) >> kC2ChunkLog));
-        if (!have && o_mine < blen) {
-          const uint32_t q = p + o_mine + off0;
-          // records are two big-endian u32 words: word 0 (the key's high half) is the low half of the 8-byte load
-          const unsigned long long raw = ring[q & (uint32_t)(RingKeys - 1)];
-          key = (raw << 32) | (raw >> 32);
-          have = true;
-          probe = 0;
-          if (o_mine == 0u) s_ref[0] = key;   // the bucket's first key is its reference (REL)
+  };
+  bucket_begin(bend - p);
+
+  constexpr int U = 4;           // keys per thread and round: all their loads are in flight together
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c & (Stages - 1);
+    mbar_wait(mbar + s, (uint32_t)((c / Stages) & 1));
+    const uint32_t chi = min((uint32_t)(((c + 1) << kC2ChunkLog) - off0), total);   // relative end of the chunk
+    while (p < chi) {
+      const uint32_t e = chi < bend ? chi : bend;
+      if (!skip) {
+        for (uint32_t q0 = p + tid; q0 < e; q0 += U * NC) {
+          unsigned long long key[U];
+          uint32_t h[U];
+          bool pend[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint32_t q = q0 + u * NC;
+            pend[u] = q < e;
+            // records are two big-endian u32 words: word 0 (the key's high half) is the low half of the 8-byte load
+            const unsigned long long raw = ring[(min(q, e - 1) + off0) & (uint32_t)(RingKeys - 1)];
+            key[u] = (raw << 32) | (raw >> 32);
+            if (q == pbeg) s_ref[0] = key[u];   // the bucket's first key is its reference (REL)
+            if constexpr (REL) h[u] = ((uint32_t)(key[u] >> key_shift) * 0x9E3779B1u) >> (32 - C::SlotsLog);
+            else h[u] = ((((uint32_t)key[u] ^ ((uint32_t)(key[u] >> 32) * 0x9E3779B1u))) * 0x85EBCA6Bu) >> (32 - C::SlotsLog);
+          }
+          // first probe of every key; what it does not settle stays pending
           if constexpr (REL) {
-            const uint32_t v = (uint32_t)(key >> key_shift);
-            h = (v * 0x9E3779B1u) >> (32 - C::SlotsLog);
+            unsigned long long sl[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) sl[u] = *reinterpret_cast<volatile unsigned long long *>(tab + h[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (pend[u]) {
+                const unsigned long long v = (key[u] >> key_shift) & (~0ull >> CB);
+                unsigned long long sv = sl[u];
+                if (sv == 0ull) sv = atomicCAS(tab + h[u], 0ull, (v << CB) | 1ull);
+                if (sv == 0ull) {
+                  pend[u] = false;
+                } else if ((sv >> CB) == v) {
+                  atomicAdd(reinterpret_cast<uint32_t *>(tab + h[u]), 1u);   // the count is the low word (CB <= 32 bits of it)
+                  pend[u] = false;
+                }
+              }
+            }
+            // the rest: linear probing (a few lanes, a few steps)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (pend[u]) {
+                const unsigned long long v = (key[u] >> key_shift) & (~0ull >> CB);
+                uint32_t hh = h[u];
+                int probe = 1;
+                for (;;) {
+                  hh = (hh + 1) & (Slots - 1);
+                  unsigned long long sv = *reinterpret_cast<volatile unsigned long long *>(tab + hh);
+                  if (sv == 0ull) sv = atomicCAS(tab + hh, 0ull, (v << CB) | 1ull);
+                  if (sv == 0ull) break;
+                  if ((sv >> CB) == v) { atomicAdd(reinterpret_cast<uint32_t *>(tab + hh), 1u); break; }
+                  if (++probe >= kCsProbeLimit) { s_flag[0] = 1; break; }   // table too crowded: the bucket bails
+                }
+              }
+            }
           } else {
-            const uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
-            h = (x * 0x85EBCA6Bu) >> (32 - C::SlotsLog);
+            unsigned long long sl[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) sl[u] = *reinterpret_cast<volatile unsigned long long *>(tab + h[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (pend[u]) {
+                unsigned long long cur = sl[u];
+                if (cur == kEmptyKey) cur = atomicCAS(tab + h[u], kEmptyKey, key[u]);
+                if (cur == kEmptyKey || cur == key[u]) {
+                  atomicAdd(tcnt + h[u], 1u);
+                  pend[u] = false;
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (pend[u]) {
+                uint32_t hh = h[u];
+                int probe = 1;
+                for (;;) {
+                  hh = (hh + 1) & (Slots - 1);
+                  unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tab + hh);
+                  if (cur == kEmptyKey) cur = atomicCAS(tab + hh, kEmptyKey, key[u]);
+                  if (cur == kEmptyKey || cur == key[u]) { atomicAdd(tcnt + hh, 1u); break; }
+                  if (++probe >= kCsProbeLimit) { s_flag[0] = 1; break; }
+                }
+              }
+            }
           }
         }
-        t += nn;
-        // chunks below the warp's next key (or the bucket end) are done with for this warp
-        release_below((int)((p + min(pos_of(t), blen) + off0) >> kC2ChunkLog));
       }
-      if (!__any_sync(0xffffffffu, have)) break;
-      if (have) {
-        if constexpr (REL) {
-          const unsigned long long v = (key >> key_shift) & (~0ull >> CB);
-          unsigned long long s = *reinterpret_cast<volatile unsigned long long *>(tab + h);
-          if (s == 0ull) s = atomicCAS(tab + h, 0ull, (v << CB) | 1ull);
-          if (s == 0ull) {
-            have = false;                                          // claimed, count = 1
-          } else if ((s >> CB) == v) {
-            atomicAdd(reinterpret_cast<uint32_t *>(tab + h), 1u);   // the count is the low word (CB <= 32 bits of it)
-            have = false;
-          } else {
-            h = (h + 1) & (Slots - 1);
-            if (++probe >= kCsProbeLimit) { s_flag[0] = 1; have = false; }   // table too crowded: the bucket bails
-          }
-        } else {
-          unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tab + h);
-          if (cur == kEmptyKey) cur = atomicCAS(tab + h, kEmptyKey, key);
-          if (cur == kEmptyKey || cur == key) {
-            atomicAdd(tcnt + h, 1u);
-            have = false;
-          } else {
-            h = (h + 1) & (Slots - 1);
-            if (++probe >= kCsProbeLimit) { s_flag[0] = 1; have = false; }
-          }
-        }
+      p = e;
+      if (p == bend) {
+        c2_sync();
+        finish_bucket(cur_b);
+        ++cur_b;
+        advance();
+        pbeg = p;
+        bucket_begin(bend - p);
+        c2_sync();
       }
     }
-    // whatever this warp handed out (or skipped) of the bucket is fetched: chunks below the next bucket's first key may go
-    release_below((int)((bend + off0) >> kC2ChunkLog));
-    p = bend;
-    c2_sync();
-    finish_bucket(cur_b);
-    ++cur_b;
-    advance();
-    c2_sync();
+    // this warp is done with stage s (its keys live in registers / the table now)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(mbar + 4 + s);
   }
-  release_below(nchunks);
 }
 
 }  // namespace mf

@@ -435,8 +435,9 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   if constexpr (W == 2) {
     if (tb_s[nchunk] > 0 && env_int("MFSDBG_TMA_SCATTER", 1) != 0 && bit_off < 32) {
       // 2-word records: TMA-fed tiles of 6144 (5120 with 2048 bins) records
-      const int kpt_env = env_int("MFSDBG_SCATTER_KPT", 0);
-      const int KPT = kpt_env == 7 ? 7 : (nbits <= 10 ? 12 : 10), T = 512 * KPT;
+      // 1024 threads x 6 keys (two CTAs = 64 warps per SM, 32 registers) or 512 threads x 12 keys (32 warps, 64 registers)
+      const int nt = env_int("MFSDBG_SCATTER_NT", 512) == 1024 && nbits <= 10 ? 1024 : 512;
+      const int KPT = nt == 1024 ? 6 : (nbits <= 10 ? 12 : 10), T = nt * KPT;
       std::vector<int64_t> tb_t(nchunk + 1);
       tb_t[0] = 0;
       for (int i = 0; i < nchunk; ++i) tb_t[i + 1] = tb_t[i] + div_ceil64(hc.size[i], T);
@@ -446,15 +447,16 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
       k_build_tiles<<<(unsigned)div_ceil64(tb_t[nchunk], 256), 256, 0, c.stream>>>(ChunkTable{d_start, d_size, d_seg, d_tbt, nchunk}, T,
                                                                                 tb_t[nchunk], d_tiles_t);
       MF_LAUNCH_CHECK();
-      const int bpt = std::max(1, (1 << nbits) / 512);
+      const int bpt = std::max(1, (1 << nbits) / nt);
       void (*kern)(const uint32_t *, const TileDesc *, int64_t, LevelArgs, unsigned long long *, uint32_t *) =
-          KPT == 7 ? (bpt == 1 ? k_scatter_tma<512, 7, 1> : (bpt == 2 ? k_scatter_tma<512, 7, 2> : k_scatter_tma<512, 7, 4>))
-                   : (nbits <= 10 ? (bpt == 1 ? k_scatter_tma<512, 12, 1> : k_scatter_tma<512, 12, 2>) : k_scatter_tma<512, 10, 4>);
-      const size_t smem = KPT == 7 ? scatter_tma_smem_bytes<7>(nbits) : (nbits <= 10 ? scatter_tma_smem_bytes<12>(nbits) : scatter_tma_smem_bytes<10>(nbits));
+          nt == 1024 ? k_scatter_tma<1024, 6, 1>
+                     : (nbits <= 10 ? (bpt == 1 ? k_scatter_tma<512, 12, 1> : k_scatter_tma<512, 12, 2>) : k_scatter_tma<512, 10, 4>);
+      const size_t smem = nt == 1024 ? scatter_tma_smem_bytes<6, 1024>(nbits)
+                                     : (nbits <= 10 ? scatter_tma_smem_bytes<12>(nbits) : scatter_tma_smem_bytes<10>(nbits));
       set_smem(kern, smem);
       Stage st(c, tag_s.c_str());
-      const int64_t grid_t = std::min<int64_t>(tb_t[nchunk], (int64_t)c.sm_count * env_int("MFSDBG_SCATTER_CTAS", KPT == 7 ? 3 : 2));
-      kern<<<(unsigned)grid_t, 512, smem, c.stream>>>(in, d_tiles_t, tb_t[nchunk], a, d_cur, out);
+      const int64_t grid_t = std::min<int64_t>(tb_t[nchunk], (int64_t)c.sm_count * env_int("MFSDBG_SCATTER_CTAS", 2));
+      kern<<<(unsigned)grid_t, nt, smem, c.stream>>>(in, d_tiles_t, tb_t[nchunk], a, d_cur, out);
       MF_LAUNCH_CHECK();
       c.launches += 2;
       return b;
@@ -730,12 +732,20 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
                                    int min_count, double *rho_out, int *rel_count_bits, Alloc &&alloc) {
   const double rho = probe_distinct_ratio<W>(c, *cur, l1, *bit_off, key_bits);
   *rho_out = rho;
-  const double load = env_int("MFSDBG_STREAM_LOAD_PCT", W == 2 ? 45 : 35) / 100.0;
-  double B = std::min(60000.0, std::max(1024.0, load * kCsSlots / rho));
-  *rel_count_bits = 0;
-  // --min-count 1 makes every distinct key a solid one: keep them under the per-bucket limit of the streamed kernel
+  // keys per bucket for a table of `slots` slots: 2-word keys whose slots hold "key | count" get 8192 of them (k_count_stream2<REL>),
+  // the full-key variant and the wide-key kernel 4096
+  const bool rel_wanted = W == 2 && env_int("MFSDBG_COUNT_REL", 1) != 0;
+  const double load = env_int("MFSDBG_STREAM_LOAD_PCT", W == 2 ? (rel_wanted ? 30 : 45) : 35) / 100.0;
   const int solid_max = W == 2 ? kCsSolidMax : (W == 3 ? 768 : 512);
-  if (min_count <= 1 && load <= 1.0) B = std::min(B, std::max(512.0, 0.7 * solid_max / rho));
+  auto bucket_keys = [&](int slots) {
+    double v = std::min(60000.0 * slots / kCsSlots, std::max(1024.0, load * slots / rho));
+    // --min-count 1 makes every distinct key a solid one: keep them under the per-bucket limit of the streamed kernel
+    if (min_count <= 1 && load <= 1.0) v = std::min(v, std::max(512.0, 0.7 * solid_max / rho));
+    return v;
+  };
+  bool b_is_rel = rel_wanted;
+  double B = bucket_keys(rel_wanted ? C2Cfg<true>::Slots : kCsSlots);
+  *rel_count_bits = 0;
   if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] distinct ratio %.4f -> %.0f keys per bucket\n", rho, B);
   HostChunks hc = l1;
   DevBuckets b;
@@ -756,18 +766,29 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
       int64_t nb_min = 1;
       if (W == 2 && env_int("MFSDBG_COUNT_REL", 1) != 0) {
         const int rest = key_bits - *bit_off;                       // bits the keys of a segment may differ in
-        const int over = rest - (63 - kC2MinCountBits);             // > 0: the segment must be cut into >= 2^over ranges
         int64_t tot = 0;
         for (int64_t v : seg_total) tot += v;
         const double avg_need = (double)tot / ((double)std::max(hc.nseg, 1) * B);
-        if (over <= 0) {
-          *rel_count_bits = 64 - (rest + 1);
-        } else if (over <= 10 && xbits == 16 && ((int64_t)1 << over) <= nb_cap &&
-                   (avg_need >= (double)((int64_t)1 << over) * 0.5 || env_int("MFSDBG_COUNT_REL", 1) == 2)) {
-          nb_min = (int64_t)1 << over;
-          *rel_count_bits = kC2MinCountBits;
+        const bool force = env_int("MFSDBG_COUNT_REL", 1) == 2;
+        // cutting every segment into >= 2^cut ranges is free when the segments get about that many buckets anyway (or so few
+        // that the empty ones do not matter)
+        auto cut_ok = [&](int cut) {
+          return cut <= 0 || (cut <= 10 && xbits == 16 && ((int64_t)1 << cut) <= nb_cap && (cut <= 4 || force || avg_need >= (double)((int64_t)1 << cut) * 0.5));
+        };
+        const int cut32 = rest - 31;                                // 32-bit key part + 32-bit count: the cheapest slot compare
+        const int cut_any = rest - (63 - kC2MinCountBits);
+        if (cut_ok(cut32) && env_int("MFSDBG_COUNT_REL", 1) != 3) {
+          nb_min = (int64_t)1 << std::max(cut32, 0);
+          *rel_count_bits = 32;
+        } else if (cut_ok(cut_any)) {
+          nb_min = (int64_t)1 << std::max(cut_any, 0);
+          *rel_count_bits = cut_any <= 0 ? std::min(32, 64 - (rest + 1)) : kC2MinCountBits;
         }
-        *rel_count_bits = std::min(*rel_count_bits, 32);
+      }
+      if (b_is_rel && *rel_count_bits == 0) {   // the buckets were sized for the 8192-slot table: size them for the full-key one
+        b_is_rel = false;
+        B = bucket_keys(kCsSlots);
+        continue;
       }
       std::vector<uint16_t> nb(hc.nseg);
       int mx = 1;
@@ -804,14 +825,18 @@ static void launch_count_stream(Ctx &c, const LocalArgs &a, int nslots, int64_t 
                                 int rel_count_bits) {
   k_split_ranges<<<div_ceil(grid + 1, 128), 128, 0, c.stream>>>(a.bkt_start, a.bkt_size, nslots, grid, d_cta_first);
   MF_LAUNCH_CHECK();
-  if (rel_count_bits > 0) {
+  if (rel_count_bits == 32) {
     const size_t smem = count_stream2_smem_bytes<true>();
-    set_smem(k_count_stream2<true>, smem);
-    k_count_stream2<true><<<grid, kC2NT, smem, c.stream>>>(a, d_cta_first, 64 - key_bits, rel_count_bits);
+    set_smem(k_count_stream2<true, 32>, smem);
+    k_count_stream2<true, 32><<<grid, kC2NT, smem, c.stream>>>(a, d_cta_first, 64 - key_bits, 32);
+  } else if (rel_count_bits > 0) {
+    const size_t smem = count_stream2_smem_bytes<true>();
+    set_smem(k_count_stream2<true, 0>, smem);
+    k_count_stream2<true, 0><<<grid, kC2NT, smem, c.stream>>>(a, d_cta_first, 64 - key_bits, rel_count_bits);
   } else {
     const size_t smem = count_stream2_smem_bytes<false>();
-    set_smem(k_count_stream2<false>, smem);
-    k_count_stream2<false><<<grid, kC2NT, smem, c.stream>>>(a, d_cta_first, 64 - key_bits, 0);
+    set_smem(k_count_stream2<false, 0>, smem);
+    k_count_stream2<false, 0><<<grid, kC2NT, smem, c.stream>>>(a, d_cta_first, 64 - key_bits, 0);
   }
   MF_LAUNCH_CHECK();
   c.launches += 2;
@@ -1616,9 +1641,9 @@ static void sdbg_filter(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, I
   Stage st(c, "items_filter");
   Slot *rec = c.alloc<Slot>((size_t)4 * n_edges);
   Slot *table = c.alloc<Slot>((size_t)1 << g.log_slots);
-  unsigned long long *hist = c.alloc<unsigned long long>(nbins), *cursor = c.alloc<unsigned long long>(nbins + 1);
+  unsigned long long *hist = c.alloc<unsigned long long>(nbins), *cursor = c.alloc<unsigned long long>(nbins + 3);
   MF_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * nbins, c.stream));
-  MF_CUDA(cudaMemsetAsync(cursor + nbins, 0, sizeof(unsigned long long), c.stream));
+  MF_CUDA(cudaMemsetAsync(cursor + nbins, 0, sizeof(unsigned long long) * 3, c.stream));   // miss cursor, two tile counters
   MF_CUDA(cudaMemsetAsync(table, 0xff, sizeof(Slot) << g.log_slots, c.stream));
   const unsigned hgrid = (unsigned)std::min<int64_t>(div_ceil64(n_edges, kKsNT), (int64_t)c.sm_count * 4);
   k_ks_hist<KW><<<hgrid, kKsNT, sizeof(uint32_t) * nbins, c.stream>>>(edges, n_edges, WK, WE, k, g, hist);
@@ -1634,9 +1659,9 @@ static void sdbg_filter(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, I
     k_ks_scatter<KW, 4><<<sgrid, kKsNT, ssm, c.stream>>>(edges, n_edges, WK, WE, k, g, cursor, rec);
   }
   // inserts are the first 2E records, queries the last 2E, both in slice order; the misses overwrite the (dead) inserts
-  const unsigned wgrid = (unsigned)std::min<int64_t>(div_ceil64(2 * n_edges, 256), (int64_t)c.sm_count * 8);
-  k_ks_insert<KW><<<wgrid, 256, 0, c.stream>>>(rec, 2 * n_edges, g, table);
-  k_ks_query<KW><<<wgrid, 256, 0, c.stream>>>(rec + 2 * n_edges, 2 * n_edges, g, table, rec, cursor + nbins);
+  const unsigned wgrid = (unsigned)std::min<int64_t>(div_ceil64(2 * n_edges, kKsWalkNT * kKsWalkR), (int64_t)c.sm_count * 8);
+  k_ks_insert<KW><<<wgrid, kKsWalkNT, 0, c.stream>>>(rec, 2 * n_edges, g, table, cursor + nbins + 1);
+  k_ks_query<KW><<<wgrid, kKsWalkNT, 0, c.stream>>>(rec + 2 * n_edges, 2 * n_edges, g, table, rec, cursor + nbins, cursor + nbins + 2);
   MF_LAUNCH_CHECK();
   c.launches += 5;
   unsigned long long n_miss = 0;

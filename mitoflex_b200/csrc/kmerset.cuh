@@ -181,58 +181,98 @@ __global__ void __launch_bounds__(kKsNT) k_ks_scatter(const uint32_t *__restrict
   for (uint32_t j = tid; j < total; j += NT) out[s_gd[stage_bin[j]] + (long long)j] = stage[j];
 }
 
-// ---- pass 3: inserts, in slice order (the records of a slice are contiguous; a plain grid-stride walk keeps the CTAs in flight
-// inside one or two slices, whose table lines stay in L2)
+// ---- pass 3: inserts, in slice order.  The records of a slice are contiguous, and tiles of 1024 records are handed out IN ORDER by
+// an atomic counter, so the CTAs in flight (8 per SM) always work on the ~1.2 M most recent records = one or two slices, whose
+// table lines stay in L2.  (A plain grid-stride loop does not keep that window: after a few hundred dependent DRAM round trips
+// per thread the fast warps are dozens of slices ahead of the slow ones -- ncu r2d: 131 bytes of DRAM read per insert.)
+constexpr int kKsWalkNT = 256, kKsWalkR = 4;
 template <int KW>
-__global__ void __launch_bounds__(256) k_ks_insert(const typename KsKey<KW>::Slot *__restrict__ rec, int64_t n, KsGeom g,
-                                                   typename KsKey<KW>::Slot *table) {
+__device__ __forceinline__ KsKey<KW> ks_unpack(typename KsKey<KW>::Slot x) {
+  KsKey<KW> kx;
+  if constexpr (KW == 1) kx.v = x; else { kx.v.hi = (unsigned long long)(x >> 64); kx.v.lo = (unsigned long long)x; }
+  return kx;
+}
+template <int KW>
+__global__ void __launch_bounds__(kKsWalkNT) k_ks_insert(const typename KsKey<KW>::Slot *__restrict__ rec, int64_t n, KsGeom g,
+                                                         typename KsKey<KW>::Slot *table, unsigned long long *tile_counter) {
   using Slot = typename KsKey<KW>::Slot;
+  constexpr int NT = kKsWalkNT, R = kKsWalkR;
+  __shared__ unsigned long long s_tile;
   const Slot empty = KsKey<KW>::empty();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const Slot x = rec[i];
-    KsKey<KW> kx;
-    if constexpr (KW == 1) kx.v = x; else { kx.v.hi = (unsigned long long)(x >> 64); kx.v.lo = (unsigned long long)x; }
-    unsigned long long h = g.slot(kx.hash());
-    // linear probing inside the slice (wrapping at its end), so that a probe sequence never leaves the slice's L2-resident lines
-    const unsigned long long sbase = h & ~((1ull << g.slice_log) - 1ull), smask = (1ull << g.slice_log) - 1ull;
-    for (;;) {
-      const Slot c = atomicCAS(table + h, empty, x);
-      if (c == empty || c == x) break;
-      h = sbase | ((h + 1) & smask);
+  const unsigned long long smask = (1ull << g.slice_log) - 1ull;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1ull);
+    __syncthreads();
+    const int64_t base = (int64_t)s_tile * (NT * R);
+    __syncthreads();
+    if (base >= n) return;
+    Slot x[R], c[R];
+    unsigned long long h[R];
+    bool live[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t i = base + r * NT + threadIdx.x;
+      live[r] = i < n;
+      x[r] = rec[live[r] ? i : n - 1];
+      h[r] = g.slot(ks_unpack<KW>(x[r]).hash());
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) c[r] = live[r] ? atomicCAS(table + h[r], empty, x[r]) : empty;   // all first probes in flight together
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      // linear probing inside the slice (wrapping at its end): a probe sequence never leaves the slice's L2-resident lines
+      const unsigned long long sbase = h[r] & ~smask;
+      while (c[r] != empty && c[r] != x[r]) {
+        h[r] = sbase | ((h[r] + 1) & smask);
+        c[r] = atomicCAS(table + h[r], empty, x[r]);
+      }
     }
   }
 }
-// ---- pass 4: queries, in slice order; a k-mer that is not in the set goes to the miss list (warp-aggregated append)
+// ---- pass 4: queries, in slice order (same walk); a k-mer that is not in the set goes to the miss list (warp-aggregated append)
 template <int KW>
-__global__ void __launch_bounds__(256) k_ks_query(const typename KsKey<KW>::Slot *__restrict__ rec, int64_t n, KsGeom g,
-                                                  const typename KsKey<KW>::Slot *__restrict__ table,
-                                                  typename KsKey<KW>::Slot *__restrict__ miss, unsigned long long *miss_cursor) {
+__global__ void __launch_bounds__(kKsWalkNT) k_ks_query(const typename KsKey<KW>::Slot *__restrict__ rec, int64_t n, KsGeom g,
+                                                        const typename KsKey<KW>::Slot *__restrict__ table,
+                                                        typename KsKey<KW>::Slot *__restrict__ miss, unsigned long long *miss_cursor,
+                                                        unsigned long long *tile_counter) {
   using Slot = typename KsKey<KW>::Slot;
+  constexpr int NT = kKsWalkNT, R = kKsWalkR;
+  __shared__ unsigned long long s_tile;
   const Slot empty = KsKey<KW>::empty();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n_up = (n + 31) & ~(int64_t)31;   // whole warps stay in the loop for the ballots
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_up; i += stride) {
-    bool is_miss = false;
-    Slot x = empty;
-    if (i < n) {
-      x = rec[i];
-      KsKey<KW> kx;
-      if constexpr (KW == 1) kx.v = x; else { kx.v.hi = (unsigned long long)(x >> 64); kx.v.lo = (unsigned long long)x; }
-      unsigned long long h = g.slot(kx.hash());
-      const unsigned long long sbase = h & ~((1ull << g.slice_log) - 1ull), smask = (1ull << g.slice_log) - 1ull;
-      for (;;) {
-        const Slot c = table[h];
-        if (c == x) break;
-        if (c == empty) { is_miss = true; break; }
-        h = sbase | ((h + 1) & smask);
-      }
+  const unsigned long long smask = (1ull << g.slice_log) - 1ull;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1ull);
+    __syncthreads();
+    const int64_t base = (int64_t)s_tile * (NT * R);
+    __syncthreads();
+    if (base >= n) return;
+    Slot x[R], c[R];
+    unsigned long long h[R];
+    bool live[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t i = base + r * NT + threadIdx.x;
+      live[r] = i < n;
+      x[r] = rec[live[r] ? i : n - 1];
+      h[r] = g.slot(ks_unpack<KW>(x[r]).hash());
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, is_miss);
-    if (bal) {
-      unsigned long long base = 0;
-      if ((threadIdx.x & 31) == 0) base = atomicAdd(miss_cursor, (unsigned long long)__popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (is_miss) miss[base + __popc(bal & lanemask_lt())] = x;
+#pragma unroll
+    for (int r = 0; r < R; ++r) c[r] = table[h[r]];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const unsigned long long sbase = h[r] & ~smask;
+      while (c[r] != empty && c[r] != x[r]) {
+        h[r] = sbase | ((h[r] + 1) & smask);
+        c[r] = table[h[r]];
+      }
+      const bool is_miss = live[r] && c[r] == empty;
+      const unsigned bal = __ballot_sync(0xffffffffu, is_miss);
+      if (bal) {
+        unsigned long long at = 0;
+        if ((threadIdx.x & 31) == 0) at = atomicAdd(miss_cursor, (unsigned long long)__popc(bal));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (is_miss) miss[at + __popc(bal & lanemask_lt())] = x[r];
+      }
     }
   }
 }
