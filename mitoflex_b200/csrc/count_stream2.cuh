@@ -30,10 +30,10 @@ constexpr int kC2NW = kC2NC / 32;       // consumer warps
 constexpr int kC2NT = kC2NC + 32;       // + the producer warp
 constexpr int kC2RelSlotsLog = 13;      // REL: 8192 slots of 8 bytes (key | count)
 constexpr int kC2FullSlotsLog = 12;     // FULL: 4096 keys + 4096 counts
-constexpr int kC2ChunkLog = 11;         // 2048 keys (16 KB) per ring stage
+constexpr int kC2ChunkLog = 10;         // 1024 keys (8 KB) per ring stage
 constexpr int kC2Chunk = 1 << kC2ChunkLog;
-constexpr int kC2StagesRel = 2;         // ring stages (a power of two: the ring is addressed modulo stages * chunk)
-constexpr int kC2StagesFull = 2;
+constexpr int kC2StagesRel = 4;         // ring stages (a power of two: the ring is addressed modulo stages * chunk); with two
+constexpr int kC2StagesFull = 4;        // stages of 2048 keys 13 % of all instructions were spins on the full barrier (ncu r2e)
 constexpr int kC2MinCountBits = 17;     // REL needs room for counts up to 65535 and then some
 
 template <bool REL>
@@ -372,6 +372,57 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
     while (p < chi) {
       const uint32_t e = chi < bend ? chi : bend;
       if (!skip) {
+        if (REL && p == pbeg && tid == 0) {   // the bucket's first key is its reference (it is in the ring: p lies in this chunk)
+          const unsigned long long raw = ring[(pbeg + off0) & (uint32_t)(RingKeys - 1)];
+          s_ref[0] = (raw << 32) | (raw >> 32);
+        }
+        if constexpr (REL && CBT == 32) {
+          // slot = (key part << 32) | count: the high word is compared as it is, the low word counts.  A record is two
+          // big-endian words (x = high half of the key), so the key part is one funnel shift.
+          const uint2 *ring2 = reinterpret_cast<const uint2 *>(ring);
+          for (uint32_t q0 = p + tid; q0 < e; q0 += U * NC) {
+            uint32_t v[U], h[U];
+            uint2 sl[U];
+            bool pend[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const uint32_t q = q0 + u * NC;
+              pend[u] = q < e;
+              const uint2 w = ring2[(min(q, e - 1) + off0) & (uint32_t)(RingKeys - 1)];
+              v[u] = __funnelshift_r(w.y, w.x, key_shift);
+              h[u] = (v[u] * 0x9E3779B1u) >> (32 - C::SlotsLog);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {   // x = count, y = key part (volatile: the table changes under us)
+              const unsigned long long t = *reinterpret_cast<volatile unsigned long long *>(tab + h[u]);
+              sl[u] = make_uint2((uint32_t)t, (uint32_t)(t >> 32));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const bool hit = pend[u] && sl[u].y == v[u] && sl[u].x != 0u;   // an occupied slot has a count >= 1
+              if (hit) atomicAdd(reinterpret_cast<uint32_t *>(tab + h[u]), 1u);
+              pend[u] = pend[u] && !hit;
+            }
+            // what the first slot did not settle: claims of new keys, collisions (a few lanes each)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (pend[u]) {
+                const unsigned long long claim = ((unsigned long long)v[u] << 32) | 1ull;
+                uint32_t hh = h[u];
+                unsigned long long sv = ((unsigned long long)sl[u].y << 32) | sl[u].x;
+#pragma unroll 1
+                for (int probe = 0;;) {
+                  if (sv == 0ull) sv = atomicCAS(tab + hh, 0ull, claim);
+                  if (sv == 0ull) break;
+                  if ((uint32_t)(sv >> 32) == v[u]) { atomicAdd(reinterpret_cast<uint32_t *>(tab + hh), 1u); break; }
+                  if (++probe >= kCsProbeLimit) { s_flag[0] = 1; break; }   // table too crowded: the bucket bails
+                  hh = (hh + 1) & (Slots - 1);
+                  sv = *reinterpret_cast<volatile unsigned long long *>(tab + hh);
+                }
+              }
+            }
+          }
+        } else
         for (uint32_t q0 = p + tid; q0 < e; q0 += U * NC) {
           unsigned long long key[U];
           uint32_t h[U];
@@ -383,7 +434,6 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
             // records are two big-endian u32 words: word 0 (the key's high half) is the low half of the 8-byte load
             const unsigned long long raw = ring[(min(q, e - 1) + off0) & (uint32_t)(RingKeys - 1)];
             key[u] = (raw << 32) | (raw >> 32);
-            if (q == pbeg) s_ref[0] = key[u];   // the bucket's first key is its reference (REL)
             if constexpr (REL) h[u] = ((uint32_t)(key[u] >> key_shift) * 0x9E3779B1u) >> (32 - C::SlotsLog);
             else h[u] = ((((uint32_t)key[u] ^ ((uint32_t)(key[u] >> 32) * 0x9E3779B1u))) * 0x85EBCA6Bu) >> (32 - C::SlotsLog);
           }
@@ -413,6 +463,7 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
                 const unsigned long long v = (key[u] >> key_shift) & (~0ull >> CB);
                 uint32_t hh = h[u];
                 int probe = 1;
+#pragma unroll 1
                 for (;;) {
                   hh = (hh + 1) & (Slots - 1);
                   unsigned long long sv = *reinterpret_cast<volatile unsigned long long *>(tab + hh);
@@ -443,6 +494,7 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
               if (pend[u]) {
                 uint32_t hh = h[u];
                 int probe = 1;
+#pragma unroll 1
                 for (;;) {
                   hh = (hh + 1) & (Slots - 1);
                   unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tab + hh);

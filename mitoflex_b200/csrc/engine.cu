@@ -2108,6 +2108,21 @@ void dev_sdbg_items(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, uint3
   if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
   MF_DISPATCH_W(words_item(k), SITEMS)
 }
+// the same plus every item of the sequences (contigs): 6 n_edges + seqs.n_items items
+#define MF_DISPATCH_CASE_SITEMSQ(Wn)                                                 \
+  case Wn: {                                                                          \
+    ItemSource src;                                                                   \
+    src.edges = edges;                                                                \
+    src.n_edges = n_edges;                                                            \
+    src.seqs = seqs;                                                                  \
+    Stage st(c, "items");                                                             \
+    return sdbg_generate<Wn, 0>(c, src, k, items_out, 0, 0u, 0u, nullptr, nullptr);   \
+  }
+int64_t dev_sdbg_items_seqs(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &seqs, int k, uint32_t *items_out) {
+  if (k < 9 || k > 150) throw std::invalid_argument("k must be in [9, 150]");
+  MF_DISPATCH_W(words_item(k), SITEMSQ)
+  return 0;
+}
 // generic: histogram / partition of W-word records by their top l1_bits (one segment)
 template <int W>
 static void records_hist_impl(Ctx &c, const uint32_t *rec, int64_t n, int l1_bits, unsigned long long *hist_dev) {

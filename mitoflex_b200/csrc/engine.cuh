@@ -123,6 +123,7 @@ void dev_count_finish(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys,
                       int min_count, EdgesView *out, int64_t *counting_host);
 
 void dev_sdbg_items(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, uint32_t *items_out);
+int64_t dev_sdbg_items_seqs(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &seqs, int k, uint32_t *items_out);
 void dev_records_hist(Ctx &c, const uint32_t *rec, int64_t n, int words, int l1_bits, unsigned long long *hist_dev);
 void dev_records_scatter(Ctx &c, const uint32_t *rec, int64_t n, int words, int l1_bits, const unsigned long long *hist_dev,
                          uint32_t *out, const unsigned long long *bin_base);

@@ -424,4 +424,209 @@ void file_read2sdbg(Ctx &c, const char *read_lib_file, int k, int min_count, con
   write_sdbg(c, g, out_prefix, n_files);
 }
 
+
+// ---------------------------------------------------------------- several GPUs (multi.cu): one file per GPU
+// Rank r holds a contiguous piece of the sorted stream; its buckets go to file r in order, the meta rows are the same as in the
+// single-GPU writers (bucket -> file, offset, count).
+static void write_edges_multi(MultiGpu &mg, const std::string &prefix) {
+  const int G = mg.world();
+  int64_t total = 0;
+  for (int r = 0; r < G; ++r) total += mg.edges(r).n_edges;
+  const EdgesView &e0 = mg.edges(0);
+  std::ostringstream info;
+  info << "kmer_size " << e0.k << "\nwords_per_edge " << e0.words << "\nnum_files " << G << "\nnum_buckets " << kNumBuckets
+       << "\nnum_edges " << total << "\nis_sorted 1\n";
+  std::vector<std::string> rows(kNumBuckets);
+  for (int r = 0; r < G; ++r) {
+    Ctx &c = mg.ctx(r);
+    const EdgesView &e = mg.edges(r);
+    MF_CUDA(cudaSetDevice(c.device));
+    std::vector<uint32_t> host((size_t)e.n_edges * e.words);
+    if (e.n_edges) c.d2h(host.data(), e.edges, host.size() * 4);
+    File f(prefix + ".edges." + std::to_string(r), "wb");
+    f.write(host.data(), host.size() * 4);
+    f.close();
+    int64_t off = 0;
+    for (int b = 0; b < kNumBuckets; ++b) {
+      const int64_t cnt = c.edge_bucket_counts[b];
+      if (!cnt) continue;
+      if (!rows[b].empty()) throw std::runtime_error("bucket " + std::to_string(b) + " is held by two GPUs");
+      rows[b] = std::to_string(b) + ' ' + std::to_string(r) + ' ' + std::to_string(off) + ' ' + std::to_string(cnt) + '\n';
+      off += cnt;
+    }
+    if (off != e.n_edges) throw std::runtime_error("bucket counts do not add up to the edge count");
+  }
+  for (int b = 0; b < kNumBuckets; ++b) {
+    if (rows[b].empty()) info << b << " -1 0 0\n";
+    else info << rows[b];
+  }
+  File fi(prefix + ".edges.info", "w");   // meta file last
+  const std::string s = info.str();
+  fi.write(s.data(), s.size());
+  fi.close();
+}
+static void write_sdbg_multi(MultiGpu &mg, const std::string &prefix) {
+  const int G = mg.world();
+  const SdbgView &g0 = mg.sdbg(0);
+  std::ostringstream info;
+  info << "k " << g0.k << "\nwords_per_tip_label " << g0.words_tip << "\nnum_buckets " << kNumBuckets << "\nnum_files " << G << '\n';
+  std::vector<std::string> rows(kNumBuckets);
+  int64_t n_items = 0, n_tips = 0, n_large = 0;
+  std::vector<uint8_t> buf;
+  for (int r = 0; r < G; ++r) {
+    Ctx &c = mg.ctx(r);
+    const SdbgView &g = mg.sdbg(r);
+    MF_CUDA(cudaSetDevice(c.device));
+    std::vector<uint32_t> rec((size_t)g.n_items), labels((size_t)g.n_tips * g.words_tip);
+    if (g.n_items) c.d2h(rec.data(), g.rec, rec.size() * 4);
+    if (g.n_tips) c.d2h(labels.data(), g.labels, labels.size() * 4);
+    File f(prefix + ".sdbg." + std::to_string(r), "wb");
+    int64_t pos = 0, tpos = 0, foff = 0;
+    for (int b = 0; b < kNumBuckets; ++b) {
+      const int64_t items = c.sdbg_bucket_stats[(size_t)b * 3], tips = c.sdbg_bucket_stats[(size_t)b * 3 + 1],
+                    lg = c.sdbg_bucket_stats[(size_t)b * 3 + 2];
+      if (!items) continue;
+      if (!rows[b].empty()) throw std::runtime_error("sdbg bucket " + std::to_string(b) + " is held by two GPUs");
+      buf.clear();
+      for (int64_t i = pos; i < pos + items; ++i) {
+        const uint32_t rr = rec[(size_t)i];
+        const uint32_t m = rr >> 8;
+        const uint16_t small = (uint16_t)((rr & 0x3f) | (std::min<uint32_t>(m, 255) << 8));
+        buf.insert(buf.end(), (const uint8_t *)&small, (const uint8_t *)&small + 2);
+        if (m > 254) { const uint16_t mm = (uint16_t)m; buf.insert(buf.end(), (const uint8_t *)&mm, (const uint8_t *)&mm + 2); ++n_large; }
+        if (rr & 0x20) {
+          const uint8_t *lp = (const uint8_t *)(labels.data() + (size_t)tpos * g.words_tip);
+          buf.insert(buf.end(), lp, lp + 4 * g.words_tip);
+          ++tpos;
+        }
+      }
+      f.write(buf.data(), buf.size());
+      rows[b] = std::to_string(b) + ' ' + std::to_string(r) + ' ' + std::to_string(foff) + ' ' + std::to_string(items) + ' ' +
+                std::to_string(tips) + ' ' + std::to_string(lg) + '\n';
+      foff += (int64_t)buf.size();
+      pos += items;
+    }
+    if (pos != g.n_items || tpos != g.n_tips) throw std::runtime_error("sdbg bucket statistics do not add up");
+    f.close();
+    n_items += g.n_items;
+    n_tips += g.n_tips;
+  }
+  int64_t n_empty = 0;
+  for (int b = 0; b < kNumBuckets; ++b) {
+    if (rows[b].empty()) ++n_empty;
+    else info << rows[b];
+  }
+  for (int64_t i = 0; i < n_empty; ++i) info << "18446744073709551615 0 0 0 0 0\n";
+  info << "item_count " << n_items << "\ntip_count " << n_tips << "\nlarge_mul_count " << n_large << '\n';
+  File fi(prefix + ".sdbg_info", "w");
+  const std::string s = info.str();
+  fi.write(s.data(), s.size());
+  fi.close();
+}
+// the read library cut into `world` runs of whole reads (by read count), each unpacked on its GPU
+static std::vector<ReadsView> load_read_lib_multi(MultiGpu &mg, const char *read_lib_file) {
+  std::vector<uint8_t> raw = slurp_binary(std::string(read_lib_file) + ".bin");
+  if (raw.size() % 4) throw IoError("read library .bin is not a whole number of words");
+  const uint32_t *st = reinterpret_cast<const uint32_t *>(raw.data());
+  const int64_t nw = (int64_t)(raw.size() / 4);
+  std::vector<int64_t> rec_off;
+  for (int64_t p = 0; p < nw;) {
+    rec_off.push_back(p);
+    p += 1 + (((int64_t)st[p] + 15) >> 4);
+    if (p > nw) throw IoError("truncated read library (.bin)");
+  }
+  const int64_t n = (int64_t)rec_off.size();
+  rec_off.push_back(nw);
+  const int G = mg.world();
+  std::vector<ReadsView> out(G);
+  for (int r = 0; r < G; ++r) {
+    const int64_t lo = n * r / G, hi = n * (r + 1) / G;
+    MF_CUDA(cudaSetDevice(mg.ctx(r).device));
+    bin_stream_to_reads(mg.ctx(r), st + rec_off[lo], rec_off[hi] - rec_off[lo], &out[r]);
+  }
+  return out;
+}
+void file_count_multi(const std::vector<int> &devices, const char *read_lib_file, int k, int min_count, const char *out_prefix) {
+  MultiGpu mg(devices);
+  std::vector<ReadsView> reads = load_read_lib_multi(mg, read_lib_file);
+  mg.count(reads, k, min_count, true);
+  write_edges_multi(mg, out_prefix);
+  File fc(std::string(out_prefix) + ".counting", "w");
+  std::ostringstream ss;
+  long long acc = 0;
+  for (int i = 1; i <= kMaxMul; ++i) {
+    for (int r = 0; r < mg.world(); ++r) acc += mg.counting(r)[i];   // the GPUs hold disjoint key ranges: the histograms add
+    ss << i << ' ' << acc << '\n';
+  }
+  const std::string s = ss.str();
+  fc.write(s.data(), s.size());
+  fc.close();
+}
+void file_read2sdbg_multi(const std::vector<int> &devices, const char *read_lib_file, int k, int min_count, const char *out_prefix) {
+  MultiGpu mg(devices);
+  std::vector<ReadsView> reads = load_read_lib_multi(mg, read_lib_file);
+  mg.read2sdbg(reads, k, min_count);
+  write_sdbg_multi(mg, out_prefix);
+}
+void file_seq2sdbg_multi(const std::vector<int> &devices, int k, int k_from, const char *input_prefix, const char *contig, const char *bubble,
+                         const char *addi_contig, const char *local_contig, const char *out_prefix) {
+  HostEdges he;
+  if (input_prefix && *input_prefix) {
+    he = read_edges(input_prefix);
+    if (he.k != k) throw IoError("edges were built for k=" + std::to_string(he.k) + ", not " + std::to_string(k));
+  }
+  HostSeqs all;
+  if (contig && *contig) add_contigs(&all, contig, k, true, k_from, k);
+  if (bubble && *bubble) add_contigs(&all, bubble, k, true, k_from, k);
+  if (addi_contig && *addi_contig) add_contigs(&all, addi_contig, k, false, 0, 0);
+  if (local_contig && *local_contig) add_contigs(&all, local_contig, k, false, 0, 0);
+  MultiGpu mg(devices);
+  const int G = mg.world(), nseq = (int)all.mult.size(), words = std::max(he.words, 1);
+  std::vector<std::unique_ptr<DevMem>> keep;
+  std::vector<const uint32_t *> d_edges(G, nullptr);
+  std::vector<int64_t> n_edges(G, 0);
+  std::vector<SeqsView> seqs(G);
+  for (int r = 0; r < G; ++r) {
+    Ctx &c = mg.ctx(r);
+    MF_CUDA(cudaSetDevice(c.device));
+    // edges by index, sequences by index: any split works, the exchange routes every item to the GPU that owns its prefix
+    const int64_t e_lo = he.n * r / G, e_hi = he.n * (r + 1) / G;
+    n_edges[r] = e_hi - e_lo;
+    keep.emplace_back(new DevMem((size_t)n_edges[r] * words * 4 + 64));
+    if (n_edges[r]) c.h2d(keep.back()->p, he.data.data() + (size_t)e_lo * words, (size_t)n_edges[r] * words * 4);
+    d_edges[r] = keep.back()->as<uint32_t>();
+    const int s_lo = (int)((int64_t)nseq * r / G), s_hi = (int)((int64_t)nseq * (r + 1) / G);
+    if (s_hi > s_lo) {
+      HostSeqs part;   // re-packed so that the piece starts at base 0
+      for (int i = s_lo; i < s_hi; ++i) {
+        std::vector<uint8_t> codes((size_t)(all.starts[i + 1] - all.starts[i]));
+        for (size_t j = 0; j < codes.size(); ++j) {
+          const int64_t g = all.starts[i] + (int64_t)j;
+          codes[j] = (uint8_t)((all.packed[g >> 4] >> (30 - 2 * (g & 15))) & 3u);
+        }
+        part.add(codes, all.mult[i], k);
+      }
+      const int ns = s_hi - s_lo;
+      keep.emplace_back(new DevMem(part.packed.size() * 4 + 256));
+      MF_CUDA(cudaMemsetAsync(keep.back()->p, 0, part.packed.size() * 4 + 256, c.stream));
+      c.h2d(keep.back()->p, part.packed.data(), part.packed.size() * 4);
+      seqs[r].packed = keep.back()->as<uint32_t>();
+      keep.emplace_back(new DevMem(sizeof(int64_t) * (ns + 1)));
+      c.h2d(keep.back()->p, part.starts.data(), sizeof(int64_t) * (ns + 1));
+      seqs[r].starts = keep.back()->as<int64_t>();
+      keep.emplace_back(new DevMem(sizeof(uint16_t) * (ns + 1)));
+      c.h2d(keep.back()->p, part.mult.data(), sizeof(uint16_t) * ns);
+      seqs[r].mult = keep.back()->as<uint16_t>();
+      keep.emplace_back(new DevMem(sizeof(int64_t) * (ns + 1)));
+      c.h2d(keep.back()->p, part.item_base.data(), sizeof(int64_t) * (ns + 1));
+      seqs[r].item_base = keep.back()->as<int64_t>();
+      seqs[r].nseq = ns;
+      seqs[r].n_items = part.item_base.back();
+    }
+  }
+  mg.seq2sdbg(d_edges, n_edges, seqs, k);
+  write_sdbg_multi(mg, out_prefix);
+  keep.clear();
+}
+
 }  // namespace mf
