@@ -3,6 +3,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <vector>
 #include "engine.cuh"
 #include "hostio.h"
 #include "mfsdbg.h"
@@ -399,6 +400,12 @@ static int pick_device(const mfsdbg_opts *o) {
   if (o && o->n_gpus > 0 && o->gpu_ids) return o->gpu_ids[0];
   return 0;
 }
+// n_gpus > 1: the listed devices (or 0 .. n_gpus-1) share the job inside this one process (multi.cu)
+static std::vector<int> device_list(const mfsdbg_opts *o) {
+  std::vector<int> d;
+  for (int i = 0; i < o->n_gpus; ++i) d.push_back(o->gpu_ids ? o->gpu_ids[i] : i);
+  return d;
+}
 static int need_device() {
   if (mfsdbg_device_count() < 1) {
     g_err = "no CUDA device visible: libmfsdbg has no CPU fallback";
@@ -421,6 +428,7 @@ int mfsdbg_count(const mfsdbg_opts *o) {
   if (int rc = need_device()) return rc;
   std::lock_guard<std::mutex> lk(g_job_mutex);
   return guarded([&] {
+    if (o->n_gpus > 1) return mf::file_count_multi(device_list(o), o->read_lib_file, o->k, o->min_count, o->output_prefix);
     mf::Ctx c(pick_device(o));
     mf::file_count(c, o->read_lib_file, o->k, o->min_count, o->output_prefix, std::max(1, o->num_cpu_threads));
   });
@@ -431,6 +439,9 @@ int mfsdbg_seq2sdbg(const mfsdbg_opts *o) {
   if (int rc = need_device()) return rc;
   std::lock_guard<std::mutex> lk(g_job_mutex);
   return guarded([&] {
+    if (o->n_gpus > 1)
+      return mf::file_seq2sdbg_multi(device_list(o), o->k, o->kmer_from, o->input_prefix, o->contig, o->bubble, o->addi_contig,
+                                     o->local_contig, o->output_prefix);
     mf::Ctx c(pick_device(o));
     mf::file_seq2sdbg(c, o->k, o->kmer_from, o->input_prefix, o->contig, o->bubble, o->addi_contig, o->local_contig,
                       o->output_prefix, std::max(1, o->num_cpu_threads));
@@ -442,6 +453,7 @@ int mfsdbg_read2sdbg(const mfsdbg_opts *o) {
   if (int rc = need_device()) return rc;
   std::lock_guard<std::mutex> lk(g_job_mutex);
   return guarded([&] {
+    if (o->n_gpus > 1) return mf::file_read2sdbg_multi(device_list(o), o->read_lib_file, o->k, o->min_count, o->output_prefix);
     mf::Ctx c(pick_device(o));
     mf::file_read2sdbg(c, o->read_lib_file, o->k, o->min_count, o->output_prefix, std::max(1, o->num_cpu_threads));
   });

@@ -111,10 +111,11 @@ def main(argv=None):
             lib.buildlib(rest[0], rest[1], policy)
         else:
             opts = parse(rest)
-            if "MFSDBG_GPU" in os.environ:
+            if "MFSDBG_GPU" in os.environ:   # "0" or "0,1,2,3": several GPUs share the sub-command inside this one process
                 import ctypes
-                ids = (ctypes.c_int32 * 1)(int(os.environ["MFSDBG_GPU"]))
-                opts["n_gpus"], opts["gpu_ids"] = 1, ids
+                want = [int(x) for x in os.environ["MFSDBG_GPU"].replace(" ", "").split(",") if x != ""]
+                ids = (ctypes.c_int32 * len(want))(*want)
+                opts["n_gpus"], opts["gpu_ids"] = len(want), ids
             getattr(lib, cmd)(**opts)
     except (lib.MfsdbgError, ValueError, OSError) as e:
         sys.stderr.write(f"megahit_core {cmd}: {e}\n")
