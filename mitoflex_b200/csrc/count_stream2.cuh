@@ -30,10 +30,11 @@ constexpr int kC2NW = kC2NC / 32;       // consumer warps
 constexpr int kC2NT = kC2NC + 32;       // + the producer warp
 constexpr int kC2RelSlotsLog = 13;      // REL: 8192 slots of 8 bytes (key | count)
 constexpr int kC2FullSlotsLog = 12;     // FULL: 4096 keys + 4096 counts
-constexpr int kC2ChunkLog = 10;         // 1024 keys (8 KB) per ring stage
+constexpr int kC2ChunkLog = 11;         // 2048 keys (16 KB) per ring stage = one round of 4 keys per consumer thread
 constexpr int kC2Chunk = 1 << kC2ChunkLog;
-constexpr int kC2StagesRel = 4;         // ring stages (a power of two: the ring is addressed modulo stages * chunk); with two
-constexpr int kC2StagesFull = 4;        // stages of 2048 keys 13 % of all instructions were spins on the full barrier (ncu r2e)
+constexpr int kC2StagesRel = 2;         // ring stages (a power of two: the ring is addressed modulo stages * chunk).  Two are
+constexpr int kC2StagesFull = 2;        // enough because a warp hands a stage back as soon as its keys are in registers
+constexpr int kC2QueueCap = 112;        // per-warp queue of keys whose first slot held another key (aliases the bucket-end arrays)
 constexpr int kC2MinCountBits = 17;     // REL needs room for counts up to 65535 and then some
 
 template <bool REL>
@@ -47,8 +48,8 @@ struct C2Cfg {
 template <bool REL>
 inline size_t count_stream2_smem_bytes() {
   using C = C2Cfg<REL>;
-  // table | ring u64 | skeys u64[768] | mbar u64[8] | scnt u32[768] | bnd u32[win+2] | bins u32[260] | small u32[64]
-  // | scratch u32[40] | flag i32[16] | ref u64[2] | permA,permB,rk u16[768]
+  // table | ring u64 | mbar u64[8] | bnd u32[win+2] | small u32[64] | flag i32[16] | ref u64[2]
+  // | { skeys u64[768] | scnt u32[768] | bins u32[260] | scratch u32[40] | permA,permB,rk u16[768] }  (aliased by the queues)
   return C::TableBytes + (size_t)C::RingKeys * 8 + (size_t)kCsSolidMax * 8 + 64 + (size_t)kCsSolidMax * 4 + (size_t)(kCsWin + 2) * 4 +
          260 * 4 + 64 * 4 + 40 * 4 + 16 * 4 + 16 + 3 * (size_t)kCsSolidMax * 2;
 }
@@ -105,17 +106,19 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
   unsigned long long *tab = reinterpret_cast<unsigned long long *>(smraw);                 // REL: [8192] slots; FULL: [4096] keys
   uint32_t *tcnt = reinterpret_cast<uint32_t *>(tab + (REL ? 0 : Slots));                  // FULL: [4096] counts
   unsigned long long *ring = reinterpret_cast<unsigned long long *>(smraw + C::TableBytes);
-  unsigned long long *skeys = ring + RingKeys;
-  unsigned long long *mbar = skeys + kCsSolidMax;                                          // [0..3] full, [4..7] empty
-  uint32_t *scnt = reinterpret_cast<uint32_t *>(mbar + 8);
-  uint32_t *s_bnd = scnt + kCsSolidMax;
-  uint32_t *bins = s_bnd + kCsWin + 2;
-  uint32_t *s_small = bins + 260;
-  uint32_t *scratch = s_small + 64;
-  int *s_flag = reinterpret_cast<int *>(scratch + 40);   // 0 crowded, 1 ok, 2..3 arena base, 4 ns, 5 blk_left, 6..7 blk_pos
+  unsigned long long *mbar = ring + RingKeys;                                              // [0..3] full, [4..7] empty
+  uint32_t *s_bnd = reinterpret_cast<uint32_t *>(mbar + 8);
+  uint32_t *s_small = s_bnd + kCsWin + 2;
+  int *s_flag = reinterpret_cast<int *>(s_small + 64);   // 0 crowded, 1 ok, 2..3 arena base, 4 ns, 5 blk_left, 6..7 blk_pos
   unsigned long long *s_ref = reinterpret_cast<unsigned long long *>(s_flag + 16);         // [0] reference key of the bucket
-  uint16_t *permA = reinterpret_cast<uint16_t *>(s_ref + 2);
+  // the bucket-end arrays and the per-warp queues of the rounds are never live together (a barrier separates the phases)
+  unsigned long long *skeys = s_ref + 2;
+  uint32_t *scnt = reinterpret_cast<uint32_t *>(skeys + kCsSolidMax);
+  uint32_t *bins = scnt + kCsSolidMax;
+  uint32_t *scratch = bins + 260;
+  uint16_t *permA = reinterpret_cast<uint16_t *>(scratch + 40);
   uint16_t *permB = permA + kCsSolidMax, *rk = permB + kCsSolidMax;
+  uint2 *wqueue = reinterpret_cast<uint2 *>(skeys) + (threadIdx.x >> 5) * kC2QueueCap;     // [kC2QueueCap] (key part, slot)
   uint32_t *whist32 = reinterpret_cast<uint32_t *>(tab);   // sub-bin counters [1025] of the many-solid-keys sort alias the swept table
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -369,6 +372,7 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
     const int s = c & (Stages - 1);
     mbar_wait(mbar + s, (uint32_t)((c / Stages) & 1));
     const uint32_t chi = min((uint32_t)(((c + 1) << kC2ChunkLog) - off0), total);   // relative end of the chunk
+    bool released = false;   // this warp has handed stage s back already (warp-uniform)
     while (p < chi) {
       const uint32_t e = chi < bend ? chi : bend;
       if (!skip) {
@@ -378,7 +382,10 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
         }
         if constexpr (REL && CBT == 32) {
           // slot = (key part << 32) | count: the high word is compared as it is, the low word counts.  A record is two
-          // big-endian words (x = high half of the key), so the key part is one funnel shift.
+          // big-endian words (x = high half of the key), so the key part is one funnel shift.  Per round: 4 keys per thread,
+          // their ring and slot loads in flight together; a hit is one predicated RED, an empty slot one CAS; what met another
+          // key goes to the warp's queue and is probed on by all 32 lanes afterwards (a few keys per hundred: no lane idles in a
+          // divergent probe loop, which was where the first version of this kernel spent most of its instructions).
           const uint2 *ring2 = reinterpret_cast<const uint2 *>(ring);
           for (uint32_t q0 = p + tid; q0 < e; q0 += U * NC) {
             uint32_t v[U], h[U];
@@ -392,35 +399,55 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
               v[u] = __funnelshift_r(w.y, w.x, key_shift);
               h[u] = (v[u] * 0x9E3779B1u) >> (32 - C::SlotsLog);
             }
+            // the last keys of the chunk are in registers: the stage can be refilled while they are processed
+            if (e == chi && q0 - tid + U * NC >= e && !released) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(mbar + 4 + s);
+              released = true;
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {   // x = count, y = key part (volatile: the table changes under us)
               const unsigned long long t = *reinterpret_cast<volatile unsigned long long *>(tab + h[u]);
               sl[u] = make_uint2((uint32_t)t, (uint32_t)(t >> 32));
             }
+            uint32_t nq = 0;   // queued keys of this round (warp-uniform)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              const bool hit = pend[u] && sl[u].y == v[u] && sl[u].x != 0u;   // an occupied slot has a count >= 1
-              if (hit) atomicAdd(reinterpret_cast<uint32_t *>(tab + h[u]), 1u);
-              pend[u] = pend[u] && !hit;
-            }
-            // what the first slot did not settle: claims of new keys, collisions (a few lanes each)
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              if (pend[u]) {
-                const unsigned long long claim = ((unsigned long long)v[u] << 32) | 1ull;
-                uint32_t hh = h[u];
-                unsigned long long sv = ((unsigned long long)sl[u].y << 32) | sl[u].x;
-#pragma unroll 1
-                for (int probe = 0;;) {
-                  if (sv == 0ull) sv = atomicCAS(tab + hh, 0ull, claim);
-                  if (sv == 0ull) break;
-                  if ((uint32_t)(sv >> 32) == v[u]) { atomicAdd(reinterpret_cast<uint32_t *>(tab + hh), 1u); break; }
-                  if (++probe >= kCsProbeLimit) { s_flag[0] = 1; break; }   // table too crowded: the bucket bails
-                  hh = (hh + 1) & (Slots - 1);
-                  sv = *reinterpret_cast<volatile unsigned long long *>(tab + hh);
-                }
+              if (pend[u] && (sl[u].x | sl[u].y) == 0u) {   // empty: claim it (count 1); a lost race returns the winner's slot
+                const unsigned long long t = atomicCAS(tab + h[u], 0ull, ((unsigned long long)v[u] << 32) | 1ull);
+                sl[u] = make_uint2((uint32_t)t, (uint32_t)(t >> 32));
+                pend[u] = t != 0ull;
               }
+              const bool hit = pend[u] && sl[u].y == v[u];   // an occupied slot has a count >= 1
+              if (hit) atomicAdd(reinterpret_cast<uint32_t *>(tab + h[u]), 1u);
+              const bool more = pend[u] && !hit;
+              const unsigned bal = __ballot_sync(0xffffffffu, more);
+              const uint32_t at = nq + (uint32_t)__popc(bal & lt);
+              nq += (uint32_t)__popc(bal);
+              pend[u] = more && at >= (uint32_t)kC2QueueCap;   // no room in the queue (never, in practice): probed in line below
+              if (more && !pend[u]) wqueue[at] = make_uint2(v[u], h[u]);
             }
+            auto probe_on = [&](uint32_t vv, uint32_t hh) {   // the first slot held another key: linear probing from the next one
+              const unsigned long long claim = ((unsigned long long)vv << 32) | 1ull;
+#pragma unroll 1
+              for (int probe = 1;; ++probe) {
+                hh = (hh + 1) & (Slots - 1);
+                unsigned long long sv = *reinterpret_cast<volatile unsigned long long *>(tab + hh);
+                if (sv == 0ull) sv = atomicCAS(tab + hh, 0ull, claim);
+                if (sv == 0ull) break;
+                if ((uint32_t)(sv >> 32) == vv) { atomicAdd(reinterpret_cast<uint32_t *>(tab + hh), 1u); break; }
+                if (probe >= kCsProbeLimit) { s_flag[0] = 1; break; }   // table too crowded: the bucket bails
+              }
+            };
+            __syncwarp();
+            for (uint32_t i = lane; i < min(nq, (uint32_t)kC2QueueCap); i += 32) {
+              const uint2 qe = wqueue[i];
+              probe_on(qe.x, qe.y);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (pend[u]) probe_on(v[u], h[u]);
+            __syncwarp();   // the next round overwrites the queue
           }
         } else
         for (uint32_t q0 = p + tid; q0 < e; q0 += U * NC) {
@@ -519,8 +546,10 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
       }
     }
     // this warp is done with stage s (its keys live in registers / the table now)
-    __syncwarp();
-    if (lane == 0) mbar_arrive(mbar + 4 + s);
+    if (!released) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mbar + 4 + s);
+    }
   }
 }
 
