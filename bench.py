@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--min-count", type=int, default=2, help="solidity threshold -m (headline: 2)")
     ap.add_argument("--error-rate", type=float, default=0.005, help="substitution error rate of the synthetic reads (headline: 0.005)")
     ap.add_argument("--nuclear-len", type=int, default=50_000_000, help="nuclear background length (headline: 50 Mb)")
+    ap.add_argument("--no-config3", action="store_true", help="skip the wide-key blocks (k=119, k=141) added to the N=1 line")
     ap.add_argument("--verify-pairs", type=int, default=250_000,
                     help="N>1: read pairs per GPU of the correctness pass run before the timed region (0 = skip)")
     return ap.parse_args()
@@ -512,6 +513,38 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_baseline(args, args.cpu_seconds)
+    # ---- BASELINE configs[2]: the large-k path (multi-word keys) on the same reads, device-resident, driver-timed
+    config3 = None
+    if world == 1 and not args.no_config3 and K == 21:
+        config3 = {}
+        for kk in (119, 141):
+            try:
+                for _ in range(2):
+                    ctx.read2sdbg(reads, kk, MIN_COUNT)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                acc = {}
+                e0.record()
+                for _ in range(2):
+                    gk = ctx.read2sdbg(reads, kk, MIN_COUNT)
+                    for name, ms in ctx.last_profile().items():
+                        acc[name] = acc.get(name, 0.0) + ms / 2
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / 2
+                ek = ctx.count(reads, kk, MIN_COUNT)
+                sbk = stage_bytes(n_bases, ek.s.n_keys, ek.n, gk.n, kk)
+                domk = max((k2 for k2 in acc if k2 in sbk), key=lambda k2: acc[k2], default=None)
+                blk = {"ms_per_step": ms, "value": n_bases / (ms / 1e3), "unit": "bases/s", "keys": int(ek.s.n_keys), "solid_edges": int(ek.n),
+                       "sdbg_items": int(gk.n), "key_bytes": 4 * ((2 * (kk + 1) + 31) // 32),
+                       "stages_ms": {k2: round(v, 3) for k2, v in sorted(acc.items(), key=lambda kv: -kv[1])[:8]}}
+                if domk:
+                    achk = sbk[domk] / (acc[domk] / 1e3) / 1e9
+                    blk["roofline"] = {"bound": "hbm", "kernel": domk, "achieved": achk, "peak": peak, "unit": "GB/s", "frac": achk / peak,
+                                       "ms_per_launch": acc[domk], "algorithmic_bytes_per_launch": sbk[domk]}
+                config3[f"k{kk}"] = blk
+            except lib.MfsdbgError as ex:   # the blocks are extras: never lose the headline line over them
+                config3[f"k{kk}"] = {"error": str(ex)}
     out = {
         "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
@@ -521,6 +554,9 @@ def main():
                    "parallelism": "reads sharded by GPU, keys and items stored into the owner GPU of their prefix bin by the partition kernel itself (NVLink peer memory), disjoint key range per GPU" if world > 1 else "1 GPU"},
         "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
+    if config3 is not None:
+        out["config3"] = config3
+        out["config"]["config3"] = {k2: {"ms_per_step": v.get("ms_per_step"), "frac": (v.get("roofline") or {}).get("frac")} for k2, v in config3.items()}
     if world > 1:
         out["verified"] = bool(verify and verify.get("verified"))
         out["config"]["verified"] = out["verified"]

@@ -1,16 +1,7 @@
-// count_stream.cuh -- the count finish for keys of 33..64 bits (16 <= k <= 31): persistent CTAs stream CONTIGUOUS runs of
-// buckets out of HBM with TMA bulk copies (cp.async.bulk + mbarrier ring), so DRAM latency never meets the hash loop.
-//
-//   * a CTA owns a contiguous range of buckets == one contiguous key range; thread 0 keeps kCsStages bulk copies in
-//     flight across bucket boundaries, so the next bucket's keys arrive while the current one is being finished;
-//   * keys are grouped in a shared open-addressing table holding the keys themselves (64-bit CAS) + 32-bit counts
-//     (fire-and-forget shared REDs): a bucket of any size fits as long as its DISTINCT keys do;
-//   * bucket end: one sweep over the table collects the solid keys (count >= --min-count), feeds the multiplicity
-//     histogram and clears the slots for the next bucket; the few solid keys are ranked (all pairs, or LSD when many)
-//     and written as edge records (KmerCounter::PackEdge) into arena blocks reserved 4096 edges at a time.
-//   * probe: k_probe_distinct measures distinct/occurrences on a few whole prefix ranges beforehand, so the planner can
-//     size buckets for the table (deep coverage -> large buckets, shallow/erroneous data -> small ones).
-// Buckets whose distinct keys crowd the table or with more than kCsSolidMax solid keys go to the bail list (general path).
+// count_stream.cuh -- pieces shared by the streamed count finishes (k_count_stream2 for keys of 33..64 bits, k_count_stream_w
+// for wider ones): the mbarrier / bulk-copy primitives (cp.async.bulk + mbarrier: SASS UBLKCP + SYNCS), the split of the
+// bucket table into per-CTA ranges, the multi-pass kernel for buckets whose distinct keys crowd the shared table, the
+// distinct-ratio probe that sizes the buckets, and the TMA-fed scatter of a partition level.
 #pragma once
 #include "common.cuh"
 #include "local.cuh"
@@ -21,8 +12,6 @@ namespace mf {
 constexpr int kCsNT = 512;
 constexpr int kCsSlotsLog = 12;
 constexpr int kCsSlots = 1 << kCsSlotsLog;   // table slots
-constexpr int kCsChunk = 2048;               // keys per ring stage (16 KB bulk copy): 4 keys per thread and chunk
-constexpr int kCsStages = 3;
 constexpr int kCsSolidMax = 768;             // distinct solid keys of one bucket on this path
 constexpr int kCsWin = 256;                  // bucket boundaries held in shared memory at a time
 constexpr int kCsProbeLimit = 64;
@@ -65,11 +54,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
   }
 }
 
-inline size_t count_stream_smem_bytes() {
-  // tkeys u64[4096] | ring u64[stages*chunk] | skeys u64[1024] | mbar u64[4] | tcnt u32[4096] | scnt u32[1024]
-  // | bnd u32[win+2] | bins u32[260] | small u32[64] | scratch u32[40] | flag i32[16] | permA,permB,rk u16[1024]
-  return (size_t)kCsSlots * 8 + (size_t)kCsStages * kCsChunk * 8 + (size_t)kCsSolidMax * 8 + 64 + (size_t)kCsSlots * 4 +
-         (size_t)kCsSolidMax * 4 + (size_t)(kCsWin + 2) * 4 + 260 * 4 + 64 * 4 + 40 * 4 + 16 * 4 + 3 * (size_t)kCsSolidMax * 2;
+inline size_t count_multipass_smem_bytes() {
+  // tkeys u64[4096] | skeys u64[768] | tcnt u32[4096] | scnt u32[768] | bins u32[260] | small u32[64] | scratch u32[40]
+  // | flag i32[16] | permA,permB,rk u16[768]
+  return (size_t)kCsSlots * 8 + (size_t)kCsSolidMax * 8 + (size_t)kCsSlots * 4 + (size_t)kCsSolidMax * 4 + 260 * 4 + 64 * 4 + 40 * 4 +
+         16 * 4 + 3 * (size_t)kCsSolidMax * 2;
 }
 
 // cta_first[g] = first bucket slot of CTA g's range: ranges hold equal shares of the keys (bkt_start is monotone)
@@ -87,83 +76,35 @@ __global__ void k_split_ranges(const int64_t *bkt_start, const int64_t *bkt_size
   cta_first[g] = g == 0 ? 0 : lo;
 }
 
-// MULTIPASS = false: the streamed kernel proper.  MULTIPASS = true: one CTA per bucket that bailed there (too many distinct
-// keys for the table): the bucket's key range is cut into 2^passes_log equal sub-ranges and the bucket is re-read once per
-// sub-range and sweep (sweep 1 totals the solid keys so that the arena space is reserved in one piece, sweep 2 emits), keys
-// outside the pass's sub-range are skipped -- the table only ever holds a fraction of the distinct keys, output stays sorted.
-template <bool MULTIPASS>
-__global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const int32_t *__restrict__ cta_first, int passes_log) {
+// One CTA per bucket whose DISTINCT keys crowd the streamed kernel's table (k_count_stream2 puts it on the bail list): the
+// bucket's key range is cut into 2^passes_log equal sub-ranges and the bucket is re-read once per sub-range and sweep (sweep 1
+// totals the solid keys so that the arena space is reserved in one piece, sweep 2 emits); keys outside the pass's sub-range are
+// skipped -- the table only ever holds a fraction of the distinct keys, the output stays sorted.
+__global__ void __launch_bounds__(kCsNT, 2) k_count_multipass(LocalArgs a, int passes_log) {
   extern __shared__ __align__(128) unsigned char smraw[];
   constexpr int NT = kCsNT;
   unsigned long long *tkeys = reinterpret_cast<unsigned long long *>(smraw);
-  unsigned long long *ring = tkeys + kCsSlots;
-  unsigned long long *skeys = ring + kCsStages * kCsChunk;
-  unsigned long long *mbar = skeys + kCsSolidMax;
-  uint32_t *tcnt = reinterpret_cast<uint32_t *>(mbar + 8);   // mbar[0..3] full, mbar[4..7] empty
+  unsigned long long *skeys = tkeys + kCsSlots;
+  uint32_t *tcnt = reinterpret_cast<uint32_t *>(skeys + kCsSolidMax);
   uint32_t *scnt = tcnt + kCsSlots;
-  uint32_t *s_bnd = scnt + kCsSolidMax;
-  uint32_t *bins = s_bnd + kCsWin + 2;
+  uint32_t *bins = scnt + kCsSolidMax;
   uint32_t *s_small = bins + 260;
   uint32_t *scratch = s_small + 64;
-  int *s_flag = reinterpret_cast<int *>(scratch + 40);   // 0 crowded, 1 ok, 2..3 arena base, 4 ns, 5 blk_left, 6..7 blk_pos
+  int *s_flag = reinterpret_cast<int *>(scratch + 40);   // 0 crowded, 1 ok, 2..3 arena base, 4 ns, 8 bail, 9 total, 10 overflow
   uint16_t *permA = reinterpret_cast<uint16_t *>(s_flag + 16);
   uint16_t *permB = permA + kCsSolidMax, *rk = permB + kCsSolidMax;
   uint32_t *whist32 = tcnt;   // sub-bin counters [1025] of the many-solid-keys sort alias the (swept, empty) counts
 
   const int tid = threadIdx.x;
-  int b0 = 0, b1 = 0;
-  int64_t rb = 0, re = 0;
-  if constexpr (!MULTIPASS) {
-    b0 = cta_first[blockIdx.x];
-    b1 = cta_first[blockIdx.x + 1];
-    if (b0 >= b1) return;
-    rb = a.bkt_start[b0];
-    re = a.bkt_start[b1 - 1] + a.bkt_size[b1 - 1];
-  }
-  const uint32_t total = (uint32_t)(re - rb);
-  if (!MULTIPASS && total == 0u) return;
-  const int64_t A = rb & ~(int64_t)1;                    // bulk copies need 16-byte aligned addresses
-  const int64_t re_up = (re + 1) & ~(int64_t)1;
-  const int nchunks = (int)((re_up - A + kCsChunk - 1) / kCsChunk);
-  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(a.in);
   const uint32_t m = (uint32_t)a.min_count;
   const int We = a.words_edge;
-
-  auto issue = [&](int c) {   // thread 0 only
-    const int s = c % kCsStages;
-    const int64_t g0 = A + (int64_t)c * kCsChunk;
-    const int64_t left = re_up - g0;
-    const uint32_t bytes = (uint32_t)(left < kCsChunk ? left : kCsChunk) * 8u;
-    mbar_expect_tx(mbar + s, bytes);
-    bulk_g2s(ring + (size_t)s * kCsChunk, src + g0, bytes, mbar + s);
-  };
-  int wb = b0;   // first bucket of the boundary window
-  auto load_window = [&]() {
-    for (int i = tid; i <= kCsWin; i += NT) {
-      const int idx = wb + i;
-      s_bnd[i] = idx < b1 ? (uint32_t)(a.bkt_start[idx] - rb) : total;
-    }
-  };
-
-  if (tid == 0) {
-    for (int s = 0; s < kCsStages; ++s) {
-      mbar_init(mbar + s, 1);              // full: the bulk copy's bytes
-      mbar_init(mbar + 4 + s, NT / 32);    // empty: one arrival per warp
-    }
-    mbar_fence_init();
-  }
   for (int i = tid; i < kCsSlots; i += NT) {
     tkeys[i] = kEmptyKey;
     tcnt[i] = 0u;
   }
   if (tid < 64) s_small[tid] = 0;
   if (tid < 16) s_flag[tid] = 0;
-  if constexpr (!MULTIPASS) load_window();
   __syncthreads();
-  if constexpr (!MULTIPASS) {
-    if (tid == 0)
-      for (int c = 0; c < kCsStages && c < nchunks; ++c) issue(c);
-  }
 
   auto insert = [&](unsigned long long key) {
     uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
@@ -177,13 +118,12 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
       }
       h = (h + 1) & (kCsSlots - 1);
     }
-    s_flag[0] = 1;   // table too crowded: this bucket takes the general path
+    s_flag[0] = 1;   // a sub-range still crowds the table: the general path takes the bucket
   };
-
-  // ---- bucket end: sweep + clear, solid keys -> ordered edge records.  Called by all threads, after a __syncthreads.
-  // mode 0: streamed bucket (reserve arena space, bail list on failure); mode 1: multi-pass count sweep (only totals the solid
-  // keys in s_flag[9], failure -> s_flag[8]); mode 2: multi-pass emit sweep (writes at the base held in s_flag[2..3] and advances it)
-  auto finish_bucket = [&](int slot, int mode) {
+  // ---- pass end: sweep + clear, solid keys -> ordered edge records.  Called by all threads, after a __syncthreads.
+  // mode 1: count sweep (only totals the solid keys in s_flag[9], failure -> s_flag[8]); mode 2: emit sweep (writes at the base
+  // held in s_flag[2..3] and advances it)
+  auto finish_pass = [&](int mode) {
     const bool crowded = s_flag[0] != 0;
     for (int h = tid; h < kCsSlots; h += NT) {
       const uint32_t c = tcnt[h];
@@ -207,8 +147,7 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
     const uint32_t ns = bail ? 0u : (uint32_t)ns_raw;
     if (a.counting && mode != 1) {
       // multiplicity histogram of the distinct keys (<prefix>.counting): small counts from shared memory, counts >= 64 are
-      // solid keys (the host routes --min-count > 64 with a histogram request to the general kernel).  A bucket that
-      // bails is counted by the general path instead.
+      // solid keys (the host routes --min-count > 64 with a histogram request to the general kernel)
       if (tid < 64) {
         const uint32_t v = s_small[tid];
         s_small[tid] = 0;
@@ -224,33 +163,8 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
         if (bail) s_flag[8] = 1;
         s_flag[9] += (int)ns;
         s_flag[1] = 0;
-      } else if (mode == 2) {
-        s_flag[1] = ns > 0 && !s_flag[10];   // the base in s_flag[2..3] is advanced after the write below
-      } else if (bail) {
-        const int p = atomicAdd(a.bail_count, 1);
-        a.bail_list[p] = slot;
-        s_flag[1] = 0;
-      } else if (ns > 0) {
-        unsigned long long pos = ((unsigned long long)(uint32_t)s_flag[7] << 32) | (uint32_t)s_flag[6];
-        int left = s_flag[5];
-        if ((int)ns > left) {   // next arena block (what is left of the old one is abandoned)
-          pos = atomicAdd(a.arena_cursor, (unsigned long long)kCsArenaBlock);
-          left = kCsArenaBlock;
-        }
-        const int ok = pos + ns <= a.arena_cap;
-        if (!ok) atomicExch(a.overflow_flag, 1);
-        a.desc_off[slot] = (int64_t)pos;
-        a.desc_cnt[slot] = ok ? (int64_t)ns : 0;
-        s_flag[1] = ok;
-        s_flag[2] = (int)(uint32_t)pos;
-        s_flag[3] = (int)(uint32_t)(pos >> 32);
-        pos += ns;
-        left -= (int)ns;
-        s_flag[5] = left;
-        s_flag[6] = (int)(uint32_t)pos;
-        s_flag[7] = (int)(uint32_t)(pos >> 32);
       } else {
-        s_flag[1] = 0;
+        s_flag[1] = ns > 0 && !s_flag[10];   // the base in s_flag[2..3] is advanced after the write below
       }
     }
     if (ns > 1 && ns <= (uint32_t)kCsPairsMax)
@@ -276,8 +190,7 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
         __syncthreads();
         cur = permA;
       } else if (ns > (uint32_t)kCsPairsMax) {
-        // many solid keys (moderate coverage): one counting split on the 10 bits below the keys' common range, then a rank
-        // fix inside each sub-bin (the keys are distinct and spread evenly, so sub-bins hold about one key)
+        // many solid keys: one counting split on the 10 bits below the keys' common range, then a rank fix inside each sub-bin
         unsigned long long *s_mm = reinterpret_cast<unsigned long long *>(scratch);   // [0] min, [1] max (8-byte aligned)
         if (tid == 0) { s_mm[0] = ~0ull; s_mm[1] = 0ull; }
         for (int i = tid; i <= 1024; i += NT) whist32[i] = 0u;
@@ -335,121 +248,69 @@ __global__ void __launch_bounds__(kCsNT, 2) k_count_stream(LocalArgs a, const in
     // the barrier the caller issues next publishes the reset
   };
 
-  if constexpr (MULTIPASS) {
-    const WorkItem wi = a.work[blockIdx.x];
-    const int slot = wi.slot;
-    const int64_t n = a.bkt_size[slot];
-    const uint2 *keys = reinterpret_cast<const uint2 *>(a.in) + a.bkt_start[slot];
-    // key range of the bucket
-    unsigned long long *s_mm = reinterpret_cast<unsigned long long *>(scratch);
-    if (tid == 0) { s_mm[0] = ~0ull; s_mm[1] = 0ull; }
-    __syncthreads();
-    {
-      unsigned long long mn = ~0ull, mx = 0ull;
+  const WorkItem wi = a.work[blockIdx.x];
+  const int slot = wi.slot;
+  const int64_t n = a.bkt_size[slot];
+  const uint2 *keys = reinterpret_cast<const uint2 *>(a.in) + a.bkt_start[slot];
+  // key range of the bucket
+  unsigned long long *s_mm = reinterpret_cast<unsigned long long *>(scratch);
+  if (tid == 0) { s_mm[0] = ~0ull; s_mm[1] = 0ull; }
+  __syncthreads();
+  {
+    unsigned long long mn = ~0ull, mx = 0ull;
+    for (int64_t i = tid; i < n; i += NT) {
+      const uint2 v = keys[i];
+      const unsigned long long key = ((unsigned long long)v.x << 32) | v.y;
+      mn = min(mn, key);
+      mx = max(mx, key);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((tid & 31) == 0) { atomicMin(s_mm, mn); atomicMax(s_mm + 1, mx); }
+  }
+  __syncthreads();
+  const unsigned long long kmin = s_mm[0];
+  const int span_bits = 64 - __clzll((long long)((s_mm[1] - kmin) | 1ull));
+  const int sh = span_bits > passes_log ? span_bits - passes_log : 0;
+  const uint32_t npass = (uint32_t)((s_mm[1] - kmin) >> sh) + 1u;
+  __syncthreads();
+  for (int sweep = 1; sweep <= 2; ++sweep) {
+    for (uint32_t ps = 0; ps < npass; ++ps) {
       for (int64_t i = tid; i < n; i += NT) {
         const uint2 v = keys[i];
         const unsigned long long key = ((unsigned long long)v.x << 32) | v.y;
-        mn = min(mn, key);
-        mx = max(mx, key);
+        if ((uint32_t)((key - kmin) >> sh) == ps) insert(key);
       }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      }
-      if ((tid & 31) == 0) { atomicMin(s_mm, mn); atomicMax(s_mm + 1, mx); }
+      __syncthreads();
+      finish_pass(sweep);
+      __syncthreads();
     }
-    __syncthreads();
-    const unsigned long long kmin = s_mm[0];
-    const int span_bits = 64 - __clzll((long long)((s_mm[1] - kmin) | 1ull));
-    const int sh = span_bits > passes_log ? span_bits - passes_log : 0;
-    const uint32_t npass = (uint32_t)((s_mm[1] - kmin) >> sh) + 1u;
-    __syncthreads();
-    for (int sweep = 1; sweep <= 2; ++sweep) {
-      for (uint32_t ps = 0; ps < npass; ++ps) {
-        for (int64_t i = tid; i < n; i += NT) {
-          const uint2 v = keys[i];
-          const unsigned long long key = ((unsigned long long)v.x << 32) | v.y;
-          if ((uint32_t)((key - kmin) >> sh) == ps) insert(key);
+    if (sweep == 1) {
+      if (tid == 0) {
+        if (s_flag[8]) {   // a sub-range still crowds the table: the general path takes the bucket
+          const int p = atomicAdd(a.bail_count, 1);
+          a.bail_list[p] = slot;
+        } else {
+          const unsigned long long tot = (unsigned long long)(uint32_t)s_flag[9];
+          const unsigned long long pos = atomicAdd(a.arena_cursor, tot);
+          const int ok = pos + tot <= a.arena_cap;
+          if (!ok) atomicExch(a.overflow_flag, 1);
+          a.desc_off[slot] = (int64_t)pos;
+          a.desc_cnt[slot] = ok ? (int64_t)tot : 0;
+          s_flag[2] = (int)(uint32_t)pos;
+          s_flag[3] = (int)(uint32_t)(pos >> 32);
+          // arena overflow: the host redoes the finish with a larger arena and WITHOUT the histogram (a retry must not
+          // count twice), so sweep 2 still runs -- for the histogram only
+          if (!ok) s_flag[10] = 1;
         }
-        __syncthreads();
-        finish_bucket(slot, sweep);
-        __syncthreads();
       }
-      if (sweep == 1) {
-        if (tid == 0) {
-          if (s_flag[8]) {   // a sub-range still crowds the table: the general path takes the bucket
-            const int p = atomicAdd(a.bail_count, 1);
-            a.bail_list[p] = slot;
-          } else {
-            const unsigned long long tot = (unsigned long long)(uint32_t)s_flag[9];
-            const unsigned long long pos = atomicAdd(a.arena_cursor, tot);
-            const int ok = pos + tot <= a.arena_cap;
-            if (!ok) atomicExch(a.overflow_flag, 1);
-            a.desc_off[slot] = (int64_t)pos;
-            a.desc_cnt[slot] = ok ? (int64_t)tot : 0;
-            s_flag[2] = (int)(uint32_t)pos;
-            s_flag[3] = (int)(uint32_t)(pos >> 32);
-            // arena overflow: the host redoes the finish with a larger arena and WITHOUT the histogram (a retry must not
-            // count twice), so sweep 2 still runs -- for the histogram only
-            if (!ok) s_flag[10] = 1;
-          }
-        }
-        __syncthreads();
-        if (s_flag[8]) return;
-        if (s_flag[10] && !a.counting) return;
-      }
+      __syncthreads();
+      if (s_flag[8]) return;
+      if (s_flag[10] && !a.counting) return;
     }
-    return;
-  } else {
-  // ---- consumer loop over the chunks of the CTA's key range
-  int cur_b = b0;
-  uint32_t p = 0, bend = 0;
-  auto advance = [&]() {   // first bucket at or after cur_b that ends beyond p (all threads, uniform)
-    while (cur_b < b1) {
-      if (cur_b + 1 - wb > kCsWin) {
-        __syncthreads();
-        wb = cur_b;
-        load_window();
-        __syncthreads();
-      }
-      bend = s_bnd[cur_b + 1 - wb];
-      if (bend > p) break;
-      ++cur_b;
-    }
-  };
-  advance();
-  const int off0 = (int)(rb - A);
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c % kCsStages;
-    mbar_wait(mbar + s, (uint32_t)((c / kCsStages) & 1));
-    const int off = off0 - c * kCsChunk;   // ring index of relative position q is q + off
-    const uint32_t chi = min((uint32_t)(kCsChunk - off), total);   // relative end of the chunk (32-bit: a CTA's range is < 4 G keys)
-    const uint2 *rs = reinterpret_cast<const uint2 *>(ring + (size_t)s * kCsChunk);
-    while (p < chi) {
-      const uint32_t e = chi < bend ? chi : bend;
-      for (uint32_t q = p + tid; q < e; q += NT) {
-        const uint2 v = rs[(int)q + off];
-        insert(((unsigned long long)v.x << 32) | v.y);
-      }
-      p = e;
-      if (p == bend) {
-        __syncthreads();
-        finish_bucket(cur_b, 0);
-        ++cur_b;
-        advance();
-        __syncthreads();
-      }
-    }
-    // this warp is done with stage s; thread 0 refills the stage of the PREVIOUS chunk once every warp has released it
-    // (no CTA-wide barrier per chunk: warps drift apart inside a bucket and only meet at bucket ends)
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(mbar + 4 + s);
-    if (tid == 0 && c >= 1 && c - 1 + kCsStages < nchunks) {
-      mbar_wait(mbar + 4 + (c - 1) % kCsStages, (uint32_t)(((c - 1) / kCsStages) & 1));
-      issue(c - 1 + kCsStages);
-    }
-  }
   }
 }
 

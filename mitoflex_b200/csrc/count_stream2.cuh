@@ -1,6 +1,6 @@
 // count_stream2.cuh -- the streamed count finish for keys of 33..64 bits (16 <= k <= 31), second generation.
 //
-// Same contract as k_count_stream<false> (count_stream.cuh): persistent CTAs own contiguous runs of buckets, the keys arrive
+// Same contract as round 1's k_count_stream: persistent CTAs own contiguous runs of buckets, the keys arrive
 // through a cp.async.bulk + mbarrier ring, a shared hash table groups them, the bucket end turns the solid keys into ordered
 // edge records (KmerCounter::PackEdge).  What changed, and why (ncu r1i/r2a: the old kernel issued ~120 thread-instructions per
 // key, 0.68 issue/cycle, stalls wait / barrier / branch_resolving):
@@ -387,7 +387,9 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
           // key goes to the warp's queue and is probed on by all 32 lanes afterwards (a few keys per hundred: no lane idles in a
           // divergent probe loop, which was where the first version of this kernel spent most of its instructions).
           const uint2 *ring2 = reinterpret_cast<const uint2 *>(ring);
-          for (uint32_t q0 = p + tid; q0 < e; q0 += U * NC) {
+          // the trip count is WARP-uniform (the round uses warp collectives): bounded by the warp's first position
+          for (uint32_t qw = p + (uint32_t)(tid & ~31); qw < e; qw += U * NC) {
+            const uint32_t q0 = qw + (uint32_t)lane;
             uint32_t v[U], h[U];
             uint2 sl[U];
             bool pend[U];
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
               h[u] = (v[u] * 0x9E3779B1u) >> (32 - C::SlotsLog);
             }
             // the last keys of the chunk are in registers: the stage can be refilled while they are processed
-            if (e == chi && q0 - tid + U * NC >= e && !released) {
+            if (e == chi && qw - (uint32_t)(tid & ~31) + U * NC >= e && !released) {
               __syncwarp();
               if (lane == 0) mbar_arrive(mbar + 4 + s);
               released = true;

@@ -937,9 +937,9 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
           MF_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int), c.stream));
           LocalArgs ma = a;
           ma.work = c.ov[7].as<WorkItem>();
-          const size_t smem = count_stream_smem_bytes();
-          set_smem(k_count_stream<true>, smem);
-          k_count_stream<true><<<(unsigned)wi.size(), kCsNT, smem, c.stream>>>(ma, nullptr, 3);
+          const size_t smem = count_multipass_smem_bytes();
+          set_smem(k_count_multipass, smem);
+          k_count_multipass<<<(unsigned)wi.size(), kCsNT, smem, c.stream>>>(ma, 3);
           MF_LAUNCH_CHECK();
           c.launches++;
           if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] count: %d of %d buckets take the multi-pass kernel\n", (int)wi.size(), b.nslots);
@@ -1659,7 +1659,7 @@ static void sdbg_filter(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, I
     k_ks_scatter<KW, 4><<<sgrid, kKsNT, ssm, c.stream>>>(edges, n_edges, WK, WE, k, g, cursor, rec);
   }
   // inserts are the first 2E records, queries the last 2E, both in slice order; the misses overwrite the (dead) inserts
-  const unsigned wgrid = (unsigned)std::min<int64_t>(div_ceil64(2 * n_edges, kKsWalkNT * kKsWalkR), (int64_t)c.sm_count * 8);
+  const unsigned wgrid = (unsigned)std::min<int64_t>(div_ceil64(2 * n_edges, kKsWalkNT * kKsWalkR), (int64_t)c.sm_count * 6);
   k_ks_insert<KW><<<wgrid, kKsWalkNT, 0, c.stream>>>(rec, 2 * n_edges, g, table, cursor + nbins + 1);
   k_ks_query<KW><<<wgrid, kKsWalkNT, 0, c.stream>>>(rec + 2 * n_edges, 2 * n_edges, g, table, rec, cursor + nbins, cursor + nbins + 2);
   MF_LAUNCH_CHECK();
