@@ -54,6 +54,24 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
   }
 }
 
+// the producer's wait: it has nothing else to do, so it polls rarely (its spin was 9 % of the count kernel's instructions)
+__device__ __forceinline__ void mbar_wait_slow(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(400);
+  }
+}
+
 inline size_t count_multipass_smem_bytes() {
   // tkeys u64[4096] | skeys u64[768] | tcnt u32[4096] | scnt u32[768] | bins u32[260] | small u32[64] | scratch u32[40]
   // | flag i32[16] | permA,permB,rk u16[768]

@@ -34,7 +34,7 @@ constexpr int kC2ChunkLog = 11;         // 2048 keys (16 KB) per ring stage = on
 constexpr int kC2Chunk = 1 << kC2ChunkLog;
 constexpr int kC2StagesRel = 2;         // ring stages (a power of two: the ring is addressed modulo stages * chunk).  Two are
 constexpr int kC2StagesFull = 2;        // enough because a warp hands a stage back as soon as its keys are in registers
-constexpr int kC2QueueCap = 112;        // per-warp queue of keys whose first slot held another key (aliases the bucket-end arrays)
+constexpr int kC2QueueCap = 128;        // per-warp queue (one round: 4 x 32 keys) of key parts the first slot did not settle; aliases the bucket-end arrays
 constexpr int kC2MinCountBits = 17;     // REL needs room for counts up to 65535 and then some
 
 template <bool REL>
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
   uint32_t *scratch = bins + 260;
   uint16_t *permA = reinterpret_cast<uint16_t *>(scratch + 40);
   uint16_t *permB = permA + kCsSolidMax, *rk = permB + kCsSolidMax;
-  uint2 *wqueue = reinterpret_cast<uint2 *>(skeys) + (threadIdx.x >> 5) * kC2QueueCap;     // [kC2QueueCap] (key part, slot)
+  uint32_t *wqueue = reinterpret_cast<uint32_t *>(skeys) + (threadIdx.x >> 5) * kC2QueueCap;   // [kC2QueueCap] key parts
   uint32_t *whist32 = reinterpret_cast<uint32_t *>(tab);   // sub-bin counters [1025] of the many-solid-keys sort alias the swept table
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
     if (lane == 0) {
       for (int c = 0; c < nchunks; ++c) {
         const int s = c & (Stages - 1);
-        if (c >= Stages) mbar_wait(mbar + 4 + s, (uint32_t)(((c / Stages) - 1) & 1));
+        if (c >= Stages) mbar_wait_slow(mbar + 4 + s, (uint32_t)(((c / Stages) - 1) & 1));
         const int64_t g0 = A + ((int64_t)c << kC2ChunkLog);
         const int64_t left = re_up - g0;
         const uint32_t bytes = (uint32_t)(left < kC2Chunk ? left : kC2Chunk) * 8u;
@@ -383,21 +383,23 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
         if constexpr (REL && CBT == 32) {
           // slot = (key part << 32) | count: the high word is compared as it is, the low word counts.  A record is two
           // big-endian words (x = high half of the key), so the key part is one funnel shift.  Per round: 4 keys per thread,
-          // their ring and slot loads in flight together; a hit is one predicated RED, an empty slot one CAS; what met another
-          // key goes to the warp's queue and is probed on by all 32 lanes afterwards (a few keys per hundred: no lane idles in a
-          // divergent probe loop, which was where the first version of this kernel spent most of its instructions).
+          // their ring and slot loads in flight together; a hit is one predicated RED; everything else (a new key, a slot held
+          // by another key) goes to the warp's queue with one ballot and is settled afterwards by all 32 lanes, one queued key
+          // each -- no lane idles in a divergent probe loop, and the round itself is branch-free.
           const uint2 *ring2 = reinterpret_cast<const uint2 *>(ring);
           // the trip count is WARP-uniform (the round uses warp collectives): bounded by the warp's first position
           for (uint32_t qw = p + (uint32_t)(tid & ~31); qw < e; qw += U * NC) {
             const uint32_t q0 = qw + (uint32_t)lane;
+            // a round lies inside one chunk = one contiguous ring stage: one address, constant offsets
+            const uint2 *rp = ring2 + ((qw + off0) & (uint32_t)(RingKeys - 1)) + lane;
             uint32_t v[U], h[U];
             uint2 sl[U];
             bool pend[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              const uint32_t q = q0 + u * NC;
-              pend[u] = q < e;
-              const uint2 w = ring2[(min(q, e - 1) + off0) & (uint32_t)(RingKeys - 1)];
+              pend[u] = q0 + u * NC < e;
+              uint2 w = make_uint2(0u, 0u);
+              if (pend[u]) w = rp[u * NC];
               v[u] = __funnelshift_r(w.y, w.x, key_shift);
               h[u] = (v[u] * 0x9E3779B1u) >> (32 - C::SlotsLog);
             }
@@ -415,40 +417,28 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
             uint32_t nq = 0;   // queued keys of this round (warp-uniform)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              if (pend[u] && (sl[u].x | sl[u].y) == 0u) {   // empty: claim it (count 1); a lost race returns the winner's slot
-                const unsigned long long t = atomicCAS(tab + h[u], 0ull, ((unsigned long long)v[u] << 32) | 1ull);
-                sl[u] = make_uint2((uint32_t)t, (uint32_t)(t >> 32));
-                pend[u] = t != 0ull;
-              }
-              const bool hit = pend[u] && sl[u].y == v[u];   // an occupied slot has a count >= 1
+              const bool hit = pend[u] && sl[u].y == v[u] && sl[u].x != 0u;   // an occupied slot has a count >= 1
               if (hit) atomicAdd(reinterpret_cast<uint32_t *>(tab + h[u]), 1u);
               const bool more = pend[u] && !hit;
               const unsigned bal = __ballot_sync(0xffffffffu, more);
-              const uint32_t at = nq + (uint32_t)__popc(bal & lt);
+              if (more) wqueue[nq + (uint32_t)__popc(bal & lt)] = v[u];
               nq += (uint32_t)__popc(bal);
-              pend[u] = more && at >= (uint32_t)kC2QueueCap;   // no room in the queue (never, in practice): probed in line below
-              if (more && !pend[u]) wqueue[at] = make_uint2(v[u], h[u]);
             }
-            auto probe_on = [&](uint32_t vv, uint32_t hh) {   // the first slot held another key: linear probing from the next one
+            __syncwarp();
+            for (uint32_t i = lane; i < nq; i += 32) {
+              const uint32_t vv = wqueue[i];
+              uint32_t hh = (vv * 0x9E3779B1u) >> (32 - C::SlotsLog);
               const unsigned long long claim = ((unsigned long long)vv << 32) | 1ull;
 #pragma unroll 1
-              for (int probe = 1;; ++probe) {
-                hh = (hh + 1) & (Slots - 1);
+              for (int probe = 0;; ++probe) {
                 unsigned long long sv = *reinterpret_cast<volatile unsigned long long *>(tab + hh);
-                if (sv == 0ull) sv = atomicCAS(tab + hh, 0ull, claim);
+                if (sv == 0ull) sv = atomicCAS(tab + hh, 0ull, claim);   // empty: claim it with count 1
                 if (sv == 0ull) break;
                 if ((uint32_t)(sv >> 32) == vv) { atomicAdd(reinterpret_cast<uint32_t *>(tab + hh), 1u); break; }
-                if (probe >= kCsProbeLimit) { s_flag[0] = 1; break; }   // table too crowded: the bucket bails
+                if (probe >= kCsProbeLimit) { s_flag[0] = 1; break; }    // table too crowded: the bucket bails
+                hh = (hh + 1) & (Slots - 1);
               }
-            };
-            __syncwarp();
-            for (uint32_t i = lane; i < min(nq, (uint32_t)kC2QueueCap); i += 32) {
-              const uint2 qe = wqueue[i];
-              probe_on(qe.x, qe.y);
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-              if (pend[u]) probe_on(v[u], h[u]);
             __syncwarp();   // the next round overwrites the queue
           }
         } else

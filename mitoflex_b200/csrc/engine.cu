@@ -1659,7 +1659,7 @@ static void sdbg_filter(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, I
     k_ks_scatter<KW, 4><<<sgrid, kKsNT, ssm, c.stream>>>(edges, n_edges, WK, WE, k, g, cursor, rec);
   }
   // inserts are the first 2E records, queries the last 2E, both in slice order; the misses overwrite the (dead) inserts
-  const unsigned wgrid = (unsigned)std::min<int64_t>(div_ceil64(2 * n_edges, kKsWalkNT * kKsWalkR), (int64_t)c.sm_count * 6);
+  const unsigned wgrid = (unsigned)std::min<int64_t>(div_ceil64(2 * n_edges, kKsWalkNT * kKsWalkR), (int64_t)c.sm_count * 8);
   k_ks_insert<KW><<<wgrid, kKsWalkNT, 0, c.stream>>>(rec, 2 * n_edges, g, table, cursor + nbins + 1);
   k_ks_query<KW><<<wgrid, kKsWalkNT, 0, c.stream>>>(rec + 2 * n_edges, 2 * n_edges, g, table, rec, cursor + nbins, cursor + nbins + 2);
   MF_LAUNCH_CHECK();

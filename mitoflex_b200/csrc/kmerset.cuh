@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kKsNT) k_ks_scatter(const uint32_t *__restrict
 // an atomic counter, one per warp, so the warps in flight always work on the ~2 M most recent records = two or three slices, whose
 // table lines stay in L2.  (A plain grid-stride loop does not keep that window: after a few hundred dependent DRAM round trips
 // per thread the fast warps are dozens of slices ahead of the slow ones -- ncu r2d: 131 bytes of DRAM read per insert.)
-constexpr int kKsWalkNT = 256, kKsWalkR = 8;
+constexpr int kKsWalkNT = 256, kKsWalkR = 4;
 template <int KW>
 __device__ __forceinline__ KsKey<KW> ks_unpack(typename KsKey<KW>::Slot x) {
   KsKey<KW> kx;
