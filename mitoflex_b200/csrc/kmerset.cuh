@@ -181,9 +181,10 @@ __global__ void __launch_bounds__(kKsNT) k_ks_scatter(const uint32_t *__restrict
   for (uint32_t j = tid; j < total; j += NT) out[s_gd[stage_bin[j]] + (long long)j] = stage[j];
 }
 
-// ---- pass 3: inserts, in slice order.  The records of a slice are contiguous, and tiles of 256 records are handed out IN ORDER by
-// an atomic counter, one per warp, so the warps in flight always work on the ~2 M most recent records = two or three slices, whose
-// table lines stay in L2.  (A plain grid-stride loop does not keep that window: after a few hundred dependent DRAM round trips
+// ---- pass 3: inserts, in slice order.  The records of a slice are contiguous, and tiles of 1024 records are handed out IN ORDER by
+// an atomic counter, so the CTAs in flight (8 per SM) always work on the ~1.2 M most recent records = one or two slices, whose
+// table lines stay in L2 (tiles per WARP and 8 records per thread were both slower: 3.3 / 4.8 ms against 2.06 ms on the 1.8 Gbp
+// sample, ncu r2h/r2i).  (A plain grid-stride loop does not keep that window: after a few hundred dependent DRAM round trips
 // per thread the fast warps are dozens of slices ahead of the slow ones -- ncu r2d: 131 bytes of DRAM read per insert.)
 constexpr int kKsWalkNT = 256, kKsWalkR = 4;
 template <int KW>
@@ -196,23 +197,22 @@ template <int KW>
 __global__ void __launch_bounds__(kKsWalkNT) k_ks_insert(const typename KsKey<KW>::Slot *__restrict__ rec, int64_t n, KsGeom g,
                                                          typename KsKey<KW>::Slot *table, unsigned long long *tile_counter) {
   using Slot = typename KsKey<KW>::Slot;
-  constexpr int R = kKsWalkR;
+  constexpr int NT = kKsWalkNT, R = kKsWalkR;
+  __shared__ unsigned long long s_tile;
   const Slot empty = KsKey<KW>::empty();
   const unsigned long long smask = (1ull << g.slice_log) - 1ull;
-  const int lane = threadIdx.x & 31;
   for (;;) {
-    // a tile = 32 x R consecutive records, taken by one warp (no CTA barrier on the way)
-    unsigned long long tile = 0;
-    if (lane == 0) tile = atomicAdd(tile_counter, 1ull);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    const int64_t base = (int64_t)tile * (32 * R);
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1ull);
+    __syncthreads();
+    const int64_t base = (int64_t)s_tile * (NT * R);
+    __syncthreads();
     if (base >= n) return;
     Slot x[R], c[R];
     unsigned long long h[R];
     bool live[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int64_t i = base + r * 32 + lane;
+      const int64_t i = base + r * NT + threadIdx.x;
       live[r] = i < n;
       x[r] = rec[live[r] ? i : n - 1];
       h[r] = g.slot(ks_unpack<KW>(x[r]).hash());
@@ -237,22 +237,22 @@ __global__ void __launch_bounds__(kKsWalkNT) k_ks_query(const typename KsKey<KW>
                                                         typename KsKey<KW>::Slot *__restrict__ miss, unsigned long long *miss_cursor,
                                                         unsigned long long *tile_counter) {
   using Slot = typename KsKey<KW>::Slot;
-  constexpr int R = kKsWalkR;
+  constexpr int NT = kKsWalkNT, R = kKsWalkR;
+  __shared__ unsigned long long s_tile;
   const Slot empty = KsKey<KW>::empty();
   const unsigned long long smask = (1ull << g.slice_log) - 1ull;
-  const int lane = threadIdx.x & 31;
   for (;;) {
-    unsigned long long tile = 0;
-    if (lane == 0) tile = atomicAdd(tile_counter, 1ull);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    const int64_t base = (int64_t)tile * (32 * R);
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1ull);
+    __syncthreads();
+    const int64_t base = (int64_t)s_tile * (NT * R);
+    __syncthreads();
     if (base >= n) return;
     Slot x[R], c[R];
     unsigned long long h[R];
     bool live[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int64_t i = base + r * 32 + lane;
+      const int64_t i = base + r * NT + threadIdx.x;
       live[r] = i < n;
       x[r] = rec[live[r] ? i : n - 1];
       h[r] = g.slot(ks_unpack<KW>(x[r]).hash());
