@@ -735,7 +735,7 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
   // keys per bucket for a table of `slots` slots: 2-word keys whose slots hold "key | count" get 8192 of them (k_count_stream2<REL>),
   // the full-key variant and the wide-key kernel 4096
   const bool rel_wanted = W == 2 && env_int("MFSDBG_COUNT_REL", 1) != 0;
-  const double load = env_int("MFSDBG_STREAM_LOAD_PCT", W == 2 ? (rel_wanted ? 30 : 45) : 35) / 100.0;
+  const double load = env_int("MFSDBG_STREAM_LOAD_PCT", W == 2 ? (rel_wanted ? 42 : 45) : 35) / 100.0;
   const int solid_max = W == 2 ? kCsSolidMax : (W == 3 ? 768 : 512);
   auto bucket_keys = [&](int slots) {
     double v = std::min(60000.0 * slots / kCsSlots, std::max(1024.0, load * slots / rho));

@@ -12,7 +12,18 @@ import numpy as np
 
 import os
 
-L1_BITS = int(os.environ.get("MFSDBG_DIST_L1_BITS", "6"))   # 64 bins: long runs for the NVLink stores (5-7 bits measured within 3 %)
+L1_BITS = int(os.environ.get("MFSDBG_DIST_L1_BITS", "0"))   # 0 = by world size (l1_bits_for)
+
+
+def l1_bits_for(world):
+    """Exchange bins = ownership granularity.  64 bins keep the runs of the NVLink stores long (5-7 bits measured within 3 % on
+    the fused kernel), but owners are cut at bin boundaries and canonical keys are twice as dense at small prefixes: with 8
+    ranks on 64 bins rank 0 held +20 % of the mean (SCALE_r01).  Half a bin of error is 1/(2 * bins) of all keys, i.e.
+    world / (2 * bins) of a rank's share: 128 bins for 4 ranks, 256 for 8 keep it near 3 % (the exchange kernel is NVLink-bound
+    there, so the extra bins cost nothing that shows)."""
+    if L1_BITS:
+        return L1_BITS
+    return 6 if world <= 2 else (7 if world <= 4 else 8)
 
 
 def assign_owners(global_hist, world):
@@ -172,14 +183,15 @@ class DistRead2Sdbg:
     def run(self, reads):
         import torch
         import torch.distributed as dist
-        ctx, k, nb = self.ctx, self.k, 1 << L1_BITS
+        L1 = l1_bits_for(dist.get_world_size())
+        ctx, k, nb = self.ctx, self.k, 1 << L1
         rank = dist.get_rank()
         stream = torch.cuda.current_stream(self.dev)
         # ---- count: histogram, owners, local partition, exchange, finish
         hist = torch.zeros(nb, dtype=torch.int64, device=self.dev)
         stream.synchronize()
         self.profile = {}
-        ctx.count_hist(reads, k, L1_BITS, hist.data_ptr())
+        ctx.count_hist(reads, k, L1, hist.data_ptr())
         self._acc()
         plan = exchange_plan(self._gather_hists(hist), rank)
         allH = self._last_hists
@@ -190,23 +202,23 @@ class DistRead2Sdbg:
             bases = torch.from_numpy(peer_bin_bases(allH, plan["bounds"], rank, self.key_buf.peers, self.Wk * 4).view(np.int64)).to(self.dev)
             scratch = torch.empty((max(plan["n_recv"], 1) + 16, self.Wk), dtype=torch.int32, device=self.dev)
             stream.synchronize()
-            ctx.count_scatter_peer(reads, k, L1_BITS, bases.data_ptr())
+            ctx.count_scatter_peer(reads, k, L1, bases.data_ptr())
             self._acc()
             dist.barrier()            # every rank's stores have landed
             edges = ctx.count_finish(self.key_buf.ptr, scratch.data_ptr(), plan["n_recv"], plan["chunk_start"], plan["chunk_size"],
-                                     plan["chunk_seg"], plan["n_segs"], k, L1_BITS, self.m)
+                                     plan["chunk_seg"], plan["n_segs"], k, L1, self.m)
             self._acc()
             del scratch
         else:
             n_buf = max(n_local, plan["n_recv"], 1)
             send = torch.empty((n_buf, self.Wk), dtype=torch.int32, device=self.dev)
             stream.synchronize()
-            ctx.count_scatter(reads, k, L1_BITS, hist.data_ptr(), send.data_ptr(), n_buf)
+            ctx.count_scatter(reads, k, L1, hist.data_ptr(), send.data_ptr(), n_buf)
             self._acc()
             recv = self._timed_a2a("a2a_keys", send[:n_local], plan["send"], plan["recv"])
             stream.synchronize()
             edges = ctx.count_finish(recv.data_ptr(), send.data_ptr(), plan["n_recv"], plan["chunk_start"], plan["chunk_size"],
-                                     plan["chunk_seg"], plan["n_segs"], k, L1_BITS, self.m)
+                                     plan["chunk_seg"], plan["n_segs"], k, L1, self.m)
             self._acc()
             del recv, send
         info = dict(n_keys=plan["n_recv"], n_edges=edges.n, exchanged_keys=n_local - int(plan["send"][rank]),
@@ -219,7 +231,7 @@ class DistRead2Sdbg:
         self._acc()
         ihist = torch.zeros(nb, dtype=torch.int64, device=self.dev)
         stream.synchronize()
-        ctx.records_hist(items.data_ptr(), n_items, self.Wi, L1_BITS, ihist.data_ptr())
+        ctx.records_hist(items.data_ptr(), n_items, self.Wi, L1, ihist.data_ptr())
         self._acc()
         iplan = exchange_plan(self._gather_hists(ihist), rank)
         iH = self._last_hists
@@ -227,27 +239,27 @@ class DistRead2Sdbg:
             self.item_buf.ensure(max(iplan["n_recv"], 1) * self.Wi * 4)
             ibases = torch.from_numpy(peer_bin_bases(iH, iplan["bounds"], rank, self.item_buf.peers, self.Wi * 4).view(np.int64)).to(self.dev)
             stream.synchronize()
-            ctx.records_scatter_peer(items.data_ptr(), n_items, self.Wi, L1_BITS, ibases.data_ptr())
+            ctx.records_scatter_peer(items.data_ptr(), n_items, self.Wi, L1, ibases.data_ptr())
             self._acc()
             dist.barrier()
             del items
             iscratch = torch.empty((max(iplan["n_recv"], 1) + 16, self.Wi), dtype=torch.int32, device=self.dev)
             stream.synchronize()
             g = ctx.sdbg_finish(self.item_buf.ptr, iscratch.data_ptr(), iplan["n_recv"], iplan["chunk_start"], iplan["chunk_size"],
-                                iplan["chunk_seg"], iplan["n_segs"], k, L1_BITS, 1)
+                                iplan["chunk_seg"], iplan["n_segs"], k, L1, 1)
             self._acc()
             del iscratch
         else:
             ibuf = max(n_items, iplan["n_recv"], 1)
             isend = torch.empty((ibuf, self.Wi), dtype=torch.int32, device=self.dev)
             stream.synchronize()
-            ctx.records_scatter(items.data_ptr(), n_items, self.Wi, L1_BITS, ihist.data_ptr(), isend.data_ptr())
+            ctx.records_scatter(items.data_ptr(), n_items, self.Wi, L1, ihist.data_ptr(), isend.data_ptr())
             self._acc()
             del items
             irecv = self._timed_a2a("a2a_items", isend[:n_items], iplan["send"], iplan["recv"])
             stream.synchronize()
             g = ctx.sdbg_finish(irecv.data_ptr(), isend.data_ptr(), iplan["n_recv"], iplan["chunk_start"], iplan["chunk_size"],
-                                iplan["chunk_seg"], iplan["n_segs"], k, L1_BITS, 1)
+                                iplan["chunk_seg"], iplan["n_segs"], k, L1, 1)
             self._acc()
             del irecv, isend
         info.update(n_items=iplan["n_recv"], exchanged_items=n_items - int(iplan["send"][rank]), sdbg_items=g.n,
