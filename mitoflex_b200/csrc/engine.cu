@@ -26,6 +26,7 @@
 #include "count_stream.cuh"
 #include "count_stream2.cuh"
 #include "kmerset.cuh"
+#include "kmerset_w.cuh"
 #include "count_stream_w.cuh"
 #include "sdbg_local.cuh"
 
@@ -1627,7 +1628,15 @@ static KsGeom ks_geometry(int64_t n_edges) {
   g.nslices = 1 << (g.log_slots - g.slice_log);
   return g;
 }
+static KsGeom ksw_geometry(int64_t n_edges) {   // k >= 64: index slots, smaller slices (the records of a slice share L2 with them)
+  KsGeom g;
+  g.log_slots = std::max(10, ceil_log2(3.0 * (double)std::max<int64_t>(n_edges, 1)));
+  g.slice_log = std::min(g.log_slots, std::max(kKswSliceLog, g.log_slots - 10));
+  g.nslices = 1 << (g.log_slots - g.slice_log);
+  return g;
+}
 static size_t ks_bytes(int64_t n_edges, int k) {   // records + table + small tables
+  if (k >= 64) return (size_t)6 * n_edges * words_tip(k) * 4 + ((size_t)8 << ksw_geometry(n_edges).log_slots) + (1 << 20);
   const size_t kb = k <= 31 ? 8 : 16;
   return (size_t)4 * n_edges * kb + ((size_t)kb << ks_geometry(n_edges).log_slots) + (1 << 20);
 }
@@ -1674,6 +1683,49 @@ static void sdbg_filter(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, I
   src->n_miss = (int64_t)n_miss;
 }
 
+// k >= 64 (kmerset_w.cuh): k-mers of WR words, the table holds indices into the scattered insert records
+template <int WK, int WR>
+static void sdbg_filter_w(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, ItemSource *src) {
+  const int WE = words_edge(k);
+  const KsGeom g = ksw_geometry(n_edges);
+  const int nbins = 2 * g.nslices;
+  Stage st(c, "items_filter");
+  uint32_t *rec = c.alloc<uint32_t>((size_t)4 * n_edges * WR + 16);
+  unsigned long long *table = c.alloc<unsigned long long>((size_t)1 << g.log_slots);
+  unsigned long long *hist = c.alloc<unsigned long long>(nbins), *cursor = c.alloc<unsigned long long>(nbins + 3);
+  MF_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * nbins, c.stream));
+  MF_CUDA(cudaMemsetAsync(cursor + nbins, 0, sizeof(unsigned long long) * 3, c.stream));   // miss cursor, two tile counters
+  MF_CUDA(cudaMemsetAsync(table, 0xff, sizeof(unsigned long long) << g.log_slots, c.stream));
+  const unsigned hgrid = (unsigned)std::min<int64_t>(div_ceil64(n_edges, kKsNT), (int64_t)c.sm_count * 4);
+  k_ksw_hist<WK, WR><<<hgrid, kKsNT, sizeof(uint32_t) * nbins, c.stream>>>(edges, n_edges, WE, k, g, hist);
+  k_excl_scan_u64_small<<<1, 1024, 0, c.stream>>>(hist, nbins, cursor);
+  const unsigned sgrid = (unsigned)div_ceil64(n_edges, kKsNT);
+  const size_t ssm = ksw_scatter_smem_bytes<WR>(nbins);
+  if (nbins <= kKsNT) {
+    set_smem(k_ksw_scatter<WK, WR, 1>, ssm);
+    k_ksw_scatter<WK, WR, 1><<<sgrid, kKsNT, ssm, c.stream>>>(edges, n_edges, WE, k, g, cursor, rec);
+  } else {
+    set_smem(k_ksw_scatter<WK, WR, 4>, ssm);
+    k_ksw_scatter<WK, WR, 4><<<sgrid, kKsNT, ssm, c.stream>>>(edges, n_edges, WE, k, g, cursor, rec);
+  }
+  const unsigned wgrid = (unsigned)std::min<int64_t>(div_ceil64(2 * n_edges, kKsWalkNT * kKsWalkR), (int64_t)c.sm_count * 8);
+  uint32_t *qrec = rec + (size_t)2 * n_edges * WR;
+  // the insert records stay live during the query walk (slots point at them), so the misses get their own worst-case buffer
+  uint32_t *missbuf = c.alloc<uint32_t>((size_t)2 * n_edges * WR + 16);
+  k_ksw_insert<WR><<<wgrid, kKsWalkNT, 0, c.stream>>>(rec, 2 * n_edges, g, table, cursor + nbins + 1);
+  k_ksw_query<WR><<<wgrid, kKsWalkNT, 0, c.stream>>>(qrec, 2 * n_edges, rec, g, table, missbuf, cursor + nbins, cursor + nbins + 2);
+  MF_LAUNCH_CHECK();
+  c.launches += 5;
+  unsigned long long n_miss = 0;
+  c.d2h(&n_miss, cursor + nbins, sizeof n_miss);
+  c.miss.reserve((size_t)n_miss * WR * 4 + 256);
+  if (n_miss) MF_CUDA(cudaMemcpyAsync(c.miss.p, missbuf, (size_t)n_miss * WR * 4, cudaMemcpyDeviceToDevice, c.stream));
+  MF_CUDA(cudaStreamSynchronize(c.stream));
+  src->filtered = true;
+  src->miss = c.miss.p;
+  src->n_miss = (int64_t)n_miss;
+}
+
 // MODE 0: all items of `src` into items[0 .. n_items) (returns the count); MODE 1: per-bin counts of the items' top bin_bits
 // bits into hist; MODE 2: the items whose bin lies in [lo, hi) appended at *cursor.
 template <int WI, int MODE>
@@ -1698,10 +1750,17 @@ static int64_t sdbg_generate(Ctx &c, const ItemSource &src, int k, uint32_t *ite
         if (k <= 31) {
           k_items_miss<1, WI, MODE><<<mgrid, kRangedNT, smem, c.stream>>>(reinterpret_cast<const unsigned long long *>(src.miss), src.n_miss, k,
                                                                          bin_bits, lo, hi, dst, cursor, hist);
-        } else {
+        } else if (k <= 63) {
           if constexpr (WI >= 3)
             k_items_miss<2, WI, MODE><<<mgrid, kRangedNT, smem, c.stream>>>(reinterpret_cast<const unsigned __int128 *>(src.miss), src.n_miss,
                                                                            k, bin_bits, lo, hi, dst, cursor, hist);
+        } else {
+          // WR = words of the k-mer = WI or WI - 1
+          if constexpr (WI >= 5) {
+            const uint32_t *mw = reinterpret_cast<const uint32_t *>(src.miss);
+            if (words_tip(k) == WI) k_items_miss_w<WI, WI, MODE><<<mgrid, kRangedNT, smem, c.stream>>>(mw, src.n_miss, k, bin_bits, lo, hi, dst, cursor, hist);
+            else k_items_miss_w<WI - 1, WI, MODE><<<mgrid, kRangedNT, smem, c.stream>>>(mw, src.n_miss, k, bin_bits, lo, hi, dst, cursor, hist);
+          }
         }
         c.launches++;
         written += 2 * src.n_miss;
@@ -2035,11 +2094,19 @@ static void sdbg_impl(Ctx &c, const uint32_t *edges, int64_t n_edges, const Seqs
   const size_t held = (size_t)n_edges * words_edge(k) * 4;
   const size_t budget = c.budget();
   // ---- which dummies reach the graph (k <= 63): afterwards the item count is exact
-  if (env_int("MFSDBG_ITEM_FILTER", 1) != 0 && k <= 63 && n_edges > 0 && ks_bytes(n_edges, k) + held < budget) {
+  if (env_int("MFSDBG_ITEM_FILTER", 1) != 0 && n_edges > 0 && ks_bytes(n_edges, k) + held < budget) {
     c.slab_reserve(ks_bytes(n_edges, k) + (1 << 20));
     c.slab_reset();
     if (k <= 31) sdbg_filter<1>(c, edges, n_edges, k, &src);
-    else sdbg_filter<2>(c, edges, n_edges, k, &src);
+    else if (k <= 63) sdbg_filter<2>(c, edges, n_edges, k, &src);
+    else {
+      // (WK, WR) = words of the (k+1)-mer and of the k-mer: equal unless 2k is a multiple of 32
+      const int WK = words_key(k), WR = words_tip(k);
+#define MF_KSW(wk, wr) if (WK == wk && WR == wr) sdbg_filter_w<wk, wr>(c, edges, n_edges, k, &src);
+      MF_KSW(5, 4) MF_KSW(5, 5) MF_KSW(6, 5) MF_KSW(6, 6) MF_KSW(7, 6) MF_KSW(7, 7) MF_KSW(8, 7) MF_KSW(8, 8) MF_KSW(9, 8) MF_KSW(9, 9)
+      MF_KSW(10, 9) MF_KSW(10, 10)
+#undef MF_KSW
+    }
   }
   const int64_t n_items = src.n_items();
   const int nb1_max = 1 << kMaxDigitBits;
