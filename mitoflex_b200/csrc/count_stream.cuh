@@ -390,7 +390,7 @@ struct Digit2 {
 };
 
 template <int NT, int KPT, int BPT>
-__global__ void __launch_bounds__(NT, (NT == 512 && KPT <= 7) ? 3 : 2) k_scatter_tma(const uint32_t *__restrict__ in, const TileDesc *__restrict__ tiles, int64_t ntiles,
+__global__ void __launch_bounds__(NT, KPT <= 7 ? 3 : 2) k_scatter_tma(const uint32_t *__restrict__ in, const TileDesc *__restrict__ tiles, int64_t ntiles,
                                                       LevelArgs a, unsigned long long *__restrict__ cursor, uint32_t *__restrict__ out) {
   extern __shared__ __align__(128) unsigned char smraw[];
   constexpr int T = NT * KPT;

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
   uint32_t *wqueue = reinterpret_cast<uint32_t *>(skeys) + (threadIdx.x >> 5) * kC2QueueCap;   // [kC2QueueCap] key parts
   uint32_t *whist32 = reinterpret_cast<uint32_t *>(tab);   // sub-bin counters [1025] of the many-solid-keys sort alias the swept table
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int b0 = cta_first[blockIdx.x], b1 = cta_first[blockIdx.x + 1];
   if (b0 >= b1) return;
   const int64_t rb = a.bkt_start[b0], re = a.bkt_start[b1 - 1] + a.bkt_size[b1 - 1];

@@ -71,8 +71,6 @@ Ctx::Ctx(int dev) : device(dev) {
   cudaDeviceProp prop;
   MF_CUDA(cudaGetDeviceProperties(&prop, dev));
   sm_count = prop.multiProcessorCount;
-  // the k-mer set of the item generator is read one random 8-byte slot at a time: do not let L2 fetch whole 128-byte lines
-  if (const char *g = getenv("MFSDBG_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
   MF_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
   stream = own_stream;
   edge_bucket_counts.assign(kNumBuckets, 0);
@@ -261,7 +259,7 @@ static Plan make_plan(int W, int part_limit, int64_t n_est, double density, bool
                       int nseg = 0) {
   Plan p;
   p.W = W;
-  p.cap = hash_family ? local_cap(W, true, false) : (env_int("MFSDBG_SDBG_NEW", 1) ? sdbg_cap(W) : local_cap(W, false, false));
+  p.cap = hash_family ? local_cap(W, true, false) : sdbg_cap(W);
   // buckets of <= 64-bit keys are streamed through a key-resident table (any size, ~10-40 % of it distinct): ~5000 keys
   // on average keeps the densest ones (2x) well inside its 4096 slots; everything else must fit shared memory whole
   const double target = (hash_family && W <= 2) ? 5000.0 : p.cap * 0.65 / density;
@@ -416,10 +414,10 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   if (tb_h[nchunk] > 0) {
     const size_t smem = ((size_t)1 << nbits) * 4 + 16;
     Stage st(c, tag_h.c_str());
-    if (env_int("MFSDBG_HIST_PERSIST", 1) != 0 && bit_off < 32) {   // the 2-word fast path reads its digit with one funnel shift
+    if (bit_off < 32) {   // the 2-word fast path reads its digit with one funnel shift
       auto kern = k_level_hist_persist<W, C::NT>;
       set_smem(kern, smem);
-      const int64_t grid = std::min<int64_t>(tb_h[nchunk], (int64_t)c.sm_count * env_int("MFSDBG_HIST_CTAS", 8));
+      const int64_t grid = std::min<int64_t>(tb_h[nchunk], (int64_t)c.sm_count * 8);
       kern<<<(unsigned)grid, C::NT, smem, c.stream>>>(in, d_tiles_h, tb_h[nchunk], a, d_hist);
     } else {
       RecordsProducer<W> ph{in, d_tiles_h, C::TH};
@@ -434,11 +432,11 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
   MF_LAUNCH_CHECK();
   c.launches++;
   if constexpr (W == 2) {
-    if (tb_s[nchunk] > 0 && env_int("MFSDBG_TMA_SCATTER", 1) != 0 && bit_off < 32) {
+    if (tb_s[nchunk] > 0 && bit_off < 32) {
       // 2-word records: TMA-fed tiles of 6144 (5120 with 2048 bins) records
-      // 1024 threads x 6 keys (two CTAs = 64 warps per SM, 32 registers) or 512 threads x 12 keys (32 warps, 64 registers)
-      const int nt = env_int("MFSDBG_SCATTER_NT", 512) == 1024 && nbits <= 10 ? 1024 : 512;
-      const int KPT = nt == 1024 ? 6 : (nbits <= 10 ? 12 : 10), T = nt * KPT;
+      // 512 threads x 12 keys (1024 threads x 6 keys at 32 registers measured the same: 18.8 against 18.3 ms, r2d)
+      const int nt = 512;
+      const int KPT = nbits <= 10 ? 12 : 10, T = nt * KPT;
       std::vector<int64_t> tb_t(nchunk + 1);
       tb_t[0] = 0;
       for (int i = 0; i < nchunk; ++i) tb_t[i + 1] = tb_t[i] + div_ceil64(hc.size[i], T);
@@ -450,13 +448,11 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
       MF_LAUNCH_CHECK();
       const int bpt = std::max(1, (1 << nbits) / nt);
       void (*kern)(const uint32_t *, const TileDesc *, int64_t, LevelArgs, unsigned long long *, uint32_t *) =
-          nt == 1024 ? k_scatter_tma<1024, 6, 1>
-                     : (nbits <= 10 ? (bpt == 1 ? k_scatter_tma<512, 12, 1> : k_scatter_tma<512, 12, 2>) : k_scatter_tma<512, 10, 4>);
-      const size_t smem = nt == 1024 ? scatter_tma_smem_bytes<6, 1024>(nbits)
-                                     : (nbits <= 10 ? scatter_tma_smem_bytes<12>(nbits) : scatter_tma_smem_bytes<10>(nbits));
+          nbits <= 10 ? (bpt == 1 ? k_scatter_tma<512, 12, 1> : k_scatter_tma<512, 12, 2>) : k_scatter_tma<512, 10, 4>;
+      const size_t smem = nbits <= 10 ? scatter_tma_smem_bytes<12>(nbits) : scatter_tma_smem_bytes<10>(nbits);
       set_smem(kern, smem);
       Stage st(c, tag_s.c_str());
-      const int64_t grid_t = std::min<int64_t>(tb_t[nchunk], (int64_t)c.sm_count * env_int("MFSDBG_SCATTER_CTAS", 2));
+      const int64_t grid_t = std::min<int64_t>(tb_t[nchunk], (int64_t)c.sm_count * 2);
       kern<<<(unsigned)grid_t, nt, smem, c.stream>>>(in, d_tiles_t, tb_t[nchunk], a, d_cur, out);
       MF_LAUNCH_CHECK();
       c.launches += 2;
@@ -464,7 +460,7 @@ static DevBuckets partition_level(Ctx &c, const uint32_t *in, uint32_t *out, con
     }
   }
   if constexpr (W >= 3 && W <= 5) {   // beyond 5 words a tile is under 2048 records and the register-staged kernel wins (measured at k=141)
-    if (tb_s[nchunk] > 0 && env_int("MFSDBG_TMA_SCATTER_W", 1) != 0 && bit_off < 32) {
+    if (tb_s[nchunk] > 0 && bit_off < 32) {
       // wide records: the shared-memory staged kernel (tiles of 48 KB whatever the width)
       using SC = ScatterWCfg<W>;
       std::vector<int64_t> tb_t(nchunk + 1);
@@ -1002,7 +998,7 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
       std::vector<WorkItem> chunks, merges;
       // one CTA per SM for these few launches: larger chunks leave fewer (key, count) pairs for the merge, which in turn
       // holds more of them (W = 8: 5100-key chunks and 3600 pairs instead of 1600 and 520)
-      const int big_cap = env_int("MFSDBG_OVERSIZED_BIG", 1) ? local_cap(W, true, false, kLocalBigSmem) : p.cap;
+      const int big_cap = local_cap(W, true, false, kLocalBigSmem);
       for (size_t i = 0; i < rs.size(); ++i) {
         WorkItem m{(int64_t)chunks.size(), 0, slots[i]};
         for (int64_t off = 0; off < rs[i].size; off += big_cap) {
@@ -1051,7 +1047,7 @@ static void count_finish_impl(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n,
         }
         LocalArgs ma = pa;
         ma.work = d_merges.as<WorkItem>();
-        ma.cap = env_int("MFSDBG_OVERSIZED_BIG", 1) ? local_cap(W + 1, true, true, kLocalBigSmem) : local_cap(W + 1, true, true);
+        ma.cap = local_cap(W + 1, true, true, kLocalBigSmem);
         ma.counting = a.counting;
         ma.bail_list = d_bail2.as<int32_t>();
         {
@@ -1857,7 +1853,6 @@ static void sdbg_finish(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n_items,
     a.bkt_size = b.size;
     a.bit_off = bit_off;
     a.sort_bits = 32 * WI - 16;   // the walker takes the largest multiplicity of equal (k-mer, b) items itself
-    a.sub_bits = std::max(0, std::min(env_int("MFSDBG_SDBG_SUB", 0), part_limit - bit_off));
     a.cap = p.cap;
     a.k = k;
     a.tip_mode = tip_mode;
@@ -1876,23 +1871,18 @@ static void sdbg_finish(Ctx &c, uint32_t *cur, uint32_t *other, int64_t n_items,
     a.bail_list = d_bail;
     a.bail_count = d_flags;
     a.overflow_flag = d_flags + 1;
-    const bool sdbg_new = env_int("MFSDBG_SDBG_NEW", 1) != 0;
     {
       Stage st(c, "local_sdbg");
-      if (sdbg_new) {
-        a.cap = sdbg_cap(WI);
-        const size_t smem = sdbg_smem_bytes(WI, a.cap);
-        set_smem(k_sdbg_local<WI>, smem);
-        k_sdbg_local<WI><<<b.nslots, kSdNT, smem, c.stream>>>(a);
-        MF_LAUNCH_CHECK();
-        c.launches++;
-      } else {
-        launch_local<WI, kSdbgEmit>(c, a, b.nslots);
-      }
+      a.cap = sdbg_cap(WI);
+      const size_t smem = sdbg_smem_bytes(WI, a.cap);
+      set_smem(k_sdbg_local<WI>, smem);
+      k_sdbg_local<WI><<<b.nslots, kSdNT, smem, c.stream>>>(a);
+      MF_LAUNCH_CHECK();
+      c.launches++;
     }
     int flags[2];
     c.d2h(flags, d_flags, sizeof(int) * 2);
-    if (sdbg_new && flags[0] > 0) {
+    if (flags[0] > 0) {
       // buckets with a crowded sub-bin (low-complexity sequence) or too many items: the general LSD kernel on those slots
       Stage st(c, "local_sdbg_general");
       if (getenv("MFSDBG_TRACE")) {

@@ -31,7 +31,6 @@ struct LocalArgs {
   const WorkItem *work;      // [grid] explicit work items, or null: blockIdx.x is the slot
   int bit_off;               // leading bits every record of a bucket shares
   int sort_bits;             // bits that take part in the order (count: 2(k+1); sdbg: all 32 W)
-  int sub_bits;              // sdbg fast sort: width of the single in-bucket split (0 = LSD passes only)
   int cap;                   // max records per CTA (shared memory capacity), even
   int k;
   // --- count ---
@@ -397,44 +396,6 @@ __global__ void __launch_bounds__(NT) k_local(LocalArgs a) {
 
   const uint16_t *cur = nullptr;   // nullptr == identity order
   bool sorted = false;
-  if constexpr (MODE == kSdbgEmit) {
-    // sdbg items are almost all distinct: one split on the next sub_bits (shared-atomic ranks, no stability needed) leaves
-    // sub-bins of a few items, which one thread each finishes by insertion.  A crowded sub-bin (repeats) sets the flag and
-    // the bucket takes the general stable-LSD route below.
-    if (a.sub_bits >= 4) {
-      const int nsb = 1 << a.sub_bits;
-      for (int i = tid; i <= nsb; i += NT) bins[i] = 0;
-      __syncthreads();
-      for (int i = tid; i < n; i += NT)
-        rk[i] = (uint16_t)atomicAdd(bins + rec_digit_mem<W>(rec + (size_t)i * W, a.bit_off, a.sub_bits), 1u);
-      __syncthreads();
-      block_excl_scan<NT>(bins, nsb + 1, scratch);
-      for (int i = tid; i < n; i += NT)
-        idxA[bins[rec_digit_mem<W>(rec + (size_t)i * W, a.bit_off, a.sub_bits)] + rk[i]] = (uint16_t)i;
-      __syncthreads();
-      int budget = 1024;
-      for (int sb = tid; sb < nsb && budget >= 0; sb += NT) {
-        const int b = (int)bins[sb], e = (int)bins[sb + 1];
-        for (int i = b + 1; i < e && budget >= 0; ++i) {
-          const uint16_t x = idxA[i];
-          const uint32_t *rx = rec + (size_t)x * W;
-          int j = i;
-          while (j > b && cmp_rec_bits<W>(rec + (size_t)idxA[j - 1] * W, rx, a.sort_bits) > 0) {
-            idxA[j] = idxA[j - 1];
-            --j;
-            --budget;
-          }
-          idxA[j] = x;
-        }
-      }
-      if (budget < 0) s_flag[6] = 1;
-      __syncthreads();
-      if (!s_flag[6]) {
-        sorted = true;
-        cur = idxA;
-      }
-    }
-  }
   // LSD sort of the index array over bits [bit_off, sort_bits), least significant digit first
   if (!sorted) {
     uint16_t *nxt = idxA;
