@@ -10,6 +10,7 @@
 #include <fstream>
 #include <memory>
 #include <sstream>
+#include <thread>
 #include "mfsdbg.h"
 
 namespace mf {
@@ -87,6 +88,90 @@ int bucket_file(int bucket, int n_files) { return (int)((int64_t)bucket * n_file
 }  // namespace
 
 // ---------------------------------------------------------------- buildlib
+namespace {
+// text bytes per file and chunk (pinned, two sets: one is read while one is packed); MFSDBG_TEXT_CHUNK overrides (tests)
+static size_t text_chunk() {
+  const char *v = getenv("MFSDBG_TEXT_CHUNK");
+  return v && *v ? (size_t)std::max(1024ll, atoll(v)) : (size_t)192 << 20;
+}
+
+// A FASTQ / FASTA text file (plain, gzip or FIFO) read in chunks that end on record boundaries (single-line records: 4 lines
+// per FASTQ record, 2 per FASTA record -- what the device parser accepts).
+struct TextStream {
+  gzFile f = nullptr;
+  std::string path;
+  std::vector<uint8_t> carry;   // the partial record (or the records handed back) behind the last chunk
+  bool eof = false;
+  int lines_per_rec = 0;
+  explicit TextStream(const std::string &p) : path(p) {
+    f = gzopen(p.c_str(), "rb");
+    if (!f) throw IoError(errno_msg("cannot open", p));
+    gzbuffer(f, 1 << 20);
+  }
+  ~TextStream() { if (f) gzclose(f); }
+  // fills buf[0 .. cap) with whole records; returns the bytes used and their record count; what is left over stays in `carry`
+  size_t next(uint8_t *buf, size_t cap, int64_t *n_rec) {
+    size_t len = carry.size();
+    if (len > cap) throw IoError("a single record of " + path + " exceeds the chunk size");
+    if (len) memcpy(buf, carry.data(), len);
+    carry.clear();
+    while (!eof && len < cap) {
+      const int got = gzread(f, buf + len, (unsigned)std::min<size_t>(cap - len, 1u << 30));
+      if (got < 0) throw IoError("read error on " + path);
+      if (got == 0) eof = true;
+      len += (size_t)got;
+    }
+    if (lines_per_rec == 0 && len > 0) lines_per_rec = buf[0] == '>' ? 2 : 4;
+    if (eof && len > 0 && buf[len - 1] != '\n' && len < cap) buf[len++] = '\n';   // last line without its newline
+    // newlines of the chunk; the cut goes behind the last one that completes a record
+    int64_t lines = 0;
+    size_t last_rec_end = 0;
+    for (const uint8_t *q = buf, *end = buf + len; q < end;) {
+      const uint8_t *nl = (const uint8_t *)memchr(q, '\n', (size_t)(end - q));
+      if (!nl) break;
+      ++lines;
+      if (lines_per_rec && lines % lines_per_rec == 0) last_rec_end = (size_t)(nl - buf) + 1;
+      q = nl + 1;
+    }
+    if (last_rec_end < len) {
+      if (eof) throw IoError("read file is not made of whole single-line FASTQ/FASTA records (multi-line records are not supported): " + path);
+      carry.assign(buf + last_rec_end, buf + len);
+    }
+    *n_rec = lines_per_rec ? (lines - lines % lines_per_rec) / lines_per_rec : 0;
+    if (last_rec_end == 0 && !eof && len == cap) throw IoError("a single record of " + path + " exceeds the chunk size");
+    return last_rec_end;
+  }
+  // keep only the first `keep` records of buf[0 .. len): the rest goes back in front of the carry.  Returns the bytes kept.
+  size_t give_back(const uint8_t *buf, size_t len, int64_t keep) {
+    int64_t lines = 0;
+    size_t cut = 0;
+    const int64_t want = keep * lines_per_rec;
+    for (const uint8_t *q = buf, *end = buf + len; q < end && lines < want;) {
+      const uint8_t *nl = (const uint8_t *)memchr(q, '\n', (size_t)(end - q));
+      if (!nl) break;
+      ++lines;
+      cut = (size_t)(nl - buf) + 1;
+      q = nl + 1;
+    }
+    if (want == 0) cut = 0;
+    std::vector<uint8_t> rest(buf + cut, buf + len);
+    rest.insert(rest.end(), carry.begin(), carry.end());
+    carry.swap(rest);
+    return cut;
+  }
+  bool done() const { return eof && carry.empty(); }
+};
+struct ChunkSet {   // one chunk of every file of a library, in pinned memory
+  HostBuf buf[2];
+  size_t len[2] = {0, 0};
+  int64_t n_rec = 0;
+  bool last = false;
+};
+}  // namespace
+
+// Streams the library through the GPU packer: while chunk i is copied, packed and written, a helper thread reads chunk i+1
+// (zlib / disk) into the other pinned set -- neither the text nor the packed reads are ever held whole (round 1 slurped every
+// file into host memory and then into HBM: 11 GB of text twice for the 5 Gbp sample).
 void file_buildlib(Ctx &c, const char *lib_file, const char *out_prefix, int n_policy) {
   std::ifstream lib(lib_file);
   if (!lib) throw IoError(errno_msg("cannot open", lib_file));
@@ -94,53 +179,93 @@ void file_buildlib(Ctx &c, const char *lib_file, const char *out_prefix, int n_p
   std::ostringstream info;
   int64_t total_reads = 0, total_bases = 0;
   std::string meta, spec;
-  while (std::getline(lib, meta)) {
-    if (!std::getline(lib, spec)) break;
-    std::istringstream ss(spec);
-    std::string type, f1, f2;
-    ss >> type >> f1 >> f2;
-    std::vector<std::vector<uint8_t>> texts;
-    bool paired = false;
-    if (type == "pe" && !f2.empty()) {
-      // open both before reading either: MitoFlex may hand over two FIFOs fed by `gzip -dc` children
-      texts.push_back(slurp(f1));
-      texts.push_back(slurp(f2));
-      paired = true;
-    } else if (type == "se" && !f1.empty()) {
-      texts.push_back(slurp(f1));
-    } else if (type == "interleaved" && !f1.empty()) {
-      texts.push_back(slurp(f1));
-      paired = true;
-    } else {
-      throw IoError("bad library line in " + std::string(lib_file) + ": " + spec);
-    }
-    std::vector<DevMem *> dev;
-    const uint8_t *ptrs[2] = {nullptr, nullptr};
-    int64_t sizes[2] = {0, 0};
-    try {
-      for (size_t i = 0; i < texts.size(); ++i) {
-        dev.push_back(new DevMem(texts[i].size() + 64));
-        c.h2d(dev.back()->p, texts[i].data(), texts[i].size());
-        ptrs[i] = dev.back()->as<uint8_t>();
-        sizes[i] = (int64_t)texts[i].size();
-        std::vector<uint8_t>().swap(texts[i]);
+  ChunkSet sets[2];
+  DevBuf d_text[2];
+  try {
+    while (std::getline(lib, meta)) {
+      if (!std::getline(lib, spec)) break;
+      std::istringstream ss(spec);
+      std::string type, f1, f2;
+      ss >> type >> f1 >> f2;
+      std::vector<std::unique_ptr<TextStream>> in;
+      bool paired = false;
+      if (type == "pe" && !f2.empty()) {
+        // open both before reading either: MitoFlex may hand over two FIFOs fed by `gzip -dc` children
+        in.emplace_back(new TextStream(f1));
+        in.emplace_back(new TextStream(f2));
+        paired = true;
+      } else if ((type == "se" || type == "interleaved") && !f1.empty()) {
+        in.emplace_back(new TextStream(f1));
+        paired = type == "interleaved";
+      } else {
+        throw IoError("bad library line in " + std::string(lib_file) + ": " + spec);
       }
-      ReadsView r;
-      int max_len = 0;
-      dev_pack_fastq(c, ptrs, sizes, (int)dev.size(), n_policy, &r, &max_len);
-      for (auto *d : dev) delete d;
-      dev.clear();
-      std::vector<uint32_t> stream;
-      reads_to_bin_stream(c, r, &stream);
-      bin.write(stream.data(), stream.size() * 4);
-      info << meta << '\n' << (paired ? "pe " : "se ") << total_reads << ' ' << total_reads + r.n_reads - 1 << ' ' << max_len << '\n';
-      total_reads += r.n_reads;
-      total_bases += r.n_bases;
-    } catch (...) {
-      for (auto *d : dev) delete d;
-      throw;
+      const int nf = (int)in.size();
+      const size_t kTextChunk = text_chunk();
+      for (auto &st : sets)
+        for (int f = 0; f < nf; ++f) st.buf[f].reserve(kTextChunk + 16);
+      auto read_chunk = [&](ChunkSet *st) {
+        int64_t nr[2] = {0, 0};
+        for (int f = 0; f < nf; ++f) st->len[f] = in[f]->next(st->buf[f].as<uint8_t>(), kTextChunk, &nr[f]);
+        if (nf == 2 && nr[0] != nr[1]) {   // the files' chunks hold different numbers of records: both keep the smaller count
+          const int big = nr[0] > nr[1] ? 0 : 1;
+          st->len[big] = in[big]->give_back(st->buf[big].as<uint8_t>(), st->len[big], nr[1 - big]);
+          nr[big] = nr[1 - big];
+        }
+        st->n_rec = nr[0];
+        st->last = true;
+        for (int f = 0; f < nf; ++f) st->last = st->last && in[f]->done();
+        if (st->last && nf == 2 && (in[0]->done() != in[1]->done())) throw IoError("paired files have different numbers of reads");
+        if (st->n_rec == 0 && !st->last) throw IoError("paired files have different numbers of reads");
+      };
+      const int64_t first_read = total_reads;
+      int lib_max_len = 0, cur = 0;
+      read_chunk(&sets[cur]);
+      for (;;) {
+        ChunkSet &st = sets[cur];
+        std::exception_ptr rerr;
+        std::thread reader;
+        if (!st.last) reader = std::thread([&, cur] { try { read_chunk(&sets[cur ^ 1]); } catch (...) { rerr = std::current_exception(); } });
+        try {
+          if (st.n_rec > 0) {
+            const uint8_t *ptrs[2] = {nullptr, nullptr};
+            int64_t sizes[2] = {0, 0};
+            for (int f = 0; f < nf; ++f) {
+              d_text[f].reserve(st.len[f] + 64);
+              MF_CUDA(cudaMemcpyAsync(d_text[f].p, st.buf[f].p, st.len[f], cudaMemcpyHostToDevice, c.stream));
+              ptrs[f] = d_text[f].as<uint8_t>();
+              sizes[f] = (int64_t)st.len[f];
+            }
+            ReadsView r;
+            int max_len = 0;
+            dev_pack_fastq(c, ptrs, sizes, nf, n_policy, &r, &max_len);
+            std::vector<uint32_t> stream;
+            reads_to_bin_stream(c, r, &stream);
+            bin.write(stream.data(), stream.size() * 4);
+            lib_max_len = std::max(lib_max_len, max_len);
+            total_reads += r.n_reads;
+            total_bases += r.n_bases;
+          }
+        } catch (...) {
+          if (reader.joinable()) reader.join();
+          throw;
+        }
+        if (reader.joinable()) reader.join();
+        if (rerr) std::rethrow_exception(rerr);
+        if (st.last) break;
+        cur ^= 1;
+      }
+      info << meta << '\n' << (paired ? "pe " : "se ") << first_read << ' ' << total_reads - 1 << ' ' << lib_max_len << '\n';
     }
+  } catch (...) {
+    for (auto &d : d_text) d.release();
+    for (auto &st : sets)
+      for (auto &b : st.buf) b.release();
+    throw;
   }
+  for (auto &d : d_text) d.release();
+  for (auto &st : sets)
+    for (auto &b : st.buf) b.release();
   bin.close();
   File fi(std::string(out_prefix) + ".lib_info", "w");   // meta file last
   std::string head = std::to_string(total_bases) + " " + std::to_string(total_reads) + "\n" + info.str();

@@ -150,3 +150,33 @@ def test_shim_and_wrapper_end_to_end(oracle, tmp_path):
     p = subprocess.run(f"{sys.executable} {exe} count -k 21 -m 2 --output_prefix {tmp_path / 'nope'} --read_lib_file {tmp_path / 'missing.lib'}",
                        shell=True, capture_output=True)
     assert p.returncode == 1 and b"cannot open" in p.stderr and not os.path.exists(str(tmp_path / "nope") + ".edges.info")
+
+
+@pytest.mark.parametrize("chunk", [4096, 50_000])
+def test_buildlib_streams_in_chunks(oracle, tmp_path, monkeypatch, chunk):
+    """buildlib reads the FASTQ files in chunks that end on record boundaries (a helper thread reads chunk i+1 while chunk i is
+    packed on the GPU); the two files of a pair have reads of different lengths, so their chunks hold different numbers of
+    records and the surplus is handed back.  Tiny chunks force hundreds of them; the .bin / .lib_info must not change."""
+    from mitoflex_b200 import lib
+    monkeypatch.setenv("MFSDBG_TEXT_CHUNK", str(chunk))
+    bases, starts = make_reads(37, 6000, 21, genome_len=20000, max_len=140, short_frac=0.3)
+    libf = _write_fastq(tmp_path, bases, starts)
+    g, o = str(tmp_path / "gpu.lib"), str(tmp_path / "orc.lib")
+    for policy in (0, 1):
+        lib.buildlib(libf, g, policy)
+        oracle.cmd_buildlib(libf, o, policy)
+        assert filecmp.cmp(g + ".bin", o + ".bin", shallow=False)
+        assert open(g + ".lib_info").read() == open(o + ".lib_info").read()
+    # single-end and a truncated pair
+    f1 = str(tmp_path / "r_1.fq")
+    se = tmp_path / "se.lib"
+    se.write_text(f"{f1}\nse {f1}\n")
+    lib.buildlib(str(se), g)
+    oracle.cmd_buildlib(str(se), o)
+    assert filecmp.cmp(g + ".bin", o + ".bin", shallow=False)
+    short = tmp_path / "short_2.fq"
+    short.write_text("".join(open(tmp_path / "r_2.fq").readlines()[:-4]))
+    bad = tmp_path / "bad.lib"
+    bad.write_text(f"{f1},{short}\npe {f1} {short}\n")
+    with pytest.raises(lib.MfsdbgError):
+        lib.buildlib(str(bad), g)
