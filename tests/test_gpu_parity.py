@@ -338,8 +338,16 @@ def test_config1_full_size_vs_oracle(oracle):
             assert_sdbg_equal(c.seq2sdbg(e_gpu, k), g_orc)
             g_gpu = c.read2sdbg(reads, k, m)
             if m == 2:   # the oracle's one-pass route sorts an item per solid read position (minutes): once is enough
-                g_orc = oracle.read2sdbg(o_reads, k, m, threads=threads)
-            assert_sdbg_equal(g_gpu, g_orc)
+                assert_sdbg_equal(g_gpu, oracle.read2sdbg(o_reads, k, m, threads=threads))
+            else:
+                # against count + seq2sdbg (proven equal to the one-pass route on the oracle): same graph; the tip labels of the
+                # two routes differ only in the bits below the bases (stage-2 items carry flag | b there, seq2sdbg items the
+                # multiplicity), so they are compared on the bases
+                gn = g_gpu.to_numpy()
+                for f in ("w", "last", "tip", "mul"):
+                    assert np.array_equal(gn[f], getattr(g_orc, f)), f
+                assert np.array_equal(gn["tip_labels"][:, 0], g_orc.tip_labels[:, 0])
+                assert np.array_equal(gn["tip_labels"][:, 1] & 0xfff00000, g_orc.tip_labels[:, 1] & 0xfff00000)
             assert g_gpu.n > 2 * e_gpu.n > 0
     finally:
         c.close()
