@@ -773,13 +773,12 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
           return cut <= 0 || (cut <= 10 && xbits == 16 && ((int64_t)1 << cut) <= nb_cap && (cut <= 4 || force || avg_need >= (double)((int64_t)1 << cut) * 0.5));
         };
         const int cut32 = rest - 31;                                // 32-bit key part + 32-bit count: the cheapest slot compare
-        const int cut_any = rest - (63 - kC2MinCountBits);
-        if (cut_ok(cut32) && env_int("MFSDBG_COUNT_REL", 1) != 3) {
+        // (a variant with a run-time split of the 64 bits -- 47-bit key part + 17-bit count for k up to 31 -- worked but its
+        // 64-bit shifts and compares made the round twice as long: 40.9 ms against 20.9 ms at k=29 / k=21 on the 5 Gbp sample;
+        // those k take the full-key variant)
+        if (cut_ok(cut32)) {
           nb_min = (int64_t)1 << std::max(cut32, 0);
           *rel_count_bits = 32;
-        } else if (cut_ok(cut_any)) {
-          nb_min = (int64_t)1 << std::max(cut_any, 0);
-          *rel_count_bits = cut_any <= 0 ? std::min(32, 64 - (rest + 1)) : kC2MinCountBits;
         }
       }
       if (b_is_rel && *rel_count_bits == 0) {   // the buckets were sized for the 8192-slot table: size them for the full-key one
@@ -826,10 +825,6 @@ static void launch_count_stream(Ctx &c, const LocalArgs &a, int nslots, int64_t 
     const size_t smem = count_stream2_smem_bytes<true>();
     set_smem(k_count_stream2<true, 32>, smem);
     k_count_stream2<true, 32><<<grid, kC2NT, smem, c.stream>>>(a, d_cta_first, 64 - key_bits, 32);
-  } else if (rel_count_bits > 0) {
-    const size_t smem = count_stream2_smem_bytes<true>();
-    set_smem(k_count_stream2<true, 0>, smem);
-    k_count_stream2<true, 0><<<grid, kC2NT, smem, c.stream>>>(a, d_cta_first, 64 - key_bits, rel_count_bits);
   } else {
     const size_t smem = count_stream2_smem_bytes<false>();
     set_smem(k_count_stream2<false, 0>, smem);
