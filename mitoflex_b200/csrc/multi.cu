@@ -21,9 +21,7 @@ namespace mf {
 
 namespace {
 
-// exchange bins = ownership granularity, as in dist.py l1_bits_for(): 64 bins for 2 GPUs, 128 for 4, 256 for 8
-static int g_multi_l1_bits = 6;
-#define kMultiL1Bits g_multi_l1_bits
+constexpr int kMultiL1Bits = 6;   // 64 exchange bins, as in dist.py l1_bits_for() (256 bins at 8 GPUs measured 2.8x slower)
 
 struct RankAborted : std::runtime_error {
   RankAborted() : std::runtime_error("another GPU's thread failed") {}
@@ -254,7 +252,6 @@ const std::vector<int64_t> &MultiGpu::counting(int r) const { return ranks[r]->c
 template <class Body>
 static void run_ranks(MultiGpu &mg, Body &&body) {
   const int world = mg.world();
-  g_multi_l1_bits = world <= 2 ? 6 : (world <= 4 ? 7 : 8);   // calls are serialised by the job mutex
   Shared sh;
   sh.world = world;
   sh.bar.reset(new Barrier(world));

@@ -17,13 +17,11 @@ L1_BITS = int(os.environ.get("MFSDBG_DIST_L1_BITS", "0"))   # 0 = by world size 
 
 def l1_bits_for(world):
     """Exchange bins = ownership granularity.  64 bins keep the runs of the NVLink stores long (5-7 bits measured within 3 % on
-    the fused kernel), but owners are cut at bin boundaries and canonical keys are twice as dense at small prefixes: with 8
-    ranks on 64 bins rank 0 held +20 % of the mean (SCALE_r01).  Half a bin of error is 1/(2 * bins) of all keys, i.e.
-    world / (2 * bins) of a rank's share: 128 bins for 4 ranks, 256 for 8 keep it near 3 % (the exchange kernel is NVLink-bound
-    there, so the extra bins cost nothing that shows)."""
-    if L1_BITS:
-        return L1_BITS
-    return 6 if world <= 2 else (7 if world <= 4 else 8)
+    the fused kernel at 2 GPUs).  Owners are cut at bin boundaries and canonical keys are twice as dense at small prefixes, so
+    with 8 ranks on 64 bins rank 0 holds +20 % of the mean (SCALE_r01) -- but finer bins are not the cure: 256 bins at 8 GPUs
+    took the fused exchange kernel from 50 to 91 ms (326 instead of 576 GB/s out of each GPU: runs of 32 keys) and the step
+    from 192 to 531 ms (gpurun_out/r2p_bench_n8*.json).  So: 64 bins whatever the world size."""
+    return L1_BITS or 6
 
 
 def assign_owners(global_hist, world):
