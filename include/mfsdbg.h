@@ -187,8 +187,11 @@ int32_t mfsdbg_words_per_edge(int32_t k);
 /* ---- host-buffer entry point: what a caller holding the packed library in host memory uses ------------ */
 /* The sdbg in (pinned, library-owned) host memory; valid until the next mfsdbg_host_* call on the context. */
 typedef struct mfsdbg_host_sdbg {
-  const uint32_t *rec;         /* host, n_items: w | last<<4 | tip<<5 | multiplicity<<8 */
+  const uint16_t *rec;         /* host, n_items: w | last<<4 | tip<<5 | min(multiplicity, 255)<<8 -- megahit's packed sdbg item
+                                  (SdbgWriter::Write); 255 = "large": the true multiplicity is in the side list below */
   const uint32_t *tip_labels;  /* host, n_tips * words_per_tip */
+  const int64_t *large_index;  /* host, n_large: item indices with multiplicity > 254, ascending */
+  const uint16_t *large_mult;  /* host, n_large: their multiplicities */
   int64_t n_items, n_tips, n_large;
   int32_t k, words_per_tip;
   int64_t h2d_bytes, d2h_bytes; /* bytes this call moved over PCIe */

@@ -1,4 +1,5 @@
 // api.cu -- the C ABI of libmfsdbg.so (include/mfsdbg.h): argument checking, error convention, no exceptions out.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -354,24 +355,44 @@ int mfsdbg_host_read2sdbg(mfsdbg_ctx *ctx, const uint32_t *packed_host, const in
     }
     mf::SdbgView g;
     mf::dev_seq2sdbg(c, e.edges, e.n_edges, mf::SeqsView{}, k, 1, &g);
-    const size_t rb = (size_t)g.n_items * 4, lb = (size_t)g.n_tips * g.words_tip * 4;
+    // over PCIe the records travel as megahit's 16-bit packed items plus the few multiplicities beyond 254 (half the bytes)
+    const size_t rb = (size_t)g.n_items * 2, lb = (size_t)g.n_tips * g.words_tip * 4, pb = (size_t)g.n_large * 8;
+    c.slab_reserve(rb + pb + 4096);
+    c.slab_reset();
+    uint16_t *d_rec16 = c.alloc<uint16_t>((size_t)g.n_items + 8);
+    unsigned long long *d_pairs = c.alloc<unsigned long long>((size_t)g.n_large + 1), *d_cur = c.alloc<unsigned long long>(1);
     c.out_rec.reserve(rb + 64);
     c.out_labels.reserve(lb + 64);
+    c.out_large.reserve(pb + 64);
     {
       mf::Stage st(c, "d2h");
-      if (rb) MF_CUDA(cudaMemcpyAsync(c.out_rec.p, g.rec, rb, cudaMemcpyDeviceToHost, c.stream));
+      mf::dev_sdbg_pack16(c, g, d_rec16, d_pairs, d_cur);
+      if (rb) MF_CUDA(cudaMemcpyAsync(c.out_rec.p, d_rec16, rb, cudaMemcpyDeviceToHost, c.stream));
       if (lb) MF_CUDA(cudaMemcpyAsync(c.out_labels.p, g.labels, lb, cudaMemcpyDeviceToHost, c.stream));
+      if (pb) MF_CUDA(cudaMemcpyAsync(c.out_large.p, d_pairs, pb, cudaMemcpyDeviceToHost, c.stream));
     }
     c.end_call();
-    out->rec = c.out_rec.as<uint32_t>();
+    {
+      unsigned long long *pairs = c.out_large.as<unsigned long long>();
+      std::sort(pairs, pairs + g.n_large);
+      c.out_large_index.resize((size_t)g.n_large);
+      c.out_large_mult.resize((size_t)g.n_large);
+      for (int64_t i = 0; i < g.n_large; ++i) {
+        c.out_large_index[(size_t)i] = (int64_t)(pairs[i] >> 16);
+        c.out_large_mult[(size_t)i] = (uint16_t)(pairs[i] & 0xffffu);
+      }
+    }
+    out->rec = c.out_rec.as<uint16_t>();
     out->tip_labels = c.out_labels.as<uint32_t>();
+    out->large_index = c.out_large_index.data();
+    out->large_mult = c.out_large_mult.data();
     out->n_items = g.n_items;
     out->n_tips = g.n_tips;
     out->n_large = g.n_large;
     out->k = g.k;
     out->words_per_tip = g.words_tip;
     out->h2d_bytes = (int64_t)(wbytes + sbytes);
-    out->d2h_bytes = (int64_t)(rb + lb);
+    out->d2h_bytes = (int64_t)(rb + lb + pb);
   });
 }
 

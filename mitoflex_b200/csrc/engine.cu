@@ -2152,6 +2152,26 @@ void dev_seq2sdbg(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView
   MF_DISPATCH_W(words_item(k), SDBG)
 }
 
+// w | last<<4 | tip<<5 | min(mult, 255)<<8 per item (SdbgWriter::Write); items with mult > 254 also go to `pairs` as
+// (index << 16 | mult), unordered (the host sorts the few of them)
+__global__ void k_sdbg_pack16(const uint32_t *__restrict__ rec, int64_t n, uint16_t *__restrict__ out, unsigned long long *pairs,
+                              unsigned long long *cursor) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = rec[i], m = r >> 8;
+    out[i] = (uint16_t)((r & 0x3fu) | (min(m, 255u) << 8));
+    if (m > 254u) pairs[atomicAdd(cursor, 1ull)] = ((unsigned long long)i << 16) | (unsigned long long)min(m, 65535u);
+  }
+}
+void dev_sdbg_pack16(Ctx &c, const SdbgView &g, uint16_t *rec16_dev, unsigned long long *pairs_dev, unsigned long long *cursor_dev) {
+  MF_CUDA(cudaMemsetAsync(cursor_dev, 0, sizeof(unsigned long long), c.stream));
+  if (g.n_items > 0) {
+    const unsigned grid = (unsigned)std::min<int64_t>(div_ceil64(g.n_items, 256), (int64_t)c.sm_count * 16);
+    k_sdbg_pack16<<<grid, 256, 0, c.stream>>>(g.rec, g.n_items, rec16_dev, pairs_dev, cursor_dev);
+    MF_LAUNCH_CHECK();
+    c.launches++;
+  }
+}
+
 // ---- staged sdbg for the multi-GPU driver: items -> (caller exchanges them by prefix) -> finish
 #define MF_DISPATCH_CASE_SITEMS(Wn)                                                  \
   case Wn: {                                                                          \

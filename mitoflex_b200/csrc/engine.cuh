@@ -50,7 +50,9 @@ struct Ctx {
   double call_t0 = 0;
   // results that outlive a call
   DevBuf edges, sdbg_rec, sdbg_labels, sdbg_buckets, sbits, pack_words, pack_starts, synth_words, synth_starts, in_words, in_starts;
-  HostBuf out_rec, out_labels;
+  HostBuf out_rec, out_labels, out_large;
+  std::vector<int64_t> out_large_index;
+  std::vector<uint16_t> out_large_mult;
   DevBuf small[3];   // per-call histograms / counters kept across calls (cudaMalloc and cudaFree stall for 100+ ms at times)
   DevBuf fb[4];      // scratch of the recursive fallback sort, one per recursion depth
   DevBuf miss;     // miss list of the sdbg item filter (kmerset.cuh): outlives the slab across the rounds of a call
@@ -114,6 +116,8 @@ void dev_count(Ctx &c, const ReadsView &r, int k, int min_count, EdgesView *out,
 bool dev_count_host(Ctx &c, const uint32_t *packed_host, const int64_t *starts_host, int64_t n_reads, int64_t n_bases, int k,
                     int min_count, EdgesView *out);
 void dev_seq2sdbg(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &seqs, int k, int tip_mode, SdbgView *out);
+// the graph's records as megahit's 16-bit packed items + (index, multiplicity) pairs of the items beyond 254, for the trip over PCIe
+void dev_sdbg_pack16(Ctx &c, const SdbgView &g, uint16_t *rec16_dev, unsigned long long *pairs_dev, unsigned long long *cursor_dev);
 void dev_count_hist(Ctx &c, const ReadsView &r, int k, int l1_bits, unsigned long long *hist_dev);
 // capacity: records keys_out can hold (checked against the histogram total; < 0 = unchecked, peer mode ignores it)
 void dev_count_scatter(Ctx &c, const ReadsView &r, int k, int l1_bits, const unsigned long long *hist_dev, uint32_t *keys_out,

@@ -44,9 +44,9 @@ class DevSdbg(C.Structure):
 
 
 class HostSdbg(C.Structure):
-    _fields_ = [("rec", C.c_void_p), ("tip_labels", C.c_void_p), ("n_items", C.c_int64), ("n_tips", C.c_int64),
-                ("n_large", C.c_int64), ("k", C.c_int32), ("words_per_tip", C.c_int32), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64)]
+    _fields_ = [("rec", C.c_void_p), ("tip_labels", C.c_void_p), ("large_index", C.c_void_p), ("large_mult", C.c_void_p),
+                ("n_items", C.c_int64), ("n_tips", C.c_int64), ("n_large", C.c_int64), ("k", C.c_int32),
+                ("words_per_tip", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
 class SynthSpec(C.Structure):

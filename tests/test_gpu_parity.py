@@ -183,13 +183,14 @@ def test_count_crowded_buckets_multipass(ctx, oracle, monkeypatch):
 @pytest.mark.parametrize("pipelined", [False, True])
 def test_host_read2sdbg_matches_oracle(ctx, oracle, monkeypatch, pipelined):
     """the end-to-end entry point (host buffers in, host buffers out); with MFSDBG_H2D_MIN_BASES=0 the transfer is cut into
-    chunks and the reads-fed partition level runs chunk by chunk behind it (several level-1 chunks per segment)."""
+    chunks and the reads-fed partition level runs chunk by chunk behind it (several level-1 chunks per segment).  The input
+    includes 400 copies of one read so that multiplicities beyond 254 travel through the side list."""
     import ctypes
     from mitoflex_b200 import lib
     if pipelined:
         monkeypatch.setenv("MFSDBG_H2D_MIN_BASES", "0")
     k, m = 21, 2
-    bases, starts = make_reads(31, 30000, k, genome_len=120000, max_len=150, err=0.005)
+    bases, starts = make_reads(31, 30000, k, genome_len=120000, max_len=150, err=0.005, dup_boost=400)
     words, st = lib.pack_reads(bases, starts)
     words = np.ascontiguousarray(words)
     st = np.ascontiguousarray(st)
@@ -197,11 +198,19 @@ def test_host_read2sdbg_matches_oracle(ctx, oracle, monkeypatch, pipelined):
     g = oracle.read2sdbg(_orc_reads(oracle, bases, starts), k, m, threads=8)
     assert out.n_items == g.n
     assert out.n_tips * out.words_per_tip == np.asarray(g.tip_labels).size
-    rec = np.ctypeslib.as_array(ctypes.cast(out.rec, ctypes.POINTER(ctypes.c_uint32)), shape=(out.n_items,)).copy()
+    # records come back as megahit's 16-bit packed items; multiplicities beyond 254 in the side list (ascending item index)
+    rec = np.ctypeslib.as_array(ctypes.cast(out.rec, ctypes.POINTER(ctypes.c_uint16)), shape=(out.n_items,)).copy()
     assert np.array_equal(rec & 0xF, g.w)
     assert np.array_equal((rec >> 4) & 1, g.last)
     assert np.array_equal((rec >> 5) & 1, g.tip)
-    assert np.array_equal(rec >> 8, g.mul)
+    mul = (rec >> 8).astype(np.int64)
+    assert np.array_equal(mul, np.minimum(g.mul, 255))
+    big = np.nonzero(g.mul > 254)[0]
+    assert out.n_large == len(big)
+    if out.n_large:
+        idx = np.ctypeslib.as_array(ctypes.cast(out.large_index, ctypes.POINTER(ctypes.c_int64)), shape=(out.n_large,)).copy()
+        lm = np.ctypeslib.as_array(ctypes.cast(out.large_mult, ctypes.POINTER(ctypes.c_uint16)), shape=(out.n_large,)).copy()
+        assert np.array_equal(idx, big) and np.array_equal(lm, g.mul[big])
     if out.n_tips:
         lab = np.ctypeslib.as_array(ctypes.cast(out.tip_labels, ctypes.POINTER(ctypes.c_uint32)),
                                     shape=(out.n_tips * out.words_per_tip,)).copy()
