@@ -194,6 +194,38 @@ __global__ void __launch_bounds__(kC2NT, 2) k_count_stream2(LocalArgs a, const i
     const bool crowded = s_flag[0] != 0;
     if constexpr (REL) {
       const unsigned long long ref = s_ref[0] >> key_shift;   // right-aligned reference key
+      if (!a.counting) {
+        // no multiplicity histogram wanted (read2sdbg, seq2sdbg's count): only the SOLID slots need work -- about one slot in
+        // twenty at assembly depths -- so the sweep first marks them (16 slots per thread, branch-free), then visits the marked
+        // ones (a warp-aggregated reservation in the solid list), then clears its 16 slots.  The plain loop below ran its
+        // occupied-slot body 16 times per warp and bucket whatever the table held: 60 % of the bucket end (ncu r2q).
+        constexpr int SPT = Slots / NC;
+        uint32_t solid = 0u;
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) {
+          const uint32_t c = (uint32_t)(tab[tid + j * NC] & cmask);
+          solid |= (c >= m ? 1u : 0u) << j;
+        }
+        while (solid) {
+          const int j = __ffs(solid) - 1;
+          solid &= solid - 1u;
+          const unsigned long long s = tab[tid + j * NC];
+          const unsigned act = __activemask();
+          const int leader = __ffs(act) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(s_flag + 4, __popc(act));
+          base = __shfl_sync(act, base, leader);
+          const int q = base + __popc(act & lt);
+          if (q < kCsSolidMax) {
+            const long long d = ((long long)(((s >> CB) - ref) << CB)) >> CB;
+            skeys[q] = (unsigned long long)((long long)ref + d) << key_shift;
+            scnt[q] = (uint32_t)(s & cmask);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) tab[tid + j * NC] = 0ull;
+      } else
       for (int h = tid; h < Slots; h += NC) {
         const unsigned long long s = tab[h];
         if (s) {
