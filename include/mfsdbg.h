@@ -184,6 +184,28 @@ int mfsdbg_dev_records_scatter_peer(mfsdbg_ctx *ctx, const uint32_t *records, in
 int32_t mfsdbg_words_per_key(int32_t k);
 int32_t mfsdbg_words_per_edge(int32_t k);
 
+/* ---- super-k-mer exchange (16 <= k <= 26): what crosses NVLink in the multi-GPU count ----------------------
+ * megahit counts in one address space (sorting/kmer_counter.cpp: every thread's lv1 scan sees every read); with the
+ * reads sharded by GPU the (k+1)-mers have to reach the GPU that counts them.  Instead of one 8-byte key per
+ * (k+1)-mer, a run of consecutive (k+1)-mers of a read whose minimizer hashes to the same destination travels as ONE
+ * 64-bit record: the run's bases left-aligned (2 bits each, first base in the top bits, true orientation, at most 30)
+ * and the run length - 1 in the low 3 bits.  A (k+1)-mer and its reverse complement share the minimizer, so every
+ * canonical key is counted on exactly one GPU.
+ *   skm_scatter : dst_ptrs[d] (host array of n_dst device addresses, peer mappings allowed) is where THIS source's records
+ *                 for destination d go, dst_caps[d] how many fit; runs that would not fit are dropped and the returned
+ *                 count exceeds the capacity (retry with more room).  dst_ptrs == NULL: count only, on every stride-th
+ *                 tile of the reads (capacity estimate).  counts_out[0 .. n_dst): records, [n_dst .. 2 n_dst): (k+1)-mers.
+ *   count_skm   : the single-GPU count over received records: `records` + chunks (start / size in records, one per
+ *                 source), n_keys = the (k+1)-mers the sources announced; keys / scratch hold `capacity` records of 2 words
+ *                 (mfsdbg_skm_key_capacity(n_keys)).  Result as mfsdbg_dev_count: this GPU's solid edges, sorted. */
+int32_t mfsdbg_skm_supported(int32_t k);
+int64_t mfsdbg_skm_key_capacity(int64_t n_keys);
+int mfsdbg_dev_skm_scatter(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int32_t k, int32_t n_dst, const uint64_t *dst_ptrs,
+                           const int64_t *dst_caps, int64_t stride, int64_t *counts_out);
+int mfsdbg_dev_count_skm(mfsdbg_ctx *ctx, const uint64_t *records, const int64_t *chunk_start, const int64_t *chunk_size,
+                         int32_t n_chunks, int64_t n_keys, int32_t k, int32_t min_count, uint32_t *keys, uint32_t *scratch,
+                         int64_t capacity, mfsdbg_dev_edges *out);
+
 /* ---- host-buffer entry point: what a caller holding the packed library in host memory uses ------------ */
 /* The sdbg in (pinned, library-owned) host memory; valid until the next mfsdbg_host_* call on the context. */
 typedef struct mfsdbg_host_sdbg {

@@ -315,6 +315,33 @@ int mfsdbg_dev_records_scatter_peer(mfsdbg_ctx *ctx, const uint32_t *records, in
     ctx->c.end_call();
   });
 }
+// ---- super-k-mer exchange (skm.cu)
+int32_t mfsdbg_skm_supported(int32_t k) { return mf::skm_supported(k) ? 1 : 0; }
+int64_t mfsdbg_skm_key_capacity(int64_t n_keys) { return mf::skm_key_capacity(n_keys < 0 ? 0 : n_keys); }
+int mfsdbg_dev_skm_scatter(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int32_t k, int32_t n_dst, const uint64_t *dst_ptrs,
+                           const int64_t *dst_caps, int64_t stride, int64_t *counts_out) {
+  if (!ctx || !reads || !counts_out || (dst_ptrs && !dst_caps)) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::dev_skm_scatter(ctx->c, view(reads), k, n_dst, dst_ptrs, dst_caps, stride, counts_out);
+    ctx->c.end_call();
+  });
+}
+int mfsdbg_dev_count_skm(mfsdbg_ctx *ctx, const uint64_t *records, const int64_t *chunk_start, const int64_t *chunk_size,
+                         int32_t n_chunks, int64_t n_keys, int32_t k, int32_t min_count, uint32_t *keys, uint32_t *scratch,
+                         int64_t capacity, mfsdbg_dev_edges *out) {
+  if (!ctx || !out || n_chunks < 0 || n_keys < 0 || capacity < 0 || (n_chunks > 0 && (!chunk_start || !chunk_size))) return MFSDBG_EINVAL;
+  if (n_keys > 0 && (!records || !keys || !scratch)) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::EdgesView e;
+    mf::dev_count_skm(ctx->c, records, chunk_start, chunk_size, n_chunks, n_keys, k, min_count, keys, scratch, capacity, &e);
+    ctx->c.end_call();
+    fill(out, e);
+  });
+}
 int mfsdbg_dev_synth_reads(mfsdbg_ctx *ctx, const mfsdbg_synth_spec *spec, mfsdbg_dev_reads *out) {
   if (!ctx || !spec || !out) return MFSDBG_EINVAL;
   std::lock_guard<std::mutex> lk(g_job_mutex);

@@ -1163,6 +1163,8 @@ static const uint32_t *build_start_bits(Ctx &c, const ReadsView &r) {
   return c.sbits.as<uint32_t>();
 }
 
+const uint32_t *dev_start_bits(Ctx &c, const ReadsView &r) { return build_start_bits(c, r); }
+
 // level-1 digit width of count
 template <int W>
 static Plan count_plan(Ctx &c, int k, int min_count, int64_t n_est) {

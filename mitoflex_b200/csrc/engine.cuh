@@ -126,6 +126,19 @@ void dev_count_finish(Ctx &c, uint32_t *keys, uint32_t *scratch, int64_t n_keys,
                       const int64_t *chunk_size, const int32_t *chunk_seg, int n_chunks, int n_segs, int k, int l1_bits,
                       int min_count, EdgesView *out, int64_t *counting_host);
 
+// the read-start bitmap of `r` (1 bit per base), rebuilt on every call into the context's buffer
+const uint32_t *dev_start_bits(Ctx &c, const ReadsView &r);
+
+// ---- super-k-mer exchange (skm.cu): the multi-GPU count sends runs of consecutive (k+1)-mers that share an owner as one
+// 64-bit record (2-bit bases + run length) instead of one 8-byte key per (k+1)-mer
+bool skm_supported(int k);
+int64_t skm_key_capacity(int64_t n_keys);
+// dst_ptrs == nullptr: count only, on every `stride`-th tile.  counts_out[2 * n_dst]: records, then keys, per destination
+void dev_skm_scatter(Ctx &c, const ReadsView &r, int k, int n_dst, const uint64_t *dst_ptrs, const int64_t *dst_caps, int64_t stride,
+                     int64_t *counts_out);
+void dev_count_skm(Ctx &c, const uint64_t *recs, const int64_t *chunk_start, const int64_t *chunk_size, int n_chunks, int64_t n_keys,
+                   int k, int min_count, uint32_t *keys, uint32_t *scratch, int64_t capacity, EdgesView *out);
+
 void dev_sdbg_items(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, uint32_t *items_out);
 int64_t dev_sdbg_items_seqs(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &seqs, int k, uint32_t *items_out);
 void dev_records_hist(Ctx &c, const uint32_t *rec, int64_t n, int words, int l1_bits, unsigned long long *hist_dev);

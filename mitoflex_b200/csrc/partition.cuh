@@ -58,7 +58,7 @@ struct TileDesc {
   int32_t n;
   int32_t seg;
 };
-__global__ void k_build_tiles(ChunkTable ct, int T, int64_t ntiles, TileDesc *out) {
+static __global__ void k_build_tiles(ChunkTable ct, int T, int64_t ntiles, TileDesc *out) {
   const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tile >= ntiles) return;
   int lo = 0, hi = ct.nchunk;  // last chunk with tile_base <= tile
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(NT) k_level_hist_persist(const uint32_t *__res
 
 // ============================================================ scan: hist -> cursors + bucket table
 // seg_total[s] = sum_d hist[s][d]
-__global__ void k_seg_totals(const unsigned long long *hist, int nbins, int nseg, int64_t *seg_total) {
+static __global__ void k_seg_totals(const unsigned long long *hist, int nbins, int nseg, int64_t *seg_total) {
   int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= nseg) return;
   unsigned long long acc = 0;
@@ -261,7 +261,7 @@ __global__ void k_seg_totals(const unsigned long long *hist, int nbins, int nseg
   if ((threadIdx.x & 31) == 0) seg_total[s] = (int64_t)acc;
 }
 // single-block exclusive scan of int64 v[0..n) -> out[0..n], out[n] = total (+base)
-__global__ void k_scan_i64(const int64_t *v, int64_t n, int64_t base, int64_t *out) {
+static __global__ void k_scan_i64(const int64_t *v, int64_t n, int64_t base, int64_t *out) {
   __shared__ int64_t s_part[1024];
   __shared__ int64_t s_run;
   const int tid = threadIdx.x;
@@ -283,7 +283,7 @@ __global__ void k_scan_i64(const int64_t *v, int64_t n, int64_t base, int64_t *o
   for (int64_t i = b; i < e; ++i) { int64_t x = v[i]; out[i] = run; run += x; }
 }
 // per segment: cursor[s][d] = seg_out_start[s] + exclusive prefix of hist[s][.]; bucket table likewise.
-__global__ void k_level_scan(const unsigned long long *hist, int nbins, const int64_t *seg_out_start,
+static __global__ void k_level_scan(const unsigned long long *hist, int nbins, const int64_t *seg_out_start,
                              unsigned long long *cursor, int64_t *bkt_start, int64_t *bkt_size) {
   // one block of 1024 threads per segment; each thread owns kMaxBins/1024 consecutive bins
   constexpr int PER = kMaxBins / 1024;

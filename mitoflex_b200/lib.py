@@ -93,6 +93,12 @@ SYMBOLS = {
     "mfsdbg_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mfsdbg_dev_count_scatter_peer": (C.c_int, [C.c_void_p, C.POINTER(DevReads), C.c_int32, C.c_int32, C.c_void_p]),
     "mfsdbg_dev_records_scatter_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "mfsdbg_skm_supported": (C.c_int32, [C.c_int32]),
+    "mfsdbg_skm_key_capacity": (C.c_int64, [C.c_int64]),
+    "mfsdbg_dev_skm_scatter": (C.c_int, [C.c_void_p, C.POINTER(DevReads), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_void_p]),
+    "mfsdbg_dev_count_skm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(DevEdges)]),
     "mfsdbg_words_per_key": (C.c_int32, [C.c_int32]),
     "mfsdbg_words_per_edge": (C.c_int32, [C.c_int32]),
     "mfsdbg_host_read2sdbg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
@@ -360,6 +366,28 @@ class Context:
 
     def records_scatter_peer(self, rec_ptr, n, words, l1_bits, bin_base_ptr):
         _check(load().mfsdbg_dev_records_scatter_peer(self._h, rec_ptr, n, words, l1_bits, bin_base_ptr))
+
+    # -- super-k-mer exchange (multi-GPU count, 16 <= k <= 26)
+    def skm_scatter(self, reads, k, n_dst, dst_ptrs=None, dst_caps=None, stride=1):
+        """Returns (records[n_dst], keys[n_dst]) this source produced per destination; dst_ptrs None = count only."""
+        counts = np.zeros(2 * n_dst, np.int64)
+        if dst_ptrs is None:
+            _check(load().mfsdbg_dev_skm_scatter(self._h, C.byref(reads.s), k, n_dst, None, None, stride, counts.ctypes.data))
+        else:
+            p = np.ascontiguousarray(dst_ptrs, dtype=np.uint64)
+            cp = np.ascontiguousarray(dst_caps, dtype=np.int64)
+            assert len(p) == n_dst and len(cp) == n_dst
+            _check(load().mfsdbg_dev_skm_scatter(self._h, C.byref(reads.s), k, n_dst, p.ctypes.data, cp.ctypes.data, 1,
+                                                 counts.ctypes.data))
+        return counts[:n_dst].copy(), counts[n_dst:].copy()
+
+    def count_skm(self, rec_ptr, chunk_start, chunk_size, n_keys, k, min_count, keys_ptr, scratch_ptr, capacity):
+        cs = np.ascontiguousarray(chunk_start, dtype=np.int64)
+        cz = np.ascontiguousarray(chunk_size, dtype=np.int64)
+        out = DevEdges()
+        _check(load().mfsdbg_dev_count_skm(self._h, rec_ptr, cs.ctypes.data, cz.ctypes.data, len(cs), int(n_keys), k, min_count,
+                                           keys_ptr, scratch_ptr, int(capacity), C.byref(out)))
+        return Edges(self, out)
 
     def sdbg_items(self, edges_ptr, n_edges, k, items_ptr):
         _check(load().mfsdbg_dev_sdbg_items(self._h, edges_ptr, n_edges, k, items_ptr))
