@@ -104,7 +104,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ roofline bookkeeping
-def stage_bytes(n_bases, n_keys, n_edges, n_items_gen, k):
+def stage_bytes(n_bases, n_keys, n_edges, n_items_gen, k, n_records_out=0, n_records_in=0):
     """ALGORITHMIC bytes per stage launch (DESIGN.md 'kernels'): what the stage must read + write once."""
     W = 4 * ((2 * (k + 1) + 31) // 32)
     We = 4 * ((2 * (k + 1) + 16 + 31) // 32)
@@ -112,6 +112,9 @@ def stage_bytes(n_bases, n_keys, n_edges, n_items_gen, k):
     return {
         "reads_hist": n_bases / 4,
         "reads_scatter": n_bases / 4 + n_keys * W,
+        # super-k-mer exchange (N > 1): reads in, 8-byte records out / records in, keys out
+        "skm_scatter": n_bases / 4 + n_records_out * 8,
+        "skm_l1_scatter": n_records_in * 8 + n_keys * W,
         "count_l2_hist": n_keys * W,
         "count_l2_scatter": 2 * n_keys * W,
         "count_l2a_hist": n_keys * W,
@@ -474,18 +477,22 @@ def main():
     # generated sdbg items: the filtered generator writes the 2 real items per edge plus the few dummies that survive,
     # which is what the graph ends up holding (res.n); the multi-GPU driver still generates all 6 per edge
     n_items_gen = (res.n if res is not None else 2 * n_edges) if world == 1 else 6 * n_edges
-    sb = stage_bytes(n_bases, n_keys, n_edges, n_items_gen, K)
+    sb = stage_bytes(n_bases, n_keys, n_edges, n_items_gen, K, info.get("records_sent", 0), info.get("records_recv", 0))
     nvlink = None
     if world > 1:
         # rank 0's share: bytes that left this GPU / time of the all-to-all, against 900 GB/s per direction nominal
-        kb = info.get("exchanged_keys", 0) * info.get("key_bytes", 8)
+        skm = info.get("exchange") == "skm"
+        kb = info.get("records_sent", 0) * 8 if skm else info.get("exchanged_keys", 0) * info.get("key_bytes", 8)
         ib = info.get("exchanged_items", 0) * info.get("item_bytes", 8)
         # fused mode ("p2p"): the scatter kernels store straight into the owners' HBM, so the exchange time IS the scatter
         # stage (reads_scatter for keys, records_scatter for items); NCCL mode has separate a2a_* stages
-        fused = info.get("exchange") == "p2p"
-        ak = stage_sum.get("reads_scatter" if fused else "a2a_keys", 0.0) / args.steps
+        fused = info.get("exchange") in ("p2p", "skm")
+        ak = stage_sum.get("skm_scatter" if skm else ("reads_scatter" if fused else "a2a_keys"), 0.0) / args.steps
         ai = stage_sum.get("records_scatter" if fused else "a2a_items", 0.0) / args.steps
-        nvlink = {"exchange": "fused partition+exchange kernel over NVLink peer memory (CUDA IPC)" if fused else "NCCL all_to_all_single",
+        nvlink = {"exchange": ("super-k-mer records (64-bit: a run of (k+1)-mers sharing a minimizer owner) stored into the owner's HBM by the "
+                               "partition kernel over NVLink peer memory (CUDA IPC)") if skm else
+                              ("fused partition+exchange kernel over NVLink peer memory (CUDA IPC)" if fused else "NCCL all_to_all_single"),
+                  "keys_exchanged": info.get("exchanged_keys"), "keys_per_record": info.get("keys_per_record"),
                   "keys_bytes_sent": kb, "keys_ms": ak, "keys_GBps": kb / ak / 1e6 if ak else None, "items_bytes_sent": ib,
                   "items_ms": ai, "items_GBps": ib / ai / 1e6 if ai else None, "peak_GBps_per_direction": 900.0,
                   "measured_peer_copy_GBps": 770.0}
@@ -551,7 +558,10 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(args.pairs, args.error_rate, args.nuclear_len), "bases_per_gpu": n_bases, "keys_per_gpu": n_keys, "solid_edges": n_edges,
                    "sdbg_items": res.n if res is not None else None, "l2_flush": "inputs and key buffers (>= 1 GB) exceed the 126 MB L2",
-                   "parallelism": "reads sharded by GPU, keys and items stored into the owner GPU of their prefix bin by the partition kernel itself (NVLink peer memory), disjoint key range per GPU" if world > 1 else "1 GPU"},
+                   "parallelism": ("reads sharded by GPU; count: (k+1)-mers routed to the GPU that owns their minimizer as super-k-mer records, items routed to the "
+                                   "owner of their prefix bin; both stored by the partition kernel itself into the owner's HBM (NVLink peer memory); rank r "
+                                   "ends with the r-th prefix range of the graph" if info.get("exchange") == "skm" else
+                                   "reads sharded by GPU, keys and items stored into the owner GPU of their prefix bin by the partition kernel itself (NVLink peer memory), disjoint key range per GPU") if world > 1 else "1 GPU"},
         "roofline": roofline, "nvlink": nvlink, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     if config3 is not None:

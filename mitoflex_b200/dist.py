@@ -141,7 +141,10 @@ class DistResult:
 class DistRead2Sdbg:
     """read2sdbg over all ranks of the default process group; each rank ends with its prefix range of the graph."""
 
-    def __init__(self, ctx, k, min_count, exchange=None):
+    def __init__(self, ctx, k, min_count, exchange=None, skm=None):
+        """exchange: "p2p" (records stored straight into the owner's HBM by the partition kernels) or "nccl" (all_to_all_single).
+        skm: route the count by minimizer and send super-k-mer records (csrc/skm.cu) instead of one key per (k+1)-mer; None =
+        whenever the library supports it for this k (16 <= k <= 26) in p2p mode, MFSDBG_DIST_SKM=0 switches it off."""
         import torch
         self.ctx, self.k, self.m = ctx, k, min_count
         self.dev = torch.device("cuda", ctx.device)
@@ -154,6 +157,10 @@ class DistRead2Sdbg:
         self.mode = exchange or os.environ.get("MFSDBG_EXCHANGE", "p2p")
         self.key_buf = PeerBuffer(ctx, self.dev)
         self.item_buf = PeerBuffer(ctx, self.dev)
+        if skm is None:
+            skm = os.environ.get("MFSDBG_DIST_SKM", "1") != "0"
+        self.skm = bool(skm) and self.mode == "p2p" and bool(lib.load().mfsdbg_skm_supported(k))
+        self.skm_cap = None      # records one (source, destination) region of the receive buffers holds
 
     def _acc(self):
         for name, ms in self.ctx.last_profile().items():
@@ -178,6 +185,52 @@ class DistRead2Sdbg:
         self._last_hists = allh.cpu().numpy()
         return self._last_hists
 
+    def _count_skm(self, reads):
+        """count with the super-k-mer exchange: every rank cuts its reads into runs of (k+1)-mers that share a minimizer owner
+        and stores them as 64-bit records into region [rank] of the owner's receive buffer (NVLink peer memory); the owner then
+        counts the keys of the records it received.  The counts all-gather doubles as the "stores have landed" barrier."""
+        import torch
+        import torch.distributed as dist
+        from . import lib
+        ctx, k = self.ctx, self.k
+        world, rank = dist.get_world_size(), dist.get_rank()
+        stream = torch.cuda.current_stream(self.dev)
+        if self.skm_cap is None:
+            samp, _ = ctx.skm_scatter(reads, k, world, stride=64)      # every 64th tile, count only
+            self._acc()
+            est = torch.tensor([int(samp.max()) * 64 * 1.05 + 65536], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(est, op=dist.ReduceOp.MAX)
+            self.skm_cap = int(est.item())
+        while True:
+            cap = self.skm_cap
+            self.key_buf.ensure(world * cap * 8)
+            dst = np.array([int(self.key_buf.peers[d]) + rank * cap * 8 for d in range(world)], dtype=np.uint64)
+            stream.synchronize()
+            rec, keys = ctx.skm_scatter(reads, k, world, dst, np.full(world, cap, np.int64))
+            self._acc()
+            mine = torch.from_numpy(np.concatenate([rec, keys])).to(self.dev)
+            allc = torch.empty((world, 2 * world), dtype=torch.int64, device=self.dev)
+            dist.all_gather_into_tensor(allc, mine)
+            C = allc.cpu().numpy()
+            if int(C[:, :world].max()) <= cap:
+                break
+            self.skm_cap = int(C[:, :world].max() * 1.05) + 65536   # a region overflowed somewhere: everybody retries with more room
+        chunk_start = np.arange(world, dtype=np.int64) * cap
+        chunk_size = C[:, rank].astype(np.int64)
+        n_keys = int(C[:, world + rank].sum())
+        kc = int(lib.load().mfsdbg_skm_key_capacity(n_keys))
+        keys_a = torch.empty((kc + 32, 2), dtype=torch.int32, device=self.dev)
+        keys_b = torch.empty((kc + 32, 2), dtype=torch.int32, device=self.dev)
+        stream.synchronize()
+        edges = ctx.count_skm(self.key_buf.ptr, chunk_start, chunk_size, n_keys, k, self.m, keys_a.data_ptr(), keys_b.data_ptr(), kc)
+        self._acc()
+        del keys_a, keys_b
+        sent = int(rec.sum() - rec[rank])
+        info = dict(n_keys=n_keys, n_edges=edges.n, exchanged_keys=int(keys.sum() - keys[rank]), key_bytes=4 * self.Wk, exchange="skm",
+                    records_sent=sent, records_recv=int(chunk_size.sum()), record_bytes=8,
+                    keys_per_record=float(keys.sum() / max(int(rec.sum()), 1)))
+        return edges, info
+
     def run(self, reads):
         import torch
         import torch.distributed as dist
@@ -185,10 +238,14 @@ class DistRead2Sdbg:
         ctx, k, nb = self.ctx, self.k, 1 << L1
         rank = dist.get_rank()
         stream = torch.cuda.current_stream(self.dev)
+        stream.synchronize()
+        self.profile = {}
+        if self.skm:
+            edges, info = self._count_skm(reads)
+            return self._sdbg(edges, info, L1)
         # ---- count: histogram, owners, local partition, exchange, finish
         hist = torch.zeros(nb, dtype=torch.int64, device=self.dev)
         stream.synchronize()
-        self.profile = {}
         ctx.count_hist(reads, k, L1, hist.data_ptr())
         self._acc()
         plan = exchange_plan(self._gather_hists(hist), rank)
@@ -221,7 +278,16 @@ class DistRead2Sdbg:
             del recv, send
         info = dict(n_keys=plan["n_recv"], n_edges=edges.n, exchanged_keys=n_local - int(plan["send"][rank]),
                     key_bytes=4 * self.Wk, exchange=self.mode)
-        # ---- sdbg: items of the local edges, exchange by item prefix, finish
+        return self._sdbg(edges, info, L1)
+
+    def _sdbg(self, edges, info, L1):
+        """items of the local edges, exchange by item prefix, finish: rank r ends with the r-th prefix range of the graph (the
+        edges may be any disjoint split of the solid edge set -- a key range or the minimizer-owned subsets of the skm count)"""
+        import torch
+        import torch.distributed as dist
+        ctx, k, nb = self.ctx, self.k, 1 << L1
+        rank = dist.get_rank()
+        stream = torch.cuda.current_stream(self.dev)
         n_items = 6 * edges.n
         items = torch.empty((max(n_items, 1), self.Wi), dtype=torch.int32, device=self.dev)
         stream.synchronize()

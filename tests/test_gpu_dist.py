@@ -36,7 +36,9 @@ def _worker(rank, world, port, out_dir, k, m, seed, mode):
         sb = bases[starts[lo]:starts[hi]]
         ss = starts[lo:hi + 1] - starts[lo]
         ctx = lib.Context(rank)
-        runner = mdist.DistRead2Sdbg(ctx, k, m, exchange=mode)
+        # "p2p" takes the super-k-mer count when the library supports k (16..26); "p2p-prefix" forces the prefix-bin key exchange
+        runner = mdist.DistRead2Sdbg(ctx, k, m, exchange=mode.split("-")[0], skm=False if mode.endswith("-prefix") else None)
+        assert runner.skm == (mode == "p2p" and 16 <= k <= 26)
         res = runner.run(ctx.upload_reads(sb, ss))
         g = res.sdbg.to_numpy()
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), w=g["w"], last=g["last"], tip=g["tip"], mul=g["mul"],
@@ -48,7 +50,7 @@ def _worker(rank, world, port, out_dir, k, m, seed, mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,m,mode", [(21, 2, "p2p"), (31, 1, "p2p"), (21, 2, "nccl"), (47, 2, "p2p")])
+@pytest.mark.parametrize("k,m,mode", [(21, 2, "p2p"), (21, 2, "p2p-prefix"), (26, 1, "p2p"), (31, 1, "p2p"), (21, 2, "nccl"), (47, 2, "p2p")])
 def test_two_gpu_read2sdbg_matches_oracle(oracle, tmp_path, k, m, mode):
     import torch
     if torch.cuda.device_count() < 2:
