@@ -197,7 +197,8 @@ int32_t mfsdbg_words_per_edge(int32_t k);
  *                 tile of the reads (capacity estimate).  counts_out[0 .. n_dst): records, [n_dst .. 2 n_dst): (k+1)-mers.
  *   count_skm   : the single-GPU count over received records: `records` + chunks (start / size in records, one per
  *                 source), n_keys = the (k+1)-mers the sources announced; keys / scratch hold `capacity` records of 2 words
- *                 (mfsdbg_skm_key_capacity(n_keys)).  Result as mfsdbg_dev_count: this GPU's solid edges, sorted. */
+ *                 (mfsdbg_skm_key_capacity(n_keys)).  Result: this GPU's solid edges as mfsdbg_dev_count packs them, but in NO key
+ *                 order (the count runs on bijectively mixed keys so that no minimizer crowds a bucket). */
 int32_t mfsdbg_skm_supported(int32_t k);
 int64_t mfsdbg_skm_key_capacity(int64_t n_keys);
 int mfsdbg_dev_skm_scatter(mfsdbg_ctx *ctx, const mfsdbg_dev_reads *reads, int32_t k, int32_t n_dst, const uint64_t *dst_ptrs,

@@ -7,9 +7,9 @@
 // ~5 (k+1)-mers per record at k=21: a fifth of the bytes.  Every GPU then owns a pseudo-random, well balanced subset of the
 // canonical keys (no +20 % on rank 0 from the density of canonical keys at small prefixes), receives records from every
 // source in its own region of the owner's buffer, and runs the single-GPU count on them: the level-1 partition below
-// expands the records into canonical keys (exactly KeyWindow's keys), everything after it is count_finish unchanged.
-// The ranks' edge sets are disjoint but interleaved in key order; the sdbg stage routes items by their own prefix, so it
-// does not care.
+// expands the records into canonical keys (exactly KeyWindow's keys, then mixed by one Feistel round -- see skm_mix_hi),
+// everything after it is count_finish unchanged.  The ranks' edge sets are disjoint, interleaved in key order and each in
+// mixed-key order; the sdbg stage routes items by their own prefix, so it does not care.
 //
 //   k_skm_scatter  : reads -> minimizer owner per position -> runs -> records staged by owner -> copied out to the owners
 //   k_skm_hist     : (sampled) level-1 digit histogram of the keys inside received records
@@ -198,21 +198,43 @@ __global__ void __launch_bounds__(kSkmNT, 2) k_skm_scatter(ReadsSrc src, SkmArgs
 __device__ __forceinline__ unsigned long long skm_rev64(unsigned long long b) {
   return ((unsigned long long)rev_bases((uint32_t)b) << 32) | rev_bases((uint32_t)(b >> 32));
 }
+// One Feistel round over the 2*K1 key bits (left-aligned in hi:lo): the top K1 bits are XORed with a hash of the low K1 bits.
+// A bijection and its own inverse.  Why: a GPU owns the (k+1)-mers of certain minimizers, and an m-mer with a small hash is
+// the minimizer of nearly every (k+1)-mer that STARTS with it -- so in key order a rank's keys pile up 8-fold (at 8 GPUs)
+// inside some prefix ranges and are missing from others, and the equal-key-range buckets of the count overflow their tables
+// (460 ms in the fallback sort at 8 GPUs, r2s).  Counting the mixed keys instead makes every bucket see the average
+// density, whatever the minimizers (and the 2x density of canonical keys at small prefixes goes away as well); the edges
+// come out in mixed order and are mapped back once (k_skm_unmix_edges) -- the sdbg stage routes their items by prefix anyway.
+__device__ __forceinline__ uint32_t skm_mix_hi(uint32_t hi, uint32_t lo, int K1) {
+  const uint32_t r = __funnelshift_l(lo, hi, K1) >> (32 - K1);
+  return hi ^ (((r * 0x9E3779B1u) >> (32 - K1)) << (32 - K1));
+}
 struct SkmKeys {
   unsigned long long cb, rv, mask;
-  int rsh;   // 2 * (32 - K1)
-  __device__ __forceinline__ void init(unsigned long long rec, int K1) {
+  int rsh, K1;   // rsh = 2 * (32 - K1)
+  __device__ __forceinline__ void init(unsigned long long rec, int K1_) {
     const unsigned long long b = rec & ~7ull;
+    K1 = K1_;
     cb = ~b;
     rv = skm_rev64(b);
     mask = ~0ull << (64 - 2 * K1);
     rsh = 2 * (32 - K1);
   }
+  // canonical key of the record's i-th (k+1)-mer (bit-identical to KeyWindow<2>::key), mixed
   __device__ __forceinline__ unsigned long long key(int i) const {
     const unsigned long long c = (cb << (2 * i)) & mask, r = (rv << (rsh - 2 * i)) & mask;
-    return c < r ? c : r;
+    const unsigned long long v = c < r ? c : r;
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    return ((unsigned long long)skm_mix_hi(hi, lo, K1) << 32) | lo;
   }
 };
+// edge records (key bits on top of words 0-1, multiplicity in the low 16 bits of the last word) back to true keys
+__global__ void k_skm_unmix_edges(uint32_t *edges, int64_t n, int We, int K1) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t *e = edges + i * We;
+  e[0] = skm_mix_hi(e[0], e[1], K1);
+}
 
 // records of tile `d`, two per thread; a record beyond the tile reads as "no keys"
 __device__ __forceinline__ void skm_load2(const unsigned long long *recs, const TileDesc &d, int tid, unsigned long long (&rec)[2],
@@ -504,6 +526,13 @@ void dev_count_skm(Ctx &c, const uint64_t *recs, const int64_t *chunk_start, con
   }
   if (total != n_keys) throw std::runtime_error("count_skm: the records held " + std::to_string(total) + " keys, the senders announced " + std::to_string(n_keys));
   dev_count_finish(c, keys, scratch, total, fs.data(), fz.data(), fg.data(), nb1, nb1, k, l1_bits, min_count, out, nullptr);
+  if (out->n_edges > 0) {   // the count ran on mixed keys: map the solid edges back (their order stays the mixed one)
+    Stage st(c, "skm_unmix");
+    k_skm_unmix_edges<<<(unsigned)div_ceil64(out->n_edges, 256), 256, 0, c.stream>>>(const_cast<uint32_t *>(out->edges), out->n_edges, out->words, K1);
+    MF_LAUNCH_CHECK();
+    c.launches++;
+    MF_CUDA(cudaStreamSynchronize(c.stream));
+  }
 }
 
 }  // namespace mf

@@ -57,13 +57,20 @@ def main():
         e = ctx.count_skm(buf, [0], [int(rec1[0])], int(keys1[0]), a.k, 2, ka, kb, kc)
         prof = ctx.last_profile()
     n_skm = e.n
-    chk = int(ctx.d2h(e.s.edges, min(e.n, 1 << 20) * e.s.words_per_edge * 4, np.uint32).astype(np.uint64).sum())
+    def checksum(ed):   # order-independent (the skm count returns its edges in mixed-key order)
+        w = ctx.d2h(ed.s.edges, ed.n * ed.s.words_per_edge * 4, np.uint32).reshape(-1, ed.s.words_per_edge).astype(np.uint64)
+        x = (w[:, 0] << np.uint64(32)) | w[:, 1]
+        with np.errstate(over="ignore"):
+            x = x * np.uint64(0x9E3779B97F4A7C15)
+            x ^= x >> np.uint64(31)
+            return int(x.sum(dtype=np.uint64))
+    chk = checksum(e)
     out.update(receiver_stages_ms={k: round(v, 3) for k, v in prof.items()}, receiver_ms=round(sum(prof.values()), 3), edges=int(n_skm))
     for p in (buf, ka, kb):
         ctx.dev_free(p)
     e0 = ctx.count(reads, a.k, 2)
     p0 = ctx.last_profile()
-    chk0 = int(ctx.d2h(e0.s.edges, min(e0.n, 1 << 20) * e0.s.words_per_edge * 4, np.uint32).astype(np.uint64).sum())
+    chk0 = checksum(e0)
     out.update(plain_count_stages_ms={k: round(v, 3) for k, v in p0.items()}, plain_count_ms=round(sum(p0.values()), 3),
                plain_edges=int(e0.n), same_edges=bool(e0.n == n_skm and chk == chk0))
     line = json.dumps(out)
