@@ -377,12 +377,15 @@ def main():
     t_wall0 = time.perf_counter()
     ev0.record()
     stage_sum = {}
+    host_sum = {}
     res = None
     for _ in range(args.steps):
         res = step()
         prof = runner.profile if world > 1 else ctx.last_profile()
         for name, ms in prof.items():
             stage_sum[name] = stage_sum.get(name, 0.0) + ms
+        for name, ms in (getattr(runner, "host", None) or {}).items():
+            host_sum[name] = host_sum.get(name, 0.0) + ms
     ev1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -463,6 +466,15 @@ def main():
                "d2h_bytes_per_step": int(byts[1].item()), "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e,
                "api": "per rank: pinned host packed reads -> HBM, DistRead2Sdbg.run (C-ABI staged calls), sdbg arrays -> pinned host; bytes summed over ranks"}
 
+    # per-rank view of the timed steps (N > 1): device-stage sum and host-clock phases of every rank, so that a slow rank shows
+    by_rank = None
+    if world > 1:
+        mine = {"rank": rank, "stage_ms": round(sum(stage_sum.values()) / args.steps, 3),
+                "host_ms": {k2: round(v / args.steps, 3) for k2, v in host_sum.items()},
+                "slow_stages": {k2: round(v / args.steps, 3) for k2, v in stage_sum.items()
+                                if k2 in ("local_count_multipass", "local_count_general", "oversized", "fallback_local", "sampled_overflow")}}
+        by_rank = [None] * world
+        dist.all_gather_object(by_rank, mine)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -568,6 +580,7 @@ def main():
         out["config3"] = config3
         out["config"]["config3"] = {k2: {"ms_per_step": v.get("ms_per_step"), "frac": (v.get("roofline") or {}).get("frac")} for k2, v in config3.items()}
     if world > 1:
+        out["by_rank"] = by_rank
         out["verified"] = bool(verify and verify.get("verified"))
         out["config"]["verified"] = out["verified"]
         out["config"]["verify"] = verify

@@ -717,8 +717,23 @@ static double probe_distinct_ratio(Ctx &c, const uint32_t *keys, const HostChunk
   unsigned long long st[2 * S];
   c.d2h(st, d_stats, sizeof st);
   double occ = 0, dis = 0;
-  for (int j = 0; j < S; ++j) { occ += (double)st[2 * j]; dis += (double)st[2 * j + 1]; }
+  std::vector<double> ratios;
+  for (int j = 0; j < S; ++j) {
+    occ += (double)st[2 * j];
+    dis += (double)st[2 * j + 1];
+    if (st[2 * j] >= 512) ratios.push_back((double)st[2 * j + 1] / (double)st[2 * j]);
+  }
   if (occ < 64) return 1.0;
+  // The MEDIAN of the samples' ratios, not the pooled ratio: a sample is a few thousand keys, and one high-multiplicity key in
+  // it (a mitogenome (k+1)-mer: 13 000 copies) drags the pooled ratio down several-fold -- the buckets then come out that
+  // much too large and a quarter of them overflow their tables (70 ms in the multi-pass kernel on one rank of eight, r2u).
+  // Hot keys do not crowd a table; the typical bucket is what the size must fit.
+  if (ratios.size() >= 3) {
+    std::sort(ratios.begin(), ratios.end());
+    const double med = ratios.size() % 2 ? ratios[ratios.size() / 2] : 0.5 * (ratios[ratios.size() / 2 - 1] + ratios[ratios.size() / 2]);
+    if (getenv("MFSDBG_TRACE")) fprintf(stderr, "[mfsdbg] probe: pooled %.4f, median of %d samples %.4f\n", dis / occ, (int)ratios.size(), med);
+    return std::max(med, 1e-4);
+  }
   return std::max(dis / occ, 1e-4);
 }
 

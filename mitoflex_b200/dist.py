@@ -166,6 +166,13 @@ class DistRead2Sdbg:
         for name, ms in self.ctx.last_profile().items():
             self.profile[name] = self.profile.get(name, 0.0) + ms
 
+    def _mark(self, name):
+        """host clock since the previous mark -> self.host[name] (what a phase costs on the wall, kernels + planning + waiting)"""
+        import time
+        now = time.perf_counter()
+        self.host[name] = self.host.get(name, 0.0) + (now - self._t_mark) * 1e3
+        self._t_mark = now
+
     def _timed_a2a(self, name, rows, send, recv):
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -203,15 +210,19 @@ class DistRead2Sdbg:
             self.skm_cap = int(est.item())
         while True:
             cap = self.skm_cap
+            self._mark("h_other")
             self.key_buf.ensure(world * cap * 8)
+            self._mark("h_ensure_keys")
             dst = np.array([int(self.key_buf.peers[d]) + rank * cap * 8 for d in range(world)], dtype=np.uint64)
             stream.synchronize()
             rec, keys = ctx.skm_scatter(reads, k, world, dst, np.full(world, cap, np.int64))
             self._acc()
+            self._mark("h_skm_scatter")
             mine = torch.from_numpy(np.concatenate([rec, keys])).to(self.dev)
             allc = torch.empty((world, 2 * world), dtype=torch.int64, device=self.dev)
             dist.all_gather_into_tensor(allc, mine)
             C = allc.cpu().numpy()
+            self._mark("h_gather_counts")       # includes waiting for the slowest sender
             if int(C[:, :world].max()) <= cap:
                 break
             self.skm_cap = int(C[:, :world].max() * 1.05) + 65536   # a region overflowed somewhere: everybody retries with more room
@@ -222,8 +233,10 @@ class DistRead2Sdbg:
         keys_a = torch.empty((kc + 32, 2), dtype=torch.int32, device=self.dev)
         keys_b = torch.empty((kc + 32, 2), dtype=torch.int32, device=self.dev)
         stream.synchronize()
+        self._mark("h_alloc_keys")
         edges = ctx.count_skm(self.key_buf.ptr, chunk_start, chunk_size, n_keys, k, self.m, keys_a.data_ptr(), keys_b.data_ptr(), kc)
         self._acc()
+        self._mark("h_count_skm")
         del keys_a, keys_b
         sent = int(rec.sum() - rec[rank])
         info = dict(n_keys=n_keys, n_edges=edges.n, exchanged_keys=int(keys.sum() - keys[rank]), key_bytes=4 * self.Wk, exchange="skm",
@@ -240,6 +253,8 @@ class DistRead2Sdbg:
         stream = torch.cuda.current_stream(self.dev)
         stream.synchronize()
         self.profile = {}
+        import time
+        self.host, self._t_mark = {}, time.perf_counter()
         if self.skm:
             edges, info = self._count_skm(reads)
             return self._sdbg(edges, info, L1)
@@ -293,25 +308,32 @@ class DistRead2Sdbg:
         stream.synchronize()
         ctx.sdbg_items(edges.s.edges, edges.n, k, items.data_ptr())
         self._acc()
+        self._mark("h_items")
         ihist = torch.zeros(nb, dtype=torch.int64, device=self.dev)
         stream.synchronize()
         ctx.records_hist(items.data_ptr(), n_items, self.Wi, L1, ihist.data_ptr())
         self._acc()
+        self._mark("h_items_hist")
         iplan = exchange_plan(self._gather_hists(ihist), rank)
+        self._mark("h_gather_item_hists")
         iH = self._last_hists
         if self.mode == "p2p":
             self.item_buf.ensure(max(iplan["n_recv"], 1) * self.Wi * 4)
             ibases = torch.from_numpy(peer_bin_bases(iH, iplan["bounds"], rank, self.item_buf.peers, self.Wi * 4).view(np.int64)).to(self.dev)
             stream.synchronize()
+            self._mark("h_ensure_items")
             ctx.records_scatter_peer(items.data_ptr(), n_items, self.Wi, L1, ibases.data_ptr())
             self._acc()
+            self._mark("h_items_scatter")
             dist.barrier()
+            self._mark("h_items_barrier")
             del items
             iscratch = torch.empty((max(iplan["n_recv"], 1) + 16, self.Wi), dtype=torch.int32, device=self.dev)
             stream.synchronize()
             g = ctx.sdbg_finish(self.item_buf.ptr, iscratch.data_ptr(), iplan["n_recv"], iplan["chunk_start"], iplan["chunk_size"],
                                 iplan["chunk_seg"], iplan["n_segs"], k, L1, 1)
             self._acc()
+            self._mark("h_sdbg_finish")
             del iscratch
         else:
             ibuf = max(n_items, iplan["n_recv"], 1)
