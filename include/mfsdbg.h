@@ -207,6 +207,27 @@ int mfsdbg_dev_count_skm(mfsdbg_ctx *ctx, const uint64_t *records, const int64_t
                          int32_t n_chunks, int64_t n_keys, int32_t k, int32_t min_count, uint32_t *keys, uint32_t *scratch,
                          int64_t capacity, mfsdbg_dev_edges *out);
 
+/* ---- the item filter of seq2sdbg across GPUs (16 <= k <= 31) ------------------------------------------------
+ * megahit's SeqToSdbg writes 6 items per edge and lets Lv2Postprocess drop the "$" dummies that are shadowed by a real
+ * edge; the single-GPU path asks a k-mer set instead and generates only the dummies that survive.  Across GPUs the hash
+ * slices of that set are dealt out: slice s of 2^(log_slots - slice_log) belongs to rank s * world / nslices.
+ *   ks_geometry     : table geometry for the GLOBAL edge count (all ranks must use the same)
+ *   ks_hist         : this GPU's k-mer records per bin, bin = kind * nslices + slice (kind 0 = inserts, 1 = queries)
+ *   ks_scatter_peer : record of bin b stored at bin_base_dev[b] + (running count of b) * 8 (peer addresses allowed)
+ *   ks_filter       : the owner builds its slices [slice_lo, slice_lo + n_owned) from the received inserts and probes them with
+ *                     the received queries (both slice-major); its share of the miss list stays in the context
+ *   ks_items        : 2 real items per local edge + 2 dummies per miss of the last ks_filter -> items_out */
+int32_t mfsdbg_ks_supported(int32_t k);
+int mfsdbg_ks_geometry(int64_t n_edges_global, int32_t world, int32_t *log_slots, int32_t *slice_log);
+int mfsdbg_dev_ks_hist(mfsdbg_ctx *ctx, const uint32_t *edges, int64_t n_edges, int32_t k, int32_t log_slots, int32_t slice_log,
+                       uint64_t *hist_dev);
+int mfsdbg_dev_ks_scatter_peer(mfsdbg_ctx *ctx, const uint32_t *edges, int64_t n_edges, int32_t k, int32_t log_slots,
+                               int32_t slice_log, const uint64_t *bin_base_dev);
+int mfsdbg_dev_ks_filter(mfsdbg_ctx *ctx, const uint64_t *inserts, int64_t n_inserts, const uint64_t *queries, int64_t n_queries,
+                         int32_t log_slots, int32_t slice_log, int32_t slice_lo, int32_t n_owned, int64_t *n_miss);
+int mfsdbg_dev_ks_items(mfsdbg_ctx *ctx, const uint32_t *edges, int64_t n_edges, int64_t n_miss, int32_t k, uint32_t *items_out,
+                        int64_t capacity, int64_t *n_items);
+
 /* ---- host-buffer entry point: what a caller holding the packed library in host memory uses ------------ */
 /* The sdbg in (pinned, library-owned) host memory; valid until the next mfsdbg_host_* call on the context. */
 typedef struct mfsdbg_host_sdbg {

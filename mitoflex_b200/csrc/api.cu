@@ -342,6 +342,56 @@ int mfsdbg_dev_count_skm(mfsdbg_ctx *ctx, const uint64_t *records, const int64_t
     fill(out, e);
   });
 }
+// ---- the item filter across GPUs (ksdist.cu)
+int32_t mfsdbg_ks_supported(int32_t k) { return mf::ksd_supported(k) ? 1 : 0; }
+int mfsdbg_ks_geometry(int64_t n_edges_global, int32_t world, int32_t *log_slots, int32_t *slice_log) {
+  if (!log_slots || !slice_log || n_edges_global < 0 || world < 1) return MFSDBG_EINVAL;
+  int a = 0, b = 0;
+  mf::ksd_geometry(n_edges_global, world, &a, &b);
+  *log_slots = a;
+  *slice_log = b;
+  return MFSDBG_OK;
+}
+int mfsdbg_dev_ks_hist(mfsdbg_ctx *ctx, const uint32_t *edges, int64_t n_edges, int32_t k, int32_t log_slots, int32_t slice_log,
+                       uint64_t *hist_dev) {
+  if (!ctx || !hist_dev || n_edges < 0 || (n_edges > 0 && !edges)) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::dev_ksd_hist(ctx->c, edges, n_edges, k, log_slots, slice_log, reinterpret_cast<unsigned long long *>(hist_dev));
+    ctx->c.end_call();
+  });
+}
+int mfsdbg_dev_ks_scatter_peer(mfsdbg_ctx *ctx, const uint32_t *edges, int64_t n_edges, int32_t k, int32_t log_slots, int32_t slice_log,
+                               const uint64_t *bin_base_dev) {
+  if (!ctx || !bin_base_dev || n_edges < 0 || (n_edges > 0 && !edges)) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    mf::dev_ksd_scatter(ctx->c, edges, n_edges, k, log_slots, slice_log, reinterpret_cast<const unsigned long long *>(bin_base_dev));
+    ctx->c.end_call();
+  });
+}
+int mfsdbg_dev_ks_filter(mfsdbg_ctx *ctx, const uint64_t *inserts, int64_t n_inserts, const uint64_t *queries, int64_t n_queries,
+                         int32_t log_slots, int32_t slice_log, int32_t slice_lo, int32_t n_owned, int64_t *n_miss) {
+  if (!ctx || !n_miss || n_inserts < 0 || n_queries < 0 || (n_inserts > 0 && !inserts) || (n_queries > 0 && !queries)) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    *n_miss = mf::dev_ksd_filter(ctx->c, inserts, n_inserts, queries, n_queries, log_slots, slice_log, slice_lo, n_owned);
+    ctx->c.end_call();
+  });
+}
+int mfsdbg_dev_ks_items(mfsdbg_ctx *ctx, const uint32_t *edges, int64_t n_edges, int64_t n_miss, int32_t k, uint32_t *items_out,
+                        int64_t capacity, int64_t *n_items) {
+  if (!ctx || !n_items || n_edges < 0 || n_miss < 0 || capacity < 0 || (n_edges > 0 && !edges) || (capacity > 0 && !items_out)) return MFSDBG_EINVAL;
+  std::lock_guard<std::mutex> lk(g_job_mutex);
+  return guarded([&] {
+    ctx->c.begin_call();
+    *n_items = mf::dev_ksd_items(ctx->c, edges, n_edges, n_miss, k, items_out, capacity);
+    ctx->c.end_call();
+  });
+}
 int mfsdbg_dev_synth_reads(mfsdbg_ctx *ctx, const mfsdbg_synth_spec *spec, mfsdbg_dev_reads *out) {
   if (!ctx || !spec || !out) return MFSDBG_EINVAL;
   std::lock_guard<std::mutex> lk(g_job_mutex);

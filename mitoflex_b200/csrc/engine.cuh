@@ -139,6 +139,17 @@ void dev_skm_scatter(Ctx &c, const ReadsView &r, int k, int n_dst, const uint64_
 void dev_count_skm(Ctx &c, const uint64_t *recs, const int64_t *chunk_start, const int64_t *chunk_size, int n_chunks, int64_t n_keys,
                    int k, int min_count, uint32_t *keys, uint32_t *scratch, int64_t capacity, EdgesView *out);
 
+// ---- the item filter across GPUs (ksdist.cu): hash slices of the k-mer set dealt out to the GPUs, records stored into the owner's
+// buffer by the scatter kernel, every owner probes its slices and keeps its share of the miss list in the context
+bool ksd_supported(int k);
+void ksd_geometry(int64_t n_edges_global, int world, int *log_slots, int *slice_log);
+void dev_ksd_hist(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, int log_slots, int slice_log, unsigned long long *hist_dev);
+void dev_ksd_scatter(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, int log_slots, int slice_log,
+                     const unsigned long long *bin_base_dev);
+int64_t dev_ksd_filter(Ctx &c, const uint64_t *ins, int64_t n_ins, const uint64_t *qry, int64_t n_qry, int log_slots, int slice_log,
+                       int slice_lo, int n_owned);
+int64_t dev_ksd_items(Ctx &c, const uint32_t *edges, int64_t n_edges, int64_t n_miss, int k, uint32_t *items_out, int64_t capacity);
+
 void dev_sdbg_items(Ctx &c, const uint32_t *edges, int64_t n_edges, int k, uint32_t *items_out);
 int64_t dev_sdbg_items_seqs(Ctx &c, const uint32_t *edges, int64_t n_edges, const SeqsView &seqs, int k, uint32_t *items_out);
 void dev_records_hist(Ctx &c, const uint32_t *rec, int64_t n, int words, int l1_bits, unsigned long long *hist_dev);

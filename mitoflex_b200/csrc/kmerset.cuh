@@ -129,7 +129,8 @@ inline size_t ks_scatter_smem_bytes(int nbins) {
 }
 template <int KW, int BPT>
 __global__ void __launch_bounds__(kKsNT) k_ks_scatter(const uint32_t *__restrict__ edges, int64_t n_edges, int wk, int we, int k, KsGeom g,
-                                                      unsigned long long *__restrict__ cursor, typename KsKey<KW>::Slot *__restrict__ out) {
+                                                      unsigned long long *__restrict__ cursor, typename KsKey<KW>::Slot *__restrict__ out,
+                                                      const unsigned long long *__restrict__ bin_base = nullptr) {
   extern __shared__ __align__(128) unsigned char smraw[];
   using C = KsScatterCfg<KW>;
   using Slot = typename KsKey<KW>::Slot;
@@ -178,7 +179,12 @@ __global__ void __launch_bounds__(kKsNT) k_ks_scatter(const uint32_t *__restrict
       }
   __syncthreads();
   // copy-out: consecutive staged records of a bin go to consecutive global records
-  for (uint32_t j = tid; j < total; j += NT) out[s_gd[stage_bin[j]] + (long long)j] = stage[j];
+  // (bin_base: the multi-GPU filter of ksdist.cu -- bin b lives at its own, possibly peer-GPU, address and `cursor` counts from 0)
+  for (uint32_t j = tid; j < total; j += NT) {
+    const uint32_t b = stage_bin[j];
+    Slot *dst = bin_base ? reinterpret_cast<Slot *>(bin_base[b]) : out;
+    dst[s_gd[b] + (long long)j] = stage[j];
+  }
 }
 
 // ---- pass 3: inserts, in slice order.  The records of a slice are contiguous, and tiles of 1024 records are handed out IN ORDER by

@@ -82,6 +82,37 @@ def peer_bin_bases(all_hists, bounds, rank, peer_ptrs, rec_bytes):
     return out
 
 
+def ks_slice_bounds(nslices, world):
+    """Hash slices of the k-mer set dealt out in contiguous ranges: rank r owns slices [b[r], b[r + 1])."""
+    return np.array([(r * nslices) // world for r in range(world + 1)], dtype=np.int64)
+
+
+def ks_exchange_plan(all_hists, rank):
+    """all_hists: [world, 2 * nslices] k-mer records per (source rank, kind * nslices + slice), kind 0 = inserts, 1 = queries.
+    The owner of a slice receives its inserts first, then its queries, each slice-major and source-minor (a slice's records
+    are contiguous whatever their source, which is what the owner's insert / query walks want).  Returns the record offset of
+    every bin of THIS source inside its owner's buffer, the owner of every bin, and what this rank receives."""
+    H = np.asarray(all_hists, dtype=np.int64)
+    world, nbins = H.shape
+    nsl = nbins // 2
+    b = ks_slice_bounds(nsl, world)
+    owner_of_slice = np.repeat(np.arange(world), np.diff(b))
+    col = H.sum(axis=0)                                  # records of every bin over all sources
+    before = np.cumsum(H, axis=0) - H                    # records of lower-ranked sources in the same bin
+    off = np.zeros(nbins, dtype=np.int64)
+    n_ins = np.zeros(world, dtype=np.int64)
+    n_qry = np.zeros(world, dtype=np.int64)
+    for r in range(world):
+        lo, hi = int(b[r]), int(b[r + 1])
+        ins, qry = col[lo:hi], col[nsl + lo:nsl + hi]
+        n_ins[r], n_qry[r] = ins.sum(), qry.sum()
+        off[lo:hi] = np.cumsum(ins) - ins + before[rank, lo:hi]
+        off[nsl + lo:nsl + hi] = n_ins[r] + np.cumsum(qry) - qry + before[rank, nsl + lo:nsl + hi]
+    return dict(offset=off, owner=np.concatenate([owner_of_slice, owner_of_slice]), slice_lo=int(b[rank]),
+                n_owned=int(b[rank + 1] - b[rank]), n_ins=int(n_ins[rank]), n_qry=int(n_qry[rank]),
+                recv_records=n_ins + n_qry)
+
+
 class PeerBuffer:
     """A receive buffer in this GPU's HBM that every other rank maps through CUDA IPC (NVLink peer memory)."""
 
@@ -141,7 +172,7 @@ class DistResult:
 class DistRead2Sdbg:
     """read2sdbg over all ranks of the default process group; each rank ends with its prefix range of the graph."""
 
-    def __init__(self, ctx, k, min_count, exchange=None, skm=None):
+    def __init__(self, ctx, k, min_count, exchange=None, skm=None, item_filter=None):
         """exchange: "p2p" (records stored straight into the owner's HBM by the partition kernels) or "nccl" (all_to_all_single).
         skm: route the count by minimizer and send super-k-mer records (csrc/skm.cu) instead of one key per (k+1)-mer; None =
         whenever the library supports it for this k (16 <= k <= 26) in p2p mode, MFSDBG_DIST_SKM=0 switches it off."""
@@ -161,6 +192,10 @@ class DistRead2Sdbg:
             skm = os.environ.get("MFSDBG_DIST_SKM", "1") != "0"
         self.skm = bool(skm) and self.mode == "p2p" and bool(lib.load().mfsdbg_skm_supported(k))
         self.skm_cap = None      # records one (source, destination) region of the receive buffers holds
+        # the item filter across GPUs (csrc/ksdist.cu): only the dummies that reach the graph are generated and exchanged
+        self.filter = (self.mode == "p2p" and bool(lib.load().mfsdbg_ks_supported(k))
+                       and os.environ.get("MFSDBG_DIST_FILTER", "1") != "0") if item_filter is None else bool(item_filter)
+        self.ks_buf = PeerBuffer(ctx, self.dev)
 
     def _acc(self):
         for name, ms in self.ctx.last_profile().items():
@@ -295,6 +330,47 @@ class DistRead2Sdbg:
                     key_bytes=4 * self.Wk, exchange=self.mode)
         return self._sdbg(edges, info, L1)
 
+    def _filtered_items(self, edges, info):
+        """The item filter across GPUs: every rank cuts its edges into k-mer records (2 inserts + 2 queries each) and stores
+        them into the buffer of the rank that owns their hash slice; the owners probe their slices; every rank then generates
+        2 real items per local edge and 2 dummies per miss it found."""
+        import torch
+        import torch.distributed as dist
+        import ctypes as C
+        from . import lib
+        ctx, k = self.ctx, self.k
+        world, rank = dist.get_world_size(), dist.get_rank()
+        stream = torch.cuda.current_stream(self.dev)
+        tot = torch.tensor([edges.n], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(tot)
+        ls, sl = C.c_int32(0), C.c_int32(0)
+        lib._check(lib.load().mfsdbg_ks_geometry(int(tot.item()), world, C.byref(ls), C.byref(sl)))
+        ls, sl = ls.value, sl.value
+        nbins = 2 << (ls - sl)
+        hist = torch.zeros(nbins, dtype=torch.int64, device=self.dev)
+        stream.synchronize()
+        ctx.ks_hist(edges.s.edges, edges.n, k, ls, sl, hist.data_ptr())
+        self._acc()
+        plan = ks_exchange_plan(self._gather_hists(hist), rank)
+        self.ks_buf.ensure(max(int(plan["recv_records"][rank]), 1) * 8)
+        peers = np.array([int(p) for p in self.ks_buf.peers], dtype=np.uint64)
+        bases = torch.from_numpy((peers[plan["owner"]] + (plan["offset"] * 8).astype(np.uint64)).view(np.int64)).to(self.dev)
+        stream.synchronize()
+        ctx.ks_scatter_peer(edges.s.edges, edges.n, k, ls, sl, bases.data_ptr())
+        self._acc()
+        dist.barrier()            # every rank's records have landed
+        n_miss = ctx.ks_filter(self.ks_buf.ptr, plan["n_ins"], self.ks_buf.ptr + plan["n_ins"] * 8, plan["n_qry"], ls, sl,
+                               plan["slice_lo"], plan["n_owned"])
+        self._acc()
+        n_items = 2 * edges.n + 2 * n_miss
+        items = torch.empty((max(n_items, 1), self.Wi), dtype=torch.int32, device=self.dev)
+        stream.synchronize()
+        got = ctx.ks_items(edges.s.edges, edges.n, n_miss, k, items.data_ptr(), max(n_items, 1))
+        self._acc()
+        assert got == n_items
+        info.update(item_filter=True, misses=int(n_miss), kmer_records_sent=int(4 * edges.n - self._last_hists[rank][plan["owner"] == rank].sum()))
+        return items, n_items
+
     def _sdbg(self, edges, info, L1):
         """items of the local edges, exchange by item prefix, finish: rank r ends with the r-th prefix range of the graph (the
         edges may be any disjoint split of the solid edge set -- a key range or the minimizer-owned subsets of the skm count)"""
@@ -303,11 +379,14 @@ class DistRead2Sdbg:
         ctx, k, nb = self.ctx, self.k, 1 << L1
         rank = dist.get_rank()
         stream = torch.cuda.current_stream(self.dev)
-        n_items = 6 * edges.n
-        items = torch.empty((max(n_items, 1), self.Wi), dtype=torch.int32, device=self.dev)
-        stream.synchronize()
-        ctx.sdbg_items(edges.s.edges, edges.n, k, items.data_ptr())
-        self._acc()
+        if self.filter:
+            items, n_items = self._filtered_items(edges, info)
+        else:
+            n_items = 6 * edges.n
+            items = torch.empty((max(n_items, 1), self.Wi), dtype=torch.int32, device=self.dev)
+            stream.synchronize()
+            ctx.sdbg_items(edges.s.edges, edges.n, k, items.data_ptr())
+            self._acc()
         self._mark("h_items")
         ihist = torch.zeros(nb, dtype=torch.int64, device=self.dev)
         stream.synchronize()
@@ -355,3 +434,4 @@ class DistRead2Sdbg:
     def close(self):
         self.key_buf.release()
         self.item_buf.release()
+        self.ks_buf.release()

@@ -99,6 +99,13 @@ SYMBOLS = {
                                          C.c_void_p]),
     "mfsdbg_dev_count_skm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(DevEdges)]),
+    "mfsdbg_ks_supported": (C.c_int32, [C.c_int32]),
+    "mfsdbg_ks_geometry": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mfsdbg_dev_ks_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "mfsdbg_dev_ks_scatter_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "mfsdbg_dev_ks_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.POINTER(C.c_int64)]),
+    "mfsdbg_dev_ks_items": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "mfsdbg_words_per_key": (C.c_int32, [C.c_int32]),
     "mfsdbg_words_per_edge": (C.c_int32, [C.c_int32]),
     "mfsdbg_host_read2sdbg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
@@ -388,6 +395,24 @@ class Context:
         _check(load().mfsdbg_dev_count_skm(self._h, rec_ptr, cs.ctypes.data, cz.ctypes.data, len(cs), int(n_keys), k, min_count,
                                            keys_ptr, scratch_ptr, int(capacity), C.byref(out)))
         return Edges(self, out)
+
+    # -- the item filter across GPUs (16 <= k <= 31)
+    def ks_hist(self, edges_ptr, n_edges, k, log_slots, slice_log, hist_ptr):
+        _check(load().mfsdbg_dev_ks_hist(self._h, edges_ptr, n_edges, k, log_slots, slice_log, hist_ptr))
+
+    def ks_scatter_peer(self, edges_ptr, n_edges, k, log_slots, slice_log, bin_base_ptr):
+        _check(load().mfsdbg_dev_ks_scatter_peer(self._h, edges_ptr, n_edges, k, log_slots, slice_log, bin_base_ptr))
+
+    def ks_filter(self, ins_ptr, n_ins, qry_ptr, n_qry, log_slots, slice_log, slice_lo, n_owned):
+        n = C.c_int64(0)
+        _check(load().mfsdbg_dev_ks_filter(self._h, ins_ptr, int(n_ins), qry_ptr, int(n_qry), log_slots, slice_log, slice_lo, n_owned,
+                                           C.byref(n)))
+        return n.value
+
+    def ks_items(self, edges_ptr, n_edges, n_miss, k, items_ptr, capacity):
+        n = C.c_int64(0)
+        _check(load().mfsdbg_dev_ks_items(self._h, edges_ptr, n_edges, int(n_miss), k, items_ptr, int(capacity), C.byref(n)))
+        return n.value
 
     def sdbg_items(self, edges_ptr, n_edges, k, items_ptr):
         _check(load().mfsdbg_dev_sdbg_items(self._h, edges_ptr, n_edges, k, items_ptr))

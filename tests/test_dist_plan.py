@@ -111,3 +111,33 @@ def test_exchange_over_gloo_world2(tmp_path):
     # rank order == key-range order: sorting each rank's share and concatenating gives the global sort
     glob = np.concatenate([np.sort(o) for o in outs])
     assert np.array_equal(glob, ins)
+
+
+@pytest.mark.parametrize("world,nsl", [(1, 1), (2, 8), (3, 8), (8, 1024), (4, 2)])
+def test_ks_exchange_plan_tiles_every_owner_buffer(world, nsl):
+    """the multi-GPU item filter (dist.ks_exchange_plan): every source's bins land back to back in the owner's buffer -- inserts
+    first, then queries, slice-major and source-minor -- with no gap and no overlap"""
+    from mitoflex_b200 import dist as mdist
+    rng = np.random.default_rng(world * 1000 + nsl)
+    H = rng.integers(0, 50, size=(world, 2 * nsl)).astype(np.int64)
+    H[rng.random(H.shape) < 0.2] = 0
+    plans = [mdist.ks_exchange_plan(H, r) for r in range(world)]
+    b = mdist.ks_slice_bounds(nsl, world)
+    assert b[0] == 0 and b[-1] == nsl and (np.diff(b) >= 0).all()
+    for owner in range(world):
+        n = int(plans[owner]["recv_records"][owner])
+        assert n == plans[owner]["n_ins"] + plans[owner]["n_qry"]
+        tag = np.full((n, 3), -1, dtype=np.int64)           # (kind, slice, source) of the record stored at every position
+        for src in range(world):
+            p = plans[src]
+            for bin_ in np.nonzero(p["owner"] == owner)[0]:
+                cnt, off = int(H[src, bin_]), int(p["offset"][bin_])
+                assert (tag[off:off + cnt, 0] == -1).all(), "two bins overlap"
+                tag[off:off + cnt] = (bin_ // nsl, bin_ % nsl, src)
+        assert (tag[:, 0] >= 0).all(), "a gap in the receive buffer"
+        assert (tag[:plans[owner]["n_ins"], 0] == 0).all() and (tag[plans[owner]["n_ins"]:, 0] == 1).all()
+        for kind_rows in (tag[:plans[owner]["n_ins"]], tag[plans[owner]["n_ins"]:]):
+            key = kind_rows[:, 1] * world + kind_rows[:, 2]
+            assert (np.diff(key) >= 0).all(), "not slice-major / source-minor"
+            assert ((kind_rows[:, 1] >= b[owner]) & (kind_rows[:, 1] < b[owner + 1])).all()
+        assert plans[owner]["slice_lo"] == b[owner] and plans[owner]["n_owned"] == b[owner + 1] - b[owner]

@@ -37,8 +37,12 @@ def _worker(rank, world, port, out_dir, k, m, seed, mode):
         ss = starts[lo:hi + 1] - starts[lo]
         ctx = lib.Context(rank)
         # "p2p" takes the super-k-mer count when the library supports k (16..26); "p2p-prefix" forces the prefix-bin key exchange
-        runner = mdist.DistRead2Sdbg(ctx, k, m, exchange=mode.split("-")[0], skm=False if mode.endswith("-prefix") else None)
-        assert runner.skm == (mode == "p2p" and 16 <= k <= 26)
+        # "-nofilter": all 6 items per edge instead of the item filter across GPUs (k <= 31)
+        parts_ = mode.split("-")
+        runner = mdist.DistRead2Sdbg(ctx, k, m, exchange=parts_[0], skm=False if "prefix" in parts_ else None,
+                                     item_filter=False if "nofilter" in parts_ else None)
+        assert runner.skm == (mode.startswith("p2p") and "prefix" not in parts_ and 16 <= k <= 26)
+        assert runner.filter == (parts_[0] == "p2p" and "nofilter" not in parts_ and 16 <= k <= 31)
         res = runner.run(ctx.upload_reads(sb, ss))
         g = res.sdbg.to_numpy()
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), w=g["w"], last=g["last"], tip=g["tip"], mul=g["mul"],
@@ -50,14 +54,26 @@ def _worker(rank, world, port, out_dir, k, m, seed, mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,m,mode", [(21, 2, "p2p"), (21, 2, "p2p-prefix"), (26, 1, "p2p"), (31, 1, "p2p"), (21, 2, "nccl"), (47, 2, "p2p")])
+@pytest.mark.parametrize("k,m,mode", [(21, 2, "p2p"), (21, 2, "p2p-prefix"), (26, 1, "p2p"), (31, 1, "p2p"), (21, 2, "nccl"), (47, 2, "p2p"),
+                                      (21, 2, "p2p-nofilter"), (24, 1, "p2p-prefix-nofilter")])
 def test_two_gpu_read2sdbg_matches_oracle(oracle, tmp_path, k, m, mode):
+    _run_dist_case(oracle, tmp_path, k, m, mode, 2)
+
+
+@pytest.mark.parametrize("k,m,mode", [(21, 2, "p2p"), (26, 1, "p2p"), (31, 2, "p2p"), (21, 1, "p2p-nofilter")])
+def test_one_rank_group_read2sdbg_matches_oracle(oracle, tmp_path, k, m, mode):
+    """the multi-GPU driver with a process group of ONE rank: the super-k-mer count, the item filter with its hash slices and the
+    item exchange all run (every peer is the rank itself), so a single-GPU box exercises the whole of dist.py"""
+    _run_dist_case(oracle, tmp_path, k, m, mode, 1)
+
+
+def _run_dist_case(oracle, tmp_path, k, m, mode, world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     from gpu_common import make_reads
-    seed, world = 4242 + k, 2
+    seed = 4242 + k
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), k, m, seed, mode), nprocs=world, join=True)
     bases, starts = make_reads(seed, 60000, k, genome_len=150000, max_len=150, err=0.005)
     g = oracle.read2sdbg(oracle.Reads(bases, starts), k, m, threads=8)
