@@ -51,7 +51,7 @@ struct SkmArgs {
 // hash among the NM m-mers at offsets i .. i + NM - 1.  An m-mer enters as min(complement, reverse) of its 2m bits -- the same
 // strand symmetry as the canonical key, so a (k+1)-mer and its reverse complement agree on the minimizer, hence on the owner.
 template <int NM>
-__device__ __forceinline__ unsigned long long skm_owners(const uint32_t *w, int m, int n_dst) {
+__device__ __forceinline__ unsigned long long skm_owners(const uint32_t *w, int m, int n_dst, uint32_t &chg) {
   constexpr int NH = 16 + NM - 1;
   const uint32_t cw0 = ~w[0], cw1 = ~w[1], cw2 = ~w[2];
   const uint32_t cwv[3] = {cw0, cw1, cw2};
@@ -74,14 +74,18 @@ __device__ __forceinline__ unsigned long long skm_owners(const uint32_t *w, int 
   for (int j = 0; j < NH; ++j) pre[j] = (j % NM == 0) ? h[j] : min(pre[j - 1], h[j]);
 #pragma unroll
   for (int j = NH - 1; j >= 0; --j) suf[j] = (j % NM == NM - 1 || j == NH - 1) ? h[j] : min(suf[j + 1], h[j]);
+  // The owner comes from the LOW 20 bits of the winning hash: taking the minimum biases the top bits towards zero and leaves
+  // the low ones uniform.  chg: bit i set when position i's owner differs from position i - 1's.
   unsigned long long own = 0;
+  uint32_t prev = 0xffffffffu, ch = 0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    uint32_t x = min(suf[i], pre[i + NM - 1]);
-    x = (x ^ (x >> 16)) * 0x85EBCA6Bu;
-    x ^= x >> 13;
-    own |= (unsigned long long)__umulhi(x, (uint32_t)n_dst) << (4 * i);
+    const uint32_t o = __umulhi(min(suf[i], pre[i + NM - 1]) << 12, (uint32_t)n_dst);
+    own |= (unsigned long long)o << (4 * i);
+    ch |= (o != prev ? 1u : 0u) << i;
+    prev = o;
   }
+  chg = ch;
   return own;
 }
 
@@ -120,18 +124,18 @@ __global__ void __launch_bounds__(kSkmNT, 2) k_skm_scatter(ReadsSrc src, SkmArgs
     unsigned long long own = 0;
     uint32_t bm = 0;   // bit i: a record starts at position i
     if (vm) {
-      own = skm_owners<NM>(seq + tid, a.m, a.n_dst);
-      int len = 0;
-      uint32_t prev = 16u;
+      uint32_t chg;
+      own = skm_owners<NM>(seq + tid, a.m, a.n_dst, chg);
+      // a record starts where a run of valid positions with one owner starts, and every cmax positions inside a run
+      const uint32_t ns = vm & (~(vm << 1) | chg);   // natural starts
+      const uint32_t cont = vm & ~ns;                // positions that continue a run
+      uint32_t all = cont;                           // bit p: cont at p, p - 1, ..., p - cmax + 1
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const bool v = (vm >> i) & 1u;
-        const uint32_t o = (uint32_t)(own >> (4 * i)) & 15u;
-        const bool nr = v && (len == 0 || o != prev || len == a.cmax);
-        bm |= (nr ? 1u : 0u) << i;
-        len = v ? (nr ? 1 : len + 1) : 0;
-        prev = o;
-      }
+      for (int t = 1; t < 8; ++t)
+        if (t < a.cmax) all &= cont << t;
+      bm = ns;
+      for (uint32_t f = (ns << a.cmax) & all; f & 0xffffu; f = (f << a.cmax) & all) bm |= f;
+      bm &= 0xffffu;
     }
     const uint32_t stop = bm | (~vm & 0xffffu) | 0x10000u;   // where a run ends: the next record, an invalid position, the word's end
     // phase A: records and keys per (owner, warp)
