@@ -17,6 +17,7 @@
 //
 // megahit has no counterpart (one process, shared memory): this replaces the all-to-all of SURVEY 8e.
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -28,9 +29,17 @@ namespace mf {
 
 constexpr int kSkmNT = 512;
 constexpr int kSkmMaxDst = 16;
-constexpr int kSkmRecTile = 1024;   // records per receiver tile (2 per thread, <= 8 keys each: <= 8192 staged keys)
+constexpr int kSkmTileKeys = kSkmNT * 16;   // key slots of a receiver tile: 16 per thread = 16 / SLOTS records of <= SLOTS keys
 
-__host__ __device__ inline int skm_cmax(int K1) { return 31 - K1 > 8 ? 8 : 31 - K1; }   // bases of a record <= 30
+// (k+1)-mers a record may hold: its bases must fit 60 bits, its length 3.  MFSDBG_SKM_CMAX (2..8) lowers it: shorter records
+// cost NVLink bytes but fill the receiver's per-record key slots better (a record of <= 4 keys takes the 4-slot kernel).
+static int skm_cmax(int K1) {
+  int c = 31 - K1 > 8 ? 8 : 31 - K1;
+  const char *e = getenv("MFSDBG_SKM_CMAX");
+  if (e && *e) c = std::max(2, std::min(c, atoi(e)));
+  return c;
+}
+static int skm_slots(int K1) { return skm_cmax(K1) <= 4 ? 4 : 8; }
 bool skm_supported(int k) { return k >= 16 && k <= 26; }
 int64_t skm_key_capacity(int64_t n_keys) { return (int64_t)(1.12 * (double)n_keys) + (int64_t)131072 * 1024 + 64; }
 
@@ -240,17 +249,19 @@ __global__ void k_skm_unmix_edges(uint32_t *edges, int64_t n, int We, int K1) {
   e[0] = skm_mix_hi(e[0], e[1], K1);
 }
 
-// records of tile `d`, two per thread; a record beyond the tile reads as "no keys"
-__device__ __forceinline__ void skm_load2(const unsigned long long *recs, const TileDesc &d, int tid, unsigned long long (&rec)[2],
-                                          uint32_t (&cnt)[2]) {
+// records of tile `d`, R per thread; a record beyond the tile reads as "no keys"
+template <int R>
+__device__ __forceinline__ void skm_load(const unsigned long long *recs, const TileDesc &d, int tid, unsigned long long (&rec)[R],
+                                         uint32_t (&cnt)[R]) {
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < R; ++q) {
     const int j = q * kSkmNT + tid;
     rec[q] = j < d.n ? recs[d.base + j] : 0ull;
     cnt[q] = j < d.n ? (uint32_t)(rec[q] & 7ull) + 1u : 0u;
   }
 }
 
+template <int SLOTS>
 __global__ void __launch_bounds__(kSkmNT) k_skm_hist(const unsigned long long *__restrict__ recs, const TileDesc *__restrict__ tiles,
                                                      int64_t ntiles, int64_t tstride, int K1, int nbits,
                                                      unsigned long long *__restrict__ hist) {
@@ -263,15 +274,16 @@ __global__ void __launch_bounds__(kSkmNT) k_skm_hist(const unsigned long long *_
   __syncthreads();
   for (int64_t ti = blockIdx.x; ti * tstride < ntiles; ti += gridDim.x) {
     const TileDesc d = tiles[ti * tstride];
-    unsigned long long rec[2];
-    uint32_t cnt[2];
-    skm_load2(recs, d, tid, rec, cnt);
+    constexpr int R = 16 / SLOTS;
+    unsigned long long rec[R];
+    uint32_t cnt[R];
+    skm_load<R>(recs, d, tid, rec, cnt);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < R; ++q) {
       SkmKeys sk;
       sk.init(rec[q], K1);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < SLOTS; ++i) {
         const uint32_t dg = (uint32_t)(sk.key(i) >> dsh);
         atomicAdd(s_hist + ((uint32_t)i < cnt[q] ? dg : dummy), 1u);
       }
@@ -287,9 +299,9 @@ __global__ void __launch_bounds__(kSkmNT) k_skm_hist(const unsigned long long *_
 // dynamic smem (uint32 units): s_cnt[nbins+32] | pad | s_gd i64[nbins] | scratch[36] | pad | stage[8192 * 2]
 __host__ __device__ inline size_t skm_kscatter_smem_bytes(int nbits) {
   const size_t nb = (size_t)1 << nbits;
-  return (nb + 32 + 2 + 2 * nb + 36 + 2 + (size_t)kSkmRecTile * 8 * 2) * 4;
+  return (nb + 32 + 2 + 2 * nb + 36 + 2 + (size_t)kSkmTileKeys * 2) * 4;
 }
-template <int BPT>
+template <int BPT, int SLOTS>
 __global__ void __launch_bounds__(kSkmNT, 2) k_skm_kscatter(const unsigned long long *__restrict__ recs, const TileDesc *__restrict__ tiles,
                                                          int K1, int nbits, unsigned long long *__restrict__ cursor,
                                                          const unsigned long long *__restrict__ limit, uint32_t *__restrict__ out) {
@@ -307,18 +319,19 @@ __global__ void __launch_bounds__(kSkmNT, 2) k_skm_kscatter(const unsigned long 
   const int dsh = 64 - nbits;
   for (int i = tid; i < nbins + 32; i += NT) s_cnt[i] = 0;
   const TileDesc d = tiles[blockIdx.x];
-  unsigned long long rec[2];
-  uint32_t cnt[2];
-  skm_load2(recs, d, tid, rec, cnt);
-  SkmKeys sk[2];
-  sk[0].init(rec[0], K1);
-  sk[1].init(rec[1], K1);
+  constexpr int R = 16 / SLOTS;
+  unsigned long long rec[R];
+  uint32_t cnt[R];
+  skm_load<R>(recs, d, tid, rec, cnt);
+  SkmKeys sk[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) sk[q].init(rec[q], K1);
   __syncthreads();
   // phase A: count
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < R; ++q) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < SLOTS; ++i) {
       const uint32_t dg = (uint32_t)(sk[q].key(i) >> dsh);
       atomicAdd(s_cnt + ((uint32_t)i < cnt[q] ? dg : dummy), 1u);
     }
@@ -327,9 +340,9 @@ __global__ void __launch_bounds__(kSkmNT, 2) k_skm_kscatter(const unsigned long 
   const uint32_t total = bins_scan_reserve<NT, BPT>(s_cnt, s_gd, scratch, cursor, nbins, limit);
   // phase B: keys again, each takes the next free slot of its bin
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
+  for (int q = 0; q < R; ++q) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < SLOTS; ++i) {
       const unsigned long long key = sk[q].key(i);
       const bool ok = (uint32_t)i < cnt[q];
       const uint32_t pos = atomicAdd(s_cnt + (ok ? (uint32_t)(key >> dsh) : dummy), 1u);
@@ -423,11 +436,12 @@ void dev_count_skm(Ctx &c, const uint64_t *recs, const int64_t *chunk_start, con
     dev_count_finish(c, keys, scratch, 0, &z, &z, &zs, 0, 1, k, 1, min_count, out, nullptr);
     return;
   }
-  if (n_keys < n_rec || n_keys > n_rec * 8) throw std::invalid_argument("count_skm: n_keys does not fit the record count");
+  if (n_keys < n_rec || n_keys > n_rec * skm_slots(K1)) throw std::invalid_argument("count_skm: n_keys does not fit the record count");
   // level-1 width as count_plan chooses it for the streamed finish (engine.cu): bins of ~12 M keys, 512 at 5 Gbp
   const int l1_bits = std::max(1, std::min({10, key_bits, skm_ceil_log2((double)n_keys / 1.2e7)}));
   const int nb1 = 1 << l1_bits;
-  // tiles of the chunks
+  // tiles of the chunks: 16 key slots per thread, i.e. 2 records of <= 8 keys or 4 records of <= 4
+  const int slots = skm_slots(K1), rec_tile = kSkmTileKeys / slots;
   std::vector<int64_t> cs, cz, tb;
   std::vector<int32_t> cg;
   tb.push_back(0);
@@ -436,7 +450,7 @@ void dev_count_skm(Ctx &c, const uint64_t *recs, const int64_t *chunk_start, con
     cs.push_back(chunk_start[i]);
     cz.push_back(chunk_size[i]);
     cg.push_back(0);
-    tb.push_back(tb.back() + div_ceil64(chunk_size[i], kSkmRecTile));
+    tb.push_back(tb.back() + div_ceil64(chunk_size[i], rec_tile));
   }
   const int nch = (int)cs.size();
   const int64_t ntiles = tb.back();
@@ -450,7 +464,7 @@ void dev_count_skm(Ctx &c, const uint64_t *recs, const int64_t *chunk_start, con
   MF_CUDA(cudaMemcpyAsync(d_cz, cz.data(), sizeof(int64_t) * nch, cudaMemcpyHostToDevice, c.stream));
   MF_CUDA(cudaMemcpyAsync(d_cg, cg.data(), sizeof(int32_t) * nch, cudaMemcpyHostToDevice, c.stream));
   MF_CUDA(cudaMemcpyAsync(d_tb, tb.data(), sizeof(int64_t) * (nch + 1), cudaMemcpyHostToDevice, c.stream));
-  k_build_tiles<<<(unsigned)div_ceil64(ntiles, 256), 256, 0, c.stream>>>(ChunkTable{d_cs, d_cz, d_cg, d_tb, nch}, kSkmRecTile, ntiles, d_tiles);
+  k_build_tiles<<<(unsigned)div_ceil64(ntiles, 256), 256, 0, c.stream>>>(ChunkTable{d_cs, d_cz, d_cg, d_tb, nch}, rec_tile, ntiles, d_tiles);
   MF_LAUNCH_CHECK();
   c.launches++;
   const unsigned long long *urecs = reinterpret_cast<const unsigned long long *>(recs);
@@ -466,9 +480,10 @@ void dev_count_skm(Ctx &c, const uint64_t *recs, const int64_t *chunk_start, con
     {
       Stage st(c, "skm_hist");
       const size_t smem = ((size_t)nb1 + 32) * 4;
-      skm_set_smem(k_skm_hist, smem);
+      auto hk = slots == 4 ? k_skm_hist<4> : k_skm_hist<8>;
+      skm_set_smem(hk, smem);
       const int64_t nsamp = div_ceil64(ntiles, stride);
-      k_skm_hist<<<(unsigned)std::min<int64_t>(nsamp, (int64_t)c.sm_count * 4), kSkmNT, smem, c.stream>>>(urecs, d_tiles, ntiles, stride, K1,
+      hk<<<(unsigned)std::min<int64_t>(nsamp, (int64_t)c.sm_count * 4), kSkmNT, smem, c.stream>>>(urecs, d_tiles, ntiles, stride, K1,
                                                                                                         l1_bits, d_hist);
       MF_LAUNCH_CHECK();
       c.launches++;
@@ -504,7 +519,7 @@ void dev_count_skm(Ctx &c, const uint64_t *recs, const int64_t *chunk_start, con
       Stage st(c, "skm_l1_scatter");
       const size_t smem = skm_kscatter_smem_bytes(l1_bits);
       const int bpt = std::max(1, nb1 / kSkmNT);
-      auto kern = bpt == 1 ? k_skm_kscatter<1> : k_skm_kscatter<2>;
+      auto kern = slots == 4 ? (bpt == 1 ? k_skm_kscatter<1, 4> : k_skm_kscatter<2, 4>) : (bpt == 1 ? k_skm_kscatter<1, 8> : k_skm_kscatter<2, 8>);
       skm_set_smem(kern, smem);
       kern<<<(unsigned)ntiles, kSkmNT, smem, c.stream>>>(urecs, d_tiles, K1, l1_bits, d_cursor, d_limit, keys);
       MF_LAUNCH_CHECK();

@@ -119,3 +119,15 @@ def test_skm_rejects_unsupported_k(ctx):
     bases, starts = make_reads(5, 100, 31, genome_len=2000)
     with pytest.raises(lib.MfsdbgError):
         ctx.skm_scatter(ctx.upload_reads(bases, starts), 31, 2)
+
+
+@pytest.mark.parametrize("cmax", [4, 2, 6])
+def test_skm_short_records(ctx, oracle, monkeypatch, cmax):
+    """MFSDBG_SKM_CMAX: shorter records (<= 4 keys take the receiver's 4-slot kernel); same edges"""
+    monkeypatch.setenv("MFSDBG_SKM_CMAX", str(cmax))
+    k, m, n_dst = 21, 2, 8
+    bases, starts = make_reads(4100 + cmax, 30000, k, genome_len=80000, max_len=150, err=0.01)
+    parts, rec, keys = _skm_count(ctx, ctx.upload_reads(bases, starts), k, m, n_dst)
+    want = oracle.count(oracle.Reads(bases, starts), k, m, threads=8)
+    assert np.array_equal(_merge(parts), want.data)
+    assert keys.sum() / rec.sum() <= cmax
