@@ -11,6 +11,7 @@
 // The owner builds its part of the table, probes it, and ends up with its share of the miss list; the driver then generates
 // 2 real items per local edge plus 2 dummies per local miss and exchanges items by prefix as before.
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -29,7 +30,10 @@ static int ksd_ceil_log2(double x) {
 // table geometry for `n_edges_global` edges over `world` GPUs: as ks_geometry (engine.cu), but cut into at least `world` slices
 void ksd_geometry(int64_t n_edges_global, int world, int *log_slots, int *slice_log) {
   const int ls = std::max(10, ksd_ceil_log2(3.0 * (double)std::max<int64_t>(n_edges_global, 1)));
-  int sl = std::min(ls, std::max(kKsSliceLog, ls - 10));          // at most 1024 slices of >= 16 MB
+  int min_sl = kKsSliceLog;                                        // 16 MB slices; MFSDBG_KS_SLICE_LOG (21..24) asks for larger ones:
+  if (const char *e = getenv("MFSDBG_KS_SLICE_LOG"))               // fewer exchange bins = longer NVLink runs, weaker L2 window
+    if (*e) min_sl = std::max(kKsSliceLog, std::min(24, atoi(e)));
+  int sl = std::min(ls, std::max(min_sl, ls - 10));               // at most 1024 slices of >= 16 MB
   const int wl = ksd_ceil_log2((double)std::max(world, 1));
   if (ls - sl < wl) sl = std::max(6, ls - wl);                    // small inputs: still a slice per GPU
   *log_slots = ls;
