@@ -31,13 +31,13 @@ struct CwCfg {
   static constexpr int kSolidMax = W == 3 ? 768 : 512;     // distinct solid keys of one bucket on this path
   static constexpr int kAlign = (W % 4 == 0) ? 1 : ((W % 2 == 0) ? 2 : 4);   // records per 16-byte boundary
 };
-template <int W>
+template <int W, int CH = CwCfg<W>::kChunk, int ST = kCwStages>
 inline size_t count_stream_w_smem_bytes() {
   using C = CwCfg<W>;
   // slots u64[4096] | mbar u64[4] | ring u32[stages*chunk*W] (16-byte aligned) | skw u32[solid*W] | tcnt u32[4096]
   // | srep u32[solid] | scnt u32[solid] | bnd u32[win+2] | bins u32[1026] | small u32[64] | scratch u32[40] | flag i32[16]
   // | permA, permB, rk u16[solid]
-  return (size_t)kCwSlots * 8 + 64 + (size_t)kCwStages * C::kChunk * W * 4 + (size_t)C::kSolidMax * W * 4 + (size_t)kCwSlots * 4 +
+  return (size_t)kCwSlots * 8 + 64 + (size_t)ST * CH * W * 4 + (size_t)C::kSolidMax * W * 4 + (size_t)kCwSlots * 4 +
          2 * (size_t)C::kSolidMax * 4 + (size_t)(kCwWin + 2) * 4 + 1026 * 4 + 64 * 4 + 40 * 4 + 16 * 4 + 3 * (size_t)C::kSolidMax * 2 + 16;
 }
 
@@ -55,15 +55,16 @@ __device__ __forceinline__ void hash_wide(const uint32_t *k, uint32_t &ha, uint3
   hb = b * 0x85ebca6bu;
 }
 
-template <int W>
+// CH keys per ring stage, ST stages (the defaults, or 2 x 512 for W = 7, 8: every thread has a key in every chunk)
+template <int W, int CH = CwCfg<W>::kChunk, int ST = kCwStages>
 __global__ void __launch_bounds__(kCwNT) k_count_stream_w(LocalArgs a, const int32_t *__restrict__ cta_first) {
   extern __shared__ __align__(128) unsigned char smraw[];
   using C = CwCfg<W>;
-  constexpr int NT = kCwNT, CH = C::kChunk, SMAX = C::kSolidMax, AL = C::kAlign;
+  constexpr int NT = kCwNT, SMAX = C::kSolidMax, AL = C::kAlign;
   unsigned long long *slots = reinterpret_cast<unsigned long long *>(smraw);
   unsigned long long *mbar = slots + kCwSlots;
   uint32_t *ring = reinterpret_cast<uint32_t *>(mbar + 8);   // mbar[0..3] full, mbar[4..7] empty
-  uint32_t *skw = ring + (size_t)kCwStages * CH * W;
+  uint32_t *skw = ring + (size_t)ST * CH * W;
   uint32_t *tcnt = skw + (size_t)SMAX * W;
   uint32_t *srep = tcnt + kCwSlots;
   uint32_t *scnt = srep + SMAX;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kCwNT) k_count_stream_w(LocalArgs a, const int
   const int We = a.words_edge;
 
   auto issue = [&](int c) {   // thread 0 only
-    const int s = c % kCwStages;
+    const int s = c % ST;
     const int64_t g0 = A + (int64_t)c * CH;
     const int64_t left = re_up - g0;
     const uint32_t bytes = (uint32_t)(left < CH ? left : CH) * (uint32_t)(W * 4);
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kCwNT) k_count_stream_w(LocalArgs a, const int
     }
   };
   if (tid == 0) {
-    for (int s = 0; s < kCwStages; ++s) {
+    for (int s = 0; s < ST; ++s) {
       mbar_init(mbar + s, 1);              // full: the bulk copy's bytes
       mbar_init(mbar + 4 + s, NT / 32);    // empty: one arrival per warp
     }
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(kCwNT) k_count_stream_w(LocalArgs a, const int
   load_window();
   __syncthreads();
   if (tid == 0)
-    for (int c = 0; c < kCwStages && c < nchunks; ++c) issue(c);
+    for (int c = 0; c < ST && c < nchunks; ++c) issue(c);
 
   uint32_t bbeg = 0;   // relative position of the current bucket's first key
   // key: W words in shared memory (the ring); rel: its position relative to the bucket start
@@ -325,8 +326,14 @@ __global__ void __launch_bounds__(kCwNT) k_count_stream_w(LocalArgs a, const int
   advance();
   const int off0 = (int)(rb - A);
   for (int c = 0; c < nchunks; ++c) {
-    const int s = c % kCwStages;
-    mbar_wait(mbar + s, (uint32_t)((c / kCwStages) & 1));
+    const int s = c % ST;
+    if constexpr (ST < 3) {   // two stages: the refill of the other stage cannot wait for the end of this chunk
+      if (tid == 0 && c >= 1 && c - 1 + ST < nchunks) {
+        mbar_wait(mbar + 4 + (c - 1) % ST, (uint32_t)(((c - 1) / ST) & 1));
+        issue(c - 1 + ST);
+      }
+    }
+    mbar_wait(mbar + s, (uint32_t)((c / ST) & 1));
     const int64_t g0 = A + (int64_t)c * CH;
     const int64_t ghi = g0 + CH < re ? g0 + CH : re;
     const uint32_t chi = (uint32_t)(ghi - rb);
@@ -351,9 +358,9 @@ __global__ void __launch_bounds__(kCwNT) k_count_stream_w(LocalArgs a, const int
     // this warp is done with stage s; thread 0 refills the stage of the previous chunk once every warp has released it
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(mbar + 4 + s);
-    if (tid == 0 && c >= 1 && c - 1 + kCwStages < nchunks) {
-      mbar_wait(mbar + 4 + (c - 1) % kCwStages, (uint32_t)(((c - 1) / kCwStages) & 1));
-      issue(c - 1 + kCwStages);
+    if (ST >= 3 && tid == 0 && c >= 1 && c - 1 + ST < nchunks) {
+      mbar_wait(mbar + 4 + (c - 1) % ST, (uint32_t)(((c - 1) / ST) & 1));
+      issue(c - 1 + ST);
     }
   }
 }

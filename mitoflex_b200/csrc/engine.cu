@@ -294,6 +294,21 @@ struct TileCfg {
   static constexpr int TH = NT * IPT_H;
 };
 
+// wide keys on short reads: few positions start a key (k = 141 on 150-base reads: 6 %, k = 119: 20 %), so the kernel that walks
+// the LIST of valid positions (k_reads_scatter_compact, reads.cuh) wins over the one that walks all positions -- and, staging
+// the keys of 8192 positions whatever their width, it takes 1024 level-1 bins where the walking kernel falls off a cliff beyond
+// 256, which saves the whole prefix level that used to follow (count_l2a).  Measured on the 5 Gbp set, count at k = 141 / 119 /
+// 99 / 79 / 59: 89.8 / 182.1 / 208.6 / 180.0 / 157.8 ms walking, 48.1 / 130.9 / 159.7 / 161.7 / 161.9 ms compacted with 1024
+// bins (gpurun_out/r2aa_wide_ab.json): taken when under half of the positions start a key.
+// MFSDBG_READS_COMPACT: 0 never, 1 by that rule, 2 always
+static bool reads_compact_wanted(int W, int64_t n_bases, int64_t n_reads, int k) {
+  if (W < 4) return false;
+  const int mode = env_int("MFSDBG_READS_COMPACT", 1);
+  if (mode == 0) return false;
+  const double frac = n_bases > 0 ? std::max(0.0, (double)(n_bases - n_reads * (int64_t)k)) / (double)n_bases : 1.0;
+  return mode == 2 || frac < 0.50;
+}
+
 // tile range [tile0, tile0 + ntiles) of the reads (ntiles < 0: all of them) -- the host-input pipeline runs the reads-fed
 // level chunk by chunk while later chunks are still crossing PCIe
 template <int W>
@@ -329,6 +344,33 @@ static void launch_reads_scatter(Ctx &c, const ReadsView &r, const uint32_t *sbi
   using C = ReadsTileCfg<W>;
   const int64_t tiles = ntiles >= 0 ? ntiles : div_ceil64(r.n_bases, C::T);
   if (tiles == 0) return;
+  if constexpr (W >= 4) {
+    using CC = ReadsCompactCfg<W>;
+    if ((1 << a.nbits) <= 2 * CC::NT && reads_compact_wanted(W, r.n_bases, r.n_reads, k)) {
+      const int64_t pos0 = tile0 * C::T, pos1 = std::min<int64_t>(r.n_bases, pos0 + tiles * C::T);
+      if (env_int("MFSDBG_READS_COMPACT_V", 1) == 2) {   // batches cut loose from the listing passes (reads.cuh)
+        using C2 = ReadsCompact2Cfg<W>;
+        const int64_t ctiles2 = div_ceil64(pos1 - pos0, C2::T);
+        if (ctiles2 <= 0) return;
+        const size_t smem2 = reads_compact2_smem_bytes<W>(a.nbits, k);
+        auto kern2 = k_reads_scatter_compact2<W>;
+        set_smem(kern2, smem2);
+        kern2<<<(unsigned)ctiles2, C2::NT, smem2, c.stream>>>(ReadsSrc{r.packed, sbits, r.n_bases, k}, a, cursor, out, pos0, pos1);
+        MF_LAUNCH_CHECK();
+        c.launches++;
+        return;
+      }
+      const int64_t ctiles = div_ceil64(pos1 - pos0, CC::T);
+      if (ctiles <= 0) return;
+      const size_t smem = reads_compact_smem_bytes<W>(a.nbits, k);
+      auto kern = k_reads_scatter_compact<W>;
+      set_smem(kern, smem);
+      kern<<<(unsigned)ctiles, CC::NT, smem, c.stream>>>(ReadsSrc{r.packed, sbits, r.n_bases, k}, a, cursor, out, pos0, pos1);
+      MF_LAUNCH_CHECK();
+      c.launches++;
+      return;
+    }
+  }
   const int bpt = std::max(1, (1 << a.nbits) / C::NT);   // bins per thread of the block scan
   switch (bpt) {
     case 1: launch_reads_scatter_b<W, 1>(c, r, sbits, k, a, cursor, out, tile0, tiles); break;
@@ -766,9 +808,12 @@ static DevBuckets stream_partition(Ctx &c, uint32_t **cur, uint32_t **other, con
     for (size_t i = 0; i < hc.start.size(); ++i) seg_total[hc.seg[i]] += hc.size[i];
     const int xbits = std::min(16, key_bits - *bit_off);
     // 1024 bins keep the scatter's runs long enough (2048-bin levels run at half the speed); more only as a last resort
-    const int64_t nb_cap = std::min<int64_t>(1024, (int64_t)1 << xbits);
+    int64_t nb_cap = std::min<int64_t>(1024, (int64_t)1 << xbits);
     int64_t max_need = 1;
     for (int s2 = 0; s2 < hc.nseg; ++s2) max_need = std::max<int64_t>(max_need, (int64_t)std::ceil((double)seg_total[s2] / B));
+    // wide keys: a 2048-bin level runs 1.35x slower than a 1024-bin one (k=79: 49 against 36 ms), a whole extra prefix level
+    // costs 34 ms -- take the 2048 bins when they make that level unnecessary (MFSDBG_L2_NBCAP_W=1024 turns it off)
+    if (W >= 4 && xbits == 16 && max_need > nb_cap && max_need <= std::min(kMaxBins, env_int("MFSDBG_L2_NBCAP_W", 2048))) nb_cap = max_need;
     // up to 1.5x over the bin limit the buckets simply get that much larger (the table runs fuller, what crowds it takes the
     // multi-pass kernel): cheaper than a whole extra partition level
     // (2-word keys only: wider keys have no multi-pass kernel, their crowded buckets fall to the slow general path)
@@ -854,6 +899,19 @@ static void launch_count_stream_w(Ctx &c, const LocalArgs &a, int nslots, int gr
   if constexpr (W >= 3) {
     k_split_ranges<<<div_ceil(grid + 1, 128), 128, 0, c.stream>>>(a.bkt_start, a.bkt_size, nslots, grid, d_cta_first);
     MF_LAUNCH_CHECK();
+    // W = 7, 8 (k = 96..127): 2 ring stages of 512 keys instead of 3 of 256 -- every thread has a key in every chunk, still two
+    // CTAs per SM (k=119: 50.7 -> 38.3 ms, k=99: 63.5 -> 51.5 ms; MFSDBG_CW_CHUNK=0 for the old ring).  W = 9, 10: 2 x 384 on request.
+    if constexpr (W >= 7) {
+      constexpr int CH2 = W <= 8 ? 512 : 384;
+      if (env_int("MFSDBG_CW_CHUNK", W <= 8 ? 1 : 0) == 1) {
+        const size_t smem = count_stream_w_smem_bytes<W, CH2, 2>();
+        set_smem(k_count_stream_w<W, CH2, 2>, smem);
+        k_count_stream_w<W, CH2, 2><<<grid, kCwNT, smem, c.stream>>>(a, d_cta_first);
+        MF_LAUNCH_CHECK();
+        c.launches += 2;
+        return;
+      }
+    }
     const size_t smem = count_stream_w_smem_bytes<W>();
     set_smem(k_count_stream_w<W>, smem);
     k_count_stream_w<W><<<grid, kCwNT, smem, c.stream>>>(a, d_cta_first);
@@ -1182,7 +1240,7 @@ const uint32_t *dev_start_bits(Ctx &c, const ReadsView &r) { return build_start_
 
 // level-1 digit width of count
 template <int W>
-static Plan count_plan(Ctx &c, int k, int min_count, int64_t n_est) {
+static Plan count_plan(Ctx &c, int k, int min_count, int64_t n_est, bool compact = false) {
   const int key_bits = 2 * (k + 1);
   Plan p = make_plan(W, key_bits, n_est, 2.0, true);
   if (W >= 2 && env_int("MFSDBG_L1_BITS", -1) < 0 && env_int(W == 2 ? "MFSDBG_COUNT_STREAM" : "MFSDBG_COUNT_STREAM_W", 1) != 0) {
@@ -1192,8 +1250,11 @@ static Plan count_plan(Ctx &c, int k, int min_count, int64_t n_est) {
     // keys of 4+ words are staged in small tiles (ReadsTileCfg: 256 / 128 threads, 4096 / 2048 positions, and only (L-k)/L
     // of the positions start a key): beyond 256 bins a tile holds less than a key or two per bin and the reads-fed scatter
     // falls off a cliff (k=79: 51 ms at 8 bits, 96 ms at 9); the extra bits go to the prefix level that follows anyway
-    const int l1_cap = W >= 4 ? 8 : 10;
-    p.l1_bits = std::max(1, std::min({l1_cap, key_bits, ceil_log2((double)n_est / (W == 2 ? 1.2e7 : 4.0e6))}));
+    // (the compacted scatter stages the keys of 8192 positions whatever their width and takes up to 1024 bins:
+    // MFSDBG_L1_CAP_WC / MFSDBG_L1_SEGK_WC = its bit cap and the keys, in thousands, a level-1 segment should hold)
+    const int l1_cap = W >= 4 ? (compact ? std::min(10, env_int("MFSDBG_L1_CAP_WC", 10)) : 8) : 10;
+    const double seg_keys = W == 2 ? 1.2e7 : (compact ? 1e3 * std::max(1, env_int("MFSDBG_L1_SEGK_WC", 1000)) : 4.0e6);
+    p.l1_bits = std::max(1, std::min({l1_cap, key_bits, ceil_log2((double)n_est / seg_keys)}));
     // out-of-core rounds are cut at level-1 bin boundaries: a bin (twice the average at small prefixes) must stay well
     // inside what one round may hold
     const size_t bud0 = (size_t)((double)c.budget() * 0.9);
@@ -1218,7 +1279,7 @@ static void dev_count_impl(Ctx &c, const ReadsView &r, int k, int min_count, Edg
   }
   // the plan needs the key count: it is at most one key per base
   const int64_t n_est = std::max<int64_t>(r.n_bases - r.n_reads * (int64_t)k, 1);   // one key per base minus k per read
-  Plan p = count_plan<W>(c, k, min_count, n_est);
+  Plan p = count_plan<W>(c, k, min_count, n_est, reads_compact_wanted(W, r.n_bases, r.n_reads, k));
   const int nb1 = 1 << p.l1_bits;
   c.small[1].reserve(sizeof(unsigned long long) * (kMaxBins + kNumBuckets));
   unsigned long long *d_small = c.small[1].as<unsigned long long>();   // hist | counting
@@ -1390,7 +1451,7 @@ static bool dev_count_host_impl(Ctx &c, const uint32_t *packed_host, const int64
   const int n_chunks = (int)std::min<int64_t>(env_int("MFSDBG_H2D_CHUNKS", 8), ntiles / 8);
   if (n_chunks < 2) return false;
   const int64_t n_est = std::max<int64_t>(n_bases - n_reads * (int64_t)k, 1);
-  Plan p = count_plan<W>(c, k, min_count, n_est);
+  Plan p = count_plan<W>(c, k, min_count, n_est, reads_compact_wanted(W, n_bases, n_reads, k));
   const int nb1 = 1 << p.l1_bits;
   const size_t table_bytes = (size_t)(64 << 20) + (size_t)((size_t)nb1 << kMaxDigitBits) * 96 + sizeof(int64_t) * 8 * (size_t)nb1 * n_chunks;
   const size_t budget = (size_t)((double)c.budget() * 0.9);

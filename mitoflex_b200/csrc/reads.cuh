@@ -274,4 +274,280 @@ __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a,
   }
 }
 
+// ============================================================ scatter, compacted: wide keys on short reads
+// k_reads_scatter spends its instructions per POSITION (16 per thread, predicated); with k = 141 on 150-base reads 6 % of the
+// positions start a key, at k = 119 20 %.  Here the valid positions of a tile are listed first (every thread appends the set
+// bits of its valid16 mask behind a block scan) and the threads then walk that LIST: each key is extracted on its own from
+// the tile's words in shared memory -- no rolling window, ~4W + 25 instructions per key instead of ~2W + 8 per position --
+// counted, staged in bin order and copied out like above, in batches of KCAP keys so that the staging area does not have to
+// hold a key per position.  Tiles are 8192 positions whatever the width, so the few keys of a tile still make runs.
+template <int W>
+struct ReadsCompactCfg {
+  static constexpr int NT = 512;
+  static constexpr int T = NT * 16;
+  static constexpr int KCAP = W <= 4 ? 4096 : (W <= 6 ? 2560 : (W <= 8 ? 2048 : 1536));   // 51-65 KB of staging
+};
+// dynamic smem (uint32 units): s_cnt[nbins+32] | pad | s_gd i64[nbins] | scratch[36] | s_pc[NT] | s_pos u16[T] | pad | stage[KCAP*W] | seq | sb
+template <int W>
+__host__ __device__ inline size_t reads_compact_smem_bytes(int nbits, int k) {
+  using C = ReadsCompactCfg<W>;
+  const size_t nb = (size_t)1 << nbits;
+  return (nb + 32 + 2 + 2 * nb + 36 + C::NT + C::T / 2 + 2 + (size_t)C::KCAP * W + reads_seq_words(C::NT, W) + reads_bit_words(C::NT, k)) * 4;
+}
+// first word of the canonical key that starts at tile position p (K1 = k + 1 > 16)
+__device__ __forceinline__ uint32_t reads_head_at(const uint32_t *seq, int p, int K1) {
+  const int pw = p >> 4, q = p + K1 - 16, qw = q >> 4;
+  const uint32_t c0 = ~__funnelshift_l(seq[pw + 1], seq[pw], 2 * (p & 15));
+  const uint32_t r0 = rev_bases(__funnelshift_l(seq[qw + 1], seq[qw], 2 * (q & 15)));
+  return min(c0, r0);
+}
+// the canonical key that starts at tile position p: min(complement(e), reverse(e)), W words, big-endian (= KeyWindow::key)
+template <int W>
+__device__ __forceinline__ void reads_key_at(const uint32_t *seq, int p, int K1, uint32_t (&out)[W]) {
+  const int pw = p >> 4, ps = 2 * (p & 15);
+  uint32_t wnd[W + 1], c[W], r[W];
+#pragma unroll
+  for (int j = 0; j <= W; ++j) wnd[j] = seq[pw + j];
+#pragma unroll
+  for (int j = 0; j < W; ++j) c[j] = ~__funnelshift_l(wnd[j + 1], wnd[j], ps);
+  c[W - 1] &= 0xffffffffu << (32 * W - 2 * K1);
+  // reverse(e): word w holds the bases p + K1 - 1 - 16 w downwards; the last word takes what is left of the window at p
+#pragma unroll
+  for (int w = 0; w < W - 1; ++w) {
+    const int q = p + K1 - 16 * (w + 1), qw = q >> 4;
+    r[w] = rev_bases(__funnelshift_l(seq[qw + 1], seq[qw], 2 * (q & 15)));
+  }
+  r[W - 1] = rev_bases(__funnelshift_l(wnd[1], wnd[0], ps)) << (32 * W - 2 * K1);
+  bool take_r = false, decided = false;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    if (!decided && r[j] != c[j]) {
+      take_r = r[j] < c[j];
+      decided = true;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < W; ++j) out[j] = take_r ? r[j] : c[j];
+}
+
+// positions [pos0, pos1) of the reads (pos0 a multiple of 16); one tile of 8192 positions per CTA
+template <int W>
+__global__ void __launch_bounds__(ReadsCompactCfg<W>::NT, 2) k_reads_scatter_compact(ReadsSrc src, LevelArgs a, unsigned long long *__restrict__ cursor,
+                                                                                   uint32_t *__restrict__ out, int64_t pos0, int64_t pos1) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  using C = ReadsCompactCfg<W>;
+  constexpr int NT = C::NT, T = C::T, KCAP = C::KCAP;
+  const int nbins = 1 << a.nbits, tid = threadIdx.x, K1 = src.k + 1;
+  uint32_t *s_cnt = smem;
+  uint32_t *s_gd32 = s_cnt + nbins + 32;
+  if ((reinterpret_cast<uintptr_t>(s_gd32) & 7) != 0) s_gd32 += 1;
+  long long *s_gd = reinterpret_cast<long long *>(s_gd32);
+  uint32_t *scratch = s_gd32 + 2 * nbins;
+  uint32_t *s_pc = scratch + 36;
+  uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_pc + NT);
+  uint32_t *stage = s_pc + NT + T / 2;
+  if ((reinterpret_cast<uintptr_t>(stage) & 7) != 0) stage += 1;
+  uint32_t *seq = stage + (size_t)KCAP * W;
+  uint32_t *sb = seq + reads_seq_words(NT, W);
+  const int dsh = 32 - a.nbits;
+  const uint32_t dlo = a.dlo, dspan = a.dhi - a.dlo;
+  const bool ranged = dlo != 0u || a.dhi != (1u << a.nbits);
+  const uint32_t dummy = (uint32_t)nbins + (tid & 31);
+
+  // the tile's words and start bits (positions relative to `base`); keys may start below `lim` only
+  const int64_t base = pos0 + (int64_t)blockIdx.x * T;
+  {
+    const int64_t total_words = (src.n_bases + 15) >> 4, w0 = base >> 4;
+    const int nsw = reads_seq_words(NT, W);
+    for (int i = tid; i < nsw; i += NT) seq[i] = (w0 + i < total_words) ? src.packed[w0 + i] : 0u;
+    const int64_t total_bw = (src.n_bases + 31) >> 5, b0 = base >> 5;
+    const int nbw = reads_bit_words(NT, src.k);
+    for (int i = tid; i < nbw; i += NT) sb[i] = (b0 + i < total_bw) ? src.sbits[b0 + i] : 0u;
+  }
+  int64_t lim64 = src.n_bases - K1 + 1 - base;
+  if (pos1 - base < lim64) lim64 = pos1 - base;
+  const int lim = (int)(lim64 < 0 ? 0 : (lim64 > T ? T : lim64));
+  __syncthreads();
+  const uint32_t vm = valid16(sb, tid * 16, src.k, lim);
+  s_pc[tid] = __popc(vm);
+  __syncthreads();
+  const uint32_t V = block_excl_scan<NT>(s_pc, NT, scratch);
+  {
+    uint32_t at = s_pc[tid];
+    for (uint32_t m = vm; m; m &= m - 1) s_pos[at++] = (uint16_t)(tid * 16 + __ffs(m) - 1);
+  }
+  __syncthreads();
+  for (uint32_t j0 = 0; j0 < V; j0 += KCAP) {
+    const uint32_t nb = min((uint32_t)KCAP, V - j0);
+    for (int i = tid; i < nbins + 32; i += NT) s_cnt[i] = 0;
+    __syncthreads();
+    for (uint32_t j = tid; j < nb; j += NT) {
+      const uint32_t d = reads_head_at(seq, s_pos[j0 + j], K1) >> dsh;
+      const bool ok = !ranged || (d - dlo) < dspan;
+      atomicAdd(s_cnt + (ok ? d : dummy), 1u);
+    }
+    __syncthreads();
+    const uint32_t total = bins_scan_reserve<NT, 2>(s_cnt, s_gd, scratch, cursor, nbins, a.limit);   // up to 2 NT = 1024 bins
+    for (uint32_t j = tid; j < nb; j += NT) {
+      uint32_t key[W];
+      reads_key_at<W>(seq, s_pos[j0 + j], K1, key);
+      const uint32_t d = key[0] >> dsh;
+      const bool ok = !ranged || (d - dlo) < dspan;
+      const uint32_t pos = atomicAdd(s_cnt + (ok ? d : dummy), 1u);
+      if (ok) {
+#pragma unroll
+        for (int c = 0; c < W; ++c) stage[(size_t)pos * W + c] = key[c];
+      }
+    }
+    __syncthreads();
+    const uint32_t total_words = total * W;
+    for (uint32_t x = tid; x < total_words; x += NT) {
+      const uint32_t j = x / W, c = x - j * W;
+      const uint32_t d = stage[(size_t)j * W] >> dsh;
+      uint32_t *dst = a.bin_base ? reinterpret_cast<uint32_t *>(a.bin_base[d]) : out;
+      const long long gd = s_gd[d];
+      if (gd != kDropRun) dst[(gd + (long long)j) * W + c] = stage[x];
+    }
+    __syncthreads();
+  }
+}
+
+// ---- the same, with the batch cut loose from the listing pass: a CTA owns 32768 positions (one load of the words and start
+// bits), lists the valid ones 8192 positions at a time and runs a batch whenever KCAP listed positions have come together -- at
+// k = 141 a listing pass finds ~500 keys, and a batch per pass means the block-wide scan, the global reservation and their
+// barriers are paid for 500 keys instead of 1536.
+template <int W>
+struct ReadsCompact2Cfg {
+  static constexpr int NT = 512;
+  static constexpr int SUB = NT * 16;     // positions per listing pass
+  static constexpr int NSUB = 4;
+  static constexpr int T = SUB * NSUB;    // positions per CTA (< 65536: listed as uint16)
+  static constexpr int KCAP = W <= 4 ? 3584 : ReadsCompactCfg<W>::KCAP;
+  static constexpr int PCAP = KCAP + SUB;   // listed positions held at once: what a batch left over + one pass
+};
+// dynamic smem (uint32 units): s_cnt[nbins+32] | pad | s_gd i64[nbins] | scratch[36] | s_pc[NT] | s_pos u16[PCAP] | pad | stage[KCAP*W] | seq | sb
+template <int W>
+__host__ __device__ inline int reads_compact2_seq_words() { return ReadsCompact2Cfg<W>::T / 16 + W + 1; }
+__host__ __device__ inline int reads_compact2_bit_words(int T, int k) { return T / 32 + (k + 15 + 31) / 32 + 2; }
+template <int W>
+__host__ __device__ inline size_t reads_compact2_smem_bytes(int nbits, int k) {
+  using C = ReadsCompact2Cfg<W>;
+  const size_t nb = (size_t)1 << nbits;
+  return (nb + 32 + 2 + 2 * nb + 36 + C::NT + C::PCAP / 2 + 2 + (size_t)C::KCAP * W + reads_compact2_seq_words<W>() + reads_compact2_bit_words(C::T, k)) * 4;
+}
+
+template <int W>
+__global__ void __launch_bounds__(ReadsCompact2Cfg<W>::NT, 2) k_reads_scatter_compact2(ReadsSrc src, LevelArgs a, unsigned long long *__restrict__ cursor,
+                                                                                     uint32_t *__restrict__ out, int64_t pos0, int64_t pos1) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  using C = ReadsCompact2Cfg<W>;
+  constexpr int NT = C::NT, T = C::T, SUB = C::SUB, NSUB = C::NSUB, KCAP = C::KCAP;
+  static_assert(KCAP % NT == 0 && C::PCAP % 2 == 0 && T <= 65536, "compact2 tiling");
+  const int nbins = 1 << a.nbits, tid = threadIdx.x, K1 = src.k + 1;
+  uint32_t *s_cnt = smem;
+  uint32_t *s_gd32 = s_cnt + nbins + 32;
+  if ((reinterpret_cast<uintptr_t>(s_gd32) & 7) != 0) s_gd32 += 1;
+  long long *s_gd = reinterpret_cast<long long *>(s_gd32);
+  uint32_t *scratch = s_gd32 + 2 * nbins;
+  uint32_t *s_pc = scratch + 36;
+  uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_pc + NT);
+  uint32_t *stage = s_pc + NT + C::PCAP / 2;
+  if ((reinterpret_cast<uintptr_t>(stage) & 7) != 0) stage += 1;
+  uint32_t *seq = stage + (size_t)KCAP * W;
+  uint32_t *sb = seq + reads_compact2_seq_words<W>();
+  const int dsh = 32 - a.nbits;
+  const uint32_t dlo = a.dlo, dspan = a.dhi - a.dlo;
+  const bool ranged = dlo != 0u || a.dhi != (1u << a.nbits);
+  const uint32_t dummy = (uint32_t)nbins + (tid & 31);
+
+  const int64_t base = pos0 + (int64_t)blockIdx.x * T;
+  {
+    const int64_t total_words = (src.n_bases + 15) >> 4, w0 = base >> 4;
+    const int nsw = reads_compact2_seq_words<W>();
+    for (int i = tid; i < nsw; i += NT) seq[i] = (w0 + i < total_words) ? src.packed[w0 + i] : 0u;
+    const int64_t total_bw = (src.n_bases + 31) >> 5, b0 = base >> 5;
+    const int nbw = reads_compact2_bit_words(T, src.k);
+    for (int i = tid; i < nbw; i += NT) sb[i] = (b0 + i < total_bw) ? src.sbits[b0 + i] : 0u;
+  }
+  int64_t lim64 = src.n_bases - K1 + 1 - base;
+  if (pos1 - base < lim64) lim64 = pos1 - base;
+  const int lim = (int)(lim64 < 0 ? 0 : (lim64 > T ? T : lim64));
+  __syncthreads();
+
+  // keys of the listed positions s_pos[j0 .. j0 + nb): counted, global ranges reserved, staged in bin order, copied out
+  auto batch = [&](uint32_t j0, uint32_t nb) {
+    for (int i = tid; i < nbins + 32; i += NT) s_cnt[i] = 0;
+    __syncthreads();
+    for (uint32_t j = tid; j < nb; j += NT) {
+      const uint32_t d = reads_head_at(seq, s_pos[j0 + j], K1) >> dsh;
+      const bool ok = !ranged || (d - dlo) < dspan;
+      atomicAdd(s_cnt + (ok ? d : dummy), 1u);
+    }
+    __syncthreads();
+    const uint32_t total = bins_scan_reserve<NT, 2>(s_cnt, s_gd, scratch, cursor, nbins, a.limit);
+    for (uint32_t j = tid; j < nb; j += NT) {
+      uint32_t key[W];
+      reads_key_at<W>(seq, s_pos[j0 + j], K1, key);
+      const uint32_t d = key[0] >> dsh;
+      const bool ok = !ranged || (d - dlo) < dspan;
+      const uint32_t pos = atomicAdd(s_cnt + (ok ? d : dummy), 1u);
+      if (ok) {
+#pragma unroll
+        for (int c = 0; c < W; ++c) stage[(size_t)pos * W + c] = key[c];
+      }
+    }
+    __syncthreads();
+    const uint32_t total_words = total * W;
+    for (uint32_t x = tid; x < total_words; x += NT) {
+      const uint32_t j = x / W, c = x - j * W;
+      const uint32_t d = stage[(size_t)j * W] >> dsh;
+      uint32_t *dst = a.bin_base ? reinterpret_cast<uint32_t *>(a.bin_base[d]) : out;
+      const long long gd = s_gd[d];
+      if (gd != kDropRun) dst[(gd + (long long)j) * W + c] = stage[x];
+    }
+    __syncthreads();
+  };
+
+  uint32_t cnt = 0;   // listed and not yet scattered (block-uniform)
+  for (int s = 0; s < NSUB; ++s) {
+    if (s * SUB >= lim) break;
+    const int p0 = s * SUB + tid * 16;
+    const uint32_t vm = valid16(sb, p0, src.k, lim);
+    s_pc[tid] = __popc(vm);
+    __syncthreads();
+    const uint32_t V = block_excl_scan<NT>(s_pc, NT, scratch);
+    {
+      uint32_t at = cnt + s_pc[tid];
+      for (uint32_t m = vm; m; m &= m - 1) s_pos[at++] = (uint16_t)(p0 + __ffs(m) - 1);
+    }
+    cnt += V;
+    __syncthreads();
+    const bool last = s == NSUB - 1 || (s + 1) * SUB >= lim;
+    uint32_t j0 = 0;
+    while (cnt - j0 >= (uint32_t)KCAP || (last && cnt > j0)) {
+      const uint32_t nb = min((uint32_t)KCAP, cnt - j0);
+      batch(j0, nb);
+      j0 += nb;
+    }
+    if (last) break;
+    if (j0) {   // what the batches left over (< KCAP positions) moves to the front
+      const uint32_t rest = cnt - j0;
+      uint16_t tmp[KCAP / NT];
+#pragma unroll
+      for (int i = 0; i < KCAP / NT; ++i) {
+        const uint32_t idx = (uint32_t)(i * NT + tid);
+        tmp[i] = idx < rest ? s_pos[j0 + idx] : (uint16_t)0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < KCAP / NT; ++i) {
+        const uint32_t idx = (uint32_t)(i * NT + tid);
+        if (idx < rest) s_pos[idx] = tmp[i];
+      }
+      cnt = rest;
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace mf

@@ -404,3 +404,31 @@ def test_count_stream2_slot_layouts(ctx, oracle, monkeypatch, k, env):
         e_orc = oracle.count(_orc_reads(oracle, bases2, starts2), k, m, threads=8)
         assert_edges_equal(e_gpu, e_orc)
         assert np.array_equal(e_gpu.counting, e_orc.counting)
+
+
+_WIDE_PLANS = {
+    "default": {},
+    "walk": {"MFSDBG_READS_COMPACT": "0", "MFSDBG_L2_NBCAP_W": "1024", "MFSDBG_CW_CHUNK": "0"},
+    "compact": {"MFSDBG_READS_COMPACT": "2", "MFSDBG_L1_CAP_WC": "8"},
+    # 1024 level-1 bins, 2048-bin level 2, the 2 x 512-key ring of k_count_stream_w<7 | 8>
+    "compact_fine": {"MFSDBG_READS_COMPACT": "2", "MFSDBG_L1_CAP_WC": "10", "MFSDBG_L1_SEGK_WC": "1", "MFSDBG_L2_NBCAP_W": "2048",
+                     "MFSDBG_CW_CHUNK": "1"},
+    # batches cut loose from the listing passes (k_reads_scatter_compact2)
+    "compact2": {"MFSDBG_READS_COMPACT": "2", "MFSDBG_READS_COMPACT_V": "2"},
+    "compact2_fine": {"MFSDBG_READS_COMPACT": "2", "MFSDBG_READS_COMPACT_V": "2", "MFSDBG_L1_SEGK_WC": "1", "MFSDBG_CW_CHUNK": "1"},
+}
+
+
+@pytest.mark.parametrize("plan", list(_WIDE_PLANS))
+@pytest.mark.parametrize("k", [59, 90, 99, 119, 141])
+def test_count_wide_reads_scatter_variants(ctx, oracle, monkeypatch, k, plan):
+    """Wide keys (4..9 words) through both reads-fed scatters: the one that walks every position (k_reads_scatter) and the one
+    that walks the list of positions that start a key (k_reads_scatter_compact; at k=59 a tile lists more keys than one staging
+    batch holds), plus the planner switches that ride on the latter.  150-base reads with a long tail of short ones."""
+    for name, v in _WIDE_PLANS[plan].items():
+        monkeypatch.setenv(name, v)
+    bases, starts = make_reads(4100 + k, 60000, k, genome_len=150000, max_len=150, err=0.005)
+    e_gpu = ctx.count(ctx.upload_reads(bases, starts), k, 2, want_counting=True)
+    e_orc = oracle.count(_orc_reads(oracle, bases, starts), k, 2, threads=8)
+    assert_edges_equal(e_gpu, e_orc)
+    assert np.array_equal(e_gpu.counting, e_orc.counting)
