@@ -557,17 +557,8 @@ __global__ void __launch_bounds__(512, 2) k_scatter_tma_w(const uint32_t *__rest
     __syncthreads();   // X is free, Y is complete
     if (tid == 0 && more) issue(dn);
     for (int i = tid; i < nbins + 32; i += NT) s_cnt[i] = 0;
-#pragma unroll
-    for (int q = 0; q < KPT; ++q) {
-      const uint32_t j = (uint32_t)(q * NT + tid);
-      if (j < total) {
-        const uint32_t *src = Y + (size_t)j * W;
-        const uint32_t dg = digit(make_uint2(src[0], src[1]));
-        uint32_t *dst = out + (s_gd[dg] + (long long)j) * W;
-#pragma unroll
-        for (int c = 0; c < W; ++c) dst[c] = src[c];
-      }
-    }
+    // W / VEC threads per record, consecutive threads write consecutive words (a thread per record wrote W words 4 W bytes apart)
+    staged_copy_out<W, NT>(Y, s_gd, total, a, out, [&](const uint32_t *r) { return digit(make_uint2(r[0], r[1])); });
     if (!more) break;
     __syncthreads();
     t = tn;

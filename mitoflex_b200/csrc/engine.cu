@@ -348,7 +348,7 @@ static void launch_reads_scatter(Ctx &c, const ReadsView &r, const uint32_t *sbi
     using CC = ReadsCompactCfg<W>;
     if ((1 << a.nbits) <= 2 * CC::NT && reads_compact_wanted(W, r.n_bases, r.n_reads, k)) {
       const int64_t pos0 = tile0 * C::T, pos1 = std::min<int64_t>(r.n_bases, pos0 + tiles * C::T);
-      if (env_int("MFSDBG_READS_COMPACT_V", 1) == 2) {   // batches cut loose from the listing passes (reads.cuh)
+      if (env_int("MFSDBG_READS_COMPACT_V", 2) == 2) {   // batches cut loose from the listing passes (reads.cuh); 1 = a batch per pass
         using C2 = ReadsCompact2Cfg<W>;
         const int64_t ctiles2 = div_ceil64(pos1 - pos0, C2::T);
         if (ctiles2 <= 0) return;
@@ -899,11 +899,11 @@ static void launch_count_stream_w(Ctx &c, const LocalArgs &a, int nslots, int gr
   if constexpr (W >= 3) {
     k_split_ranges<<<div_ceil(grid + 1, 128), 128, 0, c.stream>>>(a.bkt_start, a.bkt_size, nslots, grid, d_cta_first);
     MF_LAUNCH_CHECK();
-    // W = 7, 8 (k = 96..127): 2 ring stages of 512 keys instead of 3 of 256 -- every thread has a key in every chunk, still two
-    // CTAs per SM (k=119: 50.7 -> 38.3 ms, k=99: 63.5 -> 51.5 ms; MFSDBG_CW_CHUNK=0 for the old ring).  W = 9, 10: 2 x 384 on request.
+    // W >= 7 (k >= 96): 2 ring stages of 512 keys (W = 9, 10: 384) instead of 3 of 256 -- every thread has a key in every chunk, still
+    // two CTAs per SM (k=119: 50.7 -> 38.3 ms, k=99: 63.5 -> 51.5 ms, k=141: 20.4 -> 18.1 ms; MFSDBG_CW_CHUNK=0 for the old ring)
     if constexpr (W >= 7) {
       constexpr int CH2 = W <= 8 ? 512 : 384;
-      if (env_int("MFSDBG_CW_CHUNK", W <= 8 ? 1 : 0) == 1) {
+      if (env_int("MFSDBG_CW_CHUNK", 1) == 1) {
         const size_t smem = count_stream_w_smem_bytes<W, CH2, 2>();
         set_smem(k_count_stream_w<W, CH2, 2>, smem);
         k_count_stream_w<W, CH2, 2><<<grid, kCwNT, smem, c.stream>>>(a, d_cta_first);

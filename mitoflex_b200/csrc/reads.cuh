@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a,
   long long *s_gd = reinterpret_cast<long long *>(s_gd32);
   uint32_t *scratch = s_gd32 + 2 * nbins;
   uint32_t *stage = scratch + 36;
-  if ((reinterpret_cast<uintptr_t>(stage) & 7) != 0) stage += 1;
+  stage += ((16 - (reinterpret_cast<uintptr_t>(stage) & 15)) & 15) >> 2;   // 16-byte aligned (staged_copy_out)
   uint32_t *seq = stage + (size_t)T * W;
   uint32_t *sb = seq + reads_seq_words(NT, W);
   const int dsh = 32 - a.nbits;
@@ -263,14 +263,7 @@ __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a,
       }
     }
   } else {
-    const uint32_t total_words = total * W;
-    for (uint32_t x = tid; x < total_words; x += NT) {
-      const uint32_t j = x / W, c = x - j * W;
-      const uint32_t d = stage[(size_t)j * W] >> dsh;
-      uint32_t *dst = a.bin_base ? reinterpret_cast<uint32_t *>(a.bin_base[d]) : out;
-      const long long gd = s_gd[d];
-      if (gd != kDropRun) dst[(gd + (long long)j) * W + c] = stage[x];
-    }
+    staged_copy_out<W, NT>(stage, s_gd, total, a, out, [dsh](const uint32_t *r) { return r[0] >> dsh; });
   }
 }
 
@@ -301,23 +294,29 @@ __device__ __forceinline__ uint32_t reads_head_at(const uint32_t *seq, int p, in
   const uint32_t r0 = rev_bases(__funnelshift_l(seq[qw + 1], seq[qw], 2 * (q & 15)));
   return min(c0, r0);
 }
-// the canonical key that starts at tile position p: min(complement(e), reverse(e)), W words, big-endian (= KeyWindow::key)
+// the canonical key that starts at tile position p: min(complement(e), reverse(e)), W words, big-endian (= KeyWindow::key).
+// Both strands come from the W forward words f of the window: reversing the bases of the whole 16 W-base string puts the
+// 16 W - K1 pad bases (zeros) in front, so reverse(e) = (rev_bases(f[W-1]), ..., rev_bases(f[0])) shifted left by the pad.
 template <int W>
 __device__ __forceinline__ void reads_key_at(const uint32_t *seq, int p, int K1, uint32_t (&out)[W]) {
   const int pw = p >> 4, ps = 2 * (p & 15);
-  uint32_t wnd[W + 1], c[W], r[W];
+  const int pad2 = 2 * (16 * W - K1);   // 0..30 bits
+  uint32_t wnd[W + 1], f[W], c[W], rr[W + 1], r[W];
 #pragma unroll
   for (int j = 0; j <= W; ++j) wnd[j] = seq[pw + j];
 #pragma unroll
-  for (int j = 0; j < W; ++j) c[j] = ~__funnelshift_l(wnd[j + 1], wnd[j], ps);
-  c[W - 1] &= 0xffffffffu << (32 * W - 2 * K1);
-  // reverse(e): word w holds the bases p + K1 - 1 - 16 w downwards; the last word takes what is left of the window at p
+  for (int j = 0; j < W; ++j) f[j] = __funnelshift_l(wnd[j + 1], wnd[j], ps);
+  const uint32_t last_mask = 0xffffffffu << pad2;
+  f[W - 1] &= last_mask;
 #pragma unroll
-  for (int w = 0; w < W - 1; ++w) {
-    const int q = p + K1 - 16 * (w + 1), qw = q >> 4;
-    r[w] = rev_bases(__funnelshift_l(seq[qw + 1], seq[qw], 2 * (q & 15)));
+  for (int j = 0; j < W; ++j) {
+    c[j] = ~f[j];
+    rr[j] = rev_bases(f[W - 1 - j]);
   }
-  r[W - 1] = rev_bases(__funnelshift_l(wnd[1], wnd[0], ps)) << (32 * W - 2 * K1);
+  c[W - 1] &= last_mask;
+  rr[W] = 0u;
+#pragma unroll
+  for (int j = 0; j < W; ++j) r[j] = __funnelshift_l(rr[j + 1], rr[j], pad2);
   bool take_r = false, decided = false;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
@@ -346,7 +345,7 @@ __global__ void __launch_bounds__(ReadsCompactCfg<W>::NT, 2) k_reads_scatter_com
   uint32_t *s_pc = scratch + 36;
   uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_pc + NT);
   uint32_t *stage = s_pc + NT + T / 2;
-  if ((reinterpret_cast<uintptr_t>(stage) & 7) != 0) stage += 1;
+  stage += ((16 - (reinterpret_cast<uintptr_t>(stage) & 15)) & 15) >> 2;   // 16-byte aligned (staged_copy_out)
   uint32_t *seq = stage + (size_t)KCAP * W;
   uint32_t *sb = seq + reads_seq_words(NT, W);
   const int dsh = 32 - a.nbits;
@@ -400,14 +399,7 @@ __global__ void __launch_bounds__(ReadsCompactCfg<W>::NT, 2) k_reads_scatter_com
       }
     }
     __syncthreads();
-    const uint32_t total_words = total * W;
-    for (uint32_t x = tid; x < total_words; x += NT) {
-      const uint32_t j = x / W, c = x - j * W;
-      const uint32_t d = stage[(size_t)j * W] >> dsh;
-      uint32_t *dst = a.bin_base ? reinterpret_cast<uint32_t *>(a.bin_base[d]) : out;
-      const long long gd = s_gd[d];
-      if (gd != kDropRun) dst[(gd + (long long)j) * W + c] = stage[x];
-    }
+    staged_copy_out<W, NT>(stage, s_gd, total, a, out, [dsh](const uint32_t *r) { return r[0] >> dsh; });
     __syncthreads();
   }
 }
@@ -452,7 +444,7 @@ __global__ void __launch_bounds__(ReadsCompact2Cfg<W>::NT, 2) k_reads_scatter_co
   uint32_t *s_pc = scratch + 36;
   uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_pc + NT);
   uint32_t *stage = s_pc + NT + C::PCAP / 2;
-  if ((reinterpret_cast<uintptr_t>(stage) & 7) != 0) stage += 1;
+  stage += ((16 - (reinterpret_cast<uintptr_t>(stage) & 15)) & 15) >> 2;   // 16-byte aligned (staged_copy_out)
   uint32_t *seq = stage + (size_t)KCAP * W;
   uint32_t *sb = seq + reads_compact2_seq_words<W>();
   const int dsh = 32 - a.nbits;
@@ -497,14 +489,7 @@ __global__ void __launch_bounds__(ReadsCompact2Cfg<W>::NT, 2) k_reads_scatter_co
       }
     }
     __syncthreads();
-    const uint32_t total_words = total * W;
-    for (uint32_t x = tid; x < total_words; x += NT) {
-      const uint32_t j = x / W, c = x - j * W;
-      const uint32_t d = stage[(size_t)j * W] >> dsh;
-      uint32_t *dst = a.bin_base ? reinterpret_cast<uint32_t *>(a.bin_base[d]) : out;
-      const long long gd = s_gd[d];
-      if (gd != kDropRun) dst[(gd + (long long)j) * W + c] = stage[x];
-    }
+    staged_copy_out<W, NT>(stage, s_gd, total, a, out, [dsh](const uint32_t *r) { return r[0] >> dsh; });
     __syncthreads();
   };
 

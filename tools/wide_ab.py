@@ -25,6 +25,7 @@ CONFIGS = {
     "nb1024": {"MFSDBG_L2_NBCAP_W": "1024"},
     "cw0": {"MFSDBG_CW_CHUNK": "0"},
     "cw1": {"MFSDBG_CW_CHUNK": "1"},
+    "v1": {"MFSDBG_READS_COMPACT_V": "1"},
     "v2": {"MFSDBG_READS_COMPACT_V": "2"},
     "v2_cw1": {"MFSDBG_READS_COMPACT_V": "2", "MFSDBG_CW_CHUNK": "1"},
 }
