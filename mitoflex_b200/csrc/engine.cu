@@ -88,6 +88,8 @@ Ctx::~Ctx() {
   for (DevBuf &b : fb) b.release();
   out_rec.release();
   out_labels.release();
+  out_large.release();
+  for (HostBuf &b : io_pin) b.release();
   if (slab) cudaFree(slab);
   for (auto &s : stages) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
   for (auto e : copy_events) cudaEventDestroy(e);

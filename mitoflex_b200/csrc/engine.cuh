@@ -51,6 +51,7 @@ struct Ctx {
   // results that outlive a call
   DevBuf edges, sdbg_rec, sdbg_labels, sdbg_buckets, sbits, pack_words, pack_starts, synth_words, synth_starts, in_words, in_starts;
   HostBuf out_rec, out_labels, out_large;
+  HostBuf io_pin[2];                          // file writers: two pinned pieces of the output stream (hostio.cu)
   std::vector<int64_t> out_large_index;
   std::vector<uint16_t> out_large_mult;
   DevBuf small[3];   // per-call histograms / counters kept across calls (cudaMalloc and cudaFree stall for 100+ ms at times)

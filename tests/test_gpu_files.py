@@ -56,10 +56,15 @@ def test_buildlib_bytes(oracle, tmp_path, policy):
     assert open(g + ".lib_info").read() == open(o + ".lib_info").read()
 
 
-def test_count_seq2sdbg_read2sdbg_files(oracle, tmp_path):
+@pytest.mark.parametrize("io_chunk", [None, 1000])
+def test_count_seq2sdbg_read2sdbg_files(oracle, tmp_path, monkeypatch, io_chunk):
+    """io_chunk: the writers' pinned pieces cut down to 1000 bytes, so that the edge stream and the device-serialised sdbg stream
+    (items beyond multiplicity 254 and tip labels included: 400 copies of one read) cross piece and file boundaries everywhere."""
     from mitoflex_b200 import lib
     k, m, threads = 21, 2, 3
-    bases, starts = make_reads(77, 30000, k, genome_len=60000)
+    if io_chunk:
+        monkeypatch.setenv("MFSDBG_IO_CHUNK", str(io_chunk))
+    bases, starts = make_reads(77, 30000, k, genome_len=60000, dup_boost=400 if io_chunk else 0)
     libf = _write_fastq(tmp_path, bases, starts)
     lib.buildlib(libf, libf)
     os.makedirs(tmp_path / "g"), os.makedirs(tmp_path / "o")
