@@ -301,14 +301,15 @@ struct TileCfg {
 // the keys of 8192 positions whatever their width, it takes 1024 level-1 bins where the walking kernel falls off a cliff beyond
 // 256, which saves the whole prefix level that used to follow (count_l2a).  Measured on the 5 Gbp set, count at k = 141 / 119 /
 // 99 / 79 / 59: 89.8 / 182.1 / 208.6 / 180.0 / 157.8 ms walking, 48.1 / 130.9 / 159.7 / 161.7 / 161.9 ms compacted with 1024
-// bins (gpurun_out/r2aa_wide_ab.json): taken when under half of the positions start a key.
+// bins (profiles/r2aa_wide_ab_matrix.json); with the later kernel (compact2, grouped copy-out) it also wins at k = 69 (192.6 -> 161.1 ms)
+// and k = 59 (150.7 -> 143.6 ms; 61 % of the positions start a key), profiles/r2ag_wide_ab_matrix.json: taken below 62 %.
 // MFSDBG_READS_COMPACT: 0 never, 1 by that rule, 2 always
 static bool reads_compact_wanted(int W, int64_t n_bases, int64_t n_reads, int k) {
   if (W < 4) return false;
   const int mode = env_int("MFSDBG_READS_COMPACT", 1);
   if (mode == 0) return false;
   const double frac = n_bases > 0 ? std::max(0.0, (double)(n_bases - n_reads * (int64_t)k)) / (double)n_bases : 1.0;
-  return mode == 2 || frac < 0.50;
+  return mode == 2 || frac < 0.62;
 }
 
 // tile range [tile0, tile0 + ntiles) of the reads (ntiles < 0: all of them) -- the host-input pipeline runs the reads-fed
@@ -903,9 +904,12 @@ static void launch_count_stream_w(Ctx &c, const LocalArgs &a, int nslots, int gr
     MF_LAUNCH_CHECK();
     // W >= 7 (k >= 96): 2 ring stages of 512 keys (W = 9, 10: 384) instead of 3 of 256 -- every thread has a key in every chunk, still
     // two CTAs per SM (k=119: 50.7 -> 38.3 ms, k=99: 63.5 -> 51.5 ms, k=141: 20.4 -> 18.1 ms; MFSDBG_CW_CHUNK=0 for the old ring)
-    if constexpr (W >= 7) {
-      constexpr int CH2 = W <= 8 ? 512 : 384;
-      if (env_int("MFSDBG_CW_CHUNK", 1) == 1) {
+    {
+      // the two-stage ring at the other widths (same or less shared memory than their three-stage rings): W = 3 and 5 gain 2-3 ms
+      // (k = 39, 47, 69, 79), W = 4 nothing, W = 6 loses 6 ms with its 768-key chunks (profiles/r2ag_wide_ab_matrix.json)
+      constexpr int CH2 = W == 3 ? 1536 : (W <= 5 ? 1024 : (W == 6 ? 768 : (W <= 8 ? 512 : 384)));
+      const int want = env_int("MFSDBG_CW_CHUNK", -1);
+      if (want == 1 || (want < 0 && (W >= 7 || W == 3 || W == 5))) {
         const size_t smem = count_stream_w_smem_bytes<W, CH2, 2>();
         set_smem(k_count_stream_w<W, CH2, 2>, smem);
         k_count_stream_w<W, CH2, 2><<<grid, kCwNT, smem, c.stream>>>(a, d_cta_first);

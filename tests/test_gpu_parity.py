@@ -420,9 +420,9 @@ _WIDE_PLANS = {
 
 
 @pytest.mark.parametrize("plan", list(_WIDE_PLANS))
-@pytest.mark.parametrize("k", [59, 90, 99, 119, 141])
+@pytest.mark.parametrize("k", [39, 59, 79, 90, 99, 119, 141])
 def test_count_wide_reads_scatter_variants(ctx, oracle, monkeypatch, k, plan):
-    """Wide keys (4..9 words) through both reads-fed scatters: the one that walks every position (k_reads_scatter) and the one
+    """Wide keys (3..9 words; k=39 only meets the ring variants of k_count_stream_w) through both reads-fed scatters: the one that walks every position (k_reads_scatter) and the one
     that walks the list of positions that start a key (k_reads_scatter_compact; at k=59 a tile lists more keys than one staging
     batch holds), plus the planner switches that ride on the latter.  150-base reads with a long tail of short ones."""
     for name, v in _WIDE_PLANS[plan].items():
