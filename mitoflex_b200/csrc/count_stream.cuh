@@ -550,8 +550,10 @@ __global__ void __launch_bounds__(512, 2) k_scatter_tma_w(const uint32_t *__rest
       if (rk[q] != 0xffffffffu) {
         const uint32_t *src = Xo + (size_t)(q * NT + tid) * W;
         uint32_t *dst = Y + (size_t)(s_cnt[rk[q] >> 16] + (rk[q] & 0xffffu)) * W;
+        uint32_t rec[W];
 #pragma unroll
-        for (int c = 0; c < W; ++c) dst[c] = src[c];
+        for (int c = 0; c < W; ++c) rec[c] = src[c];
+        stage_store<W>(dst, rec);
       }
     }
     __syncthreads();   // X is free, Y is complete

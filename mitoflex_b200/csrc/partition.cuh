@@ -384,6 +384,24 @@ __device__ __forceinline__ uint32_t bins_scan_reserve(uint32_t *s_cnt, long long
   return total;
 }
 
+// a W-word record into its staging slot (16-byte aligned staging area): 16- / 8-byte stores where the record size allows.  Word
+// stores of 8-word records hit 4 of the 32 banks per instruction (slot * 8 + c): an 8-way conflict on every store, and
+// `short_scoreboard` / `mio_throttle` on top of the stall list of the wide-key scatters (ncu r2ai); records of an odd number of
+// words spread over all banks by themselves.
+template <int W>
+__device__ __forceinline__ void stage_store(uint32_t *dst, const uint32_t (&rec)[W]) {
+  if constexpr (W >= 3 && W % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) reinterpret_cast<uint4 *>(dst)[q] = make_uint4(rec[4 * q], rec[4 * q + 1], rec[4 * q + 2], rec[4 * q + 3]);
+  } else if constexpr (W >= 3 && W % 2 == 0) {
+#pragma unroll
+    for (int q = 0; q < W / 2; ++q) reinterpret_cast<uint2 *>(dst)[q] = make_uint2(rec[2 * q], rec[2 * q + 1]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < W; ++c) dst[c] = rec[c];
+  }
+}
+
 // ============================================================ copy-out of staged records
 // `total` records of W words lie in `stage` in bin order; bin d's run goes to global record s_gd[d] + (staged index).  A record is
 // moved by W / VEC threads in chunks of VEC words (4 when the record size is a multiple of 16 bytes, 2 of 8, else 1): the threads
@@ -473,8 +491,7 @@ __global__ void __launch_bounds__(NT) k_level_scatter(P prod, LevelArgs a, unsig
   for (int i = 0; i < IPT; ++i) {
     if (rk[i] != 0xffffffffu) {
       uint32_t pos = s_cnt[rk[i] >> 16] + (rk[i] & 0xffffu);
-#pragma unroll
-      for (int c = 0; c < W; ++c) stage[(size_t)pos * W + c] = rec[i][c];
+      stage_store<W>(stage + (size_t)pos * W, rec[i]);
     }
   }
   __syncthreads();

@@ -234,8 +234,7 @@ __global__ void __launch_bounds__(NT) k_reads_scatter(ReadsSrc src, LevelArgs a,
         if constexpr (W == 2) {
           *reinterpret_cast<uint2 *>(stage + (size_t)pos * 2) = make_uint2(key[0], key[1]);
         } else {
-#pragma unroll
-          for (int c = 0; c < W; ++c) stage[(size_t)pos * W + c] = key[c];
+          stage_store<W>(stage + (size_t)pos * W, key);
         }
       }
     }
@@ -394,8 +393,7 @@ __global__ void __launch_bounds__(ReadsCompactCfg<W>::NT, 2) k_reads_scatter_com
       const bool ok = !ranged || (d - dlo) < dspan;
       const uint32_t pos = atomicAdd(s_cnt + (ok ? d : dummy), 1u);
       if (ok) {
-#pragma unroll
-        for (int c = 0; c < W; ++c) stage[(size_t)pos * W + c] = key[c];
+        stage_store<W>(stage + (size_t)pos * W, key);
       }
     }
     __syncthreads();
@@ -484,8 +482,7 @@ __global__ void __launch_bounds__(ReadsCompact2Cfg<W>::NT, 2) k_reads_scatter_co
       const bool ok = !ranged || (d - dlo) < dspan;
       const uint32_t pos = atomicAdd(s_cnt + (ok ? d : dummy), 1u);
       if (ok) {
-#pragma unroll
-        for (int c = 0; c < W; ++c) stage[(size_t)pos * W + c] = key[c];
+        stage_store<W>(stage + (size_t)pos * W, key);
       }
     }
     __syncthreads();
