@@ -409,7 +409,8 @@ def test_count_stream2_slot_layouts(ctx, oracle, monkeypatch, k, env):
 _WIDE_PLANS = {
     "default": {},
     "walk": {"MFSDBG_READS_COMPACT": "0", "MFSDBG_L2_NBCAP_W": "1024", "MFSDBG_CW_CHUNK": "0"},
-    "compact": {"MFSDBG_READS_COMPACT": "2", "MFSDBG_L1_CAP_WC": "8"},
+    # a batch per listing pass (k_reads_scatter_compact, the first version of the kernel, kept as the A/B partner)
+    "compact": {"MFSDBG_READS_COMPACT": "2", "MFSDBG_READS_COMPACT_V": "1", "MFSDBG_L1_CAP_WC": "8"},
     # 1024 level-1 bins, 2048-bin level 2, the 2 x 512-key ring of k_count_stream_w<7 | 8>
     "compact_fine": {"MFSDBG_READS_COMPACT": "2", "MFSDBG_L1_CAP_WC": "10", "MFSDBG_L1_SEGK_WC": "1", "MFSDBG_L2_NBCAP_W": "2048",
                      "MFSDBG_CW_CHUNK": "1"},
